@@ -1,0 +1,206 @@
+"""ctypes binding of the C ABI declared in include/examl_b200.h.
+
+`Engine` wraps libexaml_b200.so (the CUDA engine).  The class is written against a
+(library, prefix) pair so that tests can bind the CPU oracle (oracle/liboracle.so, prefix
+`orc_`, same signatures) through the very same code path -- the product itself never does:
+`load_library()` below only ever opens the CUDA library and raises if it is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .phylo import Entry
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libexaml_b200.so")
+
+EXPORTS = [
+    "exb_create", "exb_destroy", "exb_last_error", "exb_set_partition", "exb_commit",
+    "exb_set_model", "exb_newview", "exb_evaluate", "exb_makenewz_prepare", "exb_core",
+    "exb_comm_unique_id", "exb_comm_init", "exb_read_clv", "exb_read_scaler",
+    "exb_read_sumtable", "exb_last_kernel_ms", "exb_launch_count", "exb_set_tile_sites",
+]
+UNIQUE_ID_BYTES = 128
+
+
+class ExbEntry(C.Structure):
+    _fields_ = [("tipCase", C.c_int), ("pNumber", C.c_int), ("qNumber", C.c_int), ("rNumber", C.c_int)]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib_cache = {}
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    """Open the CUDA engine.  There is no fallback: a missing library is an error."""
+    if path in _lib_cache:
+        return _lib_cache[path]
+    if not os.path.exists(path):
+        raise EngineError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  examl_b200 has no CPU fallback.")
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    _lib_cache[path] = lib
+    return lib
+
+
+def _dptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def pack_traversal(ti: Sequence[Entry], num_branches: int):
+    """Flatten a list of phylo.Entry into (exb_entry[count], qz[count*nb], rz[count*nb])."""
+    n = len(ti)
+    arr = (ExbEntry * max(n, 1))()
+    qz = np.zeros(max(n, 1) * num_branches)
+    rz = np.zeros(max(n, 1) * num_branches)
+    for i, e in enumerate(ti):
+        arr[i].tipCase, arr[i].pNumber, arr[i].qNumber, arr[i].rNumber = e.tipCase, e.pNumber, e.qNumber, e.rNumber
+        qz[i * num_branches:(i + 1) * num_branches] = e.qz[:num_branches]
+        if e.rz:
+            rz[i * num_branches:(i + 1) * num_branches] = e.rz[:num_branches]
+    return arr, qz, rz
+
+
+class Engine:
+    """One likelihood engine (one GPU).  Method names follow the reference functions they replace."""
+
+    def __init__(self, mxtips: int, num_partitions: int, num_branches: int = 1, device: int = 0,
+                 lib: Optional[C.CDLL] = None, prefix: str = "exb_", tile_sites: Optional[int] = None):
+        self.lib = lib if lib is not None else load_library()
+        self.prefix = prefix
+        self.mxtips, self.nparts, self.nbranches = mxtips, num_partitions, num_branches
+        self.states = [0] * num_partitions
+        self.widths = [0] * num_partitions
+        self._h = C.c_void_p()
+        if prefix == "exb_":
+            self._check(self._f("create")(C.byref(self._h), C.c_int(device), C.c_int(mxtips),
+                                          C.c_int(num_partitions), C.c_int(num_branches)))
+            if tile_sites is not None:
+                self._check(self._f("set_tile_sites")(self._h, C.c_int(tile_sites)))
+        else:
+            self._check(self._f("create")(C.byref(self._h), C.c_int(mxtips), C.c_int(num_partitions),
+                                          C.c_int(num_branches)))
+
+    # ---- plumbing -------------------------------------------------------------------------
+    def _f(self, name: str):
+        fn = getattr(self.lib, self.prefix + name)
+        fn.restype = C.c_int
+        return fn
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            msg = ""
+            if self.prefix == "exb_":
+                f = self.lib.exb_last_error
+                f.restype = C.c_char_p
+                msg = (f() or b"").decode()
+            raise EngineError(f"{self.prefix} call failed (rc={rc}): {msg}")
+
+    def close(self) -> None:
+        if self._h:
+            d = getattr(self.lib, self.prefix + "destroy")
+            d.restype = None
+            d(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- set-up ---------------------------------------------------------------------------
+    def set_partition(self, model: int, states: int, wgt: np.ndarray, tips: np.ndarray) -> None:
+        """tips: uint8 [mxtips, width] taxon-major (pInfo.yResource); wgt: int32 [width]."""
+        wgt = np.ascontiguousarray(wgt, dtype=np.int32)
+        tips = np.ascontiguousarray(tips, dtype=np.uint8)
+        width = int(wgt.shape[0])
+        assert tips.shape == (self.mxtips, width), (tips.shape, self.mxtips, width)
+        self.states[model], self.widths[model] = states, width
+        self._check(self._f("set_partition")(self._h, C.c_int(model), C.c_int(states), C.c_size_t(width),
+                                             _dptr(wgt), _dptr(tips)))
+
+    def commit(self) -> None:
+        if self.prefix == "exb_":
+            self._check(self._f("commit")(self._h))
+
+    def set_model(self, model: int, mc) -> None:
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in
+                (mc.EIGN, mc.EV, mc.EI, mc.tipVector, mc.gammaRates)]
+        self._check(self._f("set_model")(self._h, C.c_int(model), *[_dptr(a) for a in arrs]))
+
+    # ---- hot path ---------------------------------------------------------------------------
+    @staticmethod
+    def _mask(execute_model, n):
+        if execute_model is None:
+            return None
+        return np.ascontiguousarray(np.asarray(execute_model, dtype=np.uint8).reshape(n))
+
+    def newviewIterative(self, ti: Sequence[Entry], execute_model=None) -> None:
+        arr, qz, rz = pack_traversal(ti, self.nbranches)
+        m = self._mask(execute_model, self.nparts)
+        self._check(self._f("newview")(self._h, arr, C.c_int(len(ti)), _dptr(qz), _dptr(rz), _dptr(m)))
+
+    def evaluateIterative(self, ti: Sequence[Entry], execute_model=None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        arr, qz, rz = pack_traversal(ti, self.nbranches)
+        m = self._mask(execute_model, self.nparts)
+        lh = np.zeros(self.nparts) if out is None else out
+        self._check(self._f("evaluate")(self._h, arr, C.c_int(len(ti)), _dptr(qz), _dptr(rz), _dptr(m), _dptr(lh)))
+        return lh
+
+    def makenewzIterative(self, ti: Sequence[Entry], execute_model=None) -> None:
+        arr, qz, rz = pack_traversal(ti, self.nbranches)
+        m = self._mask(execute_model, self.nparts)
+        self._check(self._f("makenewz_prepare")(self._h, arr, C.c_int(len(ti)), _dptr(qz), _dptr(rz), _dptr(m)))
+
+    def execCore(self, lz: Sequence[float], execute_model=None):
+        lzv = np.ascontiguousarray(np.asarray(lz, dtype=np.float64).reshape(self.nbranches))
+        m = self._mask(execute_model, self.nparts)
+        d1 = np.zeros(self.nbranches)
+        d2 = np.zeros(self.nbranches)
+        self._check(self._f("core")(self._h, _dptr(lzv), _dptr(m), _dptr(d1), _dptr(d2)))
+        return d1, d2
+
+    # ---- multi-GPU -------------------------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+        self._check(self._f("comm_unique_id")(buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, nranks: int, uid: bytes) -> None:
+        buf = C.create_string_buffer(uid, UNIQUE_ID_BYTES)
+        self._check(self._f("comm_init")(self._h, C.c_int(rank), C.c_int(nranks), buf))
+
+    # ---- introspection ------------------------------------------------------------------------
+    def read_clv(self, model: int, node_number: int) -> np.ndarray:
+        out = np.zeros(self.widths[model] * 4 * self.states[model])
+        self._check(self._f("read_clv")(self._h, C.c_int(model), C.c_int(node_number), _dptr(out)))
+        return out.reshape(self.widths[model], 4, self.states[model])
+
+    def read_scaler(self, model: int, node_number: int) -> int:
+        v = C.c_uint(0)
+        self._check(self._f("read_scaler")(self._h, C.c_int(model), C.c_int(node_number), C.byref(v)))
+        return int(v.value)
+
+    def read_sumtable(self, model: int) -> np.ndarray:
+        out = np.zeros(self.widths[model] * 4 * self.states[model])
+        self._check(self._f("read_sumtable")(self._h, C.c_int(model), _dptr(out)))
+        return out.reshape(self.widths[model], 4, self.states[model])
+
+    def last_kernel_ms(self) -> float:
+        v = C.c_float(0)
+        self._check(self._f("last_kernel_ms")(self._h, C.byref(v)))
+        return float(v.value)
+
+    def launch_count(self) -> int:
+        f = self.lib.exb_launch_count
+        f.restype = C.c_long
+        return int(f(self._h))

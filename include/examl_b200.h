@@ -1,0 +1,161 @@
+/* examl_b200.h -- C ABI of the B200 likelihood engine (libexaml_b200.so).
+ *
+ * This is the boundary at which ExaML's host code hands the per-site conditional-likelihood
+ * work to the GPU.  It sits exactly where the reference crosses from its traversal executors
+ * into its SIMD kernels: every entry point below replaces one reference
+ * function, takes the same information that function reads from `tree` / `pInfo` /
+ * `traversalInfo`, flattened to plain pointers and sizes, and returns what that function
+ * leaves behind for its caller.  No torch / CUDA types appear in any signature.
+ *
+ *   reference function (file:line)                           replaced by
+ *   -------------------------------------------------------   ---------------------------
+ *   initializePartitions xVector/yVector/wgt/globalScaler      exb_create, exb_set_partition,
+ *     allocation (axml.c:1936-2104) + lazy x3 allocation        exb_commit
+ *     (newviewGenericSpecial.c:1199-1216)
+ *   reading pInfo.{EIGN,EV,EI,tipVector,gammaRates} on every   exb_set_model
+ *     call (newviewGenericSpecial.c:939-1045,
+ *     evaluateGenericSpecial.c:433-480)
+ *   newviewIterative      (newviewGenericSpecial.c:917)        exb_newview
+ *   evaluateIterative     (evaluateGenericSpecial.c:403)       exb_evaluate
+ *     + MPI_Allreduce     (evaluateGenericSpecial.c:968-975)     (all-reduce inside, NCCL)
+ *   makenewzIterative     (makenewzGenericSpecial.c:628)       exb_makenewz_prepare
+ *   execCore              (makenewzGenericSpecial.c:849)       exb_core
+ *     + MPI_Allreduce     (makenewzGenericSpecial.c:1241-1248)   (all-reduce inside, NCCL)
+ *
+ * The three public axml.h entry points (evaluateGeneric axml.h:1223, newviewGeneric :1232,
+ * makenewzGeneric :1241) are exported by the companion translation unit
+ * examl_b200/csrc/axml_backend.c, which is compiled against the reference's own axml.h and
+ * calls only the functions declared here.
+ *
+ * Conventions
+ *   - Node numbers are ExaML's: tips 1..mxtips, inner nodes mxtips+1..2*mxtips-2.
+ *   - A traversal is the reference's `traversalInfo` array without its 2x256 branch slots:
+ *     `exb_entry ti[count]` plus `qz[count*numBranches]`, `rz[count*numBranches]` holding the
+ *     raw branch values z = exp(-t) exactly as stored in traversalInfo.qz / .rz
+ *     (axml.h:434-442).  The engine applies the reference's clamp `z > zmin ? log z : log zmin`
+ *     (newviewGenericSpecial.c:983-984) itself.
+ *   - For exb_evaluate / exb_makenewz_prepare, ti[0] is the branch entry (pNumber, qNumber,
+ *     qz = branch value), exactly like td[0].ti[0] (evaluateGenericSpecial.c:410-416);
+ *     newviews are ti[1..count).  For exb_newview all entries are newviews.
+ *   - `executeModel[numPartitions]` is td[0].executeModel (1 = compute); a partition is
+ *     processed iff executeModel[m] && width > 0 (newviewGenericSpecial.c:1114).
+ *   - Branch slot of partition m is m when numBranches > 1 (-M), else 0
+ *     (newviewGenericSpecial.c:972-981).
+ *   - All likelihood arithmetic is IEEE double.  CLVs, tip codes, weights, scaler counts and
+ *     the sum table stay resident in HBM between calls; only descriptors and O(partitions)
+ *     scalars cross the bus.
+ *   - Every function returns EXB_OK (0) or a negative error code; exb_last_error() gives the
+ *     text.  There is no CPU fallback: without a usable CUDA device exb_create fails.
+ *     (The reference's own convention for unrecoverable errors is abort -- axml.c:129-140 --
+ *     and the axml backend turns any non-zero return into exactly that.)
+ */
+#ifndef EXAML_B200_H
+#define EXAML_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EXB_OK             0
+#define EXB_ERR_ARG       -1   /* bad argument / unsupported configuration */
+#define EXB_ERR_CUDA      -2   /* CUDA runtime error                        */
+#define EXB_ERR_STATE     -3   /* call sequence error                       */
+#define EXB_ERR_NCCL      -4   /* NCCL error / NCCL not loadable            */
+
+#define EXB_TIP_TIP        0   /* axml.h:302-304 */
+#define EXB_TIP_INNER      1
+#define EXB_INNER_INNER    2
+
+typedef struct exb_engine exb_engine;
+
+/* traversalInfo (axml.h:434-442) minus the branch arrays. */
+typedef struct {
+  int tipCase;
+  int pNumber;
+  int qNumber;
+  int rNumber;
+} exb_entry;
+
+/* ---- life cycle -------------------------------------------------------------------------- */
+
+/* Create an engine on CUDA device `device` for a tree with `mxtips` taxa, `numPartitions`
+ * partitions (tr->NumberOfModels) and `numBranches` branch slots (tr->numBranches). */
+int  exb_create(exb_engine **out, int device, int mxtips, int numPartitions, int numBranches);
+void exb_destroy(exb_engine *e);
+const char *exb_last_error(void);
+
+/* Describe partition `model` as this rank sees it (pInfo.states/.width/.wgt/.yResource,
+ * axml.h:533-629): `states` is 4 (DNA) or 20 (AA); `width` may be 0; `wgt[width]`;
+ * `yResource[mxtips*width]` taxon-major tip codes (byteFile.c:320-346). */
+int  exb_set_partition(exb_engine *e, int model, int states, size_t width,
+                       const int *wgt, const unsigned char *yResource);
+
+/* Freeze the layout, allocate the device arenas (CLVs for mxtips-2 inner nodes, sum table,
+ * scalers) and upload tips and weights. */
+int  exb_commit(exb_engine *e);
+
+/* ---- per-call inputs the host may have changed silently ------------------------------------- */
+
+/* Model constants of partition `model`: EIGN[S], EV[S*S], EI[S*S], tipVector[codes*S]
+ * (codes = 16 for DNA, 23 for AA), gammaRates[4] (models.c:3234-3457, 3795).  Cheap when
+ * unchanged (host-side compare). */
+int  exb_set_model(exb_engine *e, int model, const double *EIGN, const double *EV,
+                   const double *EI, const double *tipVector, const double *gammaRates);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+
+/* newviewIterative(tr, startIndex): recompute the CLVs listed in ti[0..count). */
+int  exb_newview(exb_engine *e, const exb_entry *ti, int count,
+                 const double *qz, const double *rz, const unsigned char *executeModel);
+
+/* evaluateIterative + the all-reduce of evaluateGeneric: newviews ti[1..count), then the
+ * log-likelihood at branch ti[0].  perPartitionLH[numPartitions]: executed partitions
+ * receive their (globally reduced) value, partitions with global width 0 receive 0.0,
+ * masked partitions are left untouched (evaluateGenericSpecial.c:845-860). */
+int  exb_evaluate(exb_engine *e, const exb_entry *ti, int count,
+                  const double *qz, const double *rz, const unsigned char *executeModel,
+                  double *perPartitionLH);
+
+/* makenewzIterative: newviews ti[1..count), then the per-site sum table of branch ti[0]. */
+int  exb_makenewz_prepare(exb_engine *e, const exb_entry *ti, int count,
+                          const double *qz, const double *rz, const unsigned char *executeModel);
+
+/* execCore + the all-reduce of topLevelMakenewz: first and second derivative of lnL with
+ * respect to lz = log z at the trial values lz[numBranches] (tr->coreLZ).  Outputs
+ * dlnLdlz[numBranches], d2lnLdlz2[numBranches]; with numBranches == 1 all executed partitions
+ * accumulate into slot 0 (makenewzGenericSpecial.c:921-946). */
+int  exb_core(exb_engine *e, const double *lz, const unsigned char *executeModel,
+              double *dlnLdlz, double *d2lnLdlz2);
+
+/* ---- multi-GPU (one process per GPU) ------------------------------------------------------ */
+
+/* NCCL bootstrap: rank 0 obtains an opaque id (EXB_UNIQUE_ID_BYTES bytes), the launcher
+ * distributes it, every rank calls exb_comm_init.  Afterwards exb_evaluate and exb_core
+ * sum their outputs over all ranks on the device (ncclAllReduce, double, sum) before the
+ * single device-to-host copy. */
+#define EXB_UNIQUE_ID_BYTES 128
+int  exb_comm_unique_id(void *id_out);
+int  exb_comm_init(exb_engine *e, int rank, int nranks, const void *id);
+
+/* ---- introspection (tests, benchmarks) ----------------------------------------------------- */
+
+/* Copy the CLV of inner node `nodeNumber`, partition `model`, to out[width*4*states]
+ * (layout x[i][c][k], newviewGenericSpecial.c:430-682). */
+int  exb_read_clv(exb_engine *e, int model, int nodeNumber, double *out);
+/* globalScaler[nodeNumber] of partition `model` (newviewGenericSpecial.c:1503-1506). */
+int  exb_read_scaler(exb_engine *e, int model, int nodeNumber, unsigned int *out);
+/* Copy the sum table of partition `model` to out[width*4*states]. */
+int  exb_read_sumtable(exb_engine *e, int model, double *out);
+/* Device time in milliseconds of the kernels of the most recent hot-path call (CUDA events
+ * on the engine's stream), and the number of kernel launches the engine has made so far. */
+int  exb_last_kernel_ms(exb_engine *e, float *ms);
+long exb_launch_count(exb_engine *e);
+/* Tuning knob: sites per work tile (multiple of 32).  Must be set before exb_commit. */
+int  exb_set_tile_sites(exb_engine *e, int sites);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXAML_B200_H */

@@ -1,0 +1,335 @@
+/* likelihood_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, single-threaded restatement of the reference's likelihood hot path, used only
+ * as the checker in tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.  Nothing
+ * under examl_b200/ may link, load or call it.
+ *
+ * Each function follows the reference's readable "FLEX" code (or the SSE3 kernel where the
+ * FLEX one does not exist) and cites it:
+ *   orc_make_p          newviewGenericSpecial.c:78-132  (makeP) + :983-984 (z clamp)
+ *   orc_newview_site*   newviewGenericSpecial.c:430-682 (newviewGAMMA_FLEX), scaler :1503-1506
+ *   orc_diag            evaluateGenericSpecial.c:80-119 (calcDiagptable)
+ *   evaluate            evaluateGenericSpecial.c:154-228 (evaluateGAMMA_FLEX), scaler undo :830
+ *   sum table           makenewzGenericSpecial.c:251-319 (sumGAMMA_FLEX)
+ *   core                makenewzGenericSpecial.c:2309-2393 (coreGTRGAMMA; coreGAMMA_FLEX :523
+ *                       does not compile in the reference)
+ *   partition plumbing  newviewGenericSpecial.c:1114 (executeModel && width>0), :972-981
+ *                       (branch slot), evaluateGenericSpecial.c:845-860 (masked partitions),
+ *                       makenewzGenericSpecial.c:921-946 (derivative slots)
+ *
+ * Pinning: tests/test_oracle_golden.py checks this file against values dumped from the
+ * reference's own AVX build (oracle/_ref/examl-AVX, built by oracle/Makefile from the
+ * unmodified sources) on testData/49 and testData/140: first-evaluation and final lnL,
+ * per-partition lnL, the first makenewz result, root scaler counts.  Fixtures and the
+ * script that made them: tests/golden/.
+ *
+ * The API mirrors include/examl_b200.h one to one (orc_ instead of exb_) so the parity tests
+ * drive both engines with identical arguments.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_ZMIN 1.0E-15                         /* axml.h:110 */
+#define ORC_TWOTOTHE256 115792089237316195423570985008687907853269984665640564039457584007913129639936.0 /* axml.h:113 */
+#define ORC_MINLIKELIHOOD (1.0 / ORC_TWOTOTHE256)  /* axml.h:118 */
+
+typedef struct { int tipCase, pNumber, qNumber, rNumber; } orc_entry;
+
+typedef struct {
+  int states, codes;
+  size_t width;
+  int *wgt;
+  unsigned char *tips;          /* [mxtips][width] */
+  double *clv;                  /* [(mxtips-2)][width][4][S] */
+  double *sum;                  /* [width][4][S] */
+  unsigned int *scaler;         /* [2*mxtips] (axml.c:1966-1971) */
+  double EIGN[20], EV[400], EI[400], tipVector[23 * 20], gammaRates[4];
+} orc_part;
+
+typedef struct {
+  int mxtips, nparts, nbranches;
+  orc_part *parts;
+} orc_engine;
+
+int orc_create(orc_engine **out, int mxtips, int nparts, int nbranches)
+{
+  orc_engine *e = (orc_engine *)calloc(1, sizeof *e);
+  e->mxtips = mxtips; e->nparts = nparts; e->nbranches = nbranches;
+  e->parts = (orc_part *)calloc((size_t)nparts, sizeof(orc_part));
+  *out = e;
+  return 0;
+}
+
+void orc_destroy(orc_engine *e)
+{
+  int m;
+  if (!e) return;
+  for (m = 0; m < e->nparts; m++) {
+    free(e->parts[m].wgt); free(e->parts[m].tips); free(e->parts[m].clv);
+    free(e->parts[m].sum); free(e->parts[m].scaler);
+  }
+  free(e->parts); free(e);
+}
+
+int orc_set_partition(orc_engine *e, int model, int states, size_t width, const int *wgt, const unsigned char *y)
+{
+  orc_part *p = &e->parts[model];
+  size_t span = 4 * (size_t)states;
+  p->states = states; p->codes = states == 20 ? 23 : 16; p->width = width;
+  p->wgt = (int *)malloc((width + 1) * sizeof(int));
+  p->tips = (unsigned char *)malloc((size_t)e->mxtips * width + 1);
+  memcpy(p->wgt, wgt, width * sizeof(int));
+  memcpy(p->tips, y, (size_t)e->mxtips * width);
+  p->clv = (double *)calloc((size_t)(e->mxtips - 2) * width * span + 1, sizeof(double));
+  p->sum = (double *)calloc(width * span + 1, sizeof(double));
+  p->scaler = (unsigned int *)calloc(2 * (size_t)e->mxtips, sizeof(unsigned int));
+  return 0;
+}
+
+int orc_set_model(orc_engine *e, int model, const double *EIGN, const double *EV, const double *EI,
+                  const double *tipVector, const double *gammaRates)
+{
+  orc_part *p = &e->parts[model];
+  int S = p->states;
+  memcpy(p->EIGN, EIGN, S * sizeof(double));
+  memcpy(p->EV, EV, S * S * sizeof(double));
+  memcpy(p->EI, EI, S * S * sizeof(double));
+  memcpy(p->tipVector, tipVector, (size_t)p->codes * S * sizeof(double));
+  memcpy(p->gammaRates, gammaRates, 4 * sizeof(double));
+  return 0;
+}
+
+/* P(z) for the four GAMMA categories: P[c][j][k] = exp(EIGN[k] r_c lz) EI[j][k], P[c][j][0] = 1. */
+static void orc_make_p(double z, const orc_part *p, double *P)
+{
+  int S = p->states, c, j, k;
+  double lz = (z > ORC_ZMIN) ? log(z) : log(ORC_ZMIN);
+  double d[20];
+  for (c = 0; c < 4; c++) {
+    for (k = 1; k < S; k++) d[k] = exp(p->gammaRates[c] * (p->EIGN[k] * lz));
+    for (j = 0; j < S; j++) {
+      P[c * S * S + j * S] = 1.0;
+      for (k = 1; k < S; k++) P[c * S * S + j * S + k] = d[k] * p->EI[j * S + k];
+    }
+  }
+}
+
+static double *clv_of(const orc_engine *e, const orc_part *p, int number)
+{
+  return p->clv + (size_t)(number - e->mxtips - 1) * p->width * 4 * (size_t)p->states;
+}
+static const unsigned char *tip_of(const orc_engine *e, const orc_part *p, int number)
+{
+  (void)e;
+  return p->tips + (size_t)(number - 1) * p->width;
+}
+
+/* One traversal entry for one partition. */
+static void orc_newview_entry(orc_engine *e, orc_part *p, const orc_entry *t, double qz, double rz)
+{
+  int S = p->states, span = 4 * S, c, j, l;
+  size_t i;
+  double *left = (double *)malloc(sizeof(double) * 4 * S * S), *right = (double *)malloc(sizeof(double) * 4 * S * S);
+  double a[20], b[20], v1[20], v2[20];
+  double *x3 = clv_of(e, p, t->pNumber);
+  const double *x1 = NULL, *x2 = NULL;
+  const unsigned char *tip1 = NULL, *tip2 = NULL;
+  unsigned int addScale = 0;
+
+  orc_make_p(qz, p, left);
+  orc_make_p(rz, p, right);
+
+  switch (t->tipCase) {
+  case 0: tip1 = tip_of(e, p, t->qNumber); tip2 = tip_of(e, p, t->rNumber); break;
+  case 1: tip1 = tip_of(e, p, t->qNumber); x2 = clv_of(e, p, t->rNumber); break;
+  default: x1 = clv_of(e, p, t->qNumber); x2 = clv_of(e, p, t->rNumber); break;
+  }
+
+  for (i = 0; i < p->width; i++) {
+    double *v = x3 + i * span;
+    int scale = 1;
+    for (c = 0; c < 4; c++) {
+      /* child vectors in the eigenvector basis; a tip's vector is the same for every category */
+      if (tip1) memcpy(v1, p->tipVector + (size_t)S * tip1[i], S * sizeof(double));
+      else      memcpy(v1, x1 + i * span + c * S, S * sizeof(double));
+      if (tip2) memcpy(v2, p->tipVector + (size_t)S * tip2[i], S * sizeof(double));
+      else      memcpy(v2, x2 + i * span + c * S, S * sizeof(double));
+      for (l = 0; l < S; l++) {
+        double al = 0.0, ar = 0.0;
+        for (j = 0; j < S; j++) {
+          al += v1[j] * left[c * S * S + l * S + j];
+          ar += v2[j] * right[c * S * S + l * S + j];
+        }
+        a[l] = al; b[l] = ar;
+      }
+      for (j = 0; j < S; j++) v[c * S + j] = 0.0;
+      for (l = 0; l < S; l++) {
+        double x1px2 = a[l] * b[l];
+        for (j = 0; j < S; j++) v[c * S + j] += x1px2 * p->EV[l * S + j];
+      }
+    }
+    if (t->tipCase != 0) {           /* TIP_TIP is never rescaled (newviewGenericSpecial.c:496-523) */
+      for (l = 0; scale && l < span; l++) scale = fabs(v[l]) < ORC_MINLIKELIHOOD;
+      if (scale) {
+        for (l = 0; l < span; l++) v[l] *= ORC_TWOTOTHE256;
+        addScale += (unsigned int)p->wgt[i];
+      }
+    }
+  }
+  p->scaler[t->pNumber] = p->scaler[t->qNumber] + p->scaler[t->rNumber] + addScale;
+  free(left); free(right);
+}
+
+static int executes(const orc_engine *e, const unsigned char *mask, int m)
+{
+  return (!mask || mask[m]) && e->parts[m].width > 0;
+}
+
+static void orc_run_newviews(orc_engine *e, const orc_entry *ti, int first, int count,
+                             const double *qz, const double *rz, const unsigned char *mask)
+{
+  int i, m, nb = e->nbranches;
+  for (i = first; i < count; i++)
+    for (m = 0; m < e->nparts; m++)
+      if (executes(e, mask, m)) {
+        int slot = nb > 1 ? m : 0;
+        orc_newview_entry(e, &e->parts[m], &ti[i], qz[(size_t)i * nb + slot], rz[(size_t)i * nb + slot]);
+      }
+}
+
+int orc_newview(orc_engine *e, const orc_entry *ti, int count, const double *qz, const double *rz, const unsigned char *mask)
+{
+  orc_run_newviews(e, ti, 0, count, qz, rz, mask);
+  return 0;
+}
+
+static int is_tip(const orc_engine *e, int number) { return number <= e->mxtips; }
+
+/* Resolve the two ends of branch ti[0]: if one end is a tip it becomes `tip` and the other x2
+ * (evaluateGenericSpecial.c:612-650, makenewzGenericSpecial.c:71-150). */
+static void branch_ends(const orc_engine *e, const orc_part *p, const orc_entry *t0,
+                        const unsigned char **tipA, const unsigned char **tipB, const double **xa, const double **xb)
+{
+  int P = t0->pNumber, Q = t0->qNumber;
+  *tipA = *tipB = NULL; *xa = *xb = NULL;
+  if (is_tip(e, P) && is_tip(e, Q)) { *tipA = tip_of(e, p, P); *tipB = tip_of(e, p, Q); }
+  else if (is_tip(e, Q)) { *tipA = tip_of(e, p, Q); *xb = clv_of(e, p, P); }
+  else if (is_tip(e, P)) { *tipA = tip_of(e, p, P); *xb = clv_of(e, p, Q); }
+  else { *xa = clv_of(e, p, P); *xb = clv_of(e, p, Q); }
+}
+
+int orc_evaluate(orc_engine *e, const orc_entry *ti, int count, const double *qz, const double *rz,
+                 const unsigned char *mask, double *perPartitionLH)
+{
+  int m, c, k, nb = e->nbranches;
+  orc_run_newviews(e, ti, 1, count, qz, rz, mask);
+  for (m = 0; m < e->nparts; m++) {
+    orc_part *p = &e->parts[m];
+    int S = p->states, span = 4 * S;
+    double diag[80], z, lz, sum = 0.0;
+    const unsigned char *tipA, *tipB; const double *xa, *xb;
+    size_t i;
+    if (!executes(e, mask, m)) { if (p->width == 0) perPartitionLH[m] = 0.0; continue; }
+    z = qz[nb > 1 ? m : 0];
+    lz = (z < ORC_ZMIN) ? log(ORC_ZMIN) : log(z);
+    for (c = 0; c < 4; c++) {
+      diag[c * S] = 1.0;
+      for (k = 1; k < S; k++) diag[c * S + k] = exp(p->gammaRates[c] * (p->EIGN[k] * lz));
+    }
+    branch_ends(e, p, &ti[0], &tipA, &tipB, &xa, &xb);
+    for (i = 0; i < p->width; i++) {
+      double term = 0.0;
+      for (c = 0; c < 4; c++)
+        for (k = 0; k < S; k++) {
+          double l = tipA ? p->tipVector[(size_t)S * tipA[i] + k] : xa[i * span + c * S + k];
+          double r = tipB ? p->tipVector[(size_t)S * tipB[i] + k] : xb[i * span + c * S + k];
+          term += l * r * diag[c * S + k];
+        }
+      sum += p->wgt[i] * log(0.25 * fabs(term));
+    }
+    sum += (double)(p->scaler[ti[0].pNumber] + p->scaler[ti[0].qNumber]) * log(ORC_MINLIKELIHOOD);
+    perPartitionLH[m] = sum;
+  }
+  return 0;
+}
+
+int orc_makenewz_prepare(orc_engine *e, const orc_entry *ti, int count, const double *qz, const double *rz,
+                         const unsigned char *mask)
+{
+  int m, c, k;
+  orc_run_newviews(e, ti, 1, count, qz, rz, mask);
+  for (m = 0; m < e->nparts; m++) {
+    orc_part *p = &e->parts[m];
+    int S = p->states, span = 4 * S;
+    const unsigned char *tipA, *tipB; const double *xa, *xb;
+    size_t i;
+    if (!executes(e, mask, m)) continue;
+    branch_ends(e, p, &ti[0], &tipA, &tipB, &xa, &xb);
+    for (i = 0; i < p->width; i++)
+      for (c = 0; c < 4; c++)
+        for (k = 0; k < S; k++) {
+          double l = tipA ? p->tipVector[(size_t)S * tipA[i] + k] : xa[i * span + c * S + k];
+          double r = tipB ? p->tipVector[(size_t)S * tipB[i] + k] : xb[i * span + c * S + k];
+          p->sum[i * span + c * S + k] = l * r;
+        }
+  }
+  return 0;
+}
+
+int orc_core(orc_engine *e, const double *lzv, const unsigned char *mask, double *dlnLdlz, double *d2lnLdlz2)
+{
+  int m, c, k, nb = e->nbranches;
+  for (m = 0; m < nb; m++) { dlnLdlz[m] = 0.0; d2lnLdlz2[m] = 0.0; }
+  for (m = 0; m < e->nparts; m++) {
+    orc_part *p = &e->parts[m];
+    int S = p->states, span = 4 * S, slot = nb > 1 ? m : 0;
+    double d0[80], d1[80], d2[80], lz = lzv[slot], dl = 0.0, d2l = 0.0;
+    size_t i;
+    if (!executes(e, mask, m)) continue;
+    for (c = 0; c < 4; c++) {
+      double ki = p->gammaRates[c];
+      d0[c * S] = 1.0; d1[c * S] = 0.0; d2[c * S] = 0.0;
+      for (k = 1; k < S; k++) {
+        d0[c * S + k] = exp(p->EIGN[k] * ki * lz);
+        d1[c * S + k] = p->EIGN[k] * ki;
+        d2[c * S + k] = p->EIGN[k] * p->EIGN[k] * ki * ki;
+      }
+    }
+    for (i = 0; i < p->width; i++) {
+      const double *s = p->sum + i * span;
+      double L = 0.0, L1 = 0.0, L2 = 0.0, inv;
+      for (c = 0; c < 4; c++)
+        for (k = 0; k < S; k++) {
+          double t = d0[c * S + k] * s[c * S + k];
+          L += t; L1 += t * d1[c * S + k]; L2 += t * d2[c * S + k];
+        }
+      inv = 1.0 / fabs(L);
+      L1 *= inv; L2 *= inv;
+      dl += p->wgt[i] * L1;
+      d2l += p->wgt[i] * (L2 - L1 * L1);
+    }
+    dlnLdlz[slot] += dl;
+    d2lnLdlz2[slot] += d2l;
+  }
+  return 0;
+}
+
+int orc_read_clv(orc_engine *e, int model, int number, double *out)
+{
+  orc_part *p = &e->parts[model];
+  memcpy(out, clv_of(e, p, number), p->width * 4 * (size_t)p->states * sizeof(double));
+  return 0;
+}
+int orc_read_scaler(orc_engine *e, int model, int number, unsigned int *out)
+{
+  *out = e->parts[model].scaler[number];
+  return 0;
+}
+int orc_read_sumtable(orc_engine *e, int model, double *out)
+{
+  orc_part *p = &e->parts[model];
+  memcpy(out, p->sum, p->width * 4 * (size_t)p->states * sizeof(double));
+  return 0;
+}

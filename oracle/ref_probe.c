@@ -1,0 +1,176 @@
+/* ref_probe.c -- TEST INFRASTRUCTURE.  Linked into the UNMODIFIED reference build
+ * (oracle/Makefile, outputs in oracle/_ref/) with
+ *      -Wl,--wrap=evaluateGeneric -Wl,--wrap=makenewzGeneric
+ * so that the reference's own binary can (a) dump golden states for the parity tests
+ * and (b) time its CPU likelihood path for bench.py's reference arm -- without editing or
+ * copying a single reference source line.
+ *
+ * Hooks (all driven by environment variables, inert otherwise):
+ *   EXAML_PROBE_DUMP=<prefix>   write <prefix>.first.json after the first evaluateGeneric
+ *                               (axml.c:2317 / :2760), <prefix>.mkz.json after the first
+ *                               makenewzGeneric, <prefix>.final.json at process exit
+ *                               (after one more full evaluateGeneric on the final tree).
+ *   EXAML_PROBE_BENCH=<K>       after the first evaluateGeneric: W warm-up (EXAML_PROBE_WARMUP,
+ *                               default 1) then K timed full-traversal evaluateGeneric calls;
+ *                               print one JSON line "PROBE_BENCH {...}" and exit(0).
+ *   EXAML_PROBE_NOTIPS=1        omit the alignment bytes / weights from <prefix>.first.json too
+ *                               (the mkz / final dumps never carry them).
+ *   EXAML_PROBE_EXIT_FIRST=1    exit(0) right after the first evaluateGeneric (and its dump).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+#include "axml.h"
+
+void __real_evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal);
+void __real_makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxiter, double *result, boolean mask);
+#ifdef _USE_OMP
+void allocateXVectors(tree *tr);
+#endif
+
+static tree *g_tr = NULL;
+static int g_eval_calls = 0, g_mkz_calls = 0;
+
+static double now_s(void)
+{
+  struct timeval tv;
+  gettimeofday(&tv, NULL);
+  return tv.tv_sec + 1e-6 * tv.tv_usec;
+}
+
+static void put_darr(FILE *f, const char *name, const double *v, size_t n)
+{
+  size_t i;
+  fprintf(f, "\"%s\": [", name);
+  for (i = 0; i < n; i++) fprintf(f, "%s%.17g", i ? ", " : "", v[i]);
+  fprintf(f, "]");
+}
+
+static int tip_codes(int dataType) { return dataType == AA_DATA ? 23 : (dataType == DNA_DATA ? 16 : 3); }
+
+static void dump_state(tree *tr, const char *path, int with_alignment, const char *extra)
+{
+  FILE *f = fopen(path, "w");
+  int m, i, b, nb = tr->numBranches;
+  int notips = !with_alignment || getenv("EXAML_PROBE_NOTIPS") != NULL, first_entry = 1;
+  if (!f) { perror(path); return; }
+  fprintf(f, "{\n\"mxtips\": %d, \"numBranches\": %d, \"NumberOfModels\": %d,\n", tr->mxtips, nb, tr->NumberOfModels);
+  fprintf(f, "\"likelihood\": %.17g,\n", tr->likelihood);
+  put_darr(f, "perPartitionLH", tr->perPartitionLH, (size_t)tr->NumberOfModels);
+  fprintf(f, ",\n");
+  if (extra) fprintf(f, "%s,\n", extra);
+  if (!notips && tr->nameList) {
+    fprintf(f, "\"names\": [");
+    for (i = 1; i <= tr->mxtips; i++) fprintf(f, "%s\"%s\"", i > 1 ? ", " : "", tr->nameList[i]);
+    fprintf(f, "],\n");
+  }
+  fprintf(f, "\"partitions\": [\n");
+  for (m = 0; m < tr->NumberOfModels; m++) {
+    pInfo *p = &tr->partitionData[m];
+    int S = p->states, codes = tip_codes(p->dataType);
+    size_t w;
+    fprintf(f, "{\"states\": %d, \"dataType\": %d, \"protModels\": %d, \"width\": %zu, \"alpha\": %.17g,\n",
+            S, p->dataType, p->protModels, p->width, p->alpha);
+    put_darr(f, "EIGN", p->EIGN, (size_t)S); fprintf(f, ",\n");
+    put_darr(f, "EV", p->EV, (size_t)S * S); fprintf(f, ",\n");
+    put_darr(f, "EI", p->EI, (size_t)S * S); fprintf(f, ",\n");
+    put_darr(f, "tipVector", p->tipVector, (size_t)codes * S); fprintf(f, ",\n");
+    put_darr(f, "frequencies", p->frequencies, (size_t)S); fprintf(f, ",\n");
+    put_darr(f, "gammaRates", p->gammaRates, 4); fprintf(f, ",\n");
+    fprintf(f, "\"rootScaler\": %u", p->width ?
+            p->globalScaler[tr->td[0].ti[0].pNumber] + p->globalScaler[tr->td[0].ti[0].qNumber] : 0u);
+    if (!notips) {
+      fprintf(f, ",\n\"wgt\": [");
+      for (w = 0; w < p->width; w++) fprintf(f, "%s%d", w ? "," : "", p->wgt[w]);
+      fprintf(f, "],\n\"tips\": [");
+      for (i = 1; i <= tr->mxtips; i++) {
+        fprintf(f, "%s\"", i > 1 ? ",\n" : "");
+        for (w = 0; w < p->width; w++) fprintf(f, "%02x", p->yVector[i][w]);
+        fprintf(f, "\"");
+      }
+      fprintf(f, "]");
+    }
+    fprintf(f, "}%s\n", m + 1 < tr->NumberOfModels ? "," : "");
+  }
+  fprintf(f, "],\n\"traversal\": {\"count\": %d, \"first\": %d, \"entries\": [\n", tr->td[0].count, first_entry);
+  for (i = 0; i < tr->td[0].count; i++) {
+    traversalInfo *t = &tr->td[0].ti[i];
+    fprintf(f, "{\"tipCase\": %d, \"p\": %d, \"q\": %d, \"r\": %d, \"qz\": [", i ? t->tipCase : -1, t->pNumber, t->qNumber, i ? t->rNumber : 0);
+    for (b = 0; b < nb; b++) fprintf(f, "%s%.17g", b ? "," : "", t->qz[b]);
+    fprintf(f, "], \"rz\": [");
+    for (b = 0; b < nb; b++) fprintf(f, "%s%.17g", b ? "," : "", i ? t->rz[b] : 0.0);
+    fprintf(f, "]}%s\n", i + 1 < tr->td[0].count ? "," : "");
+  }
+  fprintf(f, "]}\n}\n");
+  fclose(f);
+}
+
+static void dump_final(void)
+{
+  const char *prefix = getenv("EXAML_PROBE_DUMP");
+  char path[4096];
+  if (!prefix || !g_tr) return;
+  __real_evaluateGeneric(g_tr, g_tr->start, TRUE);
+  snprintf(path, sizeof path, "%s.final.json", prefix);
+  dump_state(g_tr, path, 0, NULL);
+}
+
+void __wrap_evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal)
+{
+  const char *prefix = getenv("EXAML_PROBE_DUMP"), *bench = getenv("EXAML_PROBE_BENCH");
+#ifdef _USE_OMP
+  if (g_eval_calls == 0 && tr->partitionData[0].xVector[0] == NULL)
+    allocateXVectors(tr);     /* the reference's -f e path forgets this under OMP (only axml.c:2752 calls it) */
+#endif
+  __real_evaluateGeneric(tr, p, fullTraversal);
+  g_eval_calls++;
+  if (g_eval_calls == 1) {
+    g_tr = tr;
+    if (prefix) {
+      char path[4096];
+      snprintf(path, sizeof path, "%s.first.json", prefix);
+      dump_state(tr, path, 1, NULL);
+      atexit(dump_final);
+    }
+    if (getenv("EXAML_PROBE_EXIT_FIRST")) { g_tr = NULL; fflush(stdout); exit(0); }
+    if (bench) {
+      int K = atoi(bench), W = getenv("EXAML_PROBE_WARMUP") ? atoi(getenv("EXAML_PROBE_WARMUP")) : 1, i, m;
+      size_t sites = 0;
+      double t0, t1;
+      for (m = 0; m < tr->NumberOfModels; m++) sites += tr->partitionData[m].width;
+      for (i = 0; i < W; i++) __real_evaluateGeneric(tr, p, TRUE);
+      t0 = now_s();
+      for (i = 0; i < K; i++) __real_evaluateGeneric(tr, p, TRUE);
+      t1 = now_s();
+      printf("PROBE_BENCH {\"steps\": %d, \"seconds\": %.9g, \"sites\": %zu, \"inner_nodes\": %d, "
+             "\"site_updates_per_s\": %.9g, \"likelihood\": %.17g}\n",
+             K, t1 - t0, sites, tr->mxtips - 2,
+             (double)K * (double)(tr->mxtips - 2) * (double)sites / (t1 - t0), tr->likelihood);
+      fflush(stdout);
+      g_tr = NULL;   /* no final dump */
+      exit(0);
+    }
+  }
+}
+
+void __wrap_makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxiter, double *result, boolean mask)
+{
+  const char *prefix = getenv("EXAML_PROBE_DUMP");
+  double z0copy[NUM_BRANCHES];
+  int b;
+  for (b = 0; b < tr->numBranches; b++) z0copy[b] = z0[b];
+  __real_makenewzGeneric(tr, p, q, z0, maxiter, result, mask);
+  g_mkz_calls++;
+  if (g_mkz_calls == 1 && prefix) {
+    char path[4096], extra[16384];
+    int off = 0;
+    off += snprintf(extra + off, sizeof extra - off, "\"makenewz\": {\"p\": %d, \"q\": %d, \"maxiter\": %d, \"z0\": [", p->number, q->number, maxiter);
+    for (b = 0; b < tr->numBranches; b++) off += snprintf(extra + off, sizeof extra - off, "%s%.17g", b ? "," : "", z0copy[b]);
+    off += snprintf(extra + off, sizeof extra - off, "], \"result\": [");
+    for (b = 0; b < tr->numBranches; b++) off += snprintf(extra + off, sizeof extra - off, "%s%.17g", b ? "," : "", result[b]);
+    off += snprintf(extra + off, sizeof extra - off, "]}");
+    snprintf(path, sizeof path, "%s.mkz.json", prefix);
+    dump_state(tr, path, 0, extra);
+  }
+}

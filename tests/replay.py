@@ -1,0 +1,67 @@
+"""Replay of the reference's golden states (tests/golden) through an engine.  The same code
+checks the CPU oracle (pinning it to the reference) and the CUDA engine (parity proper)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from examl_b200.likelihood import Likelihood
+from examl_b200.phylo import Entry, Tree
+from golden_util import load_engine, load_json, set_models, traversal_of
+
+# north_star tolerance: lnL within 1e-6 relative of the reference's AVX build.  The engines do
+# far better (reduction-order effects only), so the tests pin a much tighter bound.
+NORTH_STAR_RTOL = 1e-6
+TIGHT_RTOL = 5e-12
+
+CASES = {
+    # tag: (has mkz, has final)
+    "dna49": (True, True),
+    "dna49p": (False, True),
+    "dna49pM": (True, True),
+    "aa140": (True, True),
+    "dnaiid200": (False, False),
+    "aa60": (True, True),
+}
+
+
+def rel(a, b):
+    return abs(a - b) / abs(b)
+
+
+def replay_case(factory, tag, rtol=TIGHT_RTOL, **kw):
+    has_mkz, has_final = CASES[tag]
+    first = load_json(f"{tag}.first.json")
+    eng = load_engine(factory, first, **kw)
+    nparts = first["NumberOfModels"]
+
+    # --- first full evaluation ---------------------------------------------------------------
+    lh = eng.evaluateIterative(traversal_of(first))
+    for m in range(nparts):
+        assert rel(lh[m], first["perPartitionLH"][m]) < rtol, (tag, m, lh[m], first["perPartitionLH"][m])
+    assert rel(float(np.sum(lh)), first["likelihood"]) < rtol
+    ti0 = first["traversal"]["entries"][0]
+    for m, part in enumerate(first["partitions"]):
+        got = eng.read_scaler(m, ti0["p"]) + eng.read_scaler(m, ti0["q"])
+        assert got == part["rootScaler"], (tag, m, got, part["rootScaler"])
+
+    # --- first makenewz: descriptor + Newton-Raphson on the host, sum/core on the engine -------
+    if has_mkz:
+        mkz = load_json(f"{tag}.mkz.json")
+        tree = Tree(first["mxtips"], first["numBranches"])      # topology not needed: descriptor is given
+        lk = Likelihood(tree, eng, nparts)
+        ti = traversal_of(mkz)
+        z = lk._topLevelMakenewz(ti, list(mkz["makenewz"]["z0"]), mkz["makenewz"]["maxiter"])
+        for got, want in zip(z, mkz["makenewz"]["result"]):
+            assert rel(got, want) < 1e-9, (tag, z, mkz["makenewz"]["result"])
+
+    # --- final state of `-f e`: optimised model and branch lengths ---------------------------------
+    if has_final:
+        final = load_json(f"{tag}.final.json")
+        set_models(eng, final)
+        lh = eng.evaluateIterative(traversal_of(final))
+        for m in range(nparts):
+            assert rel(lh[m], final["perPartitionLH"][m]) < rtol, (tag, m, lh[m], final["perPartitionLH"][m])
+        assert rel(float(np.sum(lh)), final["likelihood"]) < rtol
+    eng.close()
