@@ -1,0 +1,673 @@
+// engine.cu -- host side of the B200 likelihood engine and its C ABI (include/examl_b200.h).
+//
+// Owns the HBM-resident state that the reference keeps in pInfo (axml.h:533-629): CLVs of all
+// inner nodes (xVector), tip codes (yVector), pattern weights (wgt), scaler counts (globalScaler),
+// the makenewz sum table (sumBuffer) -- and turns each *Iterative call of the reference into
+// one fused kernel launch per data-type class plus one small "finish" launch.
+#include "../../include/examl_b200.h"
+#include "engine.cuh"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+namespace exb {
+
+// ------------------------------------------------------------------------------------------------------
+// finish kernel: (1) scaler bookkeeping globalScaler[p] = globalScaler[q] + globalScaler[r] + increment
+// (newviewGenericSpecial.c:1503-1506) for every newview entry in order; (2) deterministic reduction of
+// the per-tile partial sums of each partition; (3) evaluate only: undo the scaling,
+// + (gs[p] + gs[q]) * log(minlikelihood) (evaluateGenericSpecial.c:830).  One warp per partition.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+finish_kernel(const FinishArgs a)
+{
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int part = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; part < a.nparts; part += warps) {
+    const bool exec = a.mask[part] && a.part_has_sites[part];
+    unsigned int *gs = a.gs + (size_t)part * 2 * a.mxtips;
+    if (exec && lane == 0) {
+      for (int e = a.first; e < a.count; e++) {
+        const DevEntry en = a.entries[e];
+        unsigned int *inc = &a.scale_inc[(size_t)e * a.nparts + part];
+        gs[en.p] = gs[en.q] + gs[en.r] + *inc;
+        *inc = 0;
+      }
+    }
+    __syncwarp();
+    if (a.mode == MODE_NEWVIEW || a.mode == MODE_SUM) continue;
+    double s0 = 0.0, s1 = 0.0;
+    if (exec) {
+      const double *to = (a.part_cls[part] ? a.tile_out[1] : a.tile_out[0]) + 2 * (size_t)a.part_tile_begin[part];
+      const int n = a.part_tile_count[part];
+      for (int t = lane; t < n; t += 32) { s0 += to[2 * t]; s1 += to[2 * t + 1]; }
+      #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_down_sync(0xffffffffu, s0, o);
+        s1 += __shfl_down_sync(0xffffffffu, s1, o);
+      }
+    }
+    if (lane == 0) {
+      if (a.mode == MODE_EVALUATE) {
+        if (exec) {
+          const DevEntry br = a.entries[0];
+          s0 += (double)(gs[br.p] + gs[br.q]) * a.log_minlikelihood;
+        }
+        a.out[part] = s0;
+      } else {           // MODE_CORE
+        a.out[part] = s0;
+        a.out[a.nparts + part] = s1;
+      }
+    }
+  }
+}
+
+void launch_finish(const FinishArgs &a, cudaStream_t s)
+{
+  int blocks = (a.nparts + 3) / 4;
+  if (blocks > 592) blocks = 592;
+  if (blocks < 1) blocks = 1;
+  finish_kernel<<<blocks, 128, 0, s>>>(a);
+}
+
+}  // namespace exb
+
+using namespace exb;
+
+// ------------------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(x)                                                                              \
+  do {                                                                                           \
+    cudaError_t err__ = (x);                                                                     \
+    if (err__ != cudaSuccess)                                                                    \
+      return fail(EXB_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily with dlopen so that (a) a single-GPU process never needs it and (b) inside a
+// Python process that already carries torch's bundled libnccl.so.2 the same library is reused.
+// ------------------------------------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm *ncclComm_t;
+struct NcclUniqueId { char internal[128]; };
+static_assert(sizeof(NcclUniqueId) == EXB_UNIQUE_ID_BYTES, "ncclUniqueId is 128 bytes");
+struct NcclApi {
+  void *handle = nullptr;
+  int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, NcclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+} g_nccl;
+constexpr int kNcclFloat64 = 8;   // ncclDouble
+constexpr int kNcclSum = 0;       // ncclSum
+
+int load_nccl()
+{
+  if (g_nccl.handle) return EXB_OK;
+  const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+  for (int i = 0; names[i] && !g_nccl.handle; i++) g_nccl.handle = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!g_nccl.handle) return fail(EXB_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (int (*)(NcclUniqueId *))dlsym(g_nccl.handle, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(ncclComm_t *, int, NcclUniqueId, int))dlsym(g_nccl.handle, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(g_nccl.handle, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(g_nccl.handle, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.handle, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce)
+    return fail(EXB_ERR_NCCL, "libnccl lacks an expected symbol");
+  return EXB_OK;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------------------
+struct HostPart {
+  int states = 0, cls = -1, part_cls = -1;
+  size_t width = 0, site0 = 0;
+  bool defined = false;
+  std::vector<int> wgt;
+  std::vector<unsigned char> y;        // [mxtips][width], dropped after commit
+  std::vector<double> model;           // host cache of the uploaded constants
+  bool model_set = false;
+};
+
+struct ClassState {
+  int S = 0, span = 0, codes = 0, model_doubles = 0;
+  size_t N = 0;                        // padded number of sites
+  int nparts = 0;
+  std::vector<Tile> tiles_h;
+  Tile *tiles = nullptr;
+  double *clv = nullptr, *sum = nullptr, *models = nullptr, *tile_out = nullptr;
+  uint8_t *tips = nullptr;
+  int *wgt = nullptr;
+  std::vector<double> models_h;
+  int dirty_lo = 1 << 30, dirty_hi = -1;   // range of class-partitions whose constants must be re-uploaded
+};
+
+struct exb_engine {
+  int device = 0, mxtips = 0, P = 0, nb = 1;
+  int tile_sites = 256;
+  bool committed = false;
+  std::vector<HostPart> parts;
+  ClassState cls[2];
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // per-call staging (pinned host + device mirror): entries | lzq | lzr | mask | lz(core)
+  size_t stage_bytes = 0;
+  unsigned char *stage_h = nullptr, *stage_d = nullptr;
+  size_t off_entries = 0, off_lzq = 0, off_lzr = 0, off_mask = 0, off_corelz = 0;
+  int max_entries = 0;
+  // partition tables
+  int *part_has_sites = nullptr, *part_tile_begin = nullptr, *part_tile_count = nullptr, *part_cls = nullptr;
+  unsigned int *gs = nullptr, *scale_inc = nullptr;
+  double *out_d = nullptr, *out_h = nullptr;     // [2*P]
+  long launches = 0;
+  float last_ms = 0.f;
+  ncclComm_t comm = nullptr;
+  int nranks = 1;
+};
+
+static int class_of(int states) { return states == 4 ? CLS_DNA : (states == 20 ? CLS_AA : -1); }
+
+extern "C" const char *exb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int exb_create(exb_engine **out, int device, int mxtips, int numPartitions, int numBranches)
+{
+  if (!out || mxtips < 3 || numPartitions < 1 || numBranches < 1)
+    return fail(EXB_ERR_ARG, "exb_create: bad arguments (mxtips=%d partitions=%d branches=%d)", mxtips, numPartitions, numBranches);
+  if (numBranches > 1 && numBranches != numPartitions)
+    return fail(EXB_ERR_ARG, "exb_create: numBranches must be 1 or equal to the number of partitions (makenewzGenericSpecial.c:1195)");
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0)
+    return fail(EXB_ERR_CUDA, "exb_create: no CUDA device available (%s); examl_b200 has no CPU fallback",
+                err == cudaSuccess ? "device count is 0" : cudaGetErrorString(err));
+  if (device < 0 || device >= ndev) return fail(EXB_ERR_ARG, "exb_create: device %d out of range (0..%d)", device, ndev - 1);
+  CUDA_TRY(cudaSetDevice(device));
+  exb_engine *e = new exb_engine();
+  e->device = device; e->mxtips = mxtips; e->P = numPartitions; e->nb = numBranches;
+  e->parts.resize(numPartitions);
+  e->cls[CLS_DNA].S = 4;  e->cls[CLS_DNA].span = 16; e->cls[CLS_DNA].codes = 16; e->cls[CLS_DNA].model_doubles = kDnaModelDoubles;
+  e->cls[CLS_AA].S = 20;  e->cls[CLS_AA].span = 80;  e->cls[CLS_AA].codes = 23;  e->cls[CLS_AA].model_doubles = kAaModelDoubles;
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&e->ev0));
+  CUDA_TRY(cudaEventCreate(&e->ev1));
+  *out = e;
+  return EXB_OK;
+}
+
+extern "C" void exb_destroy(exb_engine *e)
+{
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+  for (int c = 0; c < 2; c++) {
+    ClassState &k = e->cls[c];
+    cudaFree(k.tiles); cudaFree(k.clv); cudaFree(k.sum); cudaFree(k.models); cudaFree(k.tile_out);
+    cudaFree(k.tips); cudaFree(k.wgt);
+  }
+  cudaFree(e->stage_d); cudaFreeHost(e->stage_h);
+  cudaFree(e->part_has_sites); cudaFree(e->part_tile_begin); cudaFree(e->part_tile_count); cudaFree(e->part_cls);
+  cudaFree(e->gs); cudaFree(e->scale_inc); cudaFree(e->out_d); cudaFreeHost(e->out_h);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+extern "C" int exb_set_tile_sites(exb_engine *e, int sites)
+{
+  if (!e || e->committed) return fail(EXB_ERR_STATE, "exb_set_tile_sites: must be called before exb_commit");
+  if (sites < 32 || sites % 32) return fail(EXB_ERR_ARG, "exb_set_tile_sites: %d is not a positive multiple of 32", sites);
+  e->tile_sites = sites;
+  return EXB_OK;
+}
+
+extern "C" int exb_set_partition(exb_engine *e, int model, int states, size_t width,
+                                 const int *wgt, const unsigned char *yResource)
+{
+  if (!e || e->committed) return fail(EXB_ERR_STATE, "exb_set_partition: engine already committed");
+  if (model < 0 || model >= e->P) return fail(EXB_ERR_ARG, "exb_set_partition: partition %d out of range", model);
+  const int c = class_of(states);
+  if (c < 0)
+    return fail(EXB_ERR_ARG, "exb_set_partition: %d-state data is not implemented on the B200 back-end "
+                "(DNA = 4 and AA = 20 under GAMMA are)", states);
+  if (width > 0 && (!wgt || !yResource)) return fail(EXB_ERR_ARG, "exb_set_partition: null data for a non-empty partition");
+  HostPart &p = e->parts[model];
+  p.states = states; p.cls = c; p.width = width; p.defined = true;
+  p.wgt.assign(wgt, wgt + width);
+  p.y.assign(yResource, yResource + (size_t)e->mxtips * width);
+  const unsigned char maxcode = (unsigned char)(e->cls[c].codes - 1);
+  for (unsigned char v : p.y)
+    if (v > maxcode) return fail(EXB_ERR_ARG, "exb_set_partition: tip code %d out of range for %d-state data", (int)v, states);
+  p.model.assign(e->cls[c].model_doubles, 0.0);
+  return EXB_OK;
+}
+
+extern "C" int exb_commit(exb_engine *e)
+{
+  if (!e || e->committed) return fail(EXB_ERR_STATE, "exb_commit: already committed");
+  CUDA_TRY(cudaSetDevice(e->device));
+  for (int m = 0; m < e->P; m++)
+    if (!e->parts[m].defined) return fail(EXB_ERR_STATE, "exb_commit: partition %d was never described", m);
+
+  std::vector<int> has_sites(e->P), tbegin(e->P, 0), tcount(e->P, 0), pcls(e->P, 0);
+  for (int c = 0; c < 2; c++) {
+    ClassState &k = e->cls[c];
+    size_t n = 0;
+    int idx = 0;
+    for (int m = 0; m < e->P; m++) {
+      HostPart &p = e->parts[m];
+      if (p.cls != c) continue;
+      p.part_cls = idx++;
+      p.site0 = n;
+      pcls[m] = c;
+      has_sites[m] = p.width > 0;
+      tbegin[m] = (int)k.tiles_h.size();
+      for (size_t s = 0; s < p.width; s += (size_t)e->tile_sites) {
+        Tile t;
+        t.site0 = (uint32_t)(n + s);
+        t.nsites = (uint32_t)std::min<size_t>((size_t)e->tile_sites, p.width - s);
+        t.part = m; t.part_cls = p.part_cls;
+        k.tiles_h.push_back(t);
+      }
+      tcount[m] = (int)k.tiles_h.size() - tbegin[m];
+      n += (p.width + 31) / 32 * 32;            // every partition starts on a 32-site boundary
+    }
+    k.nparts = idx;
+    k.N = n;
+    if (n >= ((size_t)1 << 32)) return fail(EXB_ERR_ARG, "exb_commit: more than 2^32 sites per rank in one class");
+    if (idx == 0) continue;
+    k.models_h.assign((size_t)idx * k.model_doubles, 0.0);
+    CUDA_TRY(cudaMalloc(&k.models, k.models_h.size() * sizeof(double)));
+    if (n == 0) continue;
+    // host images of tips / weights on the class site axis (padding: gap code, weight 0)
+    std::vector<uint8_t> tips((size_t)e->mxtips * n, (uint8_t)(k.codes - 1));
+    std::vector<int> wgt(n, 0);
+    for (int m = 0; m < e->P; m++) {
+      HostPart &p = e->parts[m];
+      if (p.cls != c || p.width == 0) continue;
+      memcpy(&wgt[p.site0], p.wgt.data(), p.width * sizeof(int));
+      for (int t = 0; t < e->mxtips; t++)
+        memcpy(&tips[(size_t)t * n + p.site0], &p.y[(size_t)t * p.width], p.width);
+      std::vector<unsigned char>().swap(p.y);
+    }
+    CUDA_TRY(cudaMalloc(&k.tips, tips.size()));
+    CUDA_TRY(cudaMemcpy(k.tips, tips.data(), tips.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&k.wgt, n * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(k.wgt, wgt.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    const size_t clv_bytes = (size_t)(e->mxtips - 2) * n * k.span * sizeof(double);
+    if (cudaMalloc(&k.clv, clv_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(EXB_ERR_CUDA, "exb_commit: cannot allocate %.2f GB of HBM for the CLVs of %zu %d-state sites x %d inner nodes",
+                  clv_bytes / 1e9, n, k.S, e->mxtips - 2);
+    }
+    CUDA_TRY(cudaMemset(k.clv, 0, clv_bytes));
+    CUDA_TRY(cudaMalloc(&k.sum, n * k.span * sizeof(double)));
+    CUDA_TRY(cudaMemset(k.sum, 0, n * k.span * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&k.tiles, k.tiles_h.size() * sizeof(Tile)));
+    CUDA_TRY(cudaMemcpy(k.tiles, k.tiles_h.data(), k.tiles_h.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&k.tile_out, k.tiles_h.size() * 2 * sizeof(double)));
+    CUDA_TRY(cudaMemset(k.tile_out, 0, k.tiles_h.size() * 2 * sizeof(double)));
+  }
+
+  auto upload_ints = [&](int **dst, const std::vector<int> &src) -> cudaError_t {
+    cudaError_t r = cudaMalloc(dst, src.size() * sizeof(int));
+    if (r != cudaSuccess) return r;
+    return cudaMemcpy(*dst, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice);
+  };
+  CUDA_TRY(upload_ints(&e->part_has_sites, has_sites));
+  CUDA_TRY(upload_ints(&e->part_tile_begin, tbegin));
+  CUDA_TRY(upload_ints(&e->part_tile_count, tcount));
+  CUDA_TRY(upload_ints(&e->part_cls, pcls));
+
+  e->max_entries = e->mxtips + 1;                 // td[0].ti holds mxtips entries (axml.c:595)
+  CUDA_TRY(cudaMalloc(&e->gs, (size_t)e->P * 2 * e->mxtips * sizeof(unsigned int)));
+  CUDA_TRY(cudaMemset(e->gs, 0, (size_t)e->P * 2 * e->mxtips * sizeof(unsigned int)));
+  CUDA_TRY(cudaMalloc(&e->scale_inc, (size_t)e->max_entries * e->P * sizeof(unsigned int)));
+  CUDA_TRY(cudaMemset(e->scale_inc, 0, (size_t)e->max_entries * e->P * sizeof(unsigned int)));
+  CUDA_TRY(cudaMalloc(&e->out_d, (size_t)2 * e->P * sizeof(double)));
+  CUDA_TRY(cudaMemset(e->out_d, 0, (size_t)2 * e->P * sizeof(double)));
+  CUDA_TRY(cudaMallocHost(&e->out_h, (size_t)2 * e->P * sizeof(double)));
+
+  auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  size_t off = 0;
+  e->off_entries = off; off = align16(off + (size_t)e->max_entries * sizeof(DevEntry));
+  e->off_lzq = off;     off = align16(off + (size_t)e->max_entries * e->nb * sizeof(double));
+  e->off_lzr = off;     off = align16(off + (size_t)e->max_entries * e->nb * sizeof(double));
+  e->off_corelz = off;  off = align16(off + (size_t)e->nb * sizeof(double));
+  e->off_mask = off;    off = align16(off + (size_t)e->P);
+  e->stage_bytes = off;
+  CUDA_TRY(cudaMallocHost(&e->stage_h, off));
+  CUDA_TRY(cudaMalloc(&e->stage_d, off));
+  e->committed = true;
+  return EXB_OK;
+}
+
+extern "C" int exb_set_model(exb_engine *e, int model, const double *EIGN, const double *EV,
+                             const double *EI, const double *tipVector, const double *gammaRates)
+{
+  if (!e || !e->committed) return fail(EXB_ERR_STATE, "exb_set_model: call exb_commit first");
+  if (model < 0 || model >= e->P) return fail(EXB_ERR_ARG, "exb_set_model: partition %d out of range", model);
+  HostPart &p = e->parts[model];
+  ClassState &k = e->cls[p.cls];
+  const int S = k.S;
+  std::vector<double> m((size_t)k.model_doubles);
+  double *w = m.data();
+  memcpy(w, EIGN, S * sizeof(double)); w += S;
+  memcpy(w, gammaRates, 4 * sizeof(double)); w += 4;
+  memcpy(w, EI, (size_t)S * S * sizeof(double)); w += S * S;
+  memcpy(w, EV, (size_t)S * S * sizeof(double)); w += S * S;
+  memcpy(w, tipVector, (size_t)k.codes * S * sizeof(double));
+  if (p.model_set && memcmp(m.data(), p.model.data(), m.size() * sizeof(double)) == 0) return EXB_OK;
+  p.model = m;
+  p.model_set = true;
+  memcpy(&k.models_h[(size_t)p.part_cls * k.model_doubles], m.data(), m.size() * sizeof(double));
+  k.dirty_lo = std::min(k.dirty_lo, p.part_cls);
+  k.dirty_hi = std::max(k.dirty_hi, p.part_cls);
+  return EXB_OK;
+}
+
+// Upload whatever the host changed since the last call.
+static int flush_models(exb_engine *e)
+{
+  for (int c = 0; c < 2; c++) {
+    ClassState &k = e->cls[c];
+    if (k.dirty_hi < k.dirty_lo) continue;
+    const size_t off = (size_t)k.dirty_lo * k.model_doubles, cnt = (size_t)(k.dirty_hi - k.dirty_lo + 1) * k.model_doubles;
+    // pageable source: the copy is staged by the driver before the call returns, so models_h may change afterwards
+    CUDA_TRY(cudaMemcpyAsync(k.models + off, &k.models_h[off], cnt * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    k.dirty_lo = 1 << 30; k.dirty_hi = -1;
+  }
+  return EXB_OK;
+}
+
+static int check_models(exb_engine *e, const unsigned char *mask)
+{
+  for (int m = 0; m < e->P; m++)
+    if ((!mask || mask[m]) && e->parts[m].width > 0 && !e->parts[m].model_set)
+      return fail(EXB_ERR_STATE, "partition %d has no model constants (exb_set_model)", m);
+  return EXB_OK;
+}
+
+// Validate and stage a traversal descriptor; one H2D copy.
+static int stage_traversal(exb_engine *e, const exb_entry *ti, int count, int first, const double *qz, const double *rz,
+                           const unsigned char *mask)
+{
+  if (count < first || count > e->max_entries)
+    return fail(EXB_ERR_ARG, "traversal of %d entries (max %d)", count, e->max_entries);
+  const int lo = e->mxtips + 1, hi = 2 * e->mxtips - 2;
+  DevEntry *de = (DevEntry *)(e->stage_h + e->off_entries);
+  double *lq = (double *)(e->stage_h + e->off_lzq), *lr = (double *)(e->stage_h + e->off_lzr);
+  const double logzmin = log(kZmin);
+  for (int i = 0; i < count; i++) {
+    const exb_entry &t = ti[i];
+    if (i < first) {
+      if (t.pNumber < 1 || t.pNumber > hi || t.qNumber < 1 || t.qNumber > hi)
+        return fail(EXB_ERR_ARG, "branch entry has node numbers %d,%d outside 1..%d", t.pNumber, t.qNumber, hi);
+      de[i] = DevEntry{-1, t.pNumber, t.qNumber, 0};
+    } else {
+      bool ok = t.pNumber >= lo && t.pNumber <= hi;
+      switch (t.tipCase) {
+      case EXB_TIP_TIP:     ok = ok && t.qNumber >= 1 && t.qNumber < lo && t.rNumber >= 1 && t.rNumber < lo; break;
+      case EXB_TIP_INNER:   ok = ok && t.qNumber >= 1 && t.qNumber < lo && t.rNumber >= lo && t.rNumber <= hi; break;
+      case EXB_INNER_INNER: ok = ok && t.qNumber >= lo && t.qNumber <= hi && t.rNumber >= lo && t.rNumber <= hi; break;
+      default: ok = false;
+      }
+      if (!ok) return fail(EXB_ERR_ARG, "traversal entry %d is inconsistent (tipCase=%d p=%d q=%d r=%d, mxtips=%d)",
+                           i, t.tipCase, t.pNumber, t.qNumber, t.rNumber, e->mxtips);
+      de[i] = DevEntry{t.tipCase, t.pNumber, t.qNumber, t.rNumber};
+    }
+    for (int b = 0; b < e->nb; b++) {
+      const double zq = qz[(size_t)i * e->nb + b];
+      lq[(size_t)i * e->nb + b] = (zq > kZmin) ? log(zq) : logzmin;        // newviewGenericSpecial.c:983-984
+      const double zr = (i < first) ? 1.0 : rz[(size_t)i * e->nb + b];
+      lr[(size_t)i * e->nb + b] = (zr > kZmin) ? log(zr) : logzmin;
+    }
+  }
+  unsigned char *mk = e->stage_h + e->off_mask;
+  for (int m = 0; m < e->P; m++) mk[m] = mask ? (mask[m] != 0) : 1;
+  CUDA_TRY(cudaMemcpyAsync(e->stage_d, e->stage_h, e->stage_bytes, cudaMemcpyHostToDevice, e->stream));
+  return EXB_OK;
+}
+
+static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int first, const double *qz, const double *rz,
+                         const unsigned char *mask, int mode)
+{
+  if (!e || !e->committed) return fail(EXB_ERR_STATE, "engine not committed");
+  if (!ti || !qz || (count > first && !rz)) return fail(EXB_ERR_ARG, "null traversal arguments");
+  CUDA_TRY(cudaSetDevice(e->device));
+  int rc = check_models(e, mask);
+  if (rc) return rc;
+  // the previous call has been synchronised, so the pinned staging area is free
+  rc = stage_traversal(e, ti, count, first, qz, rz, mask);
+  if (rc) return rc;
+  rc = flush_models(e);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+  for (int c = 0; c < 2; c++) {
+    ClassState &k = e->cls[c];
+    if (k.tiles_h.empty()) continue;
+    TraverseArgs a;
+    a.tiles = k.tiles; a.clv = k.clv; a.tips = k.tips; a.wgt = k.wgt; a.sum = k.sum; a.models = k.models;
+    a.N = k.N; a.mxtips = e->mxtips; a.nparts = e->P; a.nbranches = e->nb;
+    a.entries = (const DevEntry *)(e->stage_d + e->off_entries);
+    a.lzq = (const double *)(e->stage_d + e->off_lzq);
+    a.lzr = (const double *)(e->stage_d + e->off_lzr);
+    a.mask = e->stage_d + e->off_mask;
+    a.count = count; a.first = first; a.mode = mode;
+    a.scale_inc = e->scale_inc; a.tile_out = k.tile_out;
+    if (c == CLS_DNA) launch_traverse_dna(a, (int)k.tiles_h.size(), e->stream);
+    else              launch_traverse_aa(a, (int)k.tiles_h.size(), e->stream);
+    e->launches++;
+  }
+  FinishArgs f;
+  f.gs = e->gs; f.scale_inc = e->scale_inc;
+  f.entries = (const DevEntry *)(e->stage_d + e->off_entries);
+  f.count = count; f.first = first; f.mxtips = e->mxtips; f.nparts = e->P;
+  f.mask = e->stage_d + e->off_mask; f.part_has_sites = e->part_has_sites;
+  f.tile_out[0] = e->cls[0].tile_out; f.tile_out[1] = e->cls[1].tile_out;
+  f.part_tile_begin = e->part_tile_begin; f.part_tile_count = e->part_tile_count; f.part_cls = e->part_cls;
+  f.mode = mode; f.log_minlikelihood = log(kMinLikelihood); f.out = e->out_d;
+  launch_finish(f, e->stream);
+  e->launches++;
+  CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+  CUDA_TRY(cudaGetLastError());
+  return EXB_OK;
+}
+
+// all-reduce (if a communicator exists), copy n doubles of out_d to the pinned mirror, wait.
+static int collect(exb_engine *e, size_t n)
+{
+  if (e->comm) {
+    const int r = g_nccl.AllReduce(e->out_d, e->out_d, n, kNcclFloat64, kNcclSum, e->comm, e->stream);
+    if (r != 0) return fail(EXB_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  }
+  if (n) CUDA_TRY(cudaMemcpyAsync(e->out_h, e->out_d, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
+  return EXB_OK;
+}
+
+extern "C" int exb_newview(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
+                           const unsigned char *executeModel)
+{
+  if (count == 0) return EXB_OK;
+  int rc = run_traversal(e, ti, count, 0, qz, rz, executeModel, MODE_NEWVIEW);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(e->stream));     // the staging buffers are reused by the next call
+  cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
+  return EXB_OK;
+}
+
+extern "C" int exb_evaluate(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
+                            const unsigned char *executeModel, double *perPartitionLH)
+{
+  if (count < 1 || !perPartitionLH) return fail(EXB_ERR_ARG, "exb_evaluate: needs the branch entry and an output array");
+  int rc = run_traversal(e, ti, count, 1, qz, rz, executeModel, MODE_EVALUATE);
+  if (rc) return rc;
+  rc = collect(e, (size_t)e->P);
+  if (rc) return rc;
+  for (int m = 0; m < e->P; m++)
+    if (!executeModel || executeModel[m]) perPartitionLH[m] = e->out_h[m];   // masked partitions keep their value
+  return EXB_OK;
+}
+
+extern "C" int exb_makenewz_prepare(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
+                                    const unsigned char *executeModel)
+{
+  if (count < 1) return fail(EXB_ERR_ARG, "exb_makenewz_prepare: needs the branch entry");
+  int rc = run_traversal(e, ti, count, 1, qz, rz, executeModel, MODE_SUM);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
+  return EXB_OK;
+}
+
+extern "C" int exb_core(exb_engine *e, const double *lz, const unsigned char *executeModel,
+                        double *dlnLdlz, double *d2lnLdlz2)
+{
+  if (!e || !e->committed) return fail(EXB_ERR_STATE, "engine not committed");
+  if (!lz || !dlnLdlz || !d2lnLdlz2) return fail(EXB_ERR_ARG, "exb_core: null argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  memcpy(e->stage_h + e->off_corelz, lz, (size_t)e->nb * sizeof(double));
+  unsigned char *mk = e->stage_h + e->off_mask;
+  for (int m = 0; m < e->P; m++) mk[m] = executeModel ? (executeModel[m] != 0) : 1;
+  // core-lz and mask are adjacent at the tail of the staging area: one small copy
+  CUDA_TRY(cudaMemcpyAsync(e->stage_d + e->off_corelz, e->stage_h + e->off_corelz, e->stage_bytes - e->off_corelz,
+                           cudaMemcpyHostToDevice, e->stream));
+  int rc = flush_models(e);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+  for (int c = 0; c < 2; c++) {
+    ClassState &k = e->cls[c];
+    if (k.tiles_h.empty()) continue;
+    CoreArgs a;
+    a.tiles = k.tiles; a.sum = k.sum; a.wgt = k.wgt; a.models = k.models;
+    a.lz = (const double *)(e->stage_d + e->off_corelz);
+    a.mask = e->stage_d + e->off_mask; a.nbranches = e->nb; a.tile_out = k.tile_out;
+    if (c == CLS_DNA) launch_core_dna(a, (int)k.tiles_h.size(), e->stream);
+    else              launch_core_aa(a, (int)k.tiles_h.size(), e->stream);
+    e->launches++;
+  }
+  FinishArgs f;
+  memset(&f, 0, sizeof f);
+  f.gs = e->gs; f.scale_inc = e->scale_inc; f.entries = (const DevEntry *)(e->stage_d + e->off_entries);
+  f.count = 0; f.first = 0; f.mxtips = e->mxtips; f.nparts = e->P;
+  f.mask = e->stage_d + e->off_mask; f.part_has_sites = e->part_has_sites;
+  f.tile_out[0] = e->cls[0].tile_out; f.tile_out[1] = e->cls[1].tile_out;
+  f.part_tile_begin = e->part_tile_begin; f.part_tile_count = e->part_tile_count; f.part_cls = e->part_cls;
+  f.mode = MODE_CORE; f.log_minlikelihood = 0.0; f.out = e->out_d;
+  launch_finish(f, e->stream);
+  e->launches++;
+  CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+  CUDA_TRY(cudaGetLastError());
+  rc = collect(e, (size_t)2 * e->P);
+  if (rc) return rc;
+  // per-partition sums -> branch slots, in partition order (makenewzGenericSpecial.c:921-946, 1075-1076)
+  for (int b = 0; b < e->nb; b++) { dlnLdlz[b] = 0.0; d2lnLdlz2[b] = 0.0; }
+  for (int m = 0; m < e->P; m++) {
+    if (executeModel && !executeModel[m]) continue;
+    const int slot = e->nb > 1 ? m : 0;
+    dlnLdlz[slot] += e->out_h[m];
+    d2lnLdlz2[slot] += e->out_h[e->P + m];
+  }
+  return EXB_OK;
+}
+
+// ---- multi-GPU -----------------------------------------------------------------------------------------
+extern "C" int exb_comm_unique_id(void *id_out)
+{
+  int rc = load_nccl();
+  if (rc) return rc;
+  NcclUniqueId id;
+  const int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) return fail(EXB_ERR_NCCL, "ncclGetUniqueId failed (%d)", r);
+  memcpy(id_out, &id, sizeof id);
+  return EXB_OK;
+}
+
+extern "C" int exb_comm_init(exb_engine *e, int rank, int nranks, const void *id)
+{
+  if (!e) return fail(EXB_ERR_ARG, "exb_comm_init: null engine");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(EXB_ERR_ARG, "exb_comm_init: rank %d of %d", rank, nranks);
+  e->nranks = nranks;
+  if (nranks == 1) return EXB_OK;
+  int rc = load_nccl();
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  NcclUniqueId uid;
+  memcpy(&uid, id, sizeof uid);
+  const int r = g_nccl.CommInitRank(&e->comm, nranks, uid, rank);
+  if (r != 0) return fail(EXB_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return EXB_OK;
+}
+
+// ---- introspection ---------------------------------------------------------------------------------------
+extern "C" int exb_read_clv(exb_engine *e, int model, int nodeNumber, double *out)
+{
+  if (!e || !e->committed) return fail(EXB_ERR_STATE, "engine not committed");
+  if (model < 0 || model >= e->P || nodeNumber <= e->mxtips || nodeNumber > 2 * e->mxtips - 2)
+    return fail(EXB_ERR_ARG, "exb_read_clv: bad partition/node");
+  HostPart &p = e->parts[model];
+  ClassState &k = e->cls[p.cls];
+  if (p.width == 0) return EXB_OK;
+  CUDA_TRY(cudaSetDevice(e->device));
+  const double *src = k.clv + ((size_t)(nodeNumber - e->mxtips - 1) * k.N + p.site0) * k.span;
+  CUDA_TRY(cudaMemcpy(out, src, p.width * k.span * sizeof(double), cudaMemcpyDeviceToHost));
+  return EXB_OK;
+}
+
+extern "C" int exb_read_scaler(exb_engine *e, int model, int nodeNumber, unsigned int *out)
+{
+  if (!e || !e->committed) return fail(EXB_ERR_STATE, "engine not committed");
+  if (model < 0 || model >= e->P || nodeNumber < 1 || nodeNumber > 2 * e->mxtips - 2)
+    return fail(EXB_ERR_ARG, "exb_read_scaler: bad partition/node");
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(cudaMemcpy(out, e->gs + (size_t)model * 2 * e->mxtips + nodeNumber, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  return EXB_OK;
+}
+
+extern "C" int exb_read_sumtable(exb_engine *e, int model, double *out)
+{
+  if (!e || !e->committed) return fail(EXB_ERR_STATE, "engine not committed");
+  if (model < 0 || model >= e->P) return fail(EXB_ERR_ARG, "exb_read_sumtable: bad partition");
+  HostPart &p = e->parts[model];
+  ClassState &k = e->cls[p.cls];
+  if (p.width == 0) return EXB_OK;
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(cudaMemcpy(out, k.sum + p.site0 * k.span, p.width * k.span * sizeof(double), cudaMemcpyDeviceToHost));
+  return EXB_OK;
+}
+
+extern "C" int exb_last_kernel_ms(exb_engine *e, float *ms)
+{
+  if (!e || !ms) return fail(EXB_ERR_ARG, "exb_last_kernel_ms: null argument");
+  *ms = e->last_ms;
+  return EXB_OK;
+}
+
+extern "C" long exb_launch_count(exb_engine *e) { return e ? e->launches : 0; }

@@ -1,0 +1,121 @@
+// engine.cuh -- structures shared by the host engine (engine.cu) and the sm_100a kernels
+// (kernels_dna.cu, kernels_aa.cu).  See DESIGN.md for the HBM layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace exb {
+
+constexpr double kZmin = 1.0E-15;                    // axml.h:110
+constexpr double kTwoToThe256 =                      // axml.h:113-116
+    115792089237316195423570985008687907853269984665640564039457584007913129639936.0;
+constexpr double kMinLikelihood = 1.0 / kTwoToThe256;  // axml.h:118
+
+enum Mode : int { MODE_NEWVIEW = 0, MODE_EVALUATE = 1, MODE_SUM = 2, MODE_CORE = 3 };
+
+// Data-type class: all partitions with the same number of states share one site axis.
+constexpr int CLS_DNA = 0;   // 4 states, 16 tip codes, span 16 doubles  (128 B per site and node)
+constexpr int CLS_AA  = 1;   // 20 states, 23 tip codes, span 80 doubles (640 B per site and node)
+
+// Per-partition model constants as laid out in HBM (doubles).
+//   DNA: EIGN[4] rates[4] EI[16] EV[16] tip[16*4]            = 104 doubles
+//   AA : EIGN[20] rates[4] EI[400] EV[400] tip[23*20]        = 1284 doubles
+constexpr int kDnaModelDoubles = 4 + 4 + 16 + 16 + 64;
+constexpr int kAaModelDoubles  = 20 + 4 + 400 + 400 + 460;
+
+// A work tile: a run of sites of ONE partition, processed by one CTA for the whole traversal.
+struct Tile {
+  uint32_t site0;      // first site on the class site axis
+  uint32_t nsites;     // <= tile_sites
+  int32_t  part;       // global partition index (mask / scaler / branch slot)
+  int32_t  part_cls;   // index of the partition inside its class (model constants)
+};
+
+// traversalInfo without branch arrays (mirrors exb_entry)
+struct DevEntry { int tipCase, p, q, r; };
+
+// Everything a traversal kernel needs.  Passed by value (fits the 4 KB parameter space).
+struct TraverseArgs {
+  // static layout of this class
+  const Tile   *tiles;
+  double       *clv;        // [(mxtips-2)][N][span]   NOT const/restrict: read-after-write by the same thread
+  const uint8_t*tips;       // [mxtips][N]
+  const int    *wgt;        // [N]
+  double       *sum;        // [N][span]
+  const double *models;     // [parts_in_class][model doubles]
+  size_t        N;          // padded sites on the class axis
+  int           mxtips;
+  int           nparts;     // global partition count P
+  int           nbranches;
+  // per call
+  const DevEntry      *entries;   // [count]
+  const double        *lzq;       // [count][nbranches]  log(max(z, zmin)) of the q branch (entry 0: the root branch)
+  const double        *lzr;       // [count][nbranches]
+  const unsigned char *mask;      // [P] executeModel
+  int           count;
+  int           first;      // first newview entry (0 for newview, 1 when entry 0 is a branch)
+  int           mode;       // Mode
+  unsigned int *scale_inc;  // [maxEntries][P]  per-entry scaler increments (integer atomics: deterministic)
+  double       *tile_out;   // [ntiles][2]      per-tile partial sums (evaluate: lnL; core: d1,d2)
+};
+
+struct CoreArgs {
+  const Tile   *tiles;
+  const double *sum;
+  const int    *wgt;
+  const double *models;
+  const double *lz;          // [nbranches] trial log z
+  const unsigned char *mask;
+  int           nbranches;
+  double       *tile_out;    // [ntiles][2]
+};
+
+struct FinishArgs {
+  // scaler fix-up: gs[p] = gs[q] + gs[r] + inc  for every newview entry, in order
+  unsigned int *gs;          // [P][2*mxtips]
+  unsigned int *scale_inc;   // [maxEntries][P] (re-zeroed here)
+  const DevEntry *entries;
+  int           count, first;
+  int           mxtips, nparts;
+  const unsigned char *mask;
+  const int    *part_has_sites;   // [P] local width > 0
+  // reduction of tile partials
+  const double *tile_out[2];      // per class
+  const int    *part_tile_begin;  // [P] first tile of the partition inside its class list
+  const int    *part_tile_count;  // [P]
+  const int    *part_cls;         // [P] class of the partition
+  int           mode;
+  double        log_minlikelihood;
+  double       *out;              // evaluate: [P]; core: [2][P]
+};
+
+void launch_traverse_dna(const TraverseArgs &a, int ntiles, cudaStream_t s);
+void launch_core_dna(const CoreArgs &a, int ntiles, cudaStream_t s);
+void launch_traverse_aa(const TraverseArgs &a, int ntiles, cudaStream_t s);
+void launch_core_aa(const CoreArgs &a, int ntiles, cudaStream_t s);
+void launch_finish(const FinishArgs &a, cudaStream_t s);
+
+// ---- device helpers shared by the kernels --------------------------------------------------------------
+#ifdef __CUDACC__
+constexpr int kThreads = 256;
+
+// Deterministic block-wide sum: fixed shuffle tree inside each warp, then warp 0 adds the warp
+// totals in warp order.  Result valid in thread 0.
+__device__ __forceinline__ double block_sum(double v, double *smem8)
+{
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();                       // smem8 may still be in use by a previous reduction
+  if (lane == 0) smem8[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = (lane < (int)(blockDim.x >> 5)) ? smem8[lane] : 0.0;
+    #pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  }
+  return v;
+}
+#endif
+
+}  // namespace exb

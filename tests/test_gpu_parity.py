@@ -1,0 +1,174 @@
+"""Parity of the CUDA engine (through the C ABI) against the reference's goldens and the CPU oracle.
+
+Tolerances: north_star asks for lnL within 1e-6 relative of the reference's AVX build.  The CUDA
+path differs from the reference only in summation order and in exp/log ulps, so these tests hold it
+to 5e-12 relative on lnL, 1e-11 on CLV entries and exact equality on scaler counts."""
+import numpy as np
+import pytest
+
+from examl_b200.likelihood import Likelihood
+from replay import CASES, replay_case
+from synth import build_engine, random_case
+
+pytestmark = pytest.mark.gpu
+
+CLV_RTOL = 1e-11
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_reference_goldens(cuda_factory, tag):
+    replay_case(cuda_factory, tag)
+
+
+@pytest.mark.parametrize("tile", [32, 64, 256, 1024])
+def test_goldens_any_tile_size(cuda_factory, tile):
+    replay_case(cuda_factory, "dna49", tile_sites=tile)
+    replay_case(cuda_factory, "aa60", tile_sites=tile)
+
+
+def _compare_engines(gpu, cpu, tree, parts, mask=None):
+    ti = tree.full_traversal()
+    lg = gpu.evaluateIterative(ti, mask)
+    lc = cpu.evaluateIterative(ti, mask)
+    for m, (s, tips, wgt) in enumerate(parts):
+        if mask is not None and not mask[m]:
+            continue
+        if wgt.shape[0] == 0:
+            assert lg[m] == 0.0
+            continue
+        assert abs(lg[m] - lc[m]) <= 5e-12 * abs(lc[m]), (m, lg[m], lc[m])
+        for e in ti[1:]:
+            a, b = gpu.read_clv(m, e.pNumber), cpu.read_clv(m, e.pNumber)
+            scale = np.abs(b).max(axis=(1, 2), keepdims=True)
+            assert np.all(np.abs(a - b) <= CLV_RTOL * scale), (m, e.pNumber)
+            assert gpu.read_scaler(m, e.pNumber) == cpu.read_scaler(m, e.pNumber)
+    return ti
+
+
+@pytest.mark.parametrize("widths,kinds", [
+    ([1], [4]), ([31], [4]), ([33], [4]), ([257], [4]), ([1000], [4]),
+    ([1], [20]), ([65], [20]), ([300], [20]),
+    ([100, 0, 37, 64], [4, 4, 20, 4]),
+])
+def test_clv_scaler_sum_core_vs_oracle(cuda_factory, oracle_factory, widths, kinds):
+    tree, parts, models = random_case(24, widths, kinds, seed=len(widths) * 7 + widths[0])
+    gpu = build_engine(cuda_factory, tree, parts, models, tile_sites=64)
+    cpu = build_engine(oracle_factory, tree, parts, models)
+    _compare_engines(gpu, cpu, tree, parts)
+    # makenewz at an inner branch: sum table + derivatives for a few trial values
+    p = tree.start.back.next.back
+    if tree.isTip(p.number):
+        p = tree.start.back.next.next.back
+    ti = tree.partial_traversal(p)
+    gpu.makenewzIterative(ti)
+    cpu.makenewzIterative(ti)
+    for m, (s, tips, wgt) in enumerate(parts):
+        if wgt.shape[0]:
+            a, b = gpu.read_sumtable(m), cpu.read_sumtable(m)
+            assert np.all(np.abs(a - b) <= CLV_RTOL * np.abs(b).max(axis=(1, 2), keepdims=True))
+    for z in (0.9, 0.5, 0.05, 1e-15):
+        g1, g2 = gpu.execCore([np.log(z)])
+        c1, c2 = cpu.execCore([np.log(z)])
+        assert abs(g1[0] - c1[0]) <= 1e-10 * max(1.0, abs(c1[0])), (z, g1, c1)
+        assert abs(g2[0] - c2[0]) <= 1e-10 * max(1.0, abs(c2[0])), (z, g2, c2)
+
+
+def test_scaling_path_iid_dna(cuda_factory, oracle_factory):
+    """i.i.d. columns on 150 taxa: every site is rescaled at least once (SURVEY.md 4 iv)."""
+    tree, parts, models = random_case(150, [500], [4], seed=3, mode="iid")
+    gpu = build_engine(cuda_factory, tree, parts, models, tile_sites=128)
+    cpu = build_engine(oracle_factory, tree, parts, models)
+    ti = _compare_engines(gpu, cpu, tree, parts)
+    root = gpu.read_scaler(0, ti[0].pNumber) + gpu.read_scaler(0, ti[0].qNumber)
+    assert root >= int(parts[0][2].sum()), root
+
+
+def test_masks_and_per_partition_branches(cuda_factory, oracle_factory):
+    tree, parts, models = random_case(16, [90, 40, 130], [4, 20, 4], seed=11, num_branches=3)
+    gpu = build_engine(cuda_factory, tree, parts, models, tile_sites=32)
+    cpu = build_engine(oracle_factory, tree, parts, models)
+    _compare_engines(gpu, cpu, tree, parts)
+    mask = [True, False, True]
+    before = gpu.evaluateIterative(tree.full_traversal())
+    out = before.copy()
+    out[1] = 123.0                                 # a masked partition's slot must not be touched
+    gpu.evaluateIterative(tree.full_traversal(), mask, out=out)
+    assert out[1] == 123.0 and out[0] == before[0] and out[2] == before[2]
+    # derivative slots follow the partitions under -M
+    p = tree.start.back
+    ti = tree.partial_traversal(p)
+    gpu.makenewzIterative(ti)
+    cpu.makenewzIterative(ti)
+    lz = [np.log(0.8), np.log(0.6), np.log(0.4)]
+    g1, g2 = gpu.execCore(lz, [True, True, False])
+    c1, c2 = cpu.execCore(lz, [True, True, False])
+    assert g1[2] == 0.0 and g2[2] == 0.0
+    np.testing.assert_allclose(g1, c1, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(g2, c2, rtol=1e-10, atol=1e-10)
+
+
+def test_root_invariance_and_newton_raphson(cuda_factory, oracle_factory):
+    """Pulley principle: lnL is the same at every branch (partial traversals re-orient CLVs);
+    then one smoothing sweep of makenewzGeneric must not lower lnL and must track the oracle."""
+    tree, parts, models = random_case(20, [400], [4], seed=5)
+    gpu = build_engine(cuda_factory, tree, parts, models, tile_sites=64)
+    lk = Likelihood(tree, gpu, 1)
+    base = lk.evaluateGeneric(tree.start, True)
+    for a, b in list(tree.branches())[:12]:
+        assert abs(lk.evaluateGeneric(a, False) - base) <= 1e-10 * abs(base)
+    tree2, parts2, models2 = random_case(20, [400], [4], seed=5)
+    cpu = build_engine(oracle_factory, tree2, parts2, models2)
+    lk2 = Likelihood(tree2, cpu, 1)
+    lk2.evaluateGeneric(tree2.start, True)
+    for (a, b), (a2, b2) in list(zip(tree.branches(), tree2.branches()))[:10]:
+        z = lk.makenewzGeneric(a, b, a.z, 10)
+        z2 = lk2.makenewzGeneric(a2, b2, a2.z, 10)
+        assert abs(z[0] - z2[0]) <= 1e-9 * z2[0]
+        a.z[:] = z
+        a2.z[:] = z2
+    after = lk.evaluateGeneric(tree.start, True)
+    assert after >= base - 1e-9 * abs(base)
+    assert abs(after - lk2.evaluateGeneric(tree2.start, True)) <= 1e-10 * abs(after)
+
+
+def test_bitwise_repeatability(cuda_factory):
+    """optimizeModel.c:3030 asserts that two consecutive evaluations agree bit for bit."""
+    tree, parts, models = random_case(30, [5000, 777], [4, 20], seed=9)
+    gpu = build_engine(cuda_factory, tree, parts, models)
+    ti = tree.full_traversal()
+    a = gpu.evaluateIterative(ti).copy()
+    for _ in range(3):
+        b = gpu.evaluateIterative(ti)
+        assert a.tobytes() == b.tobytes()
+
+
+def test_full_size_linearity_dna(cuda_factory, oracle_factory):
+    """1 M sites x 40 taxa: the alignment is a 1 000-site block repeated 1 000 times, so
+    lnL(1 M) = 1 000 x lnL(block) -- a size-independent check at BASELINE.json's site count."""
+    tree, parts, models = random_case(40, [1000], [4], seed=21)
+    s, tips, wgt = parts[0]
+    wgt = np.ones_like(wgt)
+    cpu = build_engine(oracle_factory, tree, [(s, tips, wgt)], models)
+    ti = tree.full_traversal()
+    block = cpu.evaluateIterative(ti)[0]
+    big = [(s, np.tile(tips, (1, 1000)), np.ones(1000 * 1000, dtype=np.int32))]
+    gpu = build_engine(cuda_factory, tree, big, models)
+    total = gpu.evaluateIterative(ti)[0]
+    assert abs(total - 1000.0 * block) <= 1e-9 * abs(total), (total, block)
+
+
+def test_errors_are_loud(cuda_factory):
+    from examl_b200.capi import EngineError
+    tree, parts, models = random_case(8, [10], [4], seed=1)
+    gpu = cuda_factory(8, 1, 1)
+    with pytest.raises(EngineError):
+        gpu.set_partition(0, 2, parts[0][2], parts[0][1])       # binary data: not implemented
+    gpu.set_partition(0, 4, parts[0][2], parts[0][1])
+    gpu.commit()
+    with pytest.raises(EngineError):
+        gpu.evaluateIterative(tree.full_traversal())             # no model constants yet
+    gpu.set_model(0, models[0])
+    bad = tree.full_traversal()
+    bad[1].pNumber = 3                                           # a tip cannot be recomputed
+    with pytest.raises(EngineError):
+        gpu.evaluateIterative(bad)
