@@ -159,9 +159,10 @@ struct ClassState {
   int nparts = 0;
   std::vector<Tile> tiles_h;
   Tile *tiles = nullptr;
-  double *clv = nullptr, *sum = nullptr, *models = nullptr, *tile_out = nullptr;
+  double *clv = nullptr, *sum = nullptr, *models = nullptr, *tile_out = nullptr, *dtab = nullptr;
   uint8_t *tips = nullptr;
-  int *wgt = nullptr;
+  int *wgt = nullptr, *part_global = nullptr;   // class-partition -> global partition
+  int dtab_row = 0;
   std::vector<double> models_h;
   int dirty_lo = 1 << 30, dirty_hi = -1;   // range of class-partitions whose constants must be re-uploaded
 };
@@ -211,6 +212,7 @@ extern "C" int exb_create(exb_engine **out, int device, int mxtips, int numParti
   e->parts.resize(numPartitions);
   e->cls[CLS_DNA].S = 4;  e->cls[CLS_DNA].span = 16; e->cls[CLS_DNA].codes = 16; e->cls[CLS_DNA].model_doubles = kDnaModelDoubles;
   e->cls[CLS_AA].S = 20;  e->cls[CLS_AA].span = 80;  e->cls[CLS_AA].codes = 23;  e->cls[CLS_AA].model_doubles = kAaModelDoubles;
+  e->cls[CLS_DNA].dtab_row = kDnaDtabRow; e->cls[CLS_AA].dtab_row = kAaDtabRow;
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&e->ev0));
   CUDA_TRY(cudaEventCreate(&e->ev1));
@@ -227,7 +229,7 @@ extern "C" void exb_destroy(exb_engine *e)
   for (int c = 0; c < 2; c++) {
     ClassState &k = e->cls[c];
     cudaFree(k.tiles); cudaFree(k.clv); cudaFree(k.sum); cudaFree(k.models); cudaFree(k.tile_out);
-    cudaFree(k.tips); cudaFree(k.wgt);
+    cudaFree(k.tips); cudaFree(k.wgt); cudaFree(k.dtab); cudaFree(k.part_global);
   }
   cudaFree(e->stage_d); cudaFreeHost(e->stage_h);
   cudaFree(e->part_has_sites); cudaFree(e->part_tile_begin); cudaFree(e->part_tile_count); cudaFree(e->part_cls);
@@ -303,6 +305,14 @@ extern "C" int exb_commit(exb_engine *e)
     if (idx == 0) continue;
     k.models_h.assign((size_t)idx * k.model_doubles, 0.0);
     CUDA_TRY(cudaMalloc(&k.models, k.models_h.size() * sizeof(double)));
+    {
+      std::vector<int> pg;
+      for (int m = 0; m < e->P; m++) if (e->parts[m].cls == c) pg.push_back(m);
+      CUDA_TRY(cudaMalloc(&k.part_global, pg.size() * sizeof(int)));
+      CUDA_TRY(cudaMemcpy(k.part_global, pg.data(), pg.size() * sizeof(int), cudaMemcpyHostToDevice));
+      const size_t dbytes = (size_t)(e->mxtips + 1) * idx * k.dtab_row * sizeof(double);
+      CUDA_TRY(cudaMalloc(&k.dtab, dbytes));
+    }
     if (n == 0) continue;
     // host images of tips / weights on the class site axis (padding: gap code, weight 0)
     std::vector<uint8_t> tips((size_t)e->mxtips * n, (uint8_t)(k.codes - 1));
@@ -471,7 +481,15 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   for (int c = 0; c < 2; c++) {
     ClassState &k = e->cls[c];
     if (k.tiles_h.empty()) continue;
+    DtabArgs d;
+    d.dtab = k.dtab; d.models = k.models; d.cls_part_global = k.part_global;
+    d.lzq = (const double *)(e->stage_d + e->off_lzq); d.lzr = (const double *)(e->stage_d + e->off_lzr);
+    d.count = count; d.nparts_cls = k.nparts; d.nbranches = e->nb; d.states = k.S;
+    d.model_doubles = k.model_doubles; d.row = k.dtab_row;
+    launch_dtab(d, e->stream);
+    e->launches++;
     TraverseArgs a;
+    a.dtab = k.dtab; a.nparts_cls = k.nparts; a.tile_sites = e->tile_sites;
     a.tiles = k.tiles; a.clv = k.clv; a.tips = k.tips; a.wgt = k.wgt; a.sum = k.sum; a.models = k.models;
     a.N = k.N; a.mxtips = e->mxtips; a.nparts = e->P; a.nbranches = e->nb;
     a.entries = (const DevEntry *)(e->stage_d + e->off_entries);
@@ -480,8 +498,16 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
     a.mask = e->stage_d + e->off_mask;
     a.count = count; a.first = first; a.mode = mode;
     a.scale_inc = e->scale_inc; a.tile_out = k.tile_out;
-    if (c == CLS_DNA) launch_traverse_dna(a, (int)k.tiles_h.size(), e->stream);
-    else              launch_traverse_aa(a, (int)k.tiles_h.size(), e->stream);
+    if (c == CLS_DNA) {
+      DnaConsts kc;
+      if (k.nparts == 1) {                       // single partition: EI/EV travel as kernel parameters
+        memcpy(kc.EI, &k.models_h[8], sizeof kc.EI);
+        memcpy(kc.EV, &k.models_h[24], sizeof kc.EV);
+      }
+      launch_traverse_dna(a, k.nparts == 1 ? &kc : nullptr, (int)k.tiles_h.size(), e->stream);
+    } else {
+      launch_traverse_aa(a, (int)k.tiles_h.size(), e->stream);
+    }
     e->launches++;
   }
   FinishArgs f;

@@ -34,6 +34,21 @@ struct Tile {
 // traversalInfo without branch arrays (mirrors exb_entry)
 struct DevEntry { int tipCase, p, q, r; };
 
+// P(t) eigen-factor table, built once per call by dtab_kernel:
+//   DNA row (32 doubles) per (entry, class-partition): [c][side q/r][k] = exp(EIGN[k] * rate[c] * lz_side)
+//   AA  row (160 doubles):                             [c][side][k],  k < 20
+// Row 0 (the branch entry of evaluate) carries the diagonal table of calcDiagptable in its q side.
+constexpr int kDnaDtabRow = 32;
+constexpr int kAaDtabRow  = 160;
+
+struct DtabArgs {
+  double       *dtab;        // [count][parts_in_class][row]
+  const double *models;      // class models
+  const int    *cls_part_global;   // [parts_in_class] -> global partition index (branch slot)
+  const double *lzq, *lzr;   // [count][nbranches]
+  int count, nparts_cls, nbranches, states, model_doubles, row;
+};
+
 // Everything a traversal kernel needs.  Passed by value (fits the 4 KB parameter space).
 struct TraverseArgs {
   // static layout of this class
@@ -57,7 +72,14 @@ struct TraverseArgs {
   int           mode;       // Mode
   unsigned int *scale_inc;  // [maxEntries][P]  per-entry scaler increments (integer atomics: deterministic)
   double       *tile_out;   // [ntiles][2]      per-tile partial sums (evaluate: lnL; core: d1,d2)
+  const double *dtab;       // [count][nparts_cls][row]
+  int           nparts_cls;
+  int           tile_sites; // sites per tile (multiple of 32)
 };
+
+// DNA constants of a class that holds a single partition: passed by value so that every EI/EV
+// element is an immediate constant-bank operand of its DFMA (no load instruction at all).
+struct DnaConsts { double EI[16]; double EV[16]; };
 
 struct CoreArgs {
   const Tile   *tiles;
@@ -89,7 +111,8 @@ struct FinishArgs {
   double       *out;              // evaluate: [P]; core: [2][P]
 };
 
-void launch_traverse_dna(const TraverseArgs &a, int ntiles, cudaStream_t s);
+void launch_dtab(const DtabArgs &a, cudaStream_t s);
+void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
 void launch_core_dna(const CoreArgs &a, int ntiles, cudaStream_t s);
 void launch_traverse_aa(const TraverseArgs &a, int ntiles, cudaStream_t s);
 void launch_core_aa(const CoreArgs &a, int ntiles, cudaStream_t s);

@@ -2,32 +2,40 @@
 //
 // Replaces, for DNA partitions, the per-site loops of
 //   newviewGTRGAMMA_AVX   avxLikelihood.c:64-318          (all three tip cases + scaling)
-//   makeP                 newviewGenericSpecial.c:78-132  (folded into the kernel prologue)
+//   makeP                 newviewGenericSpecial.c:78-132  (dtab_kernel: the exponentials; the EI factor
+//                                                          is applied inside the contraction)
 //   evaluateGTRGAMMA      evaluateGenericSpecial.c:1879-1985, calcDiagptable :80-119
 //   sumGAMMA              makenewzGenericSpecial.c:1798-1848
 //   coreGTRGAMMA          makenewzGenericSpecial.c:2309-2393
 //
 // B200 restructuring of HOT LOOP A/B: the traversal loop lives INSIDE the kernel.
 // A CTA owns a tile of sites for the whole traversal and walks the descriptor entry by entry.
-// Thread t of the CTA owns (site = t/4 + 64*u, Gamma category = t%4) for every entry, so a parent
-// entry reads back exactly the 32 B this same thread stored for the child: no inter-thread
-// dependency, no barrier for data, and the child CLV is still in L2 when it is consumed.
-// One 256-bit load per child and one 256-bit store per parent (LDG/STG.E.ENL2.256); a warp covers
-// 1 KB of contiguous CLV.  The only block barrier per entry publishes the 24 exponentials of the
-// two P(t) eigen-factor tables (double-buffered in shared memory).
+// Thread t owns (site = t/4 + 64*s, Gamma category = t%4), s < NS, for every entry, so
+//   * a parent entry only ever consumes CLV words this same thread produced: no barrier, no fence;
+//   * the CLV of the entry just computed stays in registers ("carry"): in a post-order descriptor
+//     the inner child r of every entry is the previous entry, so ~3/4 of all child reads never
+//     leave the register file; the rest are L2 hits (the child was written microseconds ago);
+//   * every parent CLV is still written to HBM once (it must persist for later partial traversals):
+//     one 256-bit store per (site, category), a warp covers 1 KB contiguous.
+// HBM traffic of a full traversal is therefore ~1 write per CLV + the tip bytes, about half of the
+// algorithmic read+write bytes of a per-node implementation.
+// Eigen-basis constants EI/EV reach the DFMAs as immediate constant-bank operands when the class
+// holds one partition (kernel parameters), else from shared memory; the per-(entry, category)
+// exponentials come from the d-table built once per call by dtab_kernel (no block barrier in the
+// entry loop).
 #include "engine.cuh"
+#include <algorithm>
+#include <stdlib.h>
+#include <string.h>
 
 namespace exb {
 
 namespace {
 
 struct DnaShared {
-  double EIGN[4];
-  double rates[4];
+  double tip[64];        // tipVector[16 codes][4]
   double EI[16];
   double EV[16];
-  double tip[64];        // tipVector[16 codes][4]
-  double d[2][2][16];    // [buffer][side q/r][c*4+k] = exp(EIGN[k] * rate[c] * lz)
   double red[8];
 };
 
@@ -36,163 +44,280 @@ __device__ __forceinline__ void ld256(const double *p, double v[4])
   asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
                : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
 }
+// read-only data (d-table): may be cached / reordered freely
+__device__ __forceinline__ void ld256_ro(const double *p, double v[4])
+{
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+      : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
 __device__ __forceinline__ void st256(double *p, const double v[4])
 {
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
 
-// a[l] = sum_j P[l][j] x[j] with P[l][j] = d[j] * EI[l][j], P[l][0] = 1 (makeP, newviewGenericSpecial.c:118-129)
-__device__ __forceinline__ void apply_p(const double x[4], const double *d /*4, d[0] unused*/,
-                                        const double *EI, double a[4])
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+// d-table: exp(EIGN[k] * rate[c] * lz) for every (entry, partition of the class, side, category, k).
+// Same association as makeP / calcDiagptable: rate * (EIGN * lz).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dtab_kernel(const DtabArgs a)
 {
-  const double t1 = d[1] * x[1], t2 = d[2] * x[2], t3 = d[3] * x[3];
-  #pragma unroll
-  for (int l = 0; l < 4; l++)
-    a[l] = x[0] + EI[l * 4 + 1] * t1 + EI[l * 4 + 2] * t2 + EI[l * 4 + 3] * t3;
+  const size_t total = (size_t)a.count * a.nparts_cls * a.row;
+  const int S = a.states;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % a.row);
+    const size_t ep = i / a.row;
+    const int pc = (int)(ep % a.nparts_cls), e = (int)(ep / a.nparts_cls);
+    const int c = w / (2 * S), side = (w / S) & 1, k = w % S;
+    const double *model = a.models + (size_t)pc * a.model_doubles;   // EIGN[S] rates[4] ...
+    const int slot = a.nbranches > 1 ? a.cls_part_global[pc] : 0;
+    const double lz = side ? a.lzr[(size_t)e * a.nbranches + slot] : a.lzq[(size_t)e * a.nbranches + slot];
+    a.dtab[i] = k ? exp(model[S + c] * (model[k] * lz)) : 1.0;
+  }
 }
 
-__device__ __forceinline__ void load_model(DnaShared &sh, const double *model)
+void launch_dtab(const DtabArgs &a, cudaStream_t s)
 {
-  // model: EIGN[4] rates[4] EI[16] EV[16] tip[64]  (kDnaModelDoubles)
-  for (int i = threadIdx.x; i < kDnaModelDoubles; i += blockDim.x) {
-    const double v = model[i];
-    if (i < 4) sh.EIGN[i] = v;
-    else if (i < 8) sh.rates[i - 4] = v;
-    else if (i < 24) sh.EI[i - 8] = v;
-    else if (i < 40) sh.EV[i - 24] = v;
-    else sh.tip[i - 40] = v;
-  }
+  const size_t total = (size_t)a.count * a.nparts_cls * a.row;
+  if (total == 0) return;
+  int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+  dtab_kernel<<<blocks, 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Fused traversal: newviews [first, count) for this tile, then (optionally) evaluate or the sum table
+// at the branch described by entry 0.   NS = sites per thread (tile chunk = 64*NS sites).
+//
+// Prologue per chunk: the descriptor is expanded into shared memory (element offsets instead of node
+// numbers) and the tip-code rows the descriptor touches are brought in with one cp.async.bulk
+// (TMA, 1-D) per row, all completing on a single mbarrier -- the only cold HBM reads of the kernel
+// are issued up front and in bulk instead of one dependent byte load per entry.
+// ------------------------------------------------------------------------------------------------------
+namespace {
+
+struct SEntry {            // a traversal entry as the threads consume it (32 B)
+  int tipCase;             // -1 for the branch entry
+  int ptip_qtip;           // branch entry only: bit0 = p is a tip, bit1 = q is a tip
+  long long poff, qoff, roff;   // inner node: element offset of its CLV (node_index * N * 16, unique per node);
+                                // tip: row * TS inside the staged tip rows
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 }  // namespace
 
-// ------------------------------------------------------------------------------------------------------
-// Fused traversal: newviews [first, count) for this tile, then (optionally) evaluate or the sum table
-// at the branch described by entry 0.
-// ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 3)
-traverse_dna_kernel(const TraverseArgs a)
+template <int NS, bool PARAM, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
 {
+  constexpr int TS = 64 * NS;                  // sites per chunk = bytes per staged tip row
   __shared__ DnaShared sh;
+  __shared__ __align__(8) uint64_t mbar;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  SEntry *ents = reinterpret_cast<SEntry *>(dyn);                          // [count]
+  uint8_t *stips = dyn + (((size_t)a.count * sizeof(SEntry) + 15) & ~(size_t)15);   // [mxtips][TS]
+
   const Tile tile = a.tiles[blockIdx.x];
   if (!a.mask[tile.part]) return;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int c = tid & 3;                       // Gamma category owned by this thread
-  const int slot = a.nbranches > 1 ? tile.part : 0;
   const size_t N = a.N;
-  const int npass = (tile.nsites + 63) >> 6;   // 64 sites per pass (256 threads / 4 categories)
-
-  load_model(sh, a.models + (size_t)tile.part_cls * kDnaModelDoubles);
-  __syncthreads();
-
-  // ---------------- newview entries ----------------
-  for (int e = a.first; e < a.count; e++) {
-    const DevEntry en = a.entries[e];
-    const int buf = e & 1;
-    if (tid < 32) {                            // 2 sides x 4 categories x 4 eigenvalues
-      const int side = tid >> 4, cc = (tid >> 2) & 3, k = tid & 3;
-      const double lz = side ? a.lzr[(size_t)e * a.nbranches + slot] : a.lzq[(size_t)e * a.nbranches + slot];
-      sh.d[buf][side][cc * 4 + k] = k ? exp(sh.rates[cc] * (sh.EIGN[k] * lz)) : 1.0;
+  {
+    const double *model = a.models + (size_t)tile.part_cls * kDnaModelDoubles;   // EIGN[4] rates[4] EI[16] EV[16] tip[64]
+    if (tid < 64) sh.tip[tid] = model[40 + tid];
+    if (!PARAM && tid < 16) { sh.EI[tid] = model[8 + tid]; sh.EV[tid] = model[24 + tid]; }
+    if (tid == 0) mbar_init(&mbar, 1);
+    // expand the descriptor: node numbers -> offsets
+    for (int e = tid; e < a.count; e += kThreads) {
+      const DevEntry en = a.entries[e];
+      SEntry se;
+      se.tipCase = en.tipCase; se.ptip_qtip = (en.p <= a.mxtips ? 1 : 0) | (en.q <= a.mxtips ? 2 : 0);
+      se.poff = en.p > a.mxtips ? (long long)(en.p - a.mxtips - 1) * (long long)N * 16 : (long long)(en.p - 1) * TS;
+      se.qoff = en.q > a.mxtips ? (long long)(en.q - a.mxtips - 1) * (long long)N * 16 : (long long)(en.q - 1) * TS;
+      se.roff = en.r > a.mxtips ? (long long)(en.r - a.mxtips - 1) * (long long)N * 16 : (long long)(en.r - 1) * TS;
+      ents[e] = se;
     }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    const double *dq = &sh.d[buf][0][c * 4], *dr = &sh.d[buf][1][c * 4];
+  }
+#define EI_(i) (PARAM ? kc.EI[i] : sh.EI[i])
+#define EV_(i) (PARAM ? kc.EV[i] : sh.EV[i])
 
-    const double *x1p = nullptr, *x2p = nullptr;
-    const uint8_t *t1p = nullptr, *t2p = nullptr;
-    if (en.tipCase == 2) x1p = a.clv + (size_t)(en.q - a.mxtips - 1) * N * 16;
-    else                 t1p = a.tips + (size_t)(en.q - 1) * N;
-    if (en.tipCase == 0) t2p = a.tips + (size_t)(en.r - 1) * N;
-    else                 x2p = a.clv + (size_t)(en.r - a.mxtips - 1) * N * 16;
-    double *x3p = a.clv + (size_t)(en.p - a.mxtips - 1) * N * 16;
-    const bool may_scale = en.tipCase != 0;    // TIP_TIP is never rescaled (avxLikelihood.c:87-160)
+  const double *drow = a.dtab + ((size_t)tile.part_cls * 4 + c) * 8;       // + e * nparts_cls * 32
+  const size_t dstride = (size_t)a.nparts_cls * kDnaDtabRow;
+  const int lo = a.mode == MODE_NEWVIEW ? a.first : 0;                     // entry 0 = branch (may have tip ends)
+  double acc = 0.0;
+  uint32_t phase = 0;
 
-    unsigned int cnt = 0;
-    for (int u = 0; u < npass; u++) {
-      const int i = (u << 6) + (tid >> 2);
-      const bool valid = i < (int)tile.nsites;
-      const size_t site = (size_t)tile.site0 + (valid ? i : 0);
-      double x1[4], x2[4], al[4], ar[4], v[4];
-      if (x1p) ld256(x1p + site * 16 + c * 4, x1);
-      else { const double *tv = &sh.tip[4 * t1p[site]]; x1[0] = tv[0]; x1[1] = tv[1]; x1[2] = tv[2]; x1[3] = tv[3]; }
-      if (x2p) ld256(x2p + site * 16 + c * 4, x2);
-      else { const double *tv = &sh.tip[4 * t2p[site]]; x2[0] = tv[0]; x2[1] = tv[1]; x2[2] = tv[2]; x2[3] = tv[3]; }
-      apply_p(x1, dq, sh.EI, al);
-      apply_p(x2, dr, sh.EI, ar);
-      #pragma unroll
-      for (int m = 0; m < 4; m++) v[m] = 0.0;
-      #pragma unroll
-      for (int l = 0; l < 4; l++) {
-        const double ab = al[l] * ar[l];
-        #pragma unroll
-        for (int m = 0; m < 4; m++) v[m] += ab * sh.EV[l * 4 + m];
+  for (unsigned chunk0 = 0; chunk0 < tile.nsites; chunk0 += TS) {
+    const unsigned nchunk = min(tile.nsites - chunk0, (unsigned)TS);
+    // ---- stage the tip rows of this chunk (warp 0 issues, everybody waits on the mbarrier) ----
+    if (chunk0) __syncthreads();               // previous chunk's readers are done with stips
+    if (tid < 32) {
+      const uint32_t bytes = (nchunk + 15u) & ~15u;
+      const uint8_t *gsrc = a.tips + tile.site0 + chunk0;
+      int mine = 0;
+      for (int e = lo + lane; e < a.count; e += 32) {
+        const SEntry &se = ents[e];
+        if (se.tipCase < 0) mine += (se.ptip_qtip & 1) + ((se.ptip_qtip >> 1) & 1);
+        else                mine += (se.tipCase <= 1) + (se.tipCase == 0);
       }
-      if (may_scale) {
-        const bool small = fabs(v[0]) < kMinLikelihood && fabs(v[1]) < kMinLikelihood &&
-                           fabs(v[2]) < kMinLikelihood && fabs(v[3]) < kMinLikelihood;
-        const unsigned int b = __ballot_sync(0xffffffffu, small);
-        if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {          // all 16 values of the site are tiny
-          #pragma unroll
-          for (int m = 0; m < 4; m++) v[m] *= kTwoToThe256;
-          if (c == 0 && valid) cnt += (unsigned int)a.wgt[site];
+      const int total = __reduce_add_sync(0xffffffffu, mine);
+      if (lane == 0) mbar_expect_tx(&mbar, (uint32_t)total * bytes);
+      __syncwarp();
+      for (int e = lo + lane; e < a.count; e += 32) {
+        const SEntry &se = ents[e];
+        if (se.tipCase < 0) {
+          if (se.ptip_qtip & 1) bulk_g2s(stips + se.poff, gsrc + (size_t)(se.poff / TS) * N, bytes, &mbar);
+          if (se.ptip_qtip & 2) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TS) * N, bytes, &mbar);
+        } else {
+          if (se.tipCase <= 1) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TS) * N, bytes, &mbar);
+          if (se.tipCase == 0) bulk_g2s(stips + se.roff, gsrc + (size_t)(se.roff / TS) * N, bytes, &mbar);
         }
       }
-      if (valid) st256(x3p + site * 16 + c * 4, v);
     }
-    if (may_scale && __any_sync(0xffffffffu, cnt != 0)) {
-      const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
-      if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
-    }
-  }
 
-  if (a.mode == MODE_NEWVIEW) return;
-
-  // ---------------- branch (entry 0): evaluate or sum table ----------------
-  const DevEntry br = a.entries[0];
-  const bool ptip = br.p <= a.mxtips, qtip = br.q <= a.mxtips;
-  const double *xap = ptip ? nullptr : a.clv + (size_t)(br.p - a.mxtips - 1) * N * 16;
-  const double *xbp = qtip ? nullptr : a.clv + (size_t)(br.q - a.mxtips - 1) * N * 16;
-  const uint8_t *tap = ptip ? a.tips + (size_t)(br.p - 1) * N : nullptr;
-  const uint8_t *tbp = qtip ? a.tips + (size_t)(br.q - 1) * N : nullptr;
-
-  double diag[4] = {1.0, 1.0, 1.0, 1.0};
-  if (a.mode == MODE_EVALUATE) {
-    __syncthreads();                           // everyone is done with d[][] of the last entry
-    if (tid < 16) {
-      const int cc = tid >> 2, k = tid & 3;
-      const double lz = a.lzq[slot];           // entry 0 carries the branch value
-      sh.d[0][0][cc * 4 + k] = k ? exp(sh.rates[cc] * (sh.EIGN[k] * lz)) : 1.0;
-    }
-    __syncthreads();
+    size_t eoff[NS];                           // element offset of (site, category) inside a CLV; site = eoff >> 4
+    bool valid[NS];
+    int lsite[NS];
     #pragma unroll
-    for (int k = 0; k < 4; k++) diag[k] = sh.d[0][0][c * 4 + k];
-  }
+    for (int s = 0; s < NS; s++) {
+      const unsigned i = (unsigned)s * 64 + (tid >> 2);
+      valid[s] = i < nchunk;
+      lsite[s] = valid[s] ? (int)i : 0;
+      eoff[s] = ((size_t)tile.site0 + chunk0 + lsite[s]) * 16 + c * 4;
+    }
+    double carry[NS][4];
+    long long carry_node = -1;                 // poff of the entry whose CLV sits in carry[]
+    #pragma unroll
+    for (int s = 0; s < NS; s++) { carry[s][0] = carry[s][1] = carry[s][2] = carry[s][3] = 0.0; }
 
-  double acc = 0.0;
-  for (int u = 0; u < npass; u++) {
-    const int i = (u << 6) + (tid >> 2);
-    const bool valid = i < (int)tile.nsites;
-    const size_t site = (size_t)tile.site0 + (valid ? i : 0);
-    double xa[4], xb[4];
-    if (xap) ld256(xap + site * 16 + c * 4, xa);
-    else { const double *tv = &sh.tip[4 * tap[site]]; xa[0] = tv[0]; xa[1] = tv[1]; xa[2] = tv[2]; xa[3] = tv[3]; }
-    if (xbp) ld256(xbp + site * 16 + c * 4, xb);
-    else { const double *tv = &sh.tip[4 * tbp[site]]; xb[0] = tv[0]; xb[1] = tv[1]; xb[2] = tv[2]; xb[3] = tv[3]; }
-    if (a.mode == MODE_SUM) {
-      double s[4];
+    mbar_wait(&mbar, phase);
+    phase ^= 1;
+
+    // ---------------- newview entries ----------------
+    for (int e = a.first; e < a.count; e++) {
+      const SEntry en = ents[e];
+      double dq[4], dr[4];
+      ld256_ro(drow + (size_t)e * dstride, dq);
+      ld256_ro(drow + (size_t)e * dstride + 4, dr);
+
+      const bool q_inner = en.tipCase == 2, r_inner = en.tipCase != 0;
+      const bool q_carry = q_inner && en.qoff == carry_node, r_carry = r_inner && en.roff == carry_node;
+
+      // gather the children of all NS sites first (independent loads in flight together)
+      double x1[NS][4], x2[NS][4];
       #pragma unroll
-      for (int k = 0; k < 4; k++) s[k] = xa[k] * xb[k];
-      if (valid) st256(a.sum + site * 16 + c * 4, s);
-    } else {
-      double term = 0.0;
+      for (int s = 0; s < NS; s++) {
+        if (q_carry) { x1[s][0] = carry[s][0]; x1[s][1] = carry[s][1]; x1[s][2] = carry[s][2]; x1[s][3] = carry[s][3]; }
+        else if (q_inner) ld256(a.clv + en.qoff + eoff[s], x1[s]);
+        else { const double *tv = &sh.tip[4 * stips[en.qoff + lsite[s]]]; x1[s][0] = tv[0]; x1[s][1] = tv[1]; x1[s][2] = tv[2]; x1[s][3] = tv[3]; }
+        if (r_carry) { x2[s][0] = carry[s][0]; x2[s][1] = carry[s][1]; x2[s][2] = carry[s][2]; x2[s][3] = carry[s][3]; }
+        else if (r_inner) ld256(a.clv + en.roff + eoff[s], x2[s]);
+        else { const double *tv = &sh.tip[4 * stips[en.roff + lsite[s]]]; x2[s][0] = tv[0]; x2[s][1] = tv[1]; x2[s][2] = tv[2]; x2[s][3] = tv[3]; }
+      }
+
+      unsigned int cnt = 0;
       #pragma unroll
-      for (int k = 0; k < 4; k++) term += xa[k] * xb[k] * diag[k];
-      term += __shfl_xor_sync(0xffffffffu, term, 1);
-      term += __shfl_xor_sync(0xffffffffu, term, 2);
-      if (c == 0 && valid) acc += (double)a.wgt[site] * log(0.25 * fabs(term));
+      for (int s = 0; s < NS; s++) {
+        // a[l] = sum_j P[l][j] x[j], P[l][j] = d[j] * EI[l][j], P[l][0] = 1  (newviewGenericSpecial.c:118-129)
+        const double tq1 = dq[1] * x1[s][1], tq2 = dq[2] * x1[s][2], tq3 = dq[3] * x1[s][3];
+        const double tr1 = dr[1] * x2[s][1], tr2 = dr[2] * x2[s][2], tr3 = dr[3] * x2[s][3];
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        #pragma unroll
+        for (int l = 0; l < 4; l++) {
+          const double al = x1[s][0] + EI_(l * 4 + 1) * tq1 + EI_(l * 4 + 2) * tq2 + EI_(l * 4 + 3) * tq3;
+          const double ar = x2[s][0] + EI_(l * 4 + 1) * tr1 + EI_(l * 4 + 2) * tr2 + EI_(l * 4 + 3) * tr3;
+          const double ab = al * ar;
+          #pragma unroll
+          for (int m = 0; m < 4; m++) v[m] += ab * EV_(l * 4 + m);
+        }
+        if (r_inner) {                         // TIP_TIP is never rescaled (avxLikelihood.c:87-160)
+          const bool small = fabs(v[0]) < kMinLikelihood && fabs(v[1]) < kMinLikelihood &&
+                             fabs(v[2]) < kMinLikelihood && fabs(v[3]) < kMinLikelihood;
+          const unsigned int b = __ballot_sync(0xffffffffu, small);
+          if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {          // all 16 values of the site are tiny
+            #pragma unroll
+            for (int m = 0; m < 4; m++) v[m] *= kTwoToThe256;
+            if (c == 0 && valid[s]) cnt += (unsigned int)a.wgt[eoff[s] >> 4];
+          }
+        }
+        if (valid[s]) st256(a.clv + en.poff + eoff[s], v);
+        carry[s][0] = v[0]; carry[s][1] = v[1]; carry[s][2] = v[2]; carry[s][3] = v[3];
+      }
+      carry_node = en.poff;
+      if (r_inner && __any_sync(0xffffffffu, cnt != 0)) {
+        const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
+      }
+    }
+
+    if (a.mode == MODE_NEWVIEW) continue;
+
+    // ---------------- branch (entry 0): evaluate or sum table ----------------
+    const SEntry br = ents[0];
+    const bool ptip = br.ptip_qtip & 1, qtip = br.ptip_qtip & 2;
+    const bool p_carry = !ptip && br.poff == carry_node, q_carry = !qtip && br.qoff == carry_node;
+    double diag[4];
+    ld256_ro(drow, diag);                      // row 0, q side: calcDiagptable (diag[0] = 1)
+
+    #pragma unroll
+    for (int s = 0; s < NS; s++) {
+      double xa[4], xb[4];
+      if (p_carry) { xa[0] = carry[s][0]; xa[1] = carry[s][1]; xa[2] = carry[s][2]; xa[3] = carry[s][3]; }
+      else if (!ptip) ld256(a.clv + br.poff + eoff[s], xa);
+      else { const double *tv = &sh.tip[4 * stips[br.poff + lsite[s]]]; xa[0] = tv[0]; xa[1] = tv[1]; xa[2] = tv[2]; xa[3] = tv[3]; }
+      if (q_carry) { xb[0] = carry[s][0]; xb[1] = carry[s][1]; xb[2] = carry[s][2]; xb[3] = carry[s][3]; }
+      else if (!qtip) ld256(a.clv + br.qoff + eoff[s], xb);
+      else { const double *tv = &sh.tip[4 * stips[br.qoff + lsite[s]]]; xb[0] = tv[0]; xb[1] = tv[1]; xb[2] = tv[2]; xb[3] = tv[3]; }
+      if (a.mode == MODE_SUM) {
+        double sm[4];
+        #pragma unroll
+        for (int k = 0; k < 4; k++) sm[k] = xa[k] * xb[k];
+        if (valid[s]) st256(a.sum + eoff[s], sm);
+      } else {
+        double term = xa[0] * xb[0];           // diag[0] = 1
+        #pragma unroll
+        for (int k = 1; k < 4; k++) term += xa[k] * xb[k] * diag[k];
+        term += __shfl_xor_sync(0xffffffffu, term, 1);
+        term += __shfl_xor_sync(0xffffffffu, term, 2);
+        if (c == 0 && valid[s]) acc += (double)a.wgt[eoff[s] >> 4] * log(0.25 * fabs(term));
+      }
     }
   }
+#undef EI_
+#undef EV_
+
   if (a.mode == MODE_EVALUATE) {
     const double tot = block_sum(acc, sh.red);
     if (tid == 0) { a.tile_out[2 * (size_t)blockIdx.x] = tot; a.tile_out[2 * (size_t)blockIdx.x + 1] = 0.0; }
@@ -253,9 +378,52 @@ core_dna_kernel(const CoreArgs a)
   if (tid == 0) { a.tile_out[2 * (size_t)blockIdx.x] = t1; a.tile_out[2 * (size_t)blockIdx.x + 1] = t2; }
 }
 
-void launch_traverse_dna(const TraverseArgs &a, int ntiles, cudaStream_t s)
+size_t traverse_dna_smem(int count, int mxtips, int ns)
 {
-  if (ntiles > 0) traverse_dna_kernel<<<ntiles, kThreads, 0, s>>>(a);
+  return (((size_t)count * sizeof(SEntry) + 15) & ~(size_t)15) + (size_t)mxtips * 64 * ns;
+}
+
+template <int NS, bool PARAM, int MINB>
+static void launch_minb(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
+{
+  const size_t smem = traverse_dna_smem(a.count, a.mxtips, NS);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(traverse_dna_kernel<NS, PARAM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(227 * 1024 - 2048, std::max<size_t>(smem, 64 * 1024)));
+    configured = std::max<size_t>(smem, 64 * 1024);
+  }
+  traverse_dna_kernel<NS, PARAM, MINB><<<ntiles, kThreads, smem, s>>>(a, kc);
+}
+
+template <int NS, bool PARAM>
+static void launch_one(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
+{
+  static int minb = -1;                          // development knob: EXB_DNA_MINB = 2 | 3 (CTAs per SM the registers are budgeted for)
+  if (minb < 0) { const char *v = getenv("EXB_DNA_MINB"); minb = v ? atoi(v) : (NS >= 4 ? 2 : 3); }
+  if (minb <= 2) launch_minb<NS, PARAM, 2>(a, kc, ntiles, s);
+  else           launch_minb<NS, PARAM, 3>(a, kc, ntiles, s);
+}
+
+template <int NS>
+static void launch_ns(const TraverseArgs &a, const DnaConsts *kc, int ntiles, cudaStream_t s)
+{
+  if (kc) launch_one<NS, true>(a, *kc, ntiles, s);
+  else {
+    DnaConsts none;
+    memset(&none, 0, sizeof none);
+    launch_one<NS, false>(a, none, ntiles, s);
+  }
+}
+
+void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *kc, int ntiles, cudaStream_t s)
+{
+  if (ntiles <= 0) return;
+  // chunk = 64*NS sites; the staged tip rows (mxtips * 64 * NS bytes) must fit in shared memory
+  int ns = a.tile_sites <= 64 ? 1 : (a.tile_sites <= 128 ? 2 : 4);
+  while (ns > 1 && traverse_dna_smem(a.count, a.mxtips, ns) > 96 * 1024) ns >>= 1;
+  if (ns == 1) launch_ns<1>(a, kc, ntiles, s);
+  else if (ns == 2) launch_ns<2>(a, kc, ntiles, s);
+  else launch_ns<4>(a, kc, ntiles, s);
 }
 void launch_core_dna(const CoreArgs &a, int ntiles, cudaStream_t s)
 {
