@@ -506,7 +506,7 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
       }
       launch_traverse_dna(a, k.nparts == 1 ? &kc : nullptr, (int)k.tiles_h.size(), e->stream);
     } else {
-      launch_traverse_aa(a, (int)k.tiles_h.size(), e->stream);
+      launch_traverse_aa(a, k.nparts == 1 ? k.models_h.data() : nullptr, (int)k.tiles_h.size(), e->stream);
     }
     e->launches++;
   }

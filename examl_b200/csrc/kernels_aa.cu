@@ -7,12 +7,18 @@
 //   coreGTRGAMMAPROT         makenewzGenericSpecial.c:2581-2655
 //
 // Same structure as kernels_dna.cu: the traversal loop is inside the kernel, thread t owns
-// (site = t/4 + 64*u, category = t%4) for every entry and therefore only ever reads CLV words it
-// wrote itself.  All arithmetic is FP64 (the reference's precision; tcgen05 has no f64 kind, see
-// DESIGN.md).  P(t) is never materialised: a = EI * (d (.) x) with the category-independent EI
-// broadcast from shared memory (every lane of a warp reads the same word: conflict-free), d the 19
-// exponentials of the (entry, side, category).
+// (site = t/4, Gamma category = t%4) of a 64-site chunk for every entry, keeps the CLV it just
+// produced in registers for the parent ("carry"), writes every CLV to HBM once.
+// All arithmetic is FP64 -- the reference's precision; tcgen05 has no f64 kind.
+// P(t) is never materialised: a = EI * (d (.) x); d comes from the per-call d-table.  With a single
+// AA partition the 800 EI / EV constants travel as kernel parameters, so each of the ~1 200 DFMAs
+// per (site, category, entry) takes its matrix element as an immediate constant-bank operand: no
+// load instruction, no shared-memory traffic in the contraction.  Several AA partitions: EI^T / EV
+// are broadcast from shared memory.
 #include "engine.cuh"
+#include <algorithm>
+#include <stdlib.h>
+#include <string.h>
 
 namespace exb {
 
@@ -20,15 +26,17 @@ namespace {
 
 constexpr int S = 20;
 constexpr int SPAN = 80;
+constexpr int TS = 64;           // sites per chunk (256 threads / 4 categories)
 
 struct AaShared {
-  double EI[400];
-  double EV[400];
   double tip[460];        // tipVector[23 codes][20]
-  double EIGN[20];
-  double rates[4];
-  double d[2][2][80];     // [buffer][side][c*20+k]
   double red[8];
+};
+
+struct SEntry {
+  int tipCase;
+  int ptip_qtip;
+  long long poff, qoff, roff;
 };
 
 __device__ __forceinline__ void ld256(const double *p, double *v)
@@ -36,182 +44,310 @@ __device__ __forceinline__ void ld256(const double *p, double *v)
   asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
                : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
 }
+__device__ __forceinline__ void ld256_ro(const double *p, double *v)
+{
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+      : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ double2 ld128(const double *p)
+{
+  double2 v;
+  asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st256(double *p, const double *v)
 {
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
-
-__device__ __forceinline__ void load_vec(const double *clv, const uint8_t *tips, const double *tipv, size_t site, int c,
-                                         double x[S])
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
 {
-  if (clv) {
-    const double *p = clv + site * SPAN + c * S;
-    #pragma unroll
-    for (int j = 0; j < S; j += 4) ld256(p + j, x + j);
-  } else {
-    const double *tv = tipv + S * tips[site];
-    #pragma unroll
-    for (int j = 0; j < S; j++) x[j] = tv[j];
-  }
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void load_model(AaShared &sh, const double *model)
+enum Src : int { SRC_TIP = 0, SRC_CARRY = 1, SRC_LOAD = 2 };
+
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor pipe (SASS: DMMA.8x8x4).
+//   A: thread holds A[lane/4][lane%4]; B: thread holds B[lane%4][lane/4]; C/D: C[lane/4][2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 {
-  // model: EIGN[20] rates[4] EI[400] EV[400] tip[460]
-  for (int i = threadIdx.x; i < kAaModelDoubles; i += blockDim.x) {
-    const double v = model[i];
-    if (i < 20) sh.EIGN[i] = v;
-    else if (i < 24) sh.rates[i - 20] = v;
-    else if (i < 424) sh.EI[i - 24] = v;
-    else if (i < 824) sh.EV[i - 424] = v;
-    else sh.tip[i - 824] = v;
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// One traversal entry for the 8 sites of this warp, all four categories.  A child is either read from
+// memory (global CLV with category stride 20, or the shared-memory tip vector with stride 0) or taken
+// from the carry registers; the three combinations that occur are compiled separately so that the
+// k-step loop is branch-free and the loads of the next category can be scheduled under the DMMAs.
+template <bool QCARRY, bool RCARRY>
+__device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const double (&bEI)[5][3], const double (&bEV)[5][3],
+                                         const double *x1, int x1stride, const double *x2, int x2stride,
+                                         const double *drow, int lane, int tq)
+{
+  #pragma unroll
+  for (int c = 0; c < 4; c++) {
+    // operands of the five k-steps: (d (.) x)[g][4s+tq]
+    double a1[5], a2[5];
+    #pragma unroll
+    for (int s = 0; s < 5; s++) {
+      const int k = 4 * s + tq;
+      const int sl = (lane & ~3) | (((s & 1) << 1) | (tq >> 1));
+      if (QCARRY) {
+        const double e0 = __shfl_sync(0xffffffffu, carry[c][s >> 1][0], sl);
+        const double e1 = __shfl_sync(0xffffffffu, carry[c][s >> 1][1], sl);
+        a1[s] = (tq & 1) ? e1 : e0;
+      } else a1[s] = x1[c * x1stride + k];
+      if (RCARRY) {
+        const double e0 = __shfl_sync(0xffffffffu, carry[c][s >> 1][0], sl);
+        const double e1 = __shfl_sync(0xffffffffu, carry[c][s >> 1][1], sl);
+        a2[s] = (tq & 1) ? e1 : e0;
+      } else a2[s] = x2[c * x2stride + k];
+      a1[s] *= __ldg(drow + c * 40 + k);
+      a2[s] *= __ldg(drow + c * 40 + S + k);
+    }
+    double y1[3][2], y2[3][2];
+    #pragma unroll
+    for (int t = 0; t < 3; t++) { y1[t][0] = y1[t][1] = 0.0; y2[t][0] = y2[t][1] = 0.0; }
+    #pragma unroll
+    for (int s = 0; s < 5; s++)
+      #pragma unroll
+      for (int t = 0; t < 3; t++) {
+        dmma(y1[t][0], y1[t][1], a1[s], bEI[s][t]);
+        dmma(y2[t][0], y2[t][1], a2[s], bEI[s][t]);
+      }
+    // Z = Y1 (.) Y2 in C layout, then X3 = Z * EV
+    #pragma unroll
+    for (int t = 0; t < 3; t++) { y1[t][0] *= y2[t][0]; y1[t][1] *= y2[t][1]; }
+    double x3[3][2];
+    #pragma unroll
+    for (int t = 0; t < 3; t++) x3[t][0] = x3[t][1] = 0.0;
+    #pragma unroll
+    for (int s = 0; s < 5; s++) {
+      const int sl = (lane & ~3) | (((s & 1) << 1) | (tq >> 1));
+      const double e0 = __shfl_sync(0xffffffffu, y1[s >> 1][0], sl);
+      const double e1 = __shfl_sync(0xffffffffu, y1[s >> 1][1], sl);
+      const double az = (tq & 1) ? e1 : e0;           // Z[g][4s+tq]
+      #pragma unroll
+      for (int t = 0; t < 3; t++) dmma(x3[t][0], x3[t][1], az, bEV[s][t]);
+    }
+    #pragma unroll
+    for (int t = 0; t < 3; t++) { carry[c][t][0] = x3[t][0]; carry[c][t][1] = x3[t][1]; }
   }
 }
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------------
+// Fused traversal on the FP64 tensor pipe.
+//
+// A warp owns 8 sites (one per "row" g = lane/4) for all four Gamma categories; a CTA of 8 warps owns a
+// 64-site chunk.  For every (entry, category) the three 20x20 contractions
+//     Y1 = (d_q (.) X1) * EI^T        Y2 = (d_r (.) X2) * EI^T        X3 = (Y1 (.) Y2) * EV
+// are [8 sites x 20] x [20 x 20(24)] GEMMs = 15 DMMA.8x8x4 each.  EI^T and EV live in registers as
+// B fragments for the whole kernel (they do not depend on entry, side or category because the
+// exponentials are folded into the A operand).  The result stays in registers in C-fragment layout
+// ("carry") and is converted to an A operand for the parent with warp shuffles; it is written to HBM
+// once, 16 B per thread.  Scaling (all 80 values of a site < 2^-256) is decided after the four
+// categories are done, from the 24 register values of the 4 lanes that share a site.
+// ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1)
 traverse_aa_kernel(const TraverseArgs a)
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  AaShared &sh = *reinterpret_cast<AaShared *>(smem_raw);
+  __shared__ AaShared sh;
+  __shared__ __align__(8) uint64_t mbar;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  SEntry *ents = reinterpret_cast<SEntry *>(dyn);
+  uint8_t *stips = dyn + (((size_t)a.count * sizeof(SEntry) + 15) & ~(size_t)15);   // [mxtips][TS]
+
   const Tile tile = a.tiles[blockIdx.x];
   if (!a.mask[tile.part]) return;
 
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int c = tid & 3;
-  const int slot = a.nbranches > 1 ? tile.part : 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3;
   const size_t N = a.N;
-  const int npass = (tile.nsites + 63) >> 6;
-
-  load_model(sh, a.models + (size_t)tile.part_cls * kAaModelDoubles);
-  __syncthreads();
-
-  for (int e = a.first; e < a.count; e++) {
-    const DevEntry en = a.entries[e];
-    const int buf = e & 1;
-    if (tid < 160) {                              // 2 sides x 4 categories x 20 eigenvalues
-      const int side = tid / 80, r = tid % 80, cc = r / 20, k = r % 20;
-      const double lz = side ? a.lzr[(size_t)e * a.nbranches + slot] : a.lzq[(size_t)e * a.nbranches + slot];
-      sh.d[buf][side][r] = k ? exp(sh.rates[cc] * (sh.EIGN[k] * lz)) : 1.0;
+  const double *model = a.models + (size_t)tile.part_cls * kAaModelDoubles;   // EIGN[20] rates[4] EI[400] EV[400] tip[460]
+  {
+    for (int i = tid; i < 460; i += kThreads) sh.tip[i] = model[824 + i];
+    if (tid == 0) mbar_init(&mbar, 1);
+    for (int e = tid; e < a.count; e += kThreads) {
+      const DevEntry en = a.entries[e];
+      SEntry se;
+      se.tipCase = en.tipCase;
+      se.ptip_qtip = (en.p <= a.mxtips ? 1 : 0) | (en.q <= a.mxtips ? 2 : 0);
+      se.poff = en.p > a.mxtips ? (long long)(en.p - a.mxtips - 1) * (long long)N * SPAN : (long long)(en.p - 1) * TS;
+      se.qoff = en.q > a.mxtips ? (long long)(en.q - a.mxtips - 1) * (long long)N * SPAN : (long long)(en.q - 1) * TS;
+      se.roff = en.r > a.mxtips ? (long long)(en.r - a.mxtips - 1) * (long long)N * SPAN : (long long)(en.r - 1) * TS;
+      ents[e] = se;
     }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    const double *dq = &sh.d[buf][0][c * S], *dr = &sh.d[buf][1][c * S];
+  }
 
-    const double *x1p = nullptr, *x2p = nullptr;
-    const uint8_t *t1p = nullptr, *t2p = nullptr;
-    if (en.tipCase == 2) x1p = a.clv + (size_t)(en.q - a.mxtips - 1) * N * SPAN;
-    else                 t1p = a.tips + (size_t)(en.q - 1) * N;
-    if (en.tipCase == 0) t2p = a.tips + (size_t)(en.r - 1) * N;
-    else                 x2p = a.clv + (size_t)(en.r - a.mxtips - 1) * N * SPAN;
-    double *x3p = a.clv + (size_t)(en.p - a.mxtips - 1) * N * SPAN;
-    const bool may_scale = en.tipCase != 0;
+  // B fragments: bEI[s][t] = EI^T[k = 4s+tq][n = 8t+g] = EI[n][k];  bEV[s][t] = EV[k][n]; zero padding for n >= 20
+  double bEI[5][3], bEV[5][3];
+  #pragma unroll
+  for (int s = 0; s < 5; s++)
+    #pragma unroll
+    for (int t = 0; t < 3; t++) {
+      const int k = 4 * s + tq, n = 8 * t + g;
+      bEI[s][t] = n < S ? model[24 + n * S + k] : 0.0;
+      bEV[s][t] = n < S ? model[424 + k * S + n] : 0.0;
+    }
 
-    unsigned int cnt = 0;
-    for (int u = 0; u < npass; u++) {
-      const int i = (u << 6) + (tid >> 2);
-      const bool valid = i < (int)tile.nsites;
-      const size_t site = (size_t)tile.site0 + (valid ? i : 0);
-      double t[S], ab[S];
-      // left child: ab[l] = sum_j EI[l][j] * (dq[j] * x1[j])      (EI[l][0] = 1, dq[0] = 1)
-      load_vec(x1p, t1p, sh.tip, site, c, t);
-      #pragma unroll
-      for (int j = 1; j < S; j++) t[j] *= dq[j];
-      #pragma unroll
-      for (int l = 0; l < S; l++) {
-        double s = t[0];
-        #pragma unroll
-        for (int j = 1; j < S; j++) s += sh.EI[l * S + j] * t[j];
-        ab[l] = s;
+  const double *drow0 = a.dtab + (size_t)tile.part_cls * kAaDtabRow;     // + e * dstride + c*40 + side*20 + k
+  const size_t dstride = (size_t)a.nparts_cls * kAaDtabRow;
+  const int lo = a.mode == MODE_NEWVIEW ? a.first : 0;
+  double acc = 0.0;
+  uint32_t phase = 0;
+
+  for (unsigned chunk0 = 0; chunk0 < tile.nsites; chunk0 += TS) {
+    const unsigned nchunk = min(tile.nsites - chunk0, (unsigned)TS);
+    if (chunk0) __syncthreads();
+    if (tid < 32) {
+      const uint32_t bytes = (nchunk + 15u) & ~15u;
+      const uint8_t *gsrc = a.tips + tile.site0 + chunk0;
+      int mine = 0;
+      for (int e = lo + lane; e < a.count; e += 32) {
+        const SEntry &se = ents[e];
+        if (se.tipCase < 0) mine += (se.ptip_qtip & 1) + ((se.ptip_qtip >> 1) & 1);
+        else                mine += (se.tipCase <= 1) + (se.tipCase == 0);
       }
-      // right child, multiplied in as soon as each component is known
-      load_vec(x2p, t2p, sh.tip, site, c, t);
-      #pragma unroll
-      for (int j = 1; j < S; j++) t[j] *= dr[j];
-      #pragma unroll
-      for (int l = 0; l < S; l++) {
-        double s = t[0];
-        #pragma unroll
-        for (int j = 1; j < S; j++) s += sh.EI[l * S + j] * t[j];
-        ab[l] *= s;
+      const int total = __reduce_add_sync(0xffffffffu, mine);
+      if (lane == 0) mbar_expect_tx(&mbar, (uint32_t)total * bytes);
+      __syncwarp();
+      for (int e = lo + lane; e < a.count; e += 32) {
+        const SEntry &se = ents[e];
+        if (se.tipCase < 0) {
+          if (se.ptip_qtip & 1) bulk_g2s(stips + se.poff, gsrc + (size_t)(se.poff / TS) * N, bytes, &mbar);
+          if (se.ptip_qtip & 2) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TS) * N, bytes, &mbar);
+        } else {
+          if (se.tipCase <= 1) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TS) * N, bytes, &mbar);
+          if (se.tipCase == 0) bulk_g2s(stips + se.roff, gsrc + (size_t)(se.roff / TS) * N, bytes, &mbar);
+        }
       }
-      // back to the eigen-basis: v[m] = sum_l ab[l] * EV[l][m]   (reuses t)
+    }
+
+    const unsigned i = (unsigned)(warp * 8 + g);          // my site inside the chunk
+    const bool valid = i < nchunk;
+    const int lsite = valid ? (int)i : 0;
+    const size_t soff = ((size_t)tile.site0 + chunk0 + lsite) * SPAN;      // site = soff / SPAN
+    double carry[4][3][2];                                // CLV of the entry just computed, C-fragment layout
+    long long carry_node = -1;
+    #pragma unroll
+    for (int c = 0; c < 4; c++)
       #pragma unroll
-      for (int m = 0; m < S; m++) t[m] = 0.0;
-      #pragma unroll
-      for (int l = 0; l < S; l++) {
-        #pragma unroll
-        for (int m = 0; m < S; m++) t[m] += ab[l] * sh.EV[l * S + m];
-      }
-      if (may_scale) {
+      for (int t = 0; t < 3; t++) carry[c][t][0] = carry[c][t][1] = 0.0;
+
+    mbar_wait(&mbar, phase);
+    phase ^= 1;
+
+    for (int e = a.first; e < a.count; e++) {
+      const SEntry en = ents[e];
+      const double *drow = drow0 + (size_t)e * dstride;
+      const bool q_inner = en.tipCase == 2, r_inner = en.tipCase != 0;
+      const int qsrc = !q_inner ? SRC_TIP : (en.qoff == carry_node ? SRC_CARRY : SRC_LOAD);
+      const int rsrc = !r_inner ? SRC_TIP : (en.roff == carry_node ? SRC_CARRY : SRC_LOAD);
+      // memory sources: a global CLV (category stride 20) or the tip vector in shared memory (stride 0)
+      const double *x1 = q_inner ? a.clv + en.qoff + soff : &sh.tip[S * stips[en.qoff + lsite]];
+      const double *x2 = r_inner ? a.clv + en.roff + soff : &sh.tip[S * stips[en.roff + lsite]];
+      const int st1 = q_inner ? S : 0, st2 = r_inner ? S : 0;
+      if (rsrc == SRC_CARRY)      aa_entry<false, true>(carry, bEI, bEV, x1, st1, x2, st2, drow, lane, tq);
+      else if (qsrc == SRC_CARRY) aa_entry<true, false>(carry, bEI, bEV, x1, st1, x2, st2, drow, lane, tq);
+      else                        aa_entry<false, false>(carry, bEI, bEV, x1, st1, x2, st2, drow, lane, tq);
+
+      if (r_inner) {                            // TIP_TIP is never rescaled (avxLikelihood.c:1393-1440)
         bool small = true;
         #pragma unroll
-        for (int m = 0; m < S; m++) small = small && (fabs(t[m]) < kMinLikelihood);
-        const unsigned int b = __ballot_sync(0xffffffffu, small);
-        if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {
+        for (int c = 0; c < 4; c++)
           #pragma unroll
-          for (int m = 0; m < S; m++) t[m] *= kTwoToThe256;
-          if (c == 0 && valid) cnt += (unsigned int)a.wgt[site];
+          for (int t = 0; t < 3; t++)            // padding columns hold exact zeros and pass the test
+            small = small && (fabs(carry[c][t][0]) < kMinLikelihood) && (fabs(carry[c][t][1]) < kMinLikelihood);
+        const unsigned int b = __ballot_sync(0xffffffffu, small);
+        unsigned int cnt = 0;
+        if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {            // all 80 values of the site are tiny
+          #pragma unroll
+          for (int c = 0; c < 4; c++)
+            #pragma unroll
+            for (int t = 0; t < 3; t++) { carry[c][t][0] *= kTwoToThe256; carry[c][t][1] *= kTwoToThe256; }
+          if (tq == 0 && valid) cnt = (unsigned int)a.wgt[soff / SPAN];
+        }
+        if (__any_sync(0xffffffffu, cnt != 0)) {
+          const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
+          if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
         }
       }
       if (valid) {
-        double *dst = x3p + site * SPAN + c * S;
+        double *dst = a.clv + en.poff + soff + 2 * tq;
         #pragma unroll
-        for (int m = 0; m < S; m += 4) st256(dst + m, t + m);
+        for (int c = 0; c < 4; c++) {
+          *reinterpret_cast<double2 *>(dst + c * S) = make_double2(carry[c][0][0], carry[c][0][1]);
+          *reinterpret_cast<double2 *>(dst + c * S + 8) = make_double2(carry[c][1][0], carry[c][1][1]);
+          if (tq < 2) *reinterpret_cast<double2 *>(dst + c * S + 16) = make_double2(carry[c][2][0], carry[c][2][1]);
+        }
+      }
+      __syncwarp();
+      carry_node = en.poff;
+    }
+
+    if (a.mode == MODE_NEWVIEW) continue;
+
+    // ---------------- branch (entry 0): evaluate or sum table (C-fragment layout on both ends) ----------------
+    const SEntry br = ents[0];
+    const bool ptip = br.ptip_qtip & 1, qtip = br.ptip_qtip & 2;
+    const bool p_carry = !ptip && br.poff == carry_node, q_carry = !qtip && br.qoff == carry_node;
+    const double *tpa = ptip ? &sh.tip[S * stips[br.poff + lsite]] : sh.tip;
+    const double *tpb = qtip ? &sh.tip[S * stips[br.qoff + lsite]] : sh.tip;
+    double term = 0.0;
+    #pragma unroll
+    for (int c = 0; c < 4; c++) {
+      #pragma unroll
+      for (int t = 0; t < 3; t++) {
+        const int col = 8 * t + 2 * tq;
+        const bool live = col < S;                // t == 2 && tq >= 2: padding
+        double2 xa = make_double2(0.0, 0.0), xb = make_double2(0.0, 0.0);
+        if (p_carry) xa = make_double2(carry[c][t][0], carry[c][t][1]);
+        else if (live) xa = ptip ? *reinterpret_cast<const double2 *>(tpa + col)
+                                 : ld128(a.clv + br.poff + soff + c * S + col);
+        if (q_carry) xb = make_double2(carry[c][t][0], carry[c][t][1]);
+        else if (live) xb = qtip ? *reinterpret_cast<const double2 *>(tpb + col)
+                                 : ld128(a.clv + br.qoff + soff + c * S + col);
+        if (a.mode == MODE_SUM) {
+          if (valid && live) *reinterpret_cast<double2 *>(a.sum + soff + c * S + col) = make_double2(xa.x * xb.x, xa.y * xb.y);
+        } else if (live) {
+          const double d0 = __ldg(drow0 + c * 40 + col), d1 = __ldg(drow0 + c * 40 + col + 1);   // row 0, q side
+          term += xa.x * xb.x * d0;
+          term += xa.y * xb.y * d1;
+        }
       }
     }
-    if (may_scale && __any_sync(0xffffffffu, cnt != 0)) {
-      const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
-      if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
-    }
-  }
-
-  if (a.mode == MODE_NEWVIEW) return;
-
-  const DevEntry br = a.entries[0];
-  const bool ptip = br.p <= a.mxtips, qtip = br.q <= a.mxtips;
-  const double *xap = ptip ? nullptr : a.clv + (size_t)(br.p - a.mxtips - 1) * N * SPAN;
-  const double *xbp = qtip ? nullptr : a.clv + (size_t)(br.q - a.mxtips - 1) * N * SPAN;
-  const uint8_t *tap = ptip ? a.tips + (size_t)(br.p - 1) * N : nullptr;
-  const uint8_t *tbp = qtip ? a.tips + (size_t)(br.q - 1) * N : nullptr;
-
-  if (a.mode == MODE_EVALUATE) {
-    __syncthreads();
-    if (tid < 80) {
-      const int cc = tid / 20, k = tid % 20;
-      const double lz = a.lzq[slot];
-      sh.d[0][0][tid] = k ? exp(sh.rates[cc] * (sh.EIGN[k] * lz)) : 1.0;
-    }
-    __syncthreads();
-  }
-  const double *diag = &sh.d[0][0][c * S];
-
-  double acc = 0.0;
-  for (int u = 0; u < npass; u++) {
-    const int i = (u << 6) + (tid >> 2);
-    const bool valid = i < (int)tile.nsites;
-    const size_t site = (size_t)tile.site0 + (valid ? i : 0);
-    double xa[S], xb[S];
-    load_vec(xap, tap, sh.tip, site, c, xa);
-    load_vec(xbp, tbp, sh.tip, site, c, xb);
-    if (a.mode == MODE_SUM) {
-      #pragma unroll
-      for (int k = 0; k < S; k++) xa[k] *= xb[k];
-      if (valid) {
-        double *dst = a.sum + site * SPAN + c * S;
-        #pragma unroll
-        for (int k = 0; k < S; k += 4) st256(dst + k, xa + k);
-      }
-    } else {
-      double term = 0.0;
-      #pragma unroll
-      for (int k = 0; k < S; k++) term += xa[k] * xb[k] * diag[k];
+    if (a.mode == MODE_EVALUATE) {
       term += __shfl_xor_sync(0xffffffffu, term, 1);
       term += __shfl_xor_sync(0xffffffffu, term, 2);
-      if (c == 0 && valid) acc += (double)a.wgt[site] * log(0.25 * fabs(term));
+      if (tq == 0 && valid) acc += (double)a.wgt[soff / SPAN] * log(0.25 * fabs(term));
     }
   }
+
   if (a.mode == MODE_EVALUATE) {
     const double tot = block_sum(acc, sh.red);
     if (tid == 0) { a.tile_out[2 * (size_t)blockIdx.x] = tot; a.tile_out[2 * (size_t)blockIdx.x + 1] = 0.0; }
@@ -241,15 +377,17 @@ core_aa_kernel(const CoreArgs a)
     const int i = (u << 6) + (tid >> 2);
     const bool valid = i < (int)tile.nsites;
     const size_t site = (size_t)tile.site0 + (valid ? i : 0);
-    double s[S];
     const double *p = a.sum + site * SPAN + c * S;
-    #pragma unroll
-    for (int j = 0; j < S; j += 4) ld256(p + j, s + j);
     double L = 0.0, L1 = 0.0, L2 = 0.0;
     #pragma unroll
-    for (int k = 0; k < S; k++) {
-      const double t = d0[c * S + k] * s[k];
-      L += t; L1 += t * d1[c * S + k]; L2 += t * d2[c * S + k];
+    for (int j = 0; j < S; j += 4) {
+      double s[4];
+      ld256(p + j, s);
+      #pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const double t = d0[c * S + j + k] * s[k];
+        L += t; L1 += t * d1[c * S + j + k]; L2 += t * d2[c * S + j + k];
+      }
     }
     L  += __shfl_xor_sync(0xffffffffu, L, 1);   L  += __shfl_xor_sync(0xffffffffu, L, 2);
     L1 += __shfl_xor_sync(0xffffffffu, L1, 1);  L1 += __shfl_xor_sync(0xffffffffu, L1, 2);
@@ -267,15 +405,22 @@ core_aa_kernel(const CoreArgs a)
   if (tid == 0) { a.tile_out[2 * (size_t)blockIdx.x] = t1; a.tile_out[2 * (size_t)blockIdx.x + 1] = t2; }
 }
 
-void launch_traverse_aa(const TraverseArgs &a, int ntiles, cudaStream_t s)
+static size_t traverse_aa_smem(int count, int mxtips)
+{
+  return (((size_t)count * sizeof(SEntry) + 15) & ~(size_t)15) + (size_t)mxtips * TS;
+}
+
+void launch_traverse_aa(const TraverseArgs &a, const double *, int ntiles, cudaStream_t s)
 {
   if (ntiles <= 0) return;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(traverse_aa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AaShared));
-    configured = true;
+  const size_t smem = traverse_aa_smem(a.count, a.mxtips);
+  static size_t configured = 0;
+  if (smem > configured) {
+    const size_t want = std::min<size_t>(227 * 1024 - 8192, std::max<size_t>(smem, 64 * 1024));
+    cudaFuncSetAttribute(traverse_aa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    configured = want;
   }
-  traverse_aa_kernel<<<ntiles, kThreads, sizeof(AaShared), s>>>(a);
+  traverse_aa_kernel<<<ntiles, kThreads, smem, s>>>(a);
 }
 void launch_core_aa(const CoreArgs &a, int ntiles, cudaStream_t s)
 {
