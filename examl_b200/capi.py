@@ -1,8 +1,8 @@
 """ctypes binding of the C ABI declared in include/examl_b200.h.
 
 `Engine` wraps libexaml_b200.so (the CUDA engine).  The class is written against a
-(library, prefix) pair so that tests can bind the CPU oracle (oracle/liboracle.so, prefix
-`orc_`, same signatures) through the very same code path -- the product itself never does:
+(library, prefix) pair so that the test suite can bind its CPU checker (same signatures,
+prefix `orc_`) through the very same code path -- the product itself never does:
 `load_library()` below only ever opens the CUDA library and raises if it is missing.
 """
 from __future__ import annotations

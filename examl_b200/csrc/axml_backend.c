@@ -1,0 +1,433 @@
+/* axml_backend.c -- the B200 back-end of ExaML's likelihood API.
+ *
+ * This translation unit is compiled against the reference's own, unmodified axml.h and REPLACES
+ * the four reference objects newviewGenericSpecial.o, evaluateGenericSpecial.o,
+ * makenewzGenericSpecial.o and avxLikelihood.o (object list: examl/Makefile.AVX.gcc:18).  Every
+ * other reference file (axml.c, searchAlgo.c, optimizeModel.c, models.c, byteFile.c, ...) is
+ * compiled as it is and links against the three entry points it calls (nm on the reference
+ * objects: only these are imported from the replaced files):
+ *
+ *     void evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal);                    axml.h:1223
+ *     void newviewGeneric (tree *tr, nodeptr p, boolean masked);                           axml.h:1232
+ *     void makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxiter,
+ *                          double *result, boolean mask);                                  axml.h:1241
+ *
+ * plus the internal-but-global helpers of the replaced files, kept for API completeness:
+ * computeTraversalInfo, newviewIterative, evaluateIterative, makenewzIterative, execCore,
+ * isGap, noGap (axml.h:1224-1252, 1332-1333).
+ *
+ * What stays on the host (same behaviour as the reference, re-implemented here):
+ *   - the traversal descriptor: post-order list of CLVs that are not oriented towards the
+ *     branch of interest (reference: newviewGenericSpecial.c:691-811)
+ *   - the Newton-Raphson state machine of makenewz with its per-partition convergence masks
+ *     (reference: makenewzGenericSpecial.c:1133-1349)
+ *   - executeModel / partitionConverged bookkeeping
+ * What moves to the GPU (include/examl_b200.h): everything that touches per-site data.  CLVs,
+ * tip codes, weights, scaler counts and the sum table never exist on the host; the
+ * pInfo.xVector / sumBuffer / globalScaler arrays the reference allocates stay untouched.
+ *
+ * The two MPI_Allreduce calls of the replaced files (evaluateGenericSpecial.c:968-975,
+ * makenewzGenericSpecial.c:1241-1248) become one ncclAllReduce inside exb_evaluate / exb_core.
+ *
+ * Unsupported modes are refused loudly, the way the reference's MIC back-end does
+ * (axml.c:2645-2657): PSR/CAT rate heterogeneity, the -S memory saving option, binary data and
+ * LG4M/LG4X.  There is no CPU fallback.
+ */
+#include <assert.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "axml.h"
+#include "examl_b200.h"
+
+extern int processID;
+extern const unsigned int mask32[32];
+
+static exb_engine *g_engine = NULL;
+static exb_entry *g_entries = NULL;
+static double *g_qz = NULL, *g_rz = NULL;
+static unsigned char *g_mask = NULL;
+
+static void backend_fail(const char *what)
+{
+  fprintf(stderr, "\nExaML B200 back-end, rank %d: %s failed: %s\n", processID, what, exb_last_error());
+  MPI_Abort(MPI_COMM_WORLD, -1);
+  exit(-1);
+}
+
+static void refuse(const char *why)
+{
+  if (processID == 0)
+    fprintf(stderr, "\nThe B200 back-end of ExaML does not implement %s.\n"
+                    "Supported: DNA and protein data under the GAMMA model of rate heterogeneity (with or without -M).\n\n", why);
+  MPI_Barrier(MPI_COMM_WORLD);
+  MPI_Finalize();
+  exit(-1);
+}
+
+/* Which GPU does this rank drive?  One rank per GPU; launchers export LOCAL_RANK (torchrun),
+   OMPI_COMM_WORLD_LOCAL_RANK or SLURM_LOCALID; otherwise the rank number is used. */
+static int local_device(void)
+{
+  const char *names[] = {"EXAML_B200_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID", NULL};
+  int i;
+  for (i = 0; names[i]; i++) {
+    const char *v = getenv(names[i]);
+    if (v && *v) return atoi(v);
+  }
+  return processID;
+}
+
+/* Bootstrap of the NCCL communicator through the (shimmed or real) MPI: rank 0 creates the id and
+   broadcasts it as MPI_BYTE-sized ints. */
+static void backend_comm_init(void)
+{
+  int ranks = 1, i;
+  int idbuf[EXB_UNIQUE_ID_BYTES / sizeof(int)];
+  MPI_Comm_size(MPI_COMM_WORLD, &ranks);
+  if (ranks <= 1) return;
+  memset(idbuf, 0, sizeof idbuf);
+  if (processID == 0 && exb_comm_unique_id(idbuf) != EXB_OK) backend_fail("exb_comm_unique_id");
+  MPI_Bcast(idbuf, (int)(sizeof idbuf / sizeof(int)), MPI_INT, 0, MPI_COMM_WORLD);
+  if (exb_comm_init(g_engine, processID, ranks, idbuf) != EXB_OK) backend_fail("exb_comm_init");
+  (void)i;
+}
+
+static void backend_init(tree *tr)
+{
+  int m;
+  size_t nb = (size_t)tr->numBranches, slots = (size_t)tr->mxtips + 1;
+
+  if (tr->rateHetModel == CAT) refuse("the PSR (CAT) model of rate heterogeneity (-m PSR)");
+  if (tr->saveMemory) refuse("the memory saving option -S");
+  for (m = 0; m < tr->NumberOfModels; m++) {
+    const pInfo *p = &tr->partitionData[m];
+    if (p->states != 4 && p->states != 20) refuse("binary or multi-state data");
+    if (p->protModels == LG4M || p->protModels == LG4X) refuse("the LG4M / LG4X protein models");
+  }
+  if (exb_create(&g_engine, local_device(), tr->mxtips, tr->NumberOfModels, tr->numBranches) != EXB_OK)
+    backend_fail("exb_create");
+  for (m = 0; m < tr->NumberOfModels; m++) {
+    const pInfo *p = &tr->partitionData[m];
+    if (exb_set_partition(g_engine, m, p->states, p->width, p->wgt, p->yResource) != EXB_OK)
+      backend_fail("exb_set_partition");
+  }
+  if (exb_commit(g_engine) != EXB_OK) backend_fail("exb_commit");
+  backend_comm_init();
+  g_entries = (exb_entry *)malloc(slots * sizeof(exb_entry));
+  g_qz = (double *)malloc(slots * nb * sizeof(double));
+  g_rz = (double *)malloc(slots * nb * sizeof(double));
+  g_mask = (unsigned char *)malloc((size_t)tr->NumberOfModels);
+  if (!g_entries || !g_qz || !g_rz || !g_mask) { fprintf(stderr, "out of memory\n"); MPI_Abort(MPI_COMM_WORLD, -1); }
+}
+
+/* The host may have rewritten the model constants at any time (optimizeModel.c:419-462 gives no
+   notice); hand the current ones over before every launch.  exb_set_model compares and only
+   uploads what changed. */
+static void backend_sync(tree *tr)
+{
+  int m;
+  if (!g_engine) backend_init(tr);
+  for (m = 0; m < tr->NumberOfModels; m++) {
+    const pInfo *p = &tr->partitionData[m];
+    if (exb_set_model(g_engine, m, p->EIGN, p->EV, p->EI, p->tipVector, p->gammaRates) != EXB_OK)
+      backend_fail("exb_set_model");
+    g_mask[m] = tr->td[0].executeModel[m] ? 1 : 0;
+  }
+}
+
+/* Flatten td[0].ti[first .. count) into the C-ABI form; returns the number of entries. */
+static int pack_descriptor(tree *tr, int first)
+{
+  const int nb = tr->numBranches;
+  int i, b, n = 0;
+  for (i = first; i < tr->td[0].count; i++, n++) {
+    const traversalInfo *t = &tr->td[0].ti[i];
+    g_entries[n].tipCase = (i == 0 && first == 0 && 0) ? -1 : t->tipCase;
+    g_entries[n].pNumber = t->pNumber;
+    g_entries[n].qNumber = t->qNumber;
+    g_entries[n].rNumber = t->rNumber;
+    for (b = 0; b < nb; b++) {
+      g_qz[(size_t)n * nb + b] = t->qz[b];
+      g_rz[(size_t)n * nb + b] = t->rz[b];
+    }
+  }
+  return n;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* traversal descriptor                                                                           */
+/* ---------------------------------------------------------------------------------------------- */
+
+static void emit_entry(traversalInfo *ti, int *counter, int tipCase, nodeptr p, nodeptr q, nodeptr r, int numBranches)
+{
+  traversalInfo *t = &ti[*counter];
+  int b;
+  t->tipCase = tipCase;
+  t->pNumber = p->number;
+  t->qNumber = q->number;
+  t->rNumber = r->number;
+  for (b = 0; b < numBranches; b++) {
+    t->qz[b] = q->z[b];
+    t->rz[b] = r->z[b];
+  }
+  *counter += 1;
+}
+
+/* Post-order list of the CLVs at and below p that have to be recomputed so that p's CLV looks away
+   from p->back.  A child is descended into when it is not oriented towards p (x flag clear) or when
+   a full traversal is requested.  A tip child is always reported as q. */
+void computeTraversalInfo(nodeptr p, traversalInfo *ti, int *counter, int maxTips, int numBranches, boolean partialTraversal)
+{
+  nodeptr q, r;
+  boolean qTip, rTip;
+
+  if (isTip(p->number, maxTips)) return;
+  q = p->next->back;
+  r = p->next->next->back;
+  qTip = isTip(q->number, maxTips);
+  rTip = isTip(r->number, maxTips);
+
+  if (qTip && rTip) {
+    if (!p->x) getxnode(p);
+    emit_entry(ti, counter, TIP_TIP, p, q, r, numBranches);
+    return;
+  }
+  if (qTip || rTip) {
+    nodeptr tip = qTip ? q : r, inner = qTip ? r : q;
+    if (!inner->x || !partialTraversal)
+      computeTraversalInfo(inner, ti, counter, maxTips, numBranches, partialTraversal);
+    if (!p->x) getxnode(p);
+    assert(p->x && inner->x);
+    emit_entry(ti, counter, TIP_INNER, p, tip, inner, numBranches);
+    return;
+  }
+  if (!q->x || !partialTraversal) computeTraversalInfo(q, ti, counter, maxTips, numBranches, partialTraversal);
+  if (!r->x || !partialTraversal) computeTraversalInfo(r, ti, counter, maxTips, numBranches, partialTraversal);
+  if (!p->x) getxnode(p);
+  assert(p->x && q->x && r->x);
+  emit_entry(ti, counter, INNER_INNER, p, q, r, numBranches);
+}
+
+boolean isGap(unsigned int *x, int pos) { return (x[pos / 32] & mask32[pos % 32]); }
+boolean noGap(unsigned int *x, int pos) { return !(x[pos / 32] & mask32[pos % 32]); }
+
+/* ---------------------------------------------------------------------------------------------- */
+/* the *Iterative layer: one engine call each                                                     */
+/* ---------------------------------------------------------------------------------------------- */
+
+void newviewIterative(tree *tr, int startIndex)
+{
+  int n;
+  backend_sync(tr);
+  n = pack_descriptor(tr, startIndex);
+  if (n > 0 && exb_newview(g_engine, g_entries, n, g_qz, g_rz, g_mask) != EXB_OK) backend_fail("exb_newview");
+}
+
+/* Unlike the reference's function of the same name this returns the GLOBALLY reduced per-partition
+   log-likelihoods: the all-reduce of evaluateGeneric happens on the device, before the single
+   device-to-host copy. */
+void evaluateIterative(tree *tr)
+{
+  int n, m;
+  backend_sync(tr);
+  n = pack_descriptor(tr, 0);
+  if (exb_evaluate(g_engine, g_entries, n, g_qz, g_rz, g_mask, tr->perPartitionLH) != EXB_OK) backend_fail("exb_evaluate");
+  for (m = 0; m < tr->NumberOfModels; m++)
+    if (tr->td[0].executeModel[m] && tr->perPartitionLH[m] != 0.0)
+      assert(tr->perPartitionLH[m] < 0.0);       /* evaluateGenericSpecial.c:836 */
+}
+
+void makenewzIterative(tree *tr)
+{
+  int n;
+  backend_sync(tr);
+  n = pack_descriptor(tr, 0);
+  if (exb_makenewz_prepare(g_engine, g_entries, n, g_qz, g_rz, g_mask) != EXB_OK) backend_fail("exb_makenewz_prepare");
+}
+
+/* Globally reduced derivatives (the all-reduce of topLevelMakenewz is inside exb_core). */
+void execCore(tree *tr, volatile double *_dlnLdlz, volatile double *_d2lnLdlz2)
+{
+  double d1[NUM_BRANCHES], d2[NUM_BRANCHES];
+  int b;
+  backend_sync(tr);
+  if (exb_core(g_engine, tr->td[0].parameterValues, g_mask, d1, d2) != EXB_OK) backend_fail("exb_core");
+  for (b = 0; b < tr->numBranches; b++) {
+    _dlnLdlz[b] = d1[b];
+    _d2lnLdlz2[b] = d2[b];
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* public entry points                                                                            */
+/* ---------------------------------------------------------------------------------------------- */
+
+static void set_all_models(tree *tr, boolean value)
+{
+  int m;
+  for (m = 0; m < tr->NumberOfModels; m++) tr->executeModel[m] = value;
+}
+
+void evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal)
+{
+  nodeptr q = p->back;
+  traversalInfo *ti = tr->td[0].ti;
+  double sum = 0.0;
+  int b, m;
+
+  ti[0].pNumber = p->number;
+  ti[0].qNumber = q->number;
+  for (b = 0; b < tr->numBranches; b++) ti[0].qz[b] = q->z[b];
+  tr->td[0].count = 1;
+
+  if (fullTraversal) {
+    assert(isTip(p->number, tr->mxtips));
+    computeTraversalInfo(q, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, FALSE);
+  } else {
+    if (!p->x) computeTraversalInfo(p, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
+    if (!q->x) computeTraversalInfo(q, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
+  }
+  storeExecuteMaskInTraversalDescriptor(tr);
+  tr->td[0].traversalHasChanged = TRUE;
+
+  evaluateIterative(tr);            /* newviews + lnL at the branch + all-reduce, on the GPU */
+
+  for (m = 0; m < tr->NumberOfModels; m++) sum += tr->perPartitionLH[m];
+  tr->likelihood = sum;
+  tr->td[0].traversalHasChanged = FALSE;
+}
+
+void newviewGeneric(tree *tr, nodeptr p, boolean masked)
+{
+  int m;
+  if (isTip(p->number, tr->mxtips)) return;
+
+  tr->td[0].count = 0;
+  computeTraversalInfo(p, tr->td[0].ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
+  tr->td[0].traversalHasChanged = TRUE;
+
+  if (masked)
+    for (m = 0; m < tr->NumberOfModels; m++) tr->executeModel[m] = tr->partitionConverged[m] ? FALSE : TRUE;
+
+  if (tr->td[0].count > 0) {
+    storeExecuteMaskInTraversalDescriptor(tr);
+    newviewIterative(tr, 0);
+  }
+  if (masked) set_all_models(tr, TRUE);
+  tr->td[0].traversalHasChanged = FALSE;
+}
+
+/* Newton-Raphson on z for the branch in td[0].ti[0]; one branch slot per partition under -M,
+   a single joint slot otherwise.  Per slot the iteration is in one of three states:
+     looking for negative curvature (curvatOK == FALSE), stepping (curvatOK == TRUE), done. */
+static void newton_raphson(tree *tr, double *z0, int maxiterStart, double *result)
+{
+  const int nb = tr->numBranches;
+  double z[NUM_BRANCHES], zprev[NUM_BRANCHES], zstep[NUM_BRANCHES];
+  double d1[NUM_BRANCHES], d2[NUM_BRANCHES];
+  int budget[NUM_BRANCHES];
+  boolean done[NUM_BRANCHES], allDone, sumTableReady = FALSE;
+  int i, m;
+
+  for (i = 0; i < nb; i++) {
+    z[i] = z0[i];
+    budget[i] = maxiterStart;
+    done[i] = FALSE;
+    tr->curvatOK[i] = TRUE;
+  }
+
+  do {
+    for (i = 0; i < nb; i++)
+      if (!done[i] && tr->curvatOK[i]) {            /* start a new NR step from z */
+        tr->curvatOK[i] = FALSE;
+        zprev[i] = z[i];
+        zstep[i] = (1.0 - zmax) * z[i] + zmin;
+      }
+    for (i = 0; i < nb; i++)
+      if (!done[i] && !tr->curvatOK[i]) {
+        if (z[i] < zmin) z[i] = zmin;
+        else if (z[i] > zmax) z[i] = zmax;
+        tr->coreLZ[i] = log(z[i]);
+      }
+
+    /* only slots that still need derivatives are executed */
+    if (nb > 1) {
+      assert(nb == tr->NumberOfModels);
+      for (m = 0; m < tr->NumberOfModels; m++)
+        if (tr->executeModel[m]) tr->executeModel[m] = !tr->curvatOK[m];
+    } else {
+      set_all_models(tr, !tr->curvatOK[0]);
+    }
+    storeExecuteMaskInTraversalDescriptor(tr);
+    storeValuesInTraversalDescriptor(tr, &(tr->coreLZ[0]));
+
+    if (!sumTableReady) {
+      makenewzIterative(tr);          /* newviews + sum table, once per branch */
+      sumTableReady = TRUE;
+    }
+    execCore(tr, d1, d2);             /* globally reduced */
+
+    for (i = 0; i < nb; i++)
+      if (!done[i] && !tr->curvatOK[i]) {
+        if (d2[i] >= 0.0 && z[i] < zmax)
+          zprev[i] = z[i] = 0.37 * z[i] + 0.63;     /* wrong side of the maximum: shorten the branch */
+        else
+          tr->curvatOK[i] = TRUE;
+      }
+
+    for (i = 0; i < nb; i++)
+      if (tr->curvatOK[i] && !done[i]) {
+        if (d2[i] < 0.0) {
+          const double step = -d1[i] / d2[i];
+          const double cap = 0.25 * zprev[i] + 0.75;
+          if (step < 100) {
+            z[i] *= exp(step);
+            if (z[i] < zmin) z[i] = zmin;
+            if (z[i] > cap) z[i] = cap;
+          } else
+            z[i] = cap;
+        }
+        if (z[i] > zmax) z[i] = zmax;
+        budget[i] -= 1;
+        if (fabs(z[i] - zprev[i]) > zstep[i]) {
+          if (budget[i] < -20) {                    /* give up: keep the old branch length */
+            z[i] = z0[i];
+            done[i] = TRUE;
+          }
+        } else
+          done[i] = TRUE;
+      }
+
+    allDone = TRUE;
+    for (i = 0; i < nb; i++) allDone = allDone && done[i];
+  } while (!allDone);
+
+  set_all_models(tr, TRUE);
+  for (i = 0; i < nb; i++) result[i] = z[i];
+}
+
+void makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxiter, double *result, boolean mask)
+{
+  traversalInfo *ti = tr->td[0].ti;
+  int i;
+
+  ti[0].pNumber = p->number;
+  ti[0].qNumber = q->number;
+  for (i = 0; i < tr->numBranches; i++) {
+    ti[0].qz[i] = z0[i];
+    if (mask)
+      tr->executeModel[i] = tr->partitionConverged[i] ? FALSE : TRUE;
+    else
+      assert(tr->executeModel[i]);
+  }
+  tr->td[0].count = 1;
+  if (!p->x) computeTraversalInfo(p, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
+  if (!q->x) computeTraversalInfo(q, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
+
+  newton_raphson(tr, z0, maxiter, result);
+
+  for (i = 0; i < tr->numBranches; i++) tr->executeModel[i] = TRUE;
+}

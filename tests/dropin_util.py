@@ -1,0 +1,59 @@
+"""Helpers to run the reference-side binaries (oracle/_ref/parse-examl, bin/examl-b200-probe) on the
+alignments stored in the golden fixtures."""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+
+import numpy as np
+
+from examl_b200 import data as exdata
+from golden_util import alignment_of, load_json
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PARSER = os.path.join(ROOT, "oracle", "_ref", "parse-examl")
+DROPIN = os.path.join(ROOT, "bin", "examl-b200-probe")
+DROPIN_PLAIN = os.path.join(ROOT, "bin", "examl-b200")
+
+
+def have_binaries() -> bool:
+    return os.path.exists(PARSER) and os.path.exists(DROPIN)
+
+
+def write_inputs(tag: str, tmp: str, partition_lines=None):
+    """Rebuild a PHYLIP alignment + tree file from <tag>.first.json and parse it to ExaML's binary format.
+    The fixture holds the pattern-compressed alignment; expanding each pattern by its weight gives the
+    same multiset of columns as the original file."""
+    first = load_json(f"{tag}.first.json")
+    mxtips = first["mxtips"]
+    blocks, states = [], first["partitions"][0]["states"]
+    for part in first["partitions"]:
+        tips, wgt = alignment_of(part, mxtips)
+        blocks.append(exdata.expand_patterns(tips, wgt))
+    aln = np.concatenate(blocks, axis=1)
+    phy = os.path.join(tmp, f"{tag}.phy")
+    exdata.write_phylip(phy, first["names"], aln, states)
+    tree = os.path.join(tmp, f"{tag}.tree")
+    open(tree, "w").write(first["tree_newick"] + "\n")
+    args = [PARSER, "-s", phy, "-n", tag, "-m", "DNA" if states == 4 else "PROT"]
+    if partition_lines:
+        q = os.path.join(tmp, f"{tag}.model")
+        open(q, "w").write("\n".join(partition_lines) + "\n")
+        args += ["-q", q]
+    subprocess.run(args, cwd=tmp, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
+    return os.path.join(tmp, f"{tag}.binary"), tree, first
+
+
+def run_dropin(binary: str, tree: str, tmp: str, extra_args, env=None, exe=DROPIN):
+    e = dict(os.environ)
+    e["EXAML_PROBE_DUMP"] = os.path.join(tmp, "dump")
+    e.update(env or {})
+    r = subprocess.run([exe, "-s", binary, "-t", tree, "-m", "GAMMA", "-n", "RUN", "-w", tmp + "/"] + extra_args,
+                       cwd=tmp, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
+    dumps = {}
+    for d in ("first", "mkz", "final"):
+        p = os.path.join(tmp, f"dump.{d}.json")
+        if os.path.exists(p):
+            dumps[d] = json.load(open(p))
+    return r, dumps
