@@ -1,0 +1,73 @@
+"""Launched under torchrun with N ranks (one per GPU): the alignment is sharded by sites exactly like
+partitionAssignment.c does for a single partition; every rank must obtain the same, globally reduced lnL and
+derivatives (NCCL all-reduce inside exb_evaluate / exb_core), equal to the unsharded values.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch
+import torch.distributed as dist
+
+from examl_b200 import data as exdata
+from examl_b200.capi import Engine
+from examl_b200.likelihood import Likelihood
+from synth import build_engine, random_case
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tree, parts, models = random_case(40, [100003, 0, 5000], [4, 4, 20], seed=17)
+
+    def factory(mxtips, nparts, nb=1, **kw):
+        return Engine(mxtips, nparts, nb, device=local, **kw)
+
+    # reference values: the whole alignment on this rank's GPU, no communicator
+    full = build_engine(factory, tree, parts, models)
+    ti = tree.full_traversal()
+    want = full.evaluateIterative(ti).copy()
+    full.makenewzIterative(tree.partial_traversal(tree.start))
+    want_d = full.execCore([np.log(0.7)])
+    full.close()
+
+    # sharded: rank r owns a contiguous slice of every partition (partition 1 is empty everywhere)
+    shard = []
+    for s, tips, wgt in parts:
+        lo, hi = exdata.shard_sites(wgt.shape[0], rank, world)
+        shard.append((s, np.ascontiguousarray(tips[:, lo:hi]), wgt[lo:hi]))
+    eng = build_engine(factory, tree, shard, models)
+    uid = [eng.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    eng.comm_init(rank, world, uid[0])
+    got = eng.evaluateIterative(ti).copy()
+    eng.makenewzIterative(tree.partial_traversal(tree.start))
+    got_d = eng.execCore([np.log(0.7)])
+
+    ok = bool(np.all(np.abs(got - want) <= 1e-11 * np.maximum(np.abs(want), 1.0)))
+    ok = ok and abs(got_d[0][0] - want_d[0][0]) <= 1e-9 * max(1.0, abs(want_d[0][0]))
+    ok = ok and abs(got_d[1][0] - want_d[1][0]) <= 1e-9 * max(1.0, abs(want_d[1][0]))
+    # every rank holds bit-identical results (the all-reduce is part of the call)
+    t = torch.tensor(np.concatenate([got, got_d[0], got_d[1]]), device="cuda")
+    gathered = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    ok = ok and all(torch.equal(gathered[0], g) for g in gathered)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "PASS" if int(flag.item()) else "FAIL", "world", world, "lnL", got.tolist(), "want", want.tolist(),
+              "d", [float(got_d[0][0]), float(got_d[1][0])], "want_d", [float(want_d[0][0]), float(want_d[1][0])])
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
