@@ -143,7 +143,8 @@ def run_reference(tree: Tree, workload: str, sample_sites: int, steps: int, warm
                 open(os.path.join(tmp, "lg.model"), "w").write(f"LG, p0 = 1-{sample_sites}\n")
             subprocess.run([parser, "-s", "a.phy", "-n", "a", "-c"] + pargs, cwd=tmp, check=True,
                            stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
-            env = dict(os.environ, OMP_NUM_THREADS=str(cores), EXAML_PROBE_BENCH=str(steps), EXAML_PROBE_WARMUP=str(warmup))
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}   # a single process
+            env.update(OMP_NUM_THREADS=str(cores), EXAML_PROBE_BENCH=str(steps), EXAML_PROBE_WARMUP=str(warmup))
             r = subprocess.run([exe, "-s", "a.binary", "-t", "a.tree", "-m", "GAMMA", "-n", "B", "-f", "e", "-w", tmp + "/"],
                                cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             for line in r.stdout.splitlines():

@@ -36,7 +36,9 @@ def build(force: bool = False) -> bool:
     backend_o = os.path.join(OBJ, "axml_backend.o")
     subprocess.check_call(["gcc"] + CFLAGS + ["-I" + shim, "-I" + os.path.join(REF, "examl"), "-I" + os.path.join(ROOT, "include"),
                            "-c", "-o", backend_o, os.path.join(HERE, "csrc", "axml_backend.c")])
-    objs = [os.path.join(OBJ, "avx", k + ".o") for k in KEEP] + [backend_o, os.path.join(OBJ, "mpi_single.o")]
+    # mpi_tcp.c: rank/size from the launcher's environment (examl_b200/launch.py, torchrun --no-python);
+    # without WORLD_SIZE it is a single rank
+    objs = [os.path.join(OBJ, "avx", k + ".o") for k in KEEP] + [backend_o, os.path.join(OBJ, "mpi_tcp.o")]
     link = ["-L" + HERE, "-lexaml_b200", "-Wl,-rpath,$ORIGIN/../examl_b200", "-lm"]
     subprocess.check_call(["gcc", "-o", exe] + objs + link)
     subprocess.check_call(["gcc", "-o", exe + "-probe"] + objs + [os.path.join(OBJ, "avx", "ref_probe.o")] +

@@ -164,6 +164,7 @@ struct ClassState {
   int *wgt = nullptr, *part_global = nullptr;   // class-partition -> global partition
   int dtab_row = 0;
   std::vector<double> models_h;
+  std::vector<int> cp_tile_begin, cp_tile_count, cp_global;   // per class-partition: its run of tiles, global index
   int dirty_lo = 1 << 30, dirty_hi = -1;   // range of class-partitions whose constants must be re-uploaded
 };
 
@@ -189,6 +190,8 @@ struct exb_engine {
   ncclComm_t comm = nullptr;
   int nranks = 1;
 };
+
+constexpr int kMaxParamPartitions = 16;
 
 static int class_of(int states) { return states == 4 ? CLS_DNA : (states == 20 ? CLS_AA : -1); }
 
@@ -297,6 +300,9 @@ extern "C" int exb_commit(exb_engine *e)
         k.tiles_h.push_back(t);
       }
       tcount[m] = (int)k.tiles_h.size() - tbegin[m];
+      k.cp_tile_begin.push_back(tbegin[m]);
+      k.cp_tile_count.push_back(tcount[m]);
+      k.cp_global.push_back(m);
       n += (p.width + 31) / 32 * 32;            // every partition starts on a 32-site boundary
     }
     k.nparts = idx;
@@ -498,13 +504,21 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
     a.mask = e->stage_d + e->off_mask;
     a.count = count; a.first = first; a.mode = mode;
     a.scale_inc = e->scale_inc; a.tile_out = k.tile_out;
-    if (c == CLS_DNA) {
-      DnaConsts kc;
-      if (k.nparts == 1) {                       // single partition: EI/EV travel as kernel parameters
-        memcpy(kc.EI, &k.models_h[8], sizeof kc.EI);
-        memcpy(kc.EV, &k.models_h[24], sizeof kc.EV);
+    if (c == CLS_DNA && k.nparts <= kMaxParamPartitions) {
+      // few partitions: one launch per partition, its EI/EV travel as kernel parameters (constant bank)
+      for (int pc = 0; pc < k.nparts; pc++) {
+        if (k.cp_tile_count[pc] == 0 || !(e->stage_h + e->off_mask)[k.cp_global[pc]]) continue;   // empty or masked
+        DnaConsts kc;
+        memcpy(kc.EI, &k.models_h[(size_t)pc * k.model_doubles + 8], sizeof kc.EI);
+        memcpy(kc.EV, &k.models_h[(size_t)pc * k.model_doubles + 24], sizeof kc.EV);
+        TraverseArgs ap = a;
+        ap.tiles = k.tiles + k.cp_tile_begin[pc];
+        ap.tile_out = k.tile_out + 2 * (size_t)k.cp_tile_begin[pc];
+        launch_traverse_dna(ap, &kc, k.cp_tile_count[pc], e->stream);
+        if (pc) e->launches++;
       }
-      launch_traverse_dna(a, k.nparts == 1 ? &kc : nullptr, (int)k.tiles_h.size(), e->stream);
+    } else if (c == CLS_DNA) {
+      launch_traverse_dna(a, nullptr, (int)k.tiles_h.size(), e->stream);   // many partitions: constants via shared memory
     } else {
       launch_traverse_aa(a, k.nparts == 1 ? k.models_h.data() : nullptr, (int)k.tiles_h.size(), e->stream);
     }

@@ -420,6 +420,7 @@ void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *kc, int ntiles,
   if (ntiles <= 0) return;
   // chunk = 64*NS sites; the staged tip rows (mxtips * 64 * NS bytes) must fit in shared memory
   int ns = a.tile_sites <= 64 ? 1 : (a.tile_sites <= 128 ? 2 : 4);
+  if (!kc) ns = 1;                               // shared-memory constants: one site per thread keeps the registers in budget
   while (ns > 1 && traverse_dna_smem(a.count, a.mxtips, ns) > 96 * 1024) ns >>= 1;
   if (ns == 1) launch_ns<1>(a, kc, ntiles, s);
   else if (ns == 2) launch_ns<2>(a, kc, ntiles, s);

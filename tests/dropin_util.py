@@ -46,7 +46,7 @@ def write_inputs(tag: str, tmp: str, partition_lines=None):
 
 
 def run_dropin(binary: str, tree: str, tmp: str, extra_args, env=None, exe=DROPIN):
-    e = dict(os.environ)
+    e = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
     e["EXAML_PROBE_DUMP"] = os.path.join(tmp, "dump")
     e.update(env or {})
     r = subprocess.run([exe, "-s", binary, "-t", tree, "-m", "GAMMA", "-n", "RUN", "-w", tmp + "/"] + extra_args,

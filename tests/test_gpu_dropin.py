@@ -74,3 +74,32 @@ def test_spr_search_runs_and_improves():
         final = dumps["final"]["likelihood"]
         assert final >= -16221.368990 * (1 + NORTH_STAR_RTOL), final
         print("search final lnL", final)
+
+
+@pytest.mark.skipif(not have_binaries(), reason="bin/examl-b200-probe / oracle/_ref/parse-examl not built")
+def test_two_ranks_two_gpus():
+    """One process per GPU: ExaML's own partitionAssignment.c shards the sites, byteFile.c reads each rank's slice,
+    the back-end uploads it to the rank's GPU; control-plane collectives over mpi_tcp.c, the two hot-path
+    all-reduces over NCCL.  Same end state as the single-rank reference."""
+    import os, subprocess, sys, json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from dropin_util import DROPIN, ROOT
+    final_gold = load_json("dna49p.final.json")
+    first_gold = load_json("dna49p.first.json")
+    lo, lines = 1, []
+    for i, part in enumerate(first_gold["partitions"]):
+        n = sum(part["wgt"])
+        lines.append(f"DNA, p{i} = {lo}-{lo + n - 1}")
+        lo += n
+    with tempfile.TemporaryDirectory() as tmp:
+        binary, tree, _ = write_inputs("dna49p", tmp, lines)
+        env = dict(os.environ, EXAML_PROBE_DUMP=os.path.join(tmp, "dump"), EXAML_PROBE_NOTIPS="1", PYTHONPATH=ROOT)
+        r = subprocess.run([sys.executable, "-m", "examl_b200.launch", "-np", "2", "--", DROPIN, "-s", binary, "-t", tree,
+                            "-m", "GAMMA", "-n", "R", "-f", "e", "-w", tmp + "/"],
+                           cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-3000:]
+        got = json.load(open(os.path.join(tmp, "dump.final.json")))["likelihood"]
+        assert _rel(got, final_gold["likelihood"]) < NORTH_STAR_RTOL, (got, final_gold["likelihood"])
+        print("2 ranks / 2 GPUs final lnL", got, "reference", final_gold["likelihood"])
