@@ -159,7 +159,7 @@ struct ClassState {
   int nparts = 0;
   std::vector<Tile> tiles_h;
   Tile *tiles = nullptr;
-  double *clv = nullptr, *sum = nullptr, *models = nullptr, *tile_out = nullptr, *dtab = nullptr;
+  double *clv = nullptr, *sum = nullptr, *models = nullptr, *tile_out = nullptr, *dtab = nullptr, *lut = nullptr;
   uint8_t *tips = nullptr;
   int *wgt = nullptr, *part_global = nullptr;   // class-partition -> global partition
   int dtab_row = 0;
@@ -232,7 +232,7 @@ extern "C" void exb_destroy(exb_engine *e)
   for (int c = 0; c < 2; c++) {
     ClassState &k = e->cls[c];
     cudaFree(k.tiles); cudaFree(k.clv); cudaFree(k.sum); cudaFree(k.models); cudaFree(k.tile_out);
-    cudaFree(k.tips); cudaFree(k.wgt); cudaFree(k.dtab); cudaFree(k.part_global);
+    cudaFree(k.tips); cudaFree(k.wgt); cudaFree(k.dtab); cudaFree(k.part_global); cudaFree(k.lut);
   }
   cudaFree(e->stage_d); cudaFreeHost(e->stage_h);
   cudaFree(e->part_has_sites); cudaFree(e->part_tile_begin); cudaFree(e->part_tile_count); cudaFree(e->part_cls);
@@ -292,10 +292,12 @@ extern "C" int exb_commit(exb_engine *e)
       pcls[m] = c;
       has_sites[m] = p.width > 0;
       tbegin[m] = (int)k.tiles_h.size();
-      for (size_t s = 0; s < p.width; s += (size_t)e->tile_sites) {
+      // AA tiles are whole 96-site chunks (12 warps x 8 sites)
+      const size_t tsz = c == CLS_AA ? (size_t)((e->tile_sites + 95) / 96) * 96 : (size_t)e->tile_sites;
+      for (size_t s = 0; s < p.width; s += tsz) {
         Tile t;
         t.site0 = (uint32_t)(n + s);
-        t.nsites = (uint32_t)std::min<size_t>((size_t)e->tile_sites, p.width - s);
+        t.nsites = (uint32_t)std::min<size_t>(tsz, p.width - s);
         t.part = m; t.part_cls = p.part_cls;
         k.tiles_h.push_back(t);
       }
@@ -318,6 +320,9 @@ extern "C" int exb_commit(exb_engine *e)
       CUDA_TRY(cudaMemcpy(k.part_global, pg.data(), pg.size() * sizeof(int), cudaMemcpyHostToDevice));
       const size_t dbytes = (size_t)(e->mxtips + 1) * idx * k.dtab_row * sizeof(double);
       CUDA_TRY(cudaMalloc(&k.dtab, dbytes));
+      // AA tip look-up table (optional: skipped when it would not fit comfortably, e.g. thousands of AA partitions)
+      const size_t lbytes = (size_t)(e->mxtips + 1) * idx * 2 * kAaLutRow * sizeof(double);
+      if (c == CLS_AA && lbytes <= ((size_t)1 << 30) && !getenv("EXB_AA_NO_LUT")) CUDA_TRY(cudaMalloc(&k.lut, lbytes));
     }
     if (n == 0) continue;
     // host images of tips / weights on the class site axis (padding: gap code, weight 0)
@@ -494,8 +499,16 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
     d.model_doubles = k.model_doubles; d.row = k.dtab_row;
     launch_dtab(d, e->stream);
     e->launches++;
+    if (k.lut) {
+      LutArgs l;
+      l.lut = k.lut; l.models = k.models; l.dtab = k.dtab;
+      l.entries = (const DevEntry *)(e->stage_d + e->off_entries);
+      l.count = count; l.first = first; l.nparts_cls = k.nparts;
+      launch_aa_lut(l, e->stream);
+      e->launches++;
+    }
     TraverseArgs a;
-    a.dtab = k.dtab; a.nparts_cls = k.nparts; a.tile_sites = e->tile_sites;
+    a.dtab = k.dtab; a.lut = k.lut; a.nparts_cls = k.nparts; a.tile_sites = e->tile_sites;
     a.tiles = k.tiles; a.clv = k.clv; a.tips = k.tips; a.wgt = k.wgt; a.sum = k.sum; a.models = k.models;
     a.N = k.N; a.mxtips = e->mxtips; a.nparts = e->P; a.nbranches = e->nb;
     a.entries = (const DevEntry *)(e->stage_d + e->off_entries);

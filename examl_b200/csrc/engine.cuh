@@ -73,6 +73,7 @@ struct TraverseArgs {
   unsigned int *scale_inc;  // [maxEntries][P]  per-entry scaler increments (integer atomics: deterministic)
   double       *tile_out;   // [ntiles][2]      per-tile partial sums (evaluate: lnL; core: d1,d2)
   const double *dtab;       // [count][nparts_cls][row]
+  const double *lut;        // AA only, may be null: [count][nparts_cls][2 sides][23 codes][4][20] = P(t) * tipVector[code]
   int           nparts_cls;
   int           tile_sites; // sites per tile (multiple of 32)
 };
@@ -111,6 +112,13 @@ struct FinishArgs {
   double       *out;              // evaluate: [P]; core: [2][P]
 };
 
+// AA tip look-up table: what precomputeTips / umpX do in the reference (avxLikelihood.c:1353-1389, mic_native_aa.c:97)
+constexpr int kAaLutRow = 23 * 80;
+struct LutArgs {
+  double *lut; const double *models; const double *dtab; const DevEntry *entries;
+  int count, first, nparts_cls;
+};
+void launch_aa_lut(const LutArgs &a, cudaStream_t s);
 void launch_dtab(const DtabArgs &a, cudaStream_t s);
 void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
 void launch_core_dna(const CoreArgs &a, int ntiles, cudaStream_t s);
@@ -124,18 +132,18 @@ constexpr int kThreads = 256;
 
 // Deterministic block-wide sum: fixed shuffle tree inside each warp, then warp 0 adds the warp
 // totals in warp order.  Result valid in thread 0.
-__device__ __forceinline__ double block_sum(double v, double *smem8)
+__device__ __forceinline__ double block_sum(double v, double *smem32)
 {
   #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();                       // smem8 may still be in use by a previous reduction
-  if (lane == 0) smem8[warp] = v;
+  __syncthreads();                       // smem32 may still be in use by a previous reduction
+  if (lane == 0) smem32[warp] = v;
   __syncthreads();
   if (warp == 0) {
-    v = (lane < (int)(blockDim.x >> 5)) ? smem8[lane] : 0.0;
+    v = (lane < (int)(blockDim.x >> 5)) ? smem32[lane] : 0.0;
     #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   }
   return v;
 }

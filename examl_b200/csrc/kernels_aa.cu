@@ -26,11 +26,14 @@ namespace {
 
 constexpr int S = 20;
 constexpr int SPAN = 80;
-constexpr int TS = 64;           // sites per chunk (256 threads / 4 categories)
+constexpr int kAaThreads = 384;  // 12 warps, one CTA per SM (the register budget of the DMMA pipeline)
+constexpr int TS = 96;           // sites per chunk: 8 per warp
 
 struct AaShared {
   double tip[460];        // tipVector[23 codes][20]
-  double red[8];
+  double fragEI[15][32];  // B fragments of EI^T, [k-step * 3 + n-tile][lane]: conflict-free LDS.64
+  double fragEV[15][32];  // B fragments of EV
+  double red[32];
 };
 
 struct SEntry {
@@ -96,46 +99,61 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
       : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// One traversal entry for the 8 sites of this warp, all four categories.  A child is either read from
-// memory (global CLV with category stride 20, or the shared-memory tip vector with stride 0) or taken
-// from the carry registers; the three combinations that occur are compiled separately so that the
-// k-step loop is branch-free and the loads of the next category can be scheduled under the DMMAs.
-template <bool QCARRY, bool RCARRY>
-__device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const double (&bEI)[5][3], const double (&bEV)[5][3],
+// One traversal entry for the 8 sites of this warp, all four categories.  A child is
+//   MEM   read from memory (global CLV with category stride 20, or the shared-memory tip vector with stride 0)
+//         and contracted with EI^T on the tensor pipe,
+//   CARRY taken from the carry registers (C-fragment layout -> A operand by warp shuffles), same contraction,
+//   LUT   a tip whose product P(t) * tipVector[code] was tabulated for this (entry, side) by aa_lut_kernel:
+//         its Y comes straight from the table in C-fragment layout, no DMMA at all.
+// The combinations that occur are compiled separately so that the k-step loop is branch-free and the
+// loads of the next category can be scheduled under the DMMAs.
+enum ChildMode : int { CH_MEM = 0, CH_CARRY = 1, CH_LUT = 2 };
+
+template <int MODE>
+__device__ __forceinline__ void child_y(double (&y)[3][2], const double (&carry)[4][3][2], const double (*fEI)[32],
+                                        const double *x, int xstride, const double *lutrow, const double *dside,
+                                        int c, int lane, int tq)
+{
+  if (MODE == CH_LUT) {
+    const double *r = lutrow + c * S + 2 * tq;
+    #pragma unroll
+    for (int t = 0; t < 3; t++) {
+      double2 v = make_double2(0.0, 0.0);
+      if (t < 2 || tq < 2) v = __ldg(reinterpret_cast<const double2 *>(r + 8 * t));
+      y[t][0] = v.x; y[t][1] = v.y;
+    }
+    return;
+  }
+  double av[5];
+  #pragma unroll
+  for (int s = 0; s < 5; s++) {
+    const int k = 4 * s + tq;
+    if (MODE == CH_CARRY) {
+      const int sl = (lane & ~3) | (((s & 1) << 1) | (tq >> 1));
+      const double e0 = __shfl_sync(0xffffffffu, carry[c][s >> 1][0], sl);
+      const double e1 = __shfl_sync(0xffffffffu, carry[c][s >> 1][1], sl);
+      av[s] = (tq & 1) ? e1 : e0;
+    } else av[s] = x[c * xstride + k];
+    av[s] *= __ldg(dside + c * 40 + k);
+  }
+  #pragma unroll
+  for (int t = 0; t < 3; t++) y[t][0] = y[t][1] = 0.0;
+  #pragma unroll
+  for (int s = 0; s < 5; s++)
+    #pragma unroll
+    for (int t = 0; t < 3; t++) dmma(y[t][0], y[t][1], av[s], fEI[s * 3 + t][lane]);
+}
+
+template <int QM, int RM>
+__device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const double (*fEI)[32], const double (*fEV)[32],
                                          const double *x1, int x1stride, const double *x2, int x2stride,
-                                         const double *drow, int lane, int tq)
+                                         const double *lut1, const double *lut2, const double *drow, int lane, int tq)
 {
   #pragma unroll
   for (int c = 0; c < 4; c++) {
-    // operands of the five k-steps: (d (.) x)[g][4s+tq]
-    double a1[5], a2[5];
-    #pragma unroll
-    for (int s = 0; s < 5; s++) {
-      const int k = 4 * s + tq;
-      const int sl = (lane & ~3) | (((s & 1) << 1) | (tq >> 1));
-      if (QCARRY) {
-        const double e0 = __shfl_sync(0xffffffffu, carry[c][s >> 1][0], sl);
-        const double e1 = __shfl_sync(0xffffffffu, carry[c][s >> 1][1], sl);
-        a1[s] = (tq & 1) ? e1 : e0;
-      } else a1[s] = x1[c * x1stride + k];
-      if (RCARRY) {
-        const double e0 = __shfl_sync(0xffffffffu, carry[c][s >> 1][0], sl);
-        const double e1 = __shfl_sync(0xffffffffu, carry[c][s >> 1][1], sl);
-        a2[s] = (tq & 1) ? e1 : e0;
-      } else a2[s] = x2[c * x2stride + k];
-      a1[s] *= __ldg(drow + c * 40 + k);
-      a2[s] *= __ldg(drow + c * 40 + S + k);
-    }
     double y1[3][2], y2[3][2];
-    #pragma unroll
-    for (int t = 0; t < 3; t++) { y1[t][0] = y1[t][1] = 0.0; y2[t][0] = y2[t][1] = 0.0; }
-    #pragma unroll
-    for (int s = 0; s < 5; s++)
-      #pragma unroll
-      for (int t = 0; t < 3; t++) {
-        dmma(y1[t][0], y1[t][1], a1[s], bEI[s][t]);
-        dmma(y2[t][0], y2[t][1], a2[s], bEI[s][t]);
-      }
+    child_y<QM>(y1, carry, fEI, x1, x1stride, lut1, drow, c, lane, tq);
+    child_y<RM>(y2, carry, fEI, x2, x2stride, lut2, drow + S, c, lane, tq);
     // Z = Y1 (.) Y2 in C layout, then X3 = Z * EV
     #pragma unroll
     for (int t = 0; t < 3; t++) { y1[t][0] *= y2[t][0]; y1[t][1] *= y2[t][1]; }
@@ -149,7 +167,7 @@ __device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const double 
       const double e1 = __shfl_sync(0xffffffffu, y1[s >> 1][1], sl);
       const double az = (tq & 1) ? e1 : e0;           // Z[g][4s+tq]
       #pragma unroll
-      for (int t = 0; t < 3; t++) dmma(x3[t][0], x3[t][1], az, bEV[s][t]);
+      for (int t = 0; t < 3; t++) dmma(x3[t][0], x3[t][1], az, fEV[s * 3 + t][lane]);
     }
     #pragma unroll
     for (int t = 0; t < 3; t++) { carry[c][t][0] = x3[t][0]; carry[c][t][1] = x3[t][1]; }
@@ -171,7 +189,7 @@ __device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const double 
 // once, 16 B per thread.  Scaling (all 80 values of a site < 2^-256) is decided after the four
 // categories are done, from the 24 register values of the 4 lanes that share a site.
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kAaThreads, 1)
 traverse_aa_kernel(const TraverseArgs a)
 {
   __shared__ AaShared sh;
@@ -188,9 +206,16 @@ traverse_aa_kernel(const TraverseArgs a)
   const size_t N = a.N;
   const double *model = a.models + (size_t)tile.part_cls * kAaModelDoubles;   // EIGN[20] rates[4] EI[400] EV[400] tip[460]
   {
-    for (int i = tid; i < 460; i += kThreads) sh.tip[i] = model[824 + i];
+    for (int i = tid; i < 460; i += kAaThreads) sh.tip[i] = model[824 + i];
+    // B fragments: EI^T[k = 4s+tq][n = 8t+g] = EI[n][k];  EV[k][n];  zero padding for n >= 20
+    for (int i = tid; i < 15 * 32; i += kAaThreads) {
+      const int f = i >> 5, ln = i & 31, fs = f / 3, ft = f % 3;
+      const int k = 4 * fs + (ln & 3), n = 8 * ft + (ln >> 2);
+      sh.fragEI[f][ln] = n < S ? model[24 + n * S + k] : 0.0;
+      sh.fragEV[f][ln] = n < S ? model[424 + k * S + n] : 0.0;
+    }
     if (tid == 0) mbar_init(&mbar, 1);
-    for (int e = tid; e < a.count; e += kThreads) {
+    for (int e = tid; e < a.count; e += kAaThreads) {
       const DevEntry en = a.entries[e];
       SEntry se;
       se.tipCase = en.tipCase;
@@ -203,17 +228,6 @@ traverse_aa_kernel(const TraverseArgs a)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
   }
-
-  // B fragments: bEI[s][t] = EI^T[k = 4s+tq][n = 8t+g] = EI[n][k];  bEV[s][t] = EV[k][n]; zero padding for n >= 20
-  double bEI[5][3], bEV[5][3];
-  #pragma unroll
-  for (int s = 0; s < 5; s++)
-    #pragma unroll
-    for (int t = 0; t < 3; t++) {
-      const int k = 4 * s + tq, n = 8 * t + g;
-      bEI[s][t] = n < S ? model[24 + n * S + k] : 0.0;
-      bEV[s][t] = n < S ? model[424 + k * S + n] : 0.0;
-    }
 
   const double *drow0 = a.dtab + (size_t)tile.part_cls * kAaDtabRow;     // + e * dstride + c*40 + side*20 + k
   const size_t dstride = (size_t)a.nparts_cls * kAaDtabRow;
@@ -269,12 +283,19 @@ traverse_aa_kernel(const TraverseArgs a)
       const int qsrc = !q_inner ? SRC_TIP : (en.qoff == carry_node ? SRC_CARRY : SRC_LOAD);
       const int rsrc = !r_inner ? SRC_TIP : (en.roff == carry_node ? SRC_CARRY : SRC_LOAD);
       // memory sources: a global CLV (category stride 20) or the tip vector in shared memory (stride 0)
-      const double *x1 = q_inner ? a.clv + en.qoff + soff : &sh.tip[S * stips[en.qoff + lsite]];
-      const double *x2 = r_inner ? a.clv + en.roff + soff : &sh.tip[S * stips[en.roff + lsite]];
+      const int code1 = q_inner ? 0 : stips[en.qoff + lsite], code2 = r_inner ? 0 : stips[en.roff + lsite];
+      const double *x1 = q_inner ? a.clv + en.qoff + soff : &sh.tip[S * code1];
+      const double *x2 = r_inner ? a.clv + en.roff + soff : &sh.tip[S * code2];
       const int st1 = q_inner ? S : 0, st2 = r_inner ? S : 0;
-      if (rsrc == SRC_CARRY)      aa_entry<false, true>(carry, bEI, bEV, x1, st1, x2, st2, drow, lane, tq);
-      else if (qsrc == SRC_CARRY) aa_entry<true, false>(carry, bEI, bEV, x1, st1, x2, st2, drow, lane, tq);
-      else                        aa_entry<false, false>(carry, bEI, bEV, x1, st1, x2, st2, drow, lane, tq);
+      const double *lutE = a.lut ? a.lut + ((size_t)e * a.nparts_cls + tile.part_cls) * 2 * kAaLutRow : nullptr;
+      const double *lut1 = lutE + code1 * SPAN, *lut2 = lutE + kAaLutRow + code2 * SPAN;
+      const bool qlut = !q_inner && lutE, rlut = !r_inner && lutE;
+      if (qlut && rlut)                aa_entry<CH_LUT, CH_LUT>(carry, sh.fragEI, sh.fragEV, x1, st1, x2, st2, lut1, lut2, drow, lane, tq);
+      else if (qlut && rsrc == SRC_CARRY) aa_entry<CH_LUT, CH_CARRY>(carry, sh.fragEI, sh.fragEV, x1, st1, x2, st2, lut1, lut2, drow, lane, tq);
+      else if (qlut)                   aa_entry<CH_LUT, CH_MEM>(carry, sh.fragEI, sh.fragEV, x1, st1, x2, st2, lut1, lut2, drow, lane, tq);
+      else if (rsrc == SRC_CARRY)      aa_entry<CH_MEM, CH_CARRY>(carry, sh.fragEI, sh.fragEV, x1, st1, x2, st2, lut1, lut2, drow, lane, tq);
+      else if (qsrc == SRC_CARRY)      aa_entry<CH_CARRY, CH_MEM>(carry, sh.fragEI, sh.fragEV, x1, st1, x2, st2, lut1, lut2, drow, lane, tq);
+      else                             aa_entry<CH_MEM, CH_MEM>(carry, sh.fragEI, sh.fragEV, x1, st1, x2, st2, lut1, lut2, drow, lane, tq);
 
       if (r_inner) {                            // TIP_TIP is never rescaled (avxLikelihood.c:1393-1440)
         bool small = true;
@@ -354,10 +375,46 @@ traverse_aa_kernel(const TraverseArgs a)
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Tip look-up table: for every (entry, partition, side) whose child is a tip,
+//   lut[code][c][l] = sum_j EI[l][j] * d[c][side][j] * tipVector[code][j]        (23 codes x 4 x 20)
+// -- the reference's umpX1 / umpX2 (avxLikelihood.c:1353-1389), built once per call for the whole descriptor.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+aa_lut_kernel(const LutArgs a)
+{
+  __shared__ double EI[400], tip[460], d[80];
+  const int side = blockIdx.x & 1;
+  const int ep = blockIdx.x >> 1, pc = ep % a.nparts_cls, e = ep / a.nparts_cls;
+  if (e < a.first) return;
+  const int tc = a.entries[e].tipCase;
+  if (!(side == 0 ? tc <= 1 : tc == 0)) return;
+  const double *model = a.models + (size_t)pc * kAaModelDoubles;
+  const double *drow = a.dtab + ((size_t)e * a.nparts_cls + pc) * kAaDtabRow;
+  for (int i = threadIdx.x; i < 400; i += 256) EI[i] = model[24 + i];
+  for (int i = threadIdx.x; i < 460; i += 256) tip[i] = model[824 + i];
+  if (threadIdx.x < 80) d[threadIdx.x] = drow[(threadIdx.x / 20) * 40 + side * 20 + threadIdx.x % 20];
+  __syncthreads();
+  double *out = a.lut + ((size_t)ep * 2 + side) * kAaLutRow;
+  for (int i = threadIdx.x; i < kAaLutRow; i += 256) {
+    const int code = i / 80, c = (i % 80) / 20, l = i % 20;
+    double s = tip[code * 20];                       // j = 0: EI[l][0] = 1, d[0] = 1
+    #pragma unroll
+    for (int j = 1; j < 20; j++) s += EI[l * 20 + j] * (d[c * 20 + j] * tip[code * 20 + j]);
+    out[i] = s;
+  }
+}
+
+void launch_aa_lut(const LutArgs &a, cudaStream_t s)
+{
+  const int blocks = a.count * a.nparts_cls * 2;
+  if (blocks > 0) aa_lut_kernel<<<blocks, 256, 0, s>>>(a);
+}
+
 __global__ void __launch_bounds__(kThreads, 2)
 core_aa_kernel(const CoreArgs a)
 {
-  __shared__ double d0[80], d1[80], d2[80], red[8];
+  __shared__ double d0[80], d1[80], d2[80], red[32];
   const Tile tile = a.tiles[blockIdx.x];
   if (!a.mask[tile.part]) return;
   const int tid = threadIdx.x, c = tid & 3;
@@ -420,7 +477,7 @@ void launch_traverse_aa(const TraverseArgs &a, const double *, int ntiles, cudaS
     cudaFuncSetAttribute(traverse_aa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
     configured = want;
   }
-  traverse_aa_kernel<<<ntiles, kThreads, smem, s>>>(a);
+  traverse_aa_kernel<<<ntiles, kAaThreads, smem, s>>>(a);
 }
 void launch_core_aa(const CoreArgs &a, int ntiles, cudaStream_t s)
 {

@@ -36,7 +36,7 @@ struct DnaShared {
   double tip[64];        // tipVector[16 codes][4]
   double EI[16];
   double EV[16];
-  double red[8];
+  double red[32];
 };
 
 __device__ __forceinline__ void ld256(const double *p, double v[4])
@@ -330,7 +330,7 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
 __global__ void __launch_bounds__(kThreads, 4)
 core_dna_kernel(const CoreArgs a)
 {
-  __shared__ double d0[16], d1[16], d2[16], red[8];
+  __shared__ double d0[16], d1[16], d2[16], red[32];
   const Tile tile = a.tiles[blockIdx.x];
   if (!a.mask[tile.part]) return;
   const int tid = threadIdx.x, c = tid & 3;
