@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libexaml_b200.so")
 
 EXPORTS = [
     "exb_create", "exb_destroy", "exb_last_error", "exb_set_partition", "exb_commit",
-    "exb_set_model", "exb_newview", "exb_evaluate", "exb_makenewz_prepare", "exb_core",
+    "exb_set_model", "exb_newview", "exb_evaluate", "exb_makenewz_prepare", "exb_core", "exb_makenewz",
     "exb_comm_unique_id", "exb_comm_init", "exb_read_clv", "exb_read_scaler",
     "exb_read_sumtable", "exb_last_kernel_ms", "exb_launch_count", "exb_set_tile_sites",
 ]
@@ -168,6 +168,18 @@ class Engine:
         d2 = np.zeros(self.nbranches)
         self._check(self._f("core")(self._h, _dptr(lzv), _dptr(m), _dptr(d1), _dptr(d2)))
         return d1, d2
+
+    def makenewz(self, ti: Sequence[Entry], z0: Sequence[float], maxiter: int, execute_model=None):
+        """topLevelMakenewz on the device (single rank): returns (z, curvatOK, iterations)."""
+        arr, qz, rz = pack_traversal(ti, self.nbranches)
+        m = self._mask(execute_model, self.nparts)
+        z0v = np.ascontiguousarray(np.asarray(z0, dtype=np.float64).reshape(self.nbranches))
+        res = np.zeros(self.nbranches)
+        cok = np.zeros(self.nbranches, dtype=np.int32)
+        it = C.c_int(0)
+        self._check(self._f("makenewz")(self._h, arr, C.c_int(len(ti)), _dptr(qz), _dptr(rz), _dptr(m), _dptr(z0v),
+                                        C.c_int(maxiter), _dptr(res), _dptr(cok), C.byref(it)))
+        return res, cok, int(it.value)
 
     # ---- multi-GPU -------------------------------------------------------------------------
     def comm_unique_id(self) -> bytes:

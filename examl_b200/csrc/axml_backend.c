@@ -46,6 +46,7 @@ extern int processID;
 extern const unsigned int mask32[32];
 
 static exb_engine *g_engine = NULL;
+static int g_ranks = 1;
 static exb_entry *g_entries = NULL;
 static double *g_qz = NULL, *g_rz = NULL;
 static unsigned char *g_mask = NULL;
@@ -87,6 +88,7 @@ static void backend_comm_init(void)
   int ranks = 1, i;
   int idbuf[EXB_UNIQUE_ID_BYTES / sizeof(int)];
   MPI_Comm_size(MPI_COMM_WORLD, &ranks);
+  g_ranks = ranks;
   if (ranks <= 1) return;
   memset(idbuf, 0, sizeof idbuf);
   if (processID == 0 && exb_comm_unique_id(idbuf) != EXB_OK) backend_fail("exb_comm_unique_id");
@@ -145,7 +147,7 @@ static int pack_descriptor(tree *tr, int first)
   int i, b, n = 0;
   for (i = first; i < tr->td[0].count; i++, n++) {
     const traversalInfo *t = &tr->td[0].ti[i];
-    g_entries[n].tipCase = (i == 0 && first == 0 && 0) ? -1 : t->tipCase;
+    g_entries[n].tipCase = t->tipCase;          /* ignored by the engine for the branch entry */
     g_entries[n].pNumber = t->pNumber;
     g_entries[n].qNumber = t->qNumber;
     g_entries[n].rNumber = t->rNumber;
@@ -427,7 +429,18 @@ void makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxiter, do
   if (!p->x) computeTraversalInfo(p, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
   if (!q->x) computeTraversalInfo(q, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
 
-  newton_raphson(tr, z0, maxiter, result);
+  if (g_ranks == 1 && !getenv("EXAML_B200_HOST_NR")) {
+    /* single rank: the whole Newton-Raphson loop runs on the device (exb_makenewz) */
+    int cok[NUM_BRANCHES], n, m;
+    storeExecuteMaskInTraversalDescriptor(tr);
+    backend_sync(tr);
+    n = pack_descriptor(tr, 0);
+    if (exb_makenewz(g_engine, g_entries, n, g_qz, g_rz, g_mask, z0, maxiter, result, cok, NULL) != EXB_OK)
+      backend_fail("exb_makenewz");
+    for (i = 0; i < tr->numBranches; i++) tr->curvatOK[i] = cok[i] ? TRUE : FALSE;
+    for (m = 0; m < tr->NumberOfModels; m++) tr->executeModel[m] = TRUE;
+  } else
+    newton_raphson(tr, z0, maxiter, result);
 
   for (i = 0; i < tr->numBranches; i++) tr->executeModel[i] = TRUE;
 }

@@ -189,6 +189,11 @@ struct exb_engine {
   float last_ms = 0.f;
   ncclComm_t comm = nullptr;
   int nranks = 1;
+  // device-resident Newton-Raphson
+  NrState *nr_state_d = nullptr, *nr_state_h = nullptr;
+  unsigned int *nr_barrier = nullptr;
+  unsigned char *nr_mask = nullptr;
+  int nr_max_blocks = 0;
 };
 
 constexpr int kMaxParamPartitions = 16;
@@ -237,6 +242,7 @@ extern "C" void exb_destroy(exb_engine *e)
   cudaFree(e->stage_d); cudaFreeHost(e->stage_h);
   cudaFree(e->part_has_sites); cudaFree(e->part_tile_begin); cudaFree(e->part_tile_count); cudaFree(e->part_cls);
   cudaFree(e->gs); cudaFree(e->scale_inc); cudaFree(e->out_d); cudaFreeHost(e->out_h);
+  cudaFree(e->nr_state_d); cudaFreeHost(e->nr_state_h); cudaFree(e->nr_barrier); cudaFree(e->nr_mask);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -373,6 +379,12 @@ extern "C" int exb_commit(exb_engine *e)
   CUDA_TRY(cudaMalloc(&e->out_d, (size_t)2 * e->P * sizeof(double)));
   CUDA_TRY(cudaMemset(e->out_d, 0, (size_t)2 * e->P * sizeof(double)));
   CUDA_TRY(cudaMallocHost(&e->out_h, (size_t)2 * e->P * sizeof(double)));
+
+  CUDA_TRY(cudaMalloc(&e->nr_state_d, sizeof(NrState)));
+  CUDA_TRY(cudaMallocHost(&e->nr_state_h, sizeof(NrState)));
+  CUDA_TRY(cudaMalloc(&e->nr_barrier, sizeof(unsigned int)));
+  CUDA_TRY(cudaMalloc(&e->nr_mask, (size_t)e->P));
+  e->nr_max_blocks = newton_raphson_max_blocks(e->device);
 
   auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
   size_t off = 0;
@@ -648,6 +660,54 @@ extern "C" int exb_core(exb_engine *e, const double *lz, const unsigned char *ex
     dlnLdlz[slot] += e->out_h[m];
     d2lnLdlz2[slot] += e->out_h[e->P + m];
   }
+  return EXB_OK;
+}
+
+extern "C" int exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
+                            const unsigned char *executeModel, const double *z0, int maxiter,
+                            double *result, int *curvatOK, int *iterations)
+{
+  if (!e || !e->committed) return fail(EXB_ERR_STATE, "engine not committed");
+  if (e->comm) return fail(EXB_ERR_STATE, "exb_makenewz: device-resident Newton-Raphson is single-rank; use exb_makenewz_prepare + exb_core");
+  if (count < 1 || !z0 || !result) return fail(EXB_ERR_ARG, "exb_makenewz: bad arguments");
+  if (e->nb > kMaxBranchSlots) return fail(EXB_ERR_ARG, "exb_makenewz: more than %d branch slots", kMaxBranchSlots);
+  // 1. newviews + sum table (the first-iteration work of topLevelMakenewz); the mask of that pass is the one the
+  //    state machine derives in its first round: executeModel && !curvatOK, with curvatOK == FALSE for every slot
+  int rc = run_traversal(e, ti, count, 1, qz, rz, executeModel, MODE_SUM);
+  if (rc) return rc;
+  // 2. initial state
+  NrState *h = e->nr_state_h;
+  memset(h, 0, sizeof *h);
+  for (int b = 0; b < e->nb; b++) { h->z[b] = z0[b]; h->z0[b] = z0[b]; h->budget[b] = maxiter; h->done[b] = 0; h->curvatOK[b] = 1; }
+  CUDA_TRY(cudaMemcpyAsync(e->nr_state_d, h, sizeof *h, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->nr_mask, e->stage_d + e->off_mask, (size_t)e->P, cudaMemcpyDeviceToDevice, e->stream));
+  CUDA_TRY(cudaMemsetAsync(e->nr_barrier, 0, sizeof(unsigned int), e->stream));
+  NrArgs a;
+  memset(&a, 0, sizeof a);
+  a.state = e->nr_state_d; a.mask = e->nr_mask; a.barrier = e->nr_barrier;
+  int total_tiles = 0;
+  for (int c = 0; c < 2; c++) {
+    ClassState &k = e->cls[c];
+    a.tiles[c] = k.tiles; a.ntiles[c] = (int)k.tiles_h.size(); a.sum[c] = k.sum; a.wgt[c] = k.wgt;
+    a.models[c] = k.models; a.tile_out[c] = k.tile_out;
+    total_tiles += a.ntiles[c];
+  }
+  a.part_out = e->out_d;
+  a.part_has_sites = e->part_has_sites; a.part_tile_begin = e->part_tile_begin; a.part_tile_count = e->part_tile_count;
+  a.part_cls = e->part_cls; a.nparts = e->P; a.nbranches = e->nb;
+  const int blocks = std::max(1, std::min(total_tiles, e->nr_max_blocks));
+  const int lr = launch_newton_raphson(a, blocks, e->stream);
+  if (lr != 0) return fail(EXB_ERR_CUDA, "cooperative launch of the Newton-Raphson kernel failed: %s", cudaGetErrorString((cudaError_t)lr));
+  e->launches++;
+  CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(h, e->nr_state_d, sizeof *h, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
+  for (int b = 0; b < e->nb; b++) {
+    result[b] = h->z[b];
+    if (curvatOK) curvatOK[b] = h->curvatOK[b];
+  }
+  if (iterations) *iterations = h->iterations;
   return EXB_OK;
 }
 

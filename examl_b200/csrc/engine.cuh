@@ -119,6 +119,29 @@ struct LutArgs {
   int count, first, nparts_cls;
 };
 void launch_aa_lut(const LutArgs &a, cudaStream_t s);
+// ---- device-resident Newton-Raphson (kernels_nr.cu) ----
+constexpr int kMaxBranchSlots = 256;     // NUM_BRANCHES, axml.h:134
+struct NrState {
+  double z[kMaxBranchSlots], z0[kMaxBranchSlots], zprev[kMaxBranchSlots], zstep[kMaxBranchSlots], lz[kMaxBranchSlots];
+  double d1[kMaxBranchSlots], d2[kMaxBranchSlots];
+  int budget[kMaxBranchSlots];
+  unsigned char done[kMaxBranchSlots], curvatOK[kMaxBranchSlots];
+  int all_done, iterations;
+};
+struct NrArgs {
+  NrState *state;
+  unsigned char *mask;            // [P] executeModel, updated by the state machine
+  unsigned int *barrier;          // monotonic arrival counter (zeroed before the launch)
+  const Tile *tiles[2]; int ntiles[2];
+  const double *sum[2]; const int *wgt[2]; const double *models[2];
+  double *tile_out[2];
+  double *part_out;               // [2][P]
+  const int *part_has_sites, *part_tile_begin, *part_tile_count, *part_cls;
+  int nparts, nbranches;
+};
+int launch_newton_raphson(const NrArgs &a, int blocks, cudaStream_t s);
+int newton_raphson_max_blocks(int device);
+
 void launch_dtab(const DtabArgs &a, cudaStream_t s);
 void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
 void launch_core_dna(const CoreArgs &a, int ntiles, cudaStream_t s);

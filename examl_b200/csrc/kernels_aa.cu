@@ -16,6 +16,7 @@
 // load instruction, no shared-memory traffic in the contraction.  Several AA partitions: EI^T / EV
 // are broadcast from shared memory.
 #include "engine.cuh"
+#include "core_tile.cuh"
 #include <algorithm>
 #include <stdlib.h>
 #include <string.h>
@@ -414,52 +415,13 @@ void launch_aa_lut(const LutArgs &a, cudaStream_t s)
 __global__ void __launch_bounds__(kThreads, 2)
 core_aa_kernel(const CoreArgs a)
 {
-  __shared__ double d0[80], d1[80], d2[80], red[32];
+  __shared__ CoreSmem sh;
   const Tile tile = a.tiles[blockIdx.x];
   if (!a.mask[tile.part]) return;
-  const int tid = threadIdx.x, c = tid & 3;
-  const int slot = a.nbranches > 1 ? tile.part : 0;
-  const double *model = a.models + (size_t)tile.part_cls * kAaModelDoubles;
-  if (tid < 80) {
-    const int cc = tid / 20, k = tid % 20;
-    const double ki = model[20 + cc], ek = model[k], lz = a.lz[slot];
-    d0[tid] = k ? exp(ek * ki * lz) : 1.0;
-    d1[tid] = k ? ek * ki : 0.0;
-    d2[tid] = k ? ek * ek * (ki * ki) : 0.0;
-  }
-  __syncthreads();
-  double acc1 = 0.0, acc2 = 0.0;
-  const int npass = (tile.nsites + 63) >> 6;
-  for (int u = 0; u < npass; u++) {
-    const int i = (u << 6) + (tid >> 2);
-    const bool valid = i < (int)tile.nsites;
-    const size_t site = (size_t)tile.site0 + (valid ? i : 0);
-    const double *p = a.sum + site * SPAN + c * S;
-    double L = 0.0, L1 = 0.0, L2 = 0.0;
-    #pragma unroll
-    for (int j = 0; j < S; j += 4) {
-      double s[4];
-      ld256(p + j, s);
-      #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const double t = d0[c * S + j + k] * s[k];
-        L += t; L1 += t * d1[c * S + j + k]; L2 += t * d2[c * S + j + k];
-      }
-    }
-    L  += __shfl_xor_sync(0xffffffffu, L, 1);   L  += __shfl_xor_sync(0xffffffffu, L, 2);
-    L1 += __shfl_xor_sync(0xffffffffu, L1, 1);  L1 += __shfl_xor_sync(0xffffffffu, L1, 2);
-    L2 += __shfl_xor_sync(0xffffffffu, L2, 1);  L2 += __shfl_xor_sync(0xffffffffu, L2, 2);
-    if (c == 0 && valid) {
-      const double inv = 1.0 / fabs(L);
-      const double g = L1 * inv, h = L2 * inv;
-      const double w = (double)a.wgt[site];
-      acc1 += w * g;
-      acc2 += w * (h - g * g);
-    }
-  }
-  const double t1 = block_sum(acc1, red);
-  const double t2 = block_sum(acc2, red);
-  if (tid == 0) { a.tile_out[2 * (size_t)blockIdx.x] = t1; a.tile_out[2 * (size_t)blockIdx.x + 1] = t2; }
+  double t1, t2;
+  core_tile<20>(tile, a.sum, a.wgt, a.models + (size_t)tile.part_cls * kAaModelDoubles,
+                a.lz[a.nbranches > 1 ? tile.part : 0], sh, t1, t2);
+  if (threadIdx.x == 0) { a.tile_out[2 * (size_t)blockIdx.x] = t1; a.tile_out[2 * (size_t)blockIdx.x + 1] = t2; }
 }
 
 static size_t traverse_aa_smem(int count, int mxtips)

@@ -24,6 +24,7 @@
 // exponentials come from the d-table built once per call by dtab_kernel (no block barrier in the
 // entry loop).
 #include "engine.cuh"
+#include "core_tile.cuh"
 #include <algorithm>
 #include <stdlib.h>
 #include <string.h>
@@ -330,52 +331,13 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
 __global__ void __launch_bounds__(kThreads, 4)
 core_dna_kernel(const CoreArgs a)
 {
-  __shared__ double d0[16], d1[16], d2[16], red[32];
+  __shared__ CoreSmem sh;
   const Tile tile = a.tiles[blockIdx.x];
   if (!a.mask[tile.part]) return;
-  const int tid = threadIdx.x, c = tid & 3;
-  const int slot = a.nbranches > 1 ? tile.part : 0;
-  const double *model = a.models + (size_t)tile.part_cls * kDnaModelDoubles;
-  if (tid < 16) {
-    const int cc = tid >> 2, k = tid & 3;
-    const double ki = model[4 + cc], ek = model[k], lz = a.lz[slot];
-    d0[tid] = k ? exp(ek * ki * lz) : 1.0;
-    d1[tid] = k ? ek * ki : 0.0;
-    d2[tid] = k ? ek * ek * (ki * ki) : 0.0;
-  }
-  __syncthreads();
-  double e0[4], e1[4], e2[4];
-  #pragma unroll
-  for (int k = 0; k < 4; k++) { e0[k] = d0[c * 4 + k]; e1[k] = d1[c * 4 + k]; e2[k] = d2[c * 4 + k]; }
-
-  double acc1 = 0.0, acc2 = 0.0;
-  const int npass = (tile.nsites + 63) >> 6;
-  for (int u = 0; u < npass; u++) {
-    const int i = (u << 6) + (tid >> 2);
-    const bool valid = i < (int)tile.nsites;
-    const size_t site = (size_t)tile.site0 + (valid ? i : 0);
-    double s[4];
-    ld256(a.sum + site * 16 + c * 4, s);
-    double L = 0.0, L1 = 0.0, L2 = 0.0;
-    #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const double t = e0[k] * s[k];
-      L += t; L1 += t * e1[k]; L2 += t * e2[k];
-    }
-    L  += __shfl_xor_sync(0xffffffffu, L, 1);   L  += __shfl_xor_sync(0xffffffffu, L, 2);
-    L1 += __shfl_xor_sync(0xffffffffu, L1, 1);  L1 += __shfl_xor_sync(0xffffffffu, L1, 2);
-    L2 += __shfl_xor_sync(0xffffffffu, L2, 1);  L2 += __shfl_xor_sync(0xffffffffu, L2, 2);
-    if (c == 0 && valid) {
-      const double inv = 1.0 / fabs(L);
-      const double g = L1 * inv, h = L2 * inv;
-      const double w = (double)a.wgt[site];
-      acc1 += w * g;
-      acc2 += w * (h - g * g);
-    }
-  }
-  const double t1 = block_sum(acc1, red);
-  const double t2 = block_sum(acc2, red);
-  if (tid == 0) { a.tile_out[2 * (size_t)blockIdx.x] = t1; a.tile_out[2 * (size_t)blockIdx.x + 1] = t2; }
+  double t1, t2;
+  core_tile<4>(tile, a.sum, a.wgt, a.models + (size_t)tile.part_cls * kDnaModelDoubles,
+               a.lz[a.nbranches > 1 ? tile.part : 0], sh, t1, t2);
+  if (threadIdx.x == 0) { a.tile_out[2 * (size_t)blockIdx.x] = t1; a.tile_out[2 * (size_t)blockIdx.x + 1] = t2; }
 }
 
 size_t traverse_dna_smem(int count, int mxtips, int ns)

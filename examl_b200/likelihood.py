@@ -21,7 +21,8 @@ from .phylo import ZMAX, ZMIN, Entry, Node, Tree
 
 
 class Likelihood:
-    def __init__(self, tree: Tree, engine, num_partitions: int):
+    def __init__(self, tree: Tree, engine, num_partitions: int, device_newton_raphson: bool = False):
+        self.device_newton_raphson = device_newton_raphson   # run topLevelMakenewz on the GPU (single rank)
         self.tr = tree
         self.engine = engine
         self.NumberOfModels = num_partitions
@@ -69,7 +70,12 @@ class Likelihood:
             self.tr.computeTraversalInfo(p, ti, True)
         if not self.tr.isTip(q.number) and not q.x:
             self.tr.computeTraversalInfo(q, ti, True)
-        result = self._topLevelMakenewz(ti, list(z0[:nb]), maxiter)
+        if self.device_newton_raphson:
+            z, cok, self.nr_iterations = self.engine.makenewz(ti, list(z0[:nb]), maxiter, self.executeModel)
+            result, self.curvatOK = [float(v) for v in z], [bool(v) for v in cok]
+            self.executeModel = [True] * self.NumberOfModels
+        else:
+            result = self._topLevelMakenewz(ti, list(z0[:nb]), maxiter)
         for i in range(nb):
             self.executeModel[i] = True
         return result

@@ -129,6 +129,17 @@ int  exb_makenewz_prepare(exb_engine *e, const exb_entry *ti, int count,
 int  exb_core(exb_engine *e, const double *lz, const unsigned char *executeModel,
               double *dlnLdlz, double *d2lnLdlz2);
 
+/* topLevelMakenewz (makenewzGenericSpecial.c:1133-1349) entirely on the device: newviews ti[1..count), the sum
+ * table of branch ti[0], then the Newton-Raphson iteration on z for every branch slot -- derivative pass, reduction
+ * and the scalar update stay on the GPU (one cooperative kernel with grid barriers); a single copy brings back
+ * result[numBranches] (the new z, in [zmin, zmax]), curvatOK[numBranches] (tr->curvatOK) and the number of
+ * iterations (iterationsDone, may be NULL).  z0[numBranches] are the start values (= ti[0] branch values), maxiter as in makenewzGeneric,
+ * executeModel[] the initial mask.  Single rank only: with a communicator (exb_comm_init, nranks > 1) it returns
+ * EXB_ERR_STATE and the caller runs the loop itself with exb_makenewz_prepare + exb_core. */
+int  exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
+                  const unsigned char *executeModel, const double *z0, int maxiter,
+                  double *result, int *curvatOK, int *iterationsDone);
+
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------------ */
 
 /* NCCL bootstrap: rank 0 obtains an opaque id (EXB_UNIQUE_ID_BYTES bytes), the launcher

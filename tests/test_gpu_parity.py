@@ -172,3 +172,28 @@ def test_errors_are_loud(cuda_factory):
     bad[1].pNumber = 3                                           # a tip cannot be recomputed
     with pytest.raises(EngineError):
         gpu.evaluateIterative(bad)
+
+
+@pytest.mark.parametrize("widths,kinds,nb", [([400], [4], 1), ([150, 90], [4, 20], 1), ([120, 60, 200], [4, 20, 4], 3)])
+def test_device_newton_raphson_matches_host_loop(cuda_factory, oracle_factory, widths, kinds, nb):
+    """exb_makenewz (the whole NR loop in one cooperative kernel) against the host loop on the oracle:
+    same z for every branch of a smoothing sweep, same curvature flags, same end likelihood."""
+    tree, parts, models = random_case(18, widths, kinds, seed=23, num_branches=nb)
+    tree2, parts2, models2 = random_case(18, widths, kinds, seed=23, num_branches=nb)
+    gpu = build_engine(cuda_factory, tree, parts, models, tile_sites=64)
+    cpu = build_engine(oracle_factory, tree2, parts2, models2)
+    lk = Likelihood(tree, gpu, len(widths), device_newton_raphson=True)
+    lk2 = Likelihood(tree2, cpu, len(widths))
+    lk.evaluateGeneric(tree.start, True)
+    lk2.evaluateGeneric(tree2.start, True)
+    for (a, b), (a2, b2) in zip(list(tree.branches()), list(tree2.branches())):
+        z = lk.makenewzGeneric(a, b, a.z, 10)
+        z2 = lk2.makenewzGeneric(a2, b2, a2.z, 10)
+        assert lk.nr_iterations == lk2.nr_iterations
+        assert lk.curvatOK == lk2.curvatOK
+        for u, v in zip(z, z2):
+            assert abs(u - v) <= 1e-9 * v, (z, z2)
+        a.z[:] = z
+        a2.z[:] = z2
+    l1, l2 = lk.evaluateGeneric(tree.start, True), lk2.evaluateGeneric(tree2.start, True)
+    assert abs(l1 - l2) <= 1e-10 * abs(l2)
