@@ -22,7 +22,7 @@ EXPORTS = [
     "exb_create", "exb_destroy", "exb_last_error", "exb_set_partition", "exb_commit",
     "exb_set_model", "exb_newview", "exb_evaluate", "exb_makenewz_prepare", "exb_core", "exb_makenewz",
     "exb_comm_unique_id", "exb_comm_init", "exb_read_clv", "exb_read_scaler",
-    "exb_read_sumtable", "exb_last_kernel_ms", "exb_launch_count", "exb_set_tile_sites",
+    "exb_read_sumtable", "exb_last_kernel_ms", "exb_launch_count", "exb_set_tile_sites", "exb_set_timing",
 ]
 UNIQUE_ID_BYTES = 128
 

@@ -117,6 +117,7 @@ static void backend_init(tree *tr)
       backend_fail("exb_set_partition");
   }
   if (exb_commit(g_engine) != EXB_OK) backend_fail("exb_commit");
+  exb_set_timing(g_engine, 0);
   backend_comm_init();
   g_entries = (exb_entry *)malloc(slots * sizeof(exb_entry));
   g_qz = (double *)malloc(slots * nb * sizeof(double));

@@ -33,12 +33,39 @@ finish_kernel(const FinishArgs a)
   for (int part = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; part < a.nparts; part += warps) {
     const bool exec = a.mask[part] && a.part_has_sites[part];
     unsigned int *gs = a.gs + (size_t)part * 2 * a.mxtips;
-    if (exec && lane == 0) {
-      for (int e = a.first; e < a.count; e++) {
-        const DevEntry en = a.entries[e];
-        unsigned int *inc = &a.scale_inc[(size_t)e * a.nparts + part];
-        gs[en.p] = gs[en.q] + gs[en.r] + *inc;
-        *inc = 0;
+    if (exec && a.count > a.first) {
+      if (a.gs_in_smem) {
+        // the chain is sequential in the entries; run it in shared memory (one global round trip per entry would
+        // cost ~0.4 us each: 80 us for a 200-taxon full traversal)
+        extern __shared__ unsigned int gsm[];
+        unsigned int *row = gsm + (size_t)(threadIdx.x >> 5) * 2 * a.mxtips;
+        for (int i = lane; i < 2 * a.mxtips; i += 32) row[i] = gs[i];
+        __syncwarp();
+        for (int e0 = a.first; e0 < a.count; e0 += 32) {
+          const int e = e0 + lane;
+          unsigned int inc = 0; DevEntry en = {0, 0, 0, 0};
+          if (e < a.count) {
+            en = a.entries[e];
+            inc = a.scale_inc[(size_t)e * a.nparts + part];
+            if (inc) a.scale_inc[(size_t)e * a.nparts + part] = 0;
+          }
+          const int n = min(32, a.count - e0);
+          for (int j = 0; j < n; j++) {               // lane j's entry, in order
+            const int pj = __shfl_sync(0xffffffffu, en.p, j), qj = __shfl_sync(0xffffffffu, en.q, j),
+                      rj = __shfl_sync(0xffffffffu, en.r, j);
+            const unsigned int ij = __shfl_sync(0xffffffffu, inc, j);
+            if (lane == 0) row[pj] = row[qj] + row[rj] + ij;
+            __syncwarp();
+          }
+        }
+        for (int i = lane; i < 2 * a.mxtips; i += 32) gs[i] = row[i];
+      } else if (lane == 0) {
+        for (int e = a.first; e < a.count; e++) {
+          const DevEntry en = a.entries[e];
+          unsigned int *inc = &a.scale_inc[(size_t)e * a.nparts + part];
+          gs[en.p] = gs[en.q] + gs[en.r] + *inc;
+          *inc = 0;
+        }
       }
     }
     __syncwarp();
@@ -61,20 +88,38 @@ finish_kernel(const FinishArgs a)
           s0 += (double)(gs[br.p] + gs[br.q]) * a.log_minlikelihood;
         }
         a.out[part] = s0;
+        if (a.out_host) a.out_host[part] = s0;
       } else {           // MODE_CORE
         a.out[part] = s0;
         a.out[a.nparts + part] = s1;
+        if (a.out_host) { a.out_host[part] = s0; a.out_host[a.nparts + part] = s1; }
+      }
+    }
+  }
+  if (a.done_flag_host) {
+    // the last block to arrive publishes the completion flag after everybody's results are visible to the host
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int t = atomicAdd(a.ticket, 1u);
+      if (t == gridDim.x - 1) {
+        *a.ticket = 0;
+        __threadfence_system();
+        *a.done_flag_host = a.seq;
       }
     }
   }
 }
 
-void launch_finish(const FinishArgs &a, cudaStream_t s)
+void launch_finish(const FinishArgs &a0, cudaStream_t s)
 {
+  FinishArgs a = a0;
   int blocks = (a.nparts + 3) / 4;
   if (blocks > 592) blocks = 592;
   if (blocks < 1) blocks = 1;
-  finish_kernel<<<blocks, 128, 0, s>>>(a);
+  const size_t smem = (size_t)4 * 2 * a.mxtips * sizeof(unsigned int);      // one scaler row per warp
+  a.gs_in_smem = smem <= 48 * 1024;
+  finish_kernel<<<blocks, 128, a.gs_in_smem ? smem : 0, s>>>(a);
 }
 
 }  // namespace exb
@@ -187,6 +232,12 @@ struct exb_engine {
   double *out_d = nullptr, *out_h = nullptr;     // [2*P]
   long launches = 0;
   float last_ms = 0.f;
+  bool timing = true;                    // CUDA events around the kernels of every call (exb_last_kernel_ms)
+  unsigned int *ticket = nullptr;        // finish-kernel arrival counter
+  volatile unsigned int *done_flag = nullptr;   // pinned, written by the finish kernel on the single-rank path
+  unsigned int seq = 0;
+  unsigned char *stage_use = nullptr;    // what the kernels of the current call read: stage_d, or stage_h (zero copy)
+  int total_tiles = 0;
   ncclComm_t comm = nullptr;
   int nranks = 1;
   // device-resident Newton-Raphson
@@ -243,6 +294,7 @@ extern "C" void exb_destroy(exb_engine *e)
   cudaFree(e->part_has_sites); cudaFree(e->part_tile_begin); cudaFree(e->part_tile_count); cudaFree(e->part_cls);
   cudaFree(e->gs); cudaFree(e->scale_inc); cudaFree(e->out_d); cudaFreeHost(e->out_h);
   cudaFree(e->nr_state_d); cudaFreeHost(e->nr_state_h); cudaFree(e->nr_barrier); cudaFree(e->nr_mask);
+  cudaFree(e->ticket); cudaFreeHost((void *)e->done_flag);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -380,6 +432,11 @@ extern "C" int exb_commit(exb_engine *e)
   CUDA_TRY(cudaMemset(e->out_d, 0, (size_t)2 * e->P * sizeof(double)));
   CUDA_TRY(cudaMallocHost(&e->out_h, (size_t)2 * e->P * sizeof(double)));
 
+  CUDA_TRY(cudaMalloc(&e->ticket, sizeof(unsigned int)));
+  CUDA_TRY(cudaMemset(e->ticket, 0, sizeof(unsigned int)));
+  CUDA_TRY(cudaMallocHost((void **)&e->done_flag, sizeof(unsigned int)));
+  *e->done_flag = 0;
+  e->total_tiles = (int)(e->cls[0].tiles_h.size() + e->cls[1].tiles_h.size());
   CUDA_TRY(cudaMalloc(&e->nr_state_d, sizeof(NrState)));
   CUDA_TRY(cudaMallocHost(&e->nr_state_h, sizeof(NrState)));
   CUDA_TRY(cudaMalloc(&e->nr_barrier, sizeof(unsigned int)));
@@ -446,6 +503,9 @@ static int check_models(exb_engine *e, const unsigned char *mask)
   return EXB_OK;
 }
 
+struct exb_engine;
+static void set_finish_outputs(exb_engine *e, FinishArgs &f);
+
 // Validate and stage a traversal descriptor; one H2D copy.
 static int stage_traversal(exb_engine *e, const exb_entry *ti, int count, int first, const double *qz, const double *rz,
                            const unsigned char *mask)
@@ -483,6 +543,9 @@ static int stage_traversal(exb_engine *e, const exb_entry *ti, int count, int fi
   }
   unsigned char *mk = e->stage_h + e->off_mask;
   for (int m = 0; m < e->P; m++) mk[m] = mask ? (mask[m] != 0) : 1;
+  // (Reading the descriptor zero-copy from the pinned area was measured slower: three kernels each pay the PCIe
+  //  round trip on their critical path; one small async copy is cheaper.)
+  e->stage_use = e->stage_d;
   CUDA_TRY(cudaMemcpyAsync(e->stage_d, e->stage_h, e->stage_bytes, cudaMemcpyHostToDevice, e->stream));
   return EXB_OK;
 }
@@ -500,13 +563,13 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   if (rc) return rc;
   rc = flush_models(e);
   if (rc) return rc;
-  CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+  if (e->timing) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
   for (int c = 0; c < 2; c++) {
     ClassState &k = e->cls[c];
     if (k.tiles_h.empty()) continue;
     DtabArgs d;
     d.dtab = k.dtab; d.models = k.models; d.cls_part_global = k.part_global;
-    d.lzq = (const double *)(e->stage_d + e->off_lzq); d.lzr = (const double *)(e->stage_d + e->off_lzr);
+    d.lzq = (const double *)(e->stage_use + e->off_lzq); d.lzr = (const double *)(e->stage_use + e->off_lzr);
     d.count = count; d.nparts_cls = k.nparts; d.nbranches = e->nb; d.states = k.S;
     d.model_doubles = k.model_doubles; d.row = k.dtab_row;
     launch_dtab(d, e->stream);
@@ -514,7 +577,7 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
     if (k.lut) {
       LutArgs l;
       l.lut = k.lut; l.models = k.models; l.dtab = k.dtab;
-      l.entries = (const DevEntry *)(e->stage_d + e->off_entries);
+      l.entries = (const DevEntry *)(e->stage_use + e->off_entries);
       l.count = count; l.first = first; l.nparts_cls = k.nparts;
       launch_aa_lut(l, e->stream);
       e->launches++;
@@ -523,10 +586,10 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
     a.dtab = k.dtab; a.lut = k.lut; a.nparts_cls = k.nparts; a.tile_sites = e->tile_sites;
     a.tiles = k.tiles; a.clv = k.clv; a.tips = k.tips; a.wgt = k.wgt; a.sum = k.sum; a.models = k.models;
     a.N = k.N; a.mxtips = e->mxtips; a.nparts = e->P; a.nbranches = e->nb;
-    a.entries = (const DevEntry *)(e->stage_d + e->off_entries);
-    a.lzq = (const double *)(e->stage_d + e->off_lzq);
-    a.lzr = (const double *)(e->stage_d + e->off_lzr);
-    a.mask = e->stage_d + e->off_mask;
+    a.entries = (const DevEntry *)(e->stage_use + e->off_entries);
+    a.lzq = (const double *)(e->stage_use + e->off_lzq);
+    a.lzr = (const double *)(e->stage_use + e->off_lzr);
+    a.mask = e->stage_use + e->off_mask;
     a.count = count; a.first = first; a.mode = mode;
     a.scale_inc = e->scale_inc; a.tile_out = k.tile_out;
     if (c == CLS_DNA && k.nparts <= kMaxParamPartitions) {
@@ -551,30 +614,59 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   }
   FinishArgs f;
   f.gs = e->gs; f.scale_inc = e->scale_inc;
-  f.entries = (const DevEntry *)(e->stage_d + e->off_entries);
+  f.entries = (const DevEntry *)(e->stage_use + e->off_entries);
   f.count = count; f.first = first; f.mxtips = e->mxtips; f.nparts = e->P;
-  f.mask = e->stage_d + e->off_mask; f.part_has_sites = e->part_has_sites;
+  f.mask = e->stage_use + e->off_mask; f.part_has_sites = e->part_has_sites;
   f.tile_out[0] = e->cls[0].tile_out; f.tile_out[1] = e->cls[1].tile_out;
   f.part_tile_begin = e->part_tile_begin; f.part_tile_count = e->part_tile_count; f.part_cls = e->part_cls;
   f.mode = mode; f.log_minlikelihood = log(kMinLikelihood); f.out = e->out_d;
+  set_finish_outputs(e, f);
   launch_finish(f, e->stream);
   e->launches++;
-  CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+  if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
   CUDA_TRY(cudaGetLastError());
+  return EXB_OK;
+}
+
+// Single rank: the finish kernel writes results and a completion flag into pinned host memory; the host polls.
+static void set_finish_outputs(exb_engine *e, FinishArgs &f)
+{
+  f.ticket = e->ticket;
+  if (e->comm) { f.out_host = nullptr; f.done_flag_host = nullptr; f.seq = 0; return; }
+  e->seq += 1;
+  f.out_host = e->out_h; f.done_flag_host = e->done_flag; f.seq = e->seq;
+}
+
+static int wait_done(exb_engine *e)
+{
+  if (e->comm) { CUDA_TRY(cudaStreamSynchronize(e->stream)); }
+  else {
+    unsigned long spins = 0;
+    while (*e->done_flag != e->seq) {
+      if ((++spins & 0xFFFF) == 0) {                 // a faulting kernel must not hang the host
+        const cudaError_t q = cudaStreamQuery(e->stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady)
+          return fail(EXB_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(q));
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
+  if (e->timing) { CUDA_TRY(cudaEventSynchronize(e->ev1)); cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1); }
   return EXB_OK;
 }
 
 // all-reduce (if a communicator exists), copy n doubles of out_d to the pinned mirror, wait.
 static int collect(exb_engine *e, size_t n)
 {
+  if (!e->comm) return wait_done(e);                 // results already sit in out_h
   if (e->comm) {
     const int r = g_nccl.AllReduce(e->out_d, e->out_d, n, kNcclFloat64, kNcclSum, e->comm, e->stream);
     if (r != 0) return fail(EXB_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   }
   if (n) CUDA_TRY(cudaMemcpyAsync(e->out_h, e->out_d, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-  CUDA_TRY(cudaStreamSynchronize(e->stream));
-  cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
-  return EXB_OK;
+  return wait_done(e);
 }
 
 extern "C" int exb_newview(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
@@ -583,9 +675,7 @@ extern "C" int exb_newview(exb_engine *e, const exb_entry *ti, int count, const 
   if (count == 0) return EXB_OK;
   int rc = run_traversal(e, ti, count, 0, qz, rz, executeModel, MODE_NEWVIEW);
   if (rc) return rc;
-  CUDA_TRY(cudaStreamSynchronize(e->stream));     // the staging buffers are reused by the next call
-  cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
-  return EXB_OK;
+  return wait_done(e);                            // the staging buffers are reused by the next call
 }
 
 extern "C" int exb_evaluate(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
@@ -622,6 +712,7 @@ extern "C" int exb_core(exb_engine *e, const double *lz, const unsigned char *ex
   unsigned char *mk = e->stage_h + e->off_mask;
   for (int m = 0; m < e->P; m++) mk[m] = executeModel ? (executeModel[m] != 0) : 1;
   // core-lz and mask are adjacent at the tail of the staging area: one small copy
+  e->stage_use = e->stage_d;
   CUDA_TRY(cudaMemcpyAsync(e->stage_d + e->off_corelz, e->stage_h + e->off_corelz, e->stage_bytes - e->off_corelz,
                            cudaMemcpyHostToDevice, e->stream));
   int rc = flush_models(e);
@@ -632,23 +723,24 @@ extern "C" int exb_core(exb_engine *e, const double *lz, const unsigned char *ex
     if (k.tiles_h.empty()) continue;
     CoreArgs a;
     a.tiles = k.tiles; a.sum = k.sum; a.wgt = k.wgt; a.models = k.models;
-    a.lz = (const double *)(e->stage_d + e->off_corelz);
-    a.mask = e->stage_d + e->off_mask; a.nbranches = e->nb; a.tile_out = k.tile_out;
+    a.lz = (const double *)(e->stage_use + e->off_corelz);
+    a.mask = e->stage_use + e->off_mask; a.nbranches = e->nb; a.tile_out = k.tile_out;
     if (c == CLS_DNA) launch_core_dna(a, (int)k.tiles_h.size(), e->stream);
     else              launch_core_aa(a, (int)k.tiles_h.size(), e->stream);
     e->launches++;
   }
   FinishArgs f;
   memset(&f, 0, sizeof f);
-  f.gs = e->gs; f.scale_inc = e->scale_inc; f.entries = (const DevEntry *)(e->stage_d + e->off_entries);
+  f.gs = e->gs; f.scale_inc = e->scale_inc; f.entries = (const DevEntry *)(e->stage_use + e->off_entries);
   f.count = 0; f.first = 0; f.mxtips = e->mxtips; f.nparts = e->P;
-  f.mask = e->stage_d + e->off_mask; f.part_has_sites = e->part_has_sites;
+  f.mask = e->stage_use + e->off_mask; f.part_has_sites = e->part_has_sites;
   f.tile_out[0] = e->cls[0].tile_out; f.tile_out[1] = e->cls[1].tile_out;
   f.part_tile_begin = e->part_tile_begin; f.part_tile_count = e->part_tile_count; f.part_cls = e->part_cls;
   f.mode = MODE_CORE; f.log_minlikelihood = 0.0; f.out = e->out_d;
+  set_finish_outputs(e, f);
   launch_finish(f, e->stream);
   e->launches++;
-  CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+  if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
   CUDA_TRY(cudaGetLastError());
   rc = collect(e, (size_t)2 * e->P);
   if (rc) return rc;
@@ -680,7 +772,7 @@ extern "C" int exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const
   memset(h, 0, sizeof *h);
   for (int b = 0; b < e->nb; b++) { h->z[b] = z0[b]; h->z0[b] = z0[b]; h->budget[b] = maxiter; h->done[b] = 0; h->curvatOK[b] = 1; }
   CUDA_TRY(cudaMemcpyAsync(e->nr_state_d, h, sizeof *h, cudaMemcpyHostToDevice, e->stream));
-  CUDA_TRY(cudaMemcpyAsync(e->nr_mask, e->stage_d + e->off_mask, (size_t)e->P, cudaMemcpyDeviceToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->nr_mask, e->stage_h + e->off_mask, (size_t)e->P, cudaMemcpyHostToDevice, e->stream));
   CUDA_TRY(cudaMemsetAsync(e->nr_barrier, 0, sizeof(unsigned int), e->stream));
   NrArgs a;
   memset(&a, 0, sizeof a);
@@ -699,10 +791,10 @@ extern "C" int exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const
   const int lr = launch_newton_raphson(a, blocks, e->stream);
   if (lr != 0) return fail(EXB_ERR_CUDA, "cooperative launch of the Newton-Raphson kernel failed: %s", cudaGetErrorString((cudaError_t)lr));
   e->launches++;
-  CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+  if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
   CUDA_TRY(cudaMemcpyAsync(h, e->nr_state_d, sizeof *h, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
-  cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
+  if (e->timing) cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
   for (int b = 0; b < e->nb; b++) {
     result[b] = h->z[b];
     if (curvatOK) curvatOK[b] = h->curvatOK[b];
@@ -784,3 +876,10 @@ extern "C" int exb_last_kernel_ms(exb_engine *e, float *ms)
 }
 
 extern "C" long exb_launch_count(exb_engine *e) { return e ? e->launches : 0; }
+
+extern "C" int exb_set_timing(exb_engine *e, int on)
+{
+  if (!e) return fail(EXB_ERR_ARG, "exb_set_timing: null engine");
+  e->timing = on != 0;
+  return EXB_OK;
+}

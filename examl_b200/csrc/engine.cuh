@@ -110,6 +110,12 @@ struct FinishArgs {
   int           mode;
   double        log_minlikelihood;
   double       *out;              // evaluate: [P]; core: [2][P]
+  // single-rank fast path: results and a completion flag go straight to host-mapped pinned memory
+  double       *out_host;         // may be null
+  volatile unsigned int *done_flag_host;   // may be null
+  unsigned int *ticket;           // block arrival counter (self-resetting)
+  unsigned int  seq;              // value to publish in *done_flag_host
+  int           gs_in_smem;       // scaler chain staged in shared memory (set by launch_finish)
 };
 
 // AA tip look-up table: what precomputeTips / umpX do in the reference (avxLikelihood.c:1353-1389, mic_native_aa.c:97)

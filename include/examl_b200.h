@@ -162,6 +162,8 @@ int  exb_read_sumtable(exb_engine *e, int model, double *out);
 /* Device time in milliseconds of the kernels of the most recent hot-path call (CUDA events
  * on the engine's stream), and the number of kernel launches the engine has made so far. */
 int  exb_last_kernel_ms(exb_engine *e, float *ms);
+/* Switch the per-call CUDA events off (default on); saves two driver calls per hot-path call. */
+int  exb_set_timing(exb_engine *e, int on);
 long exb_launch_count(exb_engine *e);
 /* Tuning knob: sites per work tile (multiple of 32).  Must be set before exb_commit. */
 int  exb_set_tile_sites(exb_engine *e, int sites);
