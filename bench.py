@@ -305,6 +305,13 @@ def main():
         n_local = upper - lower
         abytes = algorithmic_bytes(ti, n_local, states)
         achieved = abytes / (dev_s / args.steps) / 1e9
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{sites}x{taxa}")
+            if tj and world == 1:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": metric, "value": updates / dev_s / 1e6, "unit": "M site-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -320,8 +327,8 @@ def main():
                     "note": "exb_set_model + exb_evaluate with host buffers each step (new descriptor, new model "
                             "constants in, lnL out); alignment resident since start-up like the reference's readMyData"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "traverse_%s_kernel" % args.workload,
+            "roofline": {"bound": "hbm" if states == 4 else "tensor(fp64 DMMA)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "traverse_%s_kernel" % args.workload,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
                          "algorithmic_bytes_per_launch": abytes},
             "clocks": clocks,

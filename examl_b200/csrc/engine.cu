@@ -23,23 +23,21 @@ namespace exb {
 // finish kernel: (1) scaler bookkeeping globalScaler[p] = globalScaler[q] + globalScaler[r] + increment
 // (newviewGenericSpecial.c:1503-1506) for every newview entry in order; (2) deterministic reduction of
 // the per-tile partial sums of each partition; (3) evaluate only: undo the scaling,
-// + (gs[p] + gs[q]) * log(minlikelihood) (evaluateGenericSpecial.c:830).  One warp per partition.
+// + (gs[p] + gs[q]) * log(minlikelihood) (evaluateGenericSpecial.c:830).  One block per partition.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 finish_kernel(const FinishArgs a)
 {
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int part = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; part < a.nparts; part += warps) {
+  extern __shared__ unsigned int gsm[];            // one scaler row (2*mxtips) when it fits
+  __shared__ double red0[4], red1[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int part = blockIdx.x; part < a.nparts; part += gridDim.x) {
     const bool exec = a.mask[part] && a.part_has_sites[part];
     unsigned int *gs = a.gs + (size_t)part * 2 * a.mxtips;
-    if (exec && a.count > a.first) {
+    // ---- (1) scaler chain, sequential in the entries: warp 0, in shared memory when the row fits ----
+    if (exec && a.count > a.first && warp == 0) {
       if (a.gs_in_smem) {
-        // the chain is sequential in the entries; run it in shared memory (one global round trip per entry would
-        // cost ~0.4 us each: 80 us for a 200-taxon full traversal)
-        extern __shared__ unsigned int gsm[];
-        unsigned int *row = gsm + (size_t)(threadIdx.x >> 5) * 2 * a.mxtips;
-        for (int i = lane; i < 2 * a.mxtips; i += 32) row[i] = gs[i];
+        for (int i = lane; i < 2 * a.mxtips; i += 32) gsm[i] = gs[i];
         __syncwarp();
         for (int e0 = a.first; e0 < a.count; e0 += 32) {
           const int e = e0 + lane;
@@ -54,11 +52,11 @@ finish_kernel(const FinishArgs a)
             const int pj = __shfl_sync(0xffffffffu, en.p, j), qj = __shfl_sync(0xffffffffu, en.q, j),
                       rj = __shfl_sync(0xffffffffu, en.r, j);
             const unsigned int ij = __shfl_sync(0xffffffffu, inc, j);
-            if (lane == 0) row[pj] = row[qj] + row[rj] + ij;
+            if (lane == 0) gsm[pj] = gsm[qj] + gsm[rj] + ij;
             __syncwarp();
           }
         }
-        for (int i = lane; i < 2 * a.mxtips; i += 32) gs[i] = row[i];
+        for (int i = lane; i < 2 * a.mxtips; i += 32) gs[i] = gsm[i];
       } else if (lane == 0) {
         for (int e = a.first; e < a.count; e++) {
           const DevEntry en = a.entries[e];
@@ -68,24 +66,35 @@ finish_kernel(const FinishArgs a)
         }
       }
     }
-    __syncwarp();
+    __syncthreads();                                 // gs[] of this partition is final; red[] is free
     if (a.mode == MODE_NEWVIEW || a.mode == MODE_SUM) continue;
+    // ---- (2) tile partials -> partition, fixed order: thread-strided sums (loads in flight), warp tree, 4 warps ----
     double s0 = 0.0, s1 = 0.0;
     if (exec) {
-      const double *to = (a.part_cls[part] ? a.tile_out[1] : a.tile_out[0]) + 2 * (size_t)a.part_tile_begin[part];
+      const double2 *to = reinterpret_cast<const double2 *>((a.part_cls[part] ? a.tile_out[1] : a.tile_out[0]) +
+                                                             2 * (size_t)a.part_tile_begin[part]);
       const int n = a.part_tile_count[part];
-      for (int t = lane; t < n; t += 32) { s0 += to[2 * t]; s1 += to[2 * t + 1]; }
+      int t = tid;
+      for (; t + 3 * 128 < n; t += 4 * 128) {
+        const double2 v0 = to[t], v1 = to[t + 128], v2 = to[t + 256], v3 = to[t + 384];
+        s0 += v0.x; s1 += v0.y; s0 += v1.x; s1 += v1.y; s0 += v2.x; s1 += v2.y; s0 += v3.x; s1 += v3.y;
+      }
+      for (; t < n; t += 128) { const double2 v = to[t]; s0 += v.x; s1 += v.y; }
       #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         s0 += __shfl_down_sync(0xffffffffu, s0, o);
         s1 += __shfl_down_sync(0xffffffffu, s1, o);
       }
     }
-    if (lane == 0) {
+    if (lane == 0) { red0[warp] = s0; red1[warp] = s1; }
+    __syncthreads();
+    if (tid == 0) {
+      s0 = ((red0[0] + red0[1]) + (red0[2] + red0[3]));
+      s1 = ((red1[0] + red1[1]) + (red1[2] + red1[3]));
       if (a.mode == MODE_EVALUATE) {
         if (exec) {
           const DevEntry br = a.entries[0];
-          s0 += (double)(gs[br.p] + gs[br.q]) * a.log_minlikelihood;
+          s0 += (double)(gs[br.p] + gs[br.q]) * a.log_minlikelihood;   // evaluateGenericSpecial.c:830
         }
         a.out[part] = s0;
         if (a.out_host) a.out_host[part] = s0;
@@ -95,12 +104,13 @@ finish_kernel(const FinishArgs a)
         if (a.out_host) { a.out_host[part] = s0; a.out_host[a.nparts + part] = s1; }
       }
     }
+    __syncthreads();
   }
   if (a.done_flag_host) {
     // the last block to arrive publishes the completion flag after everybody's results are visible to the host
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       const unsigned int t = atomicAdd(a.ticket, 1u);
       if (t == gridDim.x - 1) {
         *a.ticket = 0;
@@ -114,11 +124,11 @@ finish_kernel(const FinishArgs a)
 void launch_finish(const FinishArgs &a0, cudaStream_t s)
 {
   FinishArgs a = a0;
-  int blocks = (a.nparts + 3) / 4;
+  int blocks = a.nparts;                           // one block per partition, grid-stride beyond 592
   if (blocks > 592) blocks = 592;
   if (blocks < 1) blocks = 1;
-  const size_t smem = (size_t)4 * 2 * a.mxtips * sizeof(unsigned int);      // one scaler row per warp
-  a.gs_in_smem = smem <= 48 * 1024;
+  const size_t smem = (size_t)2 * a.mxtips * sizeof(unsigned int);          // one scaler row per block
+  a.gs_in_smem = smem <= 40 * 1024;
   finish_kernel<<<blocks, 128, a.gs_in_smem ? smem : 0, s>>>(a);
 }
 

@@ -84,23 +84,27 @@ newton_raphson_kernel(const NrArgs a)
     }
     grid_barrier(a.barrier, gen);
 
-    // ---- block 0: tile partials -> partitions (fixed order), partitions -> slots, NR update ----
-    if (blockIdx.x == 0) {
-      for (int part = warp; part < P; part += kThreads / 32) {
-        double s0 = 0.0, s1 = 0.0;
-        if (a.mask[part] && a.part_has_sites[part]) {
-          const double *to = a.tile_out[a.part_cls[part]] + 2 * (size_t)a.part_tile_begin[part];
-          const int n = a.part_tile_count[part];
-          for (int t = lane; t < n; t += 32) { s0 += to[2 * t]; s1 += to[2 * t + 1]; }
-          #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            s0 += __shfl_down_sync(0xffffffffu, s0, o);
-            s1 += __shfl_down_sync(0xffffffffu, s1, o);
-          }
+    // ---- tile partials -> partitions (fixed order); the partitions are spread over all CTAs ----
+    for (int part = blockIdx.x; part < P; part += gridDim.x) {
+      double s0 = 0.0, s1 = 0.0;
+      if (a.mask[part] && a.part_has_sites[part]) {
+        const double2 *to = reinterpret_cast<const double2 *>(a.tile_out[a.part_cls[part]] + 2 * (size_t)a.part_tile_begin[part]);
+        const int n = a.part_tile_count[part];
+        int t = tid;
+        for (; t + 3 * kThreads < n; t += 4 * kThreads) {
+          const double2 v0 = to[t], v1 = to[t + kThreads], v2 = to[t + 2 * kThreads], v3 = to[t + 3 * kThreads];
+          s0 += v0.x; s1 += v0.y; s0 += v1.x; s1 += v1.y; s0 += v2.x; s1 += v2.y; s0 += v3.x; s1 += v3.y;
         }
-        if (lane == 0) { a.part_out[part] = s0; a.part_out[P + part] = s1; }
+        for (; t < n; t += kThreads) { const double2 v = to[t]; s0 += v.x; s1 += v.y; }
       }
-      __syncthreads();
+      s0 = block_sum(s0, sh.red);
+      s1 = block_sum(s1, sh.red);
+      if (tid == 0) { a.part_out[part] = s0; a.part_out[P + part] = s1; }
+    }
+    grid_barrier(a.barrier, gen);
+
+    // ---- block 0: partitions -> slots, NR update ----
+    if (blockIdx.x == 0) {
       if (tid == 0) {
         // partitions -> slots in partition order (makenewzGenericSpecial.c:921-946)
         for (int i = 0; i < nb; i++) { st->d1[i] = 0.0; st->d2[i] = 0.0; }
