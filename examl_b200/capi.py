@@ -69,6 +69,15 @@ def pack_traversal(ti: Sequence[Entry], num_branches: int):
     return arr, qz, rz
 
 
+class PackedTraversal:
+    """A traversal descriptor already flattened to the C-ABI arrays (reusable across calls)."""
+    __slots__ = ("arr", "qz", "rz", "count")
+
+    def __init__(self, ti: Sequence[Entry], num_branches: int):
+        self.arr, self.qz, self.rz = pack_traversal(ti, num_branches)
+        self.count = len(ti)
+
+
 class Engine:
     """One likelihood engine (one GPU).  Method names follow the reference functions they replace."""
 
@@ -144,22 +153,25 @@ class Engine:
             return None
         return np.ascontiguousarray(np.asarray(execute_model, dtype=np.uint8).reshape(n))
 
-    def newviewIterative(self, ti: Sequence[Entry], execute_model=None) -> None:
-        arr, qz, rz = pack_traversal(ti, self.nbranches)
-        m = self._mask(execute_model, self.nparts)
-        self._check(self._f("newview")(self._h, arr, C.c_int(len(ti)), _dptr(qz), _dptr(rz), _dptr(m)))
+    def pack(self, ti) -> PackedTraversal:
+        return ti if isinstance(ti, PackedTraversal) else PackedTraversal(ti, self.nbranches)
 
-    def evaluateIterative(self, ti: Sequence[Entry], execute_model=None, out: Optional[np.ndarray] = None) -> np.ndarray:
-        arr, qz, rz = pack_traversal(ti, self.nbranches)
+    def newviewIterative(self, ti, execute_model=None) -> None:
+        t = self.pack(ti)
+        m = self._mask(execute_model, self.nparts)
+        self._check(self._f("newview")(self._h, t.arr, C.c_int(t.count), _dptr(t.qz), _dptr(t.rz), _dptr(m)))
+
+    def evaluateIterative(self, ti, execute_model=None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        t = self.pack(ti)
         m = self._mask(execute_model, self.nparts)
         lh = np.zeros(self.nparts) if out is None else out
-        self._check(self._f("evaluate")(self._h, arr, C.c_int(len(ti)), _dptr(qz), _dptr(rz), _dptr(m), _dptr(lh)))
+        self._check(self._f("evaluate")(self._h, t.arr, C.c_int(t.count), _dptr(t.qz), _dptr(t.rz), _dptr(m), _dptr(lh)))
         return lh
 
-    def makenewzIterative(self, ti: Sequence[Entry], execute_model=None) -> None:
-        arr, qz, rz = pack_traversal(ti, self.nbranches)
+    def makenewzIterative(self, ti, execute_model=None) -> None:
+        t = self.pack(ti)
         m = self._mask(execute_model, self.nparts)
-        self._check(self._f("makenewz_prepare")(self._h, arr, C.c_int(len(ti)), _dptr(qz), _dptr(rz), _dptr(m)))
+        self._check(self._f("makenewz_prepare")(self._h, t.arr, C.c_int(t.count), _dptr(t.qz), _dptr(t.rz), _dptr(m)))
 
     def execCore(self, lz: Sequence[float], execute_model=None):
         lzv = np.ascontiguousarray(np.asarray(lz, dtype=np.float64).reshape(self.nbranches))
@@ -171,13 +183,14 @@ class Engine:
 
     def makenewz(self, ti: Sequence[Entry], z0: Sequence[float], maxiter: int, execute_model=None):
         """topLevelMakenewz on the device (single rank): returns (z, curvatOK, iterations)."""
-        arr, qz, rz = pack_traversal(ti, self.nbranches)
+        t = self.pack(ti)
+        arr, qz, rz = t.arr, t.qz, t.rz
         m = self._mask(execute_model, self.nparts)
         z0v = np.ascontiguousarray(np.asarray(z0, dtype=np.float64).reshape(self.nbranches))
         res = np.zeros(self.nbranches)
         cok = np.zeros(self.nbranches, dtype=np.int32)
         it = C.c_int(0)
-        self._check(self._f("makenewz")(self._h, arr, C.c_int(len(ti)), _dptr(qz), _dptr(rz), _dptr(m), _dptr(z0v),
+        self._check(self._f("makenewz")(self._h, arr, C.c_int(t.count), _dptr(qz), _dptr(rz), _dptr(m), _dptr(z0v),
                                         C.c_int(maxiter), _dptr(res), _dptr(cok), C.byref(it)))
         return res, cok, int(it.value)
 
