@@ -23,6 +23,7 @@ EXPORTS = [
     "exb_set_model", "exb_newview", "exb_evaluate", "exb_makenewz_prepare", "exb_core", "exb_makenewz",
     "exb_comm_unique_id", "exb_comm_init", "exb_read_clv", "exb_read_scaler",
     "exb_read_sumtable", "exb_last_kernel_ms", "exb_launch_count", "exb_set_tile_sites", "exb_set_timing",
+    "exb_set_rate_model", "exb_set_categories",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -88,6 +89,7 @@ class Engine:
         self.mxtips, self.nparts, self.nbranches = mxtips, num_partitions, num_branches
         self.states = [0] * num_partitions
         self.widths = [0] * num_partitions
+        self.cat = False                  # CAT / PSR: one rate category per site (span = states)
         self._h = C.c_void_p()
         if prefix == "exb_":
             self._check(self._f("create")(C.byref(self._h), C.c_int(device), C.c_int(mxtips),
@@ -136,6 +138,18 @@ class Engine:
         self.states[model], self.widths[model] = states, width
         self._check(self._f("set_partition")(self._h, C.c_int(model), C.c_int(states), C.c_size_t(width),
                                              _dptr(wgt), _dptr(tips)))
+
+    def set_rate_model(self, rate_het_model: int, max_categories: int = 25) -> None:
+        """rateHetModel: 0 = CAT / PSR (one rate category per site), 1 = GAMMA (axml.h:349-350).  Before set_partition."""
+        self.cat = rate_het_model == 0
+        self._check(self._f("set_rate_model")(self._h, C.c_int(rate_het_model), C.c_int(max_categories)))
+
+    def set_categories(self, model: int, per_site_rates, rate_category) -> None:
+        """CAT / PSR: pInfo.perSiteRates[numberOfCategories], pInfo.rateCategory[width]."""
+        r = np.ascontiguousarray(per_site_rates, dtype=np.float64)
+        rc = np.ascontiguousarray(rate_category, dtype=np.int32)
+        assert rc.shape[0] == self.widths[model]
+        self._check(self._f("set_categories")(self._h, C.c_int(model), C.c_int(r.shape[0]), _dptr(r), _dptr(rc)))
 
     def commit(self) -> None:
         if self.prefix == "exb_":
@@ -206,9 +220,10 @@ class Engine:
 
     # ---- introspection ------------------------------------------------------------------------
     def read_clv(self, model: int, node_number: int) -> np.ndarray:
-        out = np.zeros(self.widths[model] * 4 * self.states[model])
+        R = 1 if self.cat else 4
+        out = np.zeros(self.widths[model] * R * self.states[model])
         self._check(self._f("read_clv")(self._h, C.c_int(model), C.c_int(node_number), _dptr(out)))
-        return out.reshape(self.widths[model], 4, self.states[model])
+        return out.reshape(self.widths[model], R, self.states[model])
 
     def read_scaler(self, model: int, node_number: int) -> int:
         v = C.c_uint(0)
@@ -216,9 +231,10 @@ class Engine:
         return int(v.value)
 
     def read_sumtable(self, model: int) -> np.ndarray:
-        out = np.zeros(self.widths[model] * 4 * self.states[model])
+        R = 1 if self.cat else 4
+        out = np.zeros(self.widths[model] * R * self.states[model])
         self._check(self._f("read_sumtable")(self._h, C.c_int(model), _dptr(out)))
-        return out.reshape(self.widths[model], 4, self.states[model])
+        return out.reshape(self.widths[model], R, self.states[model])
 
     def last_kernel_ms(self) -> float:
         v = C.c_float(0)

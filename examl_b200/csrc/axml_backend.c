@@ -30,8 +30,9 @@
  * makenewzGenericSpecial.c:1241-1248) become one ncclAllReduce inside exb_evaluate / exb_core.
  *
  * Unsupported modes are refused loudly, the way the reference's MIC back-end does
- * (axml.c:2645-2657): PSR/CAT rate heterogeneity, the -S memory saving option, binary data and
- * LG4M/LG4X.  There is no CPU fallback.
+ * (axml.c:2645-2657): the -S memory saving option, binary data and LG4M/LG4X.  Both rate models are
+ * implemented: GAMMA and PSR/CAT (-m PSR; its per-site rate optimisation, evaluatePartialGeneric, stays the
+ * reference's host code).  There is no CPU fallback.
  */
 #include <assert.h>
 #include <math.h>
@@ -62,7 +63,7 @@ static void refuse(const char *why)
 {
   if (processID == 0)
     fprintf(stderr, "\nThe B200 back-end of ExaML does not implement %s.\n"
-                    "Supported: DNA and protein data under the GAMMA model of rate heterogeneity (with or without -M).\n\n", why);
+                    "Supported: DNA and protein data under the GAMMA and PSR models of rate heterogeneity (with or without -M).\n\n", why);
   MPI_Barrier(MPI_COMM_WORLD);
   MPI_Finalize();
   exit(-1);
@@ -102,7 +103,6 @@ static void backend_init(tree *tr)
   int m;
   size_t nb = (size_t)tr->numBranches, slots = (size_t)tr->mxtips + 1;
 
-  if (tr->rateHetModel == CAT) refuse("the PSR (CAT) model of rate heterogeneity (-m PSR)");
   if (tr->saveMemory) refuse("the memory saving option -S");
   for (m = 0; m < tr->NumberOfModels; m++) {
     const pInfo *p = &tr->partitionData[m];
@@ -111,6 +111,9 @@ static void backend_init(tree *tr)
   }
   if (exb_create(&g_engine, local_device(), tr->mxtips, tr->NumberOfModels, tr->numBranches) != EXB_OK)
     backend_fail("exb_create");
+  if (tr->rateHetModel == CAT) {                 /* -m PSR: one rate category per site */
+    if (exb_set_rate_model(g_engine, EXB_CAT, tr->maxCategories) != EXB_OK) backend_fail("exb_set_rate_model");
+  }
   for (m = 0; m < tr->NumberOfModels; m++) {
     const pInfo *p = &tr->partitionData[m];
     if (exb_set_partition(g_engine, m, p->states, p->width, p->wgt, p->yResource) != EXB_OK)
@@ -129,6 +132,8 @@ static void backend_init(tree *tr)
 /* The host may have rewritten the model constants at any time (optimizeModel.c:419-462 gives no
    notice); hand the current ones over before every launch.  exb_set_model compares and only
    uploads what changed. */
+static int g_categories_stale = 1;      /* PSR: per-site categories must be handed over (again) */
+
 static void backend_sync(tree *tr)
 {
   int m;
@@ -137,8 +142,15 @@ static void backend_sync(tree *tr)
     const pInfo *p = &tr->partitionData[m];
     if (exb_set_model(g_engine, m, p->EIGN, p->EV, p->EI, p->tipVector, p->gammaRates) != EXB_OK)
       backend_fail("exb_set_model");
+    /* PSR: rateCategory[] / perSiteRates[] are rewritten by optimizeRateCategories (optimizeModel.c:2403) and at
+       start-up / restart only, and each of those is followed by a full-traversal evaluateGeneric; comparing a
+       per-site array on every small call would cost more than the call, so it is done on full traversals. */
+    if (tr->rateHetModel == CAT && g_categories_stale &&
+        exb_set_categories(g_engine, m, p->numberOfCategories, p->perSiteRates, p->rateCategory) != EXB_OK)
+      backend_fail("exb_set_categories");
     g_mask[m] = tr->td[0].executeModel[m] ? 1 : 0;
   }
+  g_categories_stale = 0;
 }
 
 /* Flatten td[0].ti[first .. count) into the C-ABI form; returns the number of entries. */
@@ -288,6 +300,7 @@ void evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal)
 
   if (fullTraversal) {
     assert(isTip(p->number, tr->mxtips));
+    g_categories_stale = 1;
     computeTraversalInfo(q, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, FALSE);
   } else {
     if (!p->x) computeTraversalInfo(p, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);

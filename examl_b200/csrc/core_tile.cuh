@@ -64,4 +64,48 @@ __device__ __forceinline__ void core_tile(const Tile &tile, const double *sum, c
   out2 = block_sum(acc2, sh.red);
 }
 
+// CAT / PSR: one rate category per site (coreCAT_FLEX makenewzGenericSpecial.c:394-519).  Thread = site.
+//   d[cat][k] = exp((EIGN[k] lz) r_cat);  L = sum_k d s,  L' = sum_k d s EIGN[k],  L'' = sum_k d s EIGN[k]^2
+//   dlnL += (r w) L'/|L|,   d2lnL += (r^2 w) (L''/|L| - (L'/|L|)^2)
+struct CoreCatSmem { double d[64 * 20]; double red[32]; };
+
+template <int S>
+__device__ __forceinline__ void core_tile_cat(const Tile &tile, const double *sum, const int *wgt, const double *model,
+                                              const int *rate_cat, const double *rates, int max_cats,
+                                              double lz, CoreCatSmem &sh, double &out1, double &out2)
+{
+  const int tid = threadIdx.x;
+  __syncthreads();
+  for (int i = tid; i < max_cats * S; i += blockDim.x) {
+    const int n = i / S, k = i % S;
+    sh.d[i] = k ? exp((model[k] * lz) * rates[n]) : 1.0;
+  }
+  __syncthreads();
+  double acc1 = 0.0, acc2 = 0.0;
+  for (unsigned i = tid; i < tile.nsites; i += blockDim.x) {
+    const size_t site = (size_t)tile.site0 + i;
+    const int cat = rate_cat[site];
+    const double *p = sum + site * S;
+    const double *d = sh.d + cat * S;
+    double L = 0.0, L1 = 0.0, L2 = 0.0;
+    #pragma unroll
+    for (int j = 0; j < S; j += 4) {
+      double s[4];
+      core_ld256(p + j, s);
+      #pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (j + k == 0) { L = s[0]; continue; }
+        const double ek = model[j + k], t = d[j + k] * s[k];
+        L += t; L1 += t * ek; L2 += t * (ek * ek);
+      }
+    }
+    const double inv = 1.0 / fabs(L), r = rates[cat], w = (double)wgt[site];
+    const double g = L1 * inv, h = L2 * inv;
+    acc1 += (r * w) * g;
+    acc2 += (r * r * w) * (h - g * g);
+  }
+  out1 = block_sum(acc1, sh.red);
+  out2 = block_sum(acc2, sh.red);
+}
+
 }  // namespace exb

@@ -206,6 +206,11 @@ struct HostPart {
   std::vector<unsigned char> y;        // [mxtips][width], dropped after commit
   std::vector<double> model;           // host cache of the uploaded constants
   bool model_set = false;
+  // CAT / PSR
+  int ncat = 0;
+  std::vector<double> cat_rates;       // perSiteRates[ncat]
+  std::vector<int> rate_category;      // [width]
+  bool cats_set = false;
 };
 
 struct ClassState {
@@ -218,6 +223,8 @@ struct ClassState {
   uint8_t *tips = nullptr;
   int *wgt = nullptr, *part_global = nullptr;   // class-partition -> global partition
   int dtab_row = 0;
+  int *rate_cat = nullptr;             // CAT: [N] category of every site
+  double *cat_rates = nullptr;         // CAT: [nparts][max_cats]
   std::vector<double> models_h;
   std::vector<int> cp_tile_begin, cp_tile_count, cp_global;   // per class-partition: its run of tiles, global index
   int dirty_lo = 1 << 30, dirty_hi = -1;   // range of class-partitions whose constants must be re-uploaded
@@ -229,6 +236,8 @@ struct exb_engine {
   bool committed = false;
   std::vector<HostPart> parts;
   ClassState cls[2];
+  bool cat = false;                    // CAT / PSR: one rate category per site (span = S)
+  int max_cats = 4;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // per-call staging (pinned host + device mirror): entries | lzq | lzr | mask | lz(core)
@@ -299,6 +308,7 @@ extern "C" void exb_destroy(exb_engine *e)
     ClassState &k = e->cls[c];
     cudaFree(k.tiles); cudaFree(k.clv); cudaFree(k.sum); cudaFree(k.models); cudaFree(k.tile_out);
     cudaFree(k.tips); cudaFree(k.wgt); cudaFree(k.dtab); cudaFree(k.part_global); cudaFree(k.lut);
+    cudaFree(k.rate_cat); cudaFree(k.cat_rates);
   }
   cudaFree(e->stage_d); cudaFreeHost(e->stage_h);
   cudaFree(e->part_has_sites); cudaFree(e->part_tile_begin); cudaFree(e->part_tile_count); cudaFree(e->part_cls);
@@ -309,6 +319,56 @@ extern "C" void exb_destroy(exb_engine *e)
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
+}
+
+extern "C" int exb_set_rate_model(exb_engine *e, int rateHetModel, int maxCategories)
+{
+  if (!e || e->committed) return fail(EXB_ERR_STATE, "exb_set_rate_model: must be called before exb_commit");
+  for (const HostPart &p : e->parts)
+    if (p.defined) return fail(EXB_ERR_STATE, "exb_set_rate_model: must be called before exb_set_partition");
+  if (rateHetModel == 1) { e->cat = false; e->max_cats = 4; }
+  else if (rateHetModel == 0) {
+    if (maxCategories < 1 || maxCategories > 64) return fail(EXB_ERR_ARG, "exb_set_rate_model: %d rate categories (1..64 supported)", maxCategories);
+    e->cat = true; e->max_cats = maxCategories;
+  } else return fail(EXB_ERR_ARG, "exb_set_rate_model: rateHetModel %d is neither CAT (0) nor GAMMA (1)", rateHetModel);
+  for (int c = 0; c < 2; c++) {
+    ClassState &k = e->cls[c];
+    k.span = (e->cat ? 1 : 4) * k.S;
+    k.dtab_row = (e->cat ? e->max_cats : 4) * 2 * k.S;
+  }
+  return EXB_OK;
+}
+
+extern "C" int exb_set_categories(exb_engine *e, int model, int numberOfCategories, const double *perSiteRates, const int *rateCategory)
+{
+  if (!e || !e->committed) return fail(EXB_ERR_STATE, "exb_set_categories: call exb_commit first");
+  if (!e->cat) return fail(EXB_ERR_STATE, "exb_set_categories: the engine runs the GAMMA model (exb_set_rate_model)");
+  if (model < 0 || model >= e->P) return fail(EXB_ERR_ARG, "exb_set_categories: partition %d out of range", model);
+  if (numberOfCategories < 1 || numberOfCategories > e->max_cats)
+    return fail(EXB_ERR_ARG, "exb_set_categories: %d categories, engine was set up for at most %d", numberOfCategories, e->max_cats);
+  HostPart &p = e->parts[model];
+  ClassState &k = e->cls[p.cls];
+  for (size_t i = 0; i < p.width; i++)
+    if (rateCategory[i] < 0 || rateCategory[i] >= numberOfCategories)
+      return fail(EXB_ERR_ARG, "exb_set_categories: site %zu has category %d of %d", i, rateCategory[i], numberOfCategories);
+  const bool same_rates = p.cats_set && p.ncat == numberOfCategories &&
+                          memcmp(p.cat_rates.data(), perSiteRates, (size_t)numberOfCategories * sizeof(double)) == 0;
+  const bool same_cats = p.cats_set && (p.width == 0 || memcmp(p.rate_category.data(), rateCategory, p.width * sizeof(int)) == 0);
+  if (same_rates && same_cats) return EXB_OK;
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (!same_rates) {
+    p.ncat = numberOfCategories;
+    p.cat_rates.assign(e->max_cats, 0.0);
+    memcpy(p.cat_rates.data(), perSiteRates, (size_t)numberOfCategories * sizeof(double));
+    CUDA_TRY(cudaMemcpyAsync(k.cat_rates + (size_t)p.part_cls * e->max_cats, p.cat_rates.data(), (size_t)e->max_cats * sizeof(double),
+                             cudaMemcpyHostToDevice, e->stream));
+  }
+  if (!same_cats && p.width) {
+    p.rate_category.assign(rateCategory, rateCategory + p.width);
+    CUDA_TRY(cudaMemcpyAsync(k.rate_cat + p.site0, p.rate_category.data(), p.width * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  }
+  p.cats_set = true;
+  return EXB_OK;
 }
 
 extern "C" int exb_set_tile_sites(exb_engine *e, int sites)
@@ -361,7 +421,9 @@ extern "C" int exb_commit(exb_engine *e)
       has_sites[m] = p.width > 0;
       tbegin[m] = (int)k.tiles_h.size();
       // AA tiles are whole 96-site chunks (12 warps x 8 sites)
-      const size_t tsz = c == CLS_AA ? (size_t)((e->tile_sites + 95) / 96) * 96 : (size_t)e->tile_sites;
+      // (CAT: 384-site chunks, 12 warps x 32 sites)
+      const size_t aachunk = e->cat ? 384 : 96;
+      const size_t tsz = c == CLS_AA ? (size_t)((e->tile_sites + aachunk - 1) / aachunk) * aachunk : (size_t)e->tile_sites;
       for (size_t s = 0; s < p.width; s += tsz) {
         Tile t;
         t.site0 = (uint32_t)(n + s);
@@ -388,8 +450,12 @@ extern "C" int exb_commit(exb_engine *e)
       CUDA_TRY(cudaMemcpy(k.part_global, pg.data(), pg.size() * sizeof(int), cudaMemcpyHostToDevice));
       const size_t dbytes = (size_t)(e->mxtips + 1) * idx * k.dtab_row * sizeof(double);
       CUDA_TRY(cudaMalloc(&k.dtab, dbytes));
+      if (e->cat) {
+        CUDA_TRY(cudaMalloc(&k.cat_rates, (size_t)idx * e->max_cats * sizeof(double)));
+        CUDA_TRY(cudaMemset(k.cat_rates, 0, (size_t)idx * e->max_cats * sizeof(double)));
+      }
       // AA tip look-up table (optional: skipped when it would not fit comfortably, e.g. thousands of AA partitions)
-      const size_t lbytes = (size_t)(e->mxtips + 1) * idx * 2 * kAaLutRow * sizeof(double);
+      const size_t lbytes = (size_t)(e->mxtips + 1) * idx * 2 * 23 * 20 * (e->cat ? e->max_cats : 4) * sizeof(double);
       if (c == CLS_AA && lbytes <= ((size_t)1 << 30) && !getenv("EXB_AA_NO_LUT")) CUDA_TRY(cudaMalloc(&k.lut, lbytes));
     }
     if (n == 0) continue;
@@ -408,6 +474,10 @@ extern "C" int exb_commit(exb_engine *e)
     CUDA_TRY(cudaMemcpy(k.tips, tips.data(), tips.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&k.wgt, n * sizeof(int)));
     CUDA_TRY(cudaMemcpy(k.wgt, wgt.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    if (e->cat) {
+      CUDA_TRY(cudaMalloc(&k.rate_cat, n * sizeof(int)));
+      CUDA_TRY(cudaMemset(k.rate_cat, 0, n * sizeof(int)));
+    }
     const size_t clv_bytes = (size_t)(e->mxtips - 2) * n * k.span * sizeof(double);
     if (cudaMalloc(&k.clv, clv_bytes) != cudaSuccess) {
       cudaGetLastError();
@@ -510,6 +580,9 @@ static int check_models(exb_engine *e, const unsigned char *mask)
   for (int m = 0; m < e->P; m++)
     if ((!mask || mask[m]) && e->parts[m].width > 0 && !e->parts[m].model_set)
       return fail(EXB_ERR_STATE, "partition %d has no model constants (exb_set_model)", m);
+  for (int m = 0; m < e->P && e->cat; m++)
+    if ((!mask || mask[m]) && e->parts[m].width > 0 && !e->parts[m].cats_set)
+      return fail(EXB_ERR_STATE, "partition %d has no rate categories (exb_set_categories)", m);
   return EXB_OK;
 }
 
@@ -582,6 +655,7 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
     d.lzq = (const double *)(e->stage_use + e->off_lzq); d.lzr = (const double *)(e->stage_use + e->off_lzr);
     d.count = count; d.nparts_cls = k.nparts; d.nbranches = e->nb; d.states = k.S;
     d.model_doubles = k.model_doubles; d.row = k.dtab_row;
+    d.cat_rates = e->cat ? k.cat_rates : nullptr; d.max_cats = e->max_cats;
     launch_dtab(d, e->stream);
     e->launches++;
     if (k.lut) {
@@ -589,11 +663,13 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
       l.lut = k.lut; l.models = k.models; l.dtab = k.dtab;
       l.entries = (const DevEntry *)(e->stage_use + e->off_entries);
       l.count = count; l.first = first; l.nparts_cls = k.nparts;
+      l.ncat = e->cat ? e->max_cats : 4; l.dtab_row = k.dtab_row;
       launch_aa_lut(l, e->stream);
       e->launches++;
     }
     TraverseArgs a;
     a.dtab = k.dtab; a.lut = k.lut; a.nparts_cls = k.nparts; a.tile_sites = e->tile_sites;
+    a.rate_cat = e->cat ? k.rate_cat : nullptr; a.max_cats = e->max_cats; a.dtab_row = k.dtab_row;
     a.tiles = k.tiles; a.clv = k.clv; a.tips = k.tips; a.wgt = k.wgt; a.sum = k.sum; a.models = k.models;
     a.N = k.N; a.mxtips = e->mxtips; a.nparts = e->P; a.nbranches = e->nb;
     a.entries = (const DevEntry *)(e->stage_use + e->off_entries);
@@ -612,11 +688,13 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
         TraverseArgs ap = a;
         ap.tiles = k.tiles + k.cp_tile_begin[pc];
         ap.tile_out = k.tile_out + 2 * (size_t)k.cp_tile_begin[pc];
-        launch_traverse_dna(ap, &kc, k.cp_tile_count[pc], e->stream);
+        if (e->cat) launch_traverse_dna_cat(ap, &kc, k.cp_tile_count[pc], e->stream);
+        else        launch_traverse_dna(ap, &kc, k.cp_tile_count[pc], e->stream);
         if (pc) e->launches++;
       }
     } else if (c == CLS_DNA) {
-      launch_traverse_dna(a, nullptr, (int)k.tiles_h.size(), e->stream);   // many partitions: constants via shared memory
+      if (e->cat) launch_traverse_dna_cat(a, nullptr, (int)k.tiles_h.size(), e->stream);
+      else        launch_traverse_dna(a, nullptr, (int)k.tiles_h.size(), e->stream);   // many partitions: constants via shared memory
     } else {
       launch_traverse_aa(a, k.nparts == 1 ? k.models_h.data() : nullptr, (int)k.tiles_h.size(), e->stream);
     }
@@ -733,6 +811,7 @@ extern "C" int exb_core(exb_engine *e, const double *lz, const unsigned char *ex
     if (k.tiles_h.empty()) continue;
     CoreArgs a;
     a.tiles = k.tiles; a.sum = k.sum; a.wgt = k.wgt; a.models = k.models;
+    a.rate_cat = e->cat ? k.rate_cat : nullptr; a.cat_rates = k.cat_rates; a.max_cats = e->max_cats;
     a.lz = (const double *)(e->stage_use + e->off_corelz);
     a.mask = e->stage_use + e->off_mask; a.nbranches = e->nb; a.tile_out = k.tile_out;
     if (c == CLS_DNA) launch_core_dna(a, (int)k.tiles_h.size(), e->stream);
@@ -792,11 +871,12 @@ extern "C" int exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const
     ClassState &k = e->cls[c];
     a.tiles[c] = k.tiles; a.ntiles[c] = (int)k.tiles_h.size(); a.sum[c] = k.sum; a.wgt[c] = k.wgt;
     a.models[c] = k.models; a.tile_out[c] = k.tile_out;
+    a.rate_cat[c] = e->cat ? k.rate_cat : nullptr; a.cat_rates[c] = k.cat_rates;
     total_tiles += a.ntiles[c];
   }
   a.part_out = e->out_d;
   a.part_has_sites = e->part_has_sites; a.part_tile_begin = e->part_tile_begin; a.part_tile_count = e->part_tile_count;
-  a.part_cls = e->part_cls; a.nparts = e->P; a.nbranches = e->nb;
+  a.part_cls = e->part_cls; a.nparts = e->P; a.nbranches = e->nb; a.max_cats = e->max_cats;
   const int blocks = std::max(1, std::min(total_tiles, e->nr_max_blocks));
   const int lr = launch_newton_raphson(a, blocks, e->stream);
   if (lr != 0) return fail(EXB_ERR_CUDA, "cooperative launch of the Newton-Raphson kernel failed: %s", cudaGetErrorString((cudaError_t)lr));

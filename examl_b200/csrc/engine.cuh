@@ -41,12 +41,15 @@ struct DevEntry { int tipCase, p, q, r; };
 constexpr int kDnaDtabRow = 32;
 constexpr int kAaDtabRow  = 160;
 
+// CAT / PSR (one rate category per site, axml.h:349): the table has one [2 sides][S] block per category of the
+// partition, row = max_cats * 2 * S, and a site picks its block through rate_cat[site].
 struct DtabArgs {
   double       *dtab;        // [count][parts_in_class][row]
   const double *models;      // class models
   const int    *cls_part_global;   // [parts_in_class] -> global partition index (branch slot)
   const double *lzq, *lzr;   // [count][nbranches]
-  int count, nparts_cls, nbranches, states, model_doubles, row;
+  const double *cat_rates;   // CAT: [parts_in_class][max_cats] perSiteRates; null under GAMMA
+  int count, nparts_cls, nbranches, states, model_doubles, row, max_cats;
 };
 
 // Everything a traversal kernel needs.  Passed by value (fits the 4 KB parameter space).
@@ -73,7 +76,10 @@ struct TraverseArgs {
   unsigned int *scale_inc;  // [maxEntries][P]  per-entry scaler increments (integer atomics: deterministic)
   double       *tile_out;   // [ntiles][2]      per-tile partial sums (evaluate: lnL; core: d1,d2)
   const double *dtab;       // [count][nparts_cls][row]
-  const double *lut;        // AA only, may be null: [count][nparts_cls][2 sides][23 codes][4][20] = P(t) * tipVector[code]
+  const double *lut;        // AA only, may be null: [count][nparts_cls][2 sides][23 codes][4 | max_cats][20] = P(t) * tipVector[code]
+  const int    *rate_cat;   // CAT: [N] rate category of every site; null under GAMMA
+  int           max_cats;   // CAT: categories per partition in dtab / lut rows
+  int           dtab_row;   // doubles per (entry, partition) in dtab
   int           nparts_cls;
   int           tile_sites; // sites per tile (multiple of 32)
 };
@@ -87,6 +93,9 @@ struct CoreArgs {
   const double *sum;
   const int    *wgt;
   const double *models;
+  const int    *rate_cat;    // CAT: [N]; null under GAMMA
+  const double *cat_rates;   // CAT: [parts_in_class][max_cats]
+  int           max_cats;
   const double *lz;          // [nbranches] trial log z
   const unsigned char *mask;
   int           nbranches;
@@ -123,6 +132,8 @@ constexpr int kAaLutRow = 23 * 80;
 struct LutArgs {
   double *lut; const double *models; const double *dtab; const DevEntry *entries;
   int count, first, nparts_cls;
+  int ncat;        // categories per table row: 4 (GAMMA) or max_cats (CAT)
+  int dtab_row;
 };
 void launch_aa_lut(const LutArgs &a, cudaStream_t s);
 // ---- device-resident Newton-Raphson (kernels_nr.cu) ----
@@ -140,6 +151,7 @@ struct NrArgs {
   unsigned int *barrier;          // monotonic arrival counter (zeroed before the launch)
   const Tile *tiles[2]; int ntiles[2];
   const double *sum[2]; const int *wgt[2]; const double *models[2];
+  const int *rate_cat[2]; const double *cat_rates[2]; int max_cats;     // CAT (null / 0 under GAMMA)
   double *tile_out[2];
   double *part_out;               // [2][P]
   const int *part_has_sites, *part_tile_begin, *part_tile_count, *part_cls;
@@ -150,6 +162,7 @@ int newton_raphson_max_blocks(int device);
 
 void launch_dtab(const DtabArgs &a, cudaStream_t s);
 void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
+void launch_traverse_dna_cat(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
 void launch_core_dna(const CoreArgs &a, int ntiles, cudaStream_t s);
 void launch_traverse_aa(const TraverseArgs &a, const double *single_partition_model, int ntiles, cudaStream_t s);
 void launch_core_aa(const CoreArgs &a, int ntiles, cudaStream_t s);

@@ -28,7 +28,6 @@ namespace {
 constexpr int S = 20;
 constexpr int SPAN = 80;
 constexpr int kAaThreads = 384;  // 12 warps, one CTA per SM (the register budget of the DMMA pipeline)
-constexpr int TS = 96;           // sites per chunk: 8 per warp
 
 struct AaShared {
   double tip[460];        // tipVector[23 codes][20]
@@ -112,11 +111,11 @@ enum ChildMode : int { CH_MEM = 0, CH_CARRY = 1, CH_LUT = 2 };
 
 template <int MODE>
 __device__ __forceinline__ void child_y(double (&y)[3][2], const double (&carry)[4][3][2], const double (*fEI)[32],
-                                        const double *x, int xstride, const double *lutrow, const double *dside,
+                                        const double *x, const double *lutrow, const double *dside,
                                         int c, int lane, int tq)
 {
   if (MODE == CH_LUT) {
-    const double *r = lutrow + c * S + 2 * tq;
+    const double *r = lutrow + 2 * tq;
     #pragma unroll
     for (int t = 0; t < 3; t++) {
       double2 v = make_double2(0.0, 0.0);
@@ -134,8 +133,8 @@ __device__ __forceinline__ void child_y(double (&y)[3][2], const double (&carry)
       const double e0 = __shfl_sync(0xffffffffu, carry[c][s >> 1][0], sl);
       const double e1 = __shfl_sync(0xffffffffu, carry[c][s >> 1][1], sl);
       av[s] = (tq & 1) ? e1 : e0;
-    } else av[s] = x[c * xstride + k];
-    av[s] *= __ldg(dside + c * 40 + k);
+    } else av[s] = x[k];
+    av[s] *= __ldg(dside + k);
   }
   #pragma unroll
   for (int t = 0; t < 3; t++) y[t][0] = y[t][1] = 0.0;
@@ -145,16 +144,23 @@ __device__ __forceinline__ void child_y(double (&y)[3][2], const double (&carry)
     for (int t = 0; t < 3; t++) dmma(y[t][0], y[t][1], av[s], fEI[s * 3 + t][lane]);
 }
 
+// Per-slot operands of one entry.  A "slot" is a Gamma category of the warp's 8 sites (GAMMA) or one of the
+// warp's four 8-site groups (CAT / PSR, one category per site).
+struct AaSlots {
+  const double *xq[4], *xr[4];     // child vectors (memory mode): 20 doubles of my row
+  const double *lq[4], *lr[4];     // tip table rows (LUT mode): 20 doubles
+  const double *dq[4];             // exponentials of the q side; the r side follows at +20
+};
+
 template <int QM, int RM>
 __device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const double (*fEI)[32], const double (*fEV)[32],
-                                         const double *x1, int x1stride, const double *x2, int x2stride,
-                                         const double *lut1, const double *lut2, const double *drow, int lane, int tq)
+                                         const AaSlots &sl, int lane, int tq)
 {
   #pragma unroll
   for (int c = 0; c < 4; c++) {
     double y1[3][2], y2[3][2];
-    child_y<QM>(y1, carry, fEI, x1, x1stride, lut1, drow, c, lane, tq);
-    child_y<RM>(y2, carry, fEI, x2, x2stride, lut2, drow + S, c, lane, tq);
+    child_y<QM>(y1, carry, fEI, sl.xq[c], sl.lq[c], sl.dq[c], c, lane, tq);
+    child_y<RM>(y2, carry, fEI, sl.xr[c], sl.lr[c], sl.dq[c] + S, c, lane, tq);
     // Z = Y1 (.) Y2 in C layout, then X3 = Z * EV
     #pragma unroll
     for (int t = 0; t < 3; t++) { y1[t][0] *= y2[t][0]; y1[t][1] *= y2[t][1]; }
@@ -163,9 +169,9 @@ __device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const double 
     for (int t = 0; t < 3; t++) x3[t][0] = x3[t][1] = 0.0;
     #pragma unroll
     for (int s = 0; s < 5; s++) {
-      const int sl = (lane & ~3) | (((s & 1) << 1) | (tq >> 1));
-      const double e0 = __shfl_sync(0xffffffffu, y1[s >> 1][0], sl);
-      const double e1 = __shfl_sync(0xffffffffu, y1[s >> 1][1], sl);
+      const int sh_lane = (lane & ~3) | (((s & 1) << 1) | (tq >> 1));
+      const double e0 = __shfl_sync(0xffffffffu, y1[s >> 1][0], sh_lane);
+      const double e1 = __shfl_sync(0xffffffffu, y1[s >> 1][1], sh_lane);
       const double az = (tq & 1) ? e1 : e0;           // Z[g][4s+tq]
       #pragma unroll
       for (int t = 0; t < 3; t++) dmma(x3[t][0], x3[t][1], az, fEV[s * 3 + t][lane]);
@@ -190,14 +196,23 @@ __device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const double 
 // once, 16 B per thread.  Scaling (all 80 values of a site < 2^-256) is decided after the four
 // categories are done, from the 24 register values of the 4 lanes that share a site.
 // ------------------------------------------------------------------------------------------------------
+// CAT = false: GAMMA, slot = category, 8 sites per warp, 96 per chunk, CLV = 80 doubles per site.
+// CAT = true : PSR (newviewGTRCATPROT_AVX avxLikelihood.c:487-812, evaluateGTRCATPROT evaluateGenericSpecial.c:1308-1391):
+//              slot = one of four 8-site groups of the warp (32 sites per warp, 384 per chunk), CLV = 20 doubles per
+//              site, every row scales its A operand with the exponentials of ITS site's category; scaling and the
+//              log are per site.
+template <bool CAT>
 __global__ void __launch_bounds__(kAaThreads, 1)
 traverse_aa_kernel(const TraverseArgs a)
 {
+  constexpr int TSITES = CAT ? 384 : 96;       // sites per chunk = bytes per staged tip row
+  constexpr int XSPAN = CAT ? 20 : 80;         // doubles per site in a CLV
+  constexpr int XSLOT = CAT ? 8 * 20 : 20;     // distance between consecutive slots of my row in a CLV
   __shared__ AaShared sh;
   __shared__ __align__(8) uint64_t mbar;
   extern __shared__ __align__(16) unsigned char dyn[];
   SEntry *ents = reinterpret_cast<SEntry *>(dyn);
-  uint8_t *stips = dyn + (((size_t)a.count * sizeof(SEntry) + 15) & ~(size_t)15);   // [mxtips][TS]
+  uint8_t *stips = dyn + (((size_t)a.count * sizeof(SEntry) + 15) & ~(size_t)15);   // [mxtips][TSITES]
 
   const Tile tile = a.tiles[blockIdx.x];
   if (!a.mask[tile.part]) return;
@@ -221,23 +236,25 @@ traverse_aa_kernel(const TraverseArgs a)
       SEntry se;
       se.tipCase = en.tipCase;
       se.ptip_qtip = (en.p <= a.mxtips ? 1 : 0) | (en.q <= a.mxtips ? 2 : 0);
-      se.poff = en.p > a.mxtips ? (long long)(en.p - a.mxtips - 1) * (long long)N * SPAN : (long long)(en.p - 1) * TS;
-      se.qoff = en.q > a.mxtips ? (long long)(en.q - a.mxtips - 1) * (long long)N * SPAN : (long long)(en.q - 1) * TS;
-      se.roff = en.r > a.mxtips ? (long long)(en.r - a.mxtips - 1) * (long long)N * SPAN : (long long)(en.r - 1) * TS;
+      se.poff = en.p > a.mxtips ? (long long)(en.p - a.mxtips - 1) * (long long)N * XSPAN : (long long)(en.p - 1) * TSITES;
+      se.qoff = en.q > a.mxtips ? (long long)(en.q - a.mxtips - 1) * (long long)N * XSPAN : (long long)(en.q - 1) * TSITES;
+      se.roff = en.r > a.mxtips ? (long long)(en.r - a.mxtips - 1) * (long long)N * XSPAN : (long long)(en.r - 1) * TSITES;
       ents[e] = se;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
   }
 
-  const double *drow0 = a.dtab + (size_t)tile.part_cls * kAaDtabRow;     // + e * dstride + c*40 + side*20 + k
-  const size_t dstride = (size_t)a.nparts_cls * kAaDtabRow;
+  const int ncat = CAT ? a.max_cats : 4;                                  // blocks per d-table / tip-table row
+  const double *drow0 = a.dtab + (size_t)tile.part_cls * a.dtab_row;      // + e * dstride + cat*40 + side*20 + k
+  const size_t dstride = (size_t)a.nparts_cls * a.dtab_row;
+  const size_t lutside = (size_t)23 * ncat * S;                           // doubles per (entry, partition, side)
   const int lo = a.mode == MODE_NEWVIEW ? a.first : 0;
   double acc = 0.0;
   uint32_t phase = 0;
 
-  for (unsigned chunk0 = 0; chunk0 < tile.nsites; chunk0 += TS) {
-    const unsigned nchunk = min(tile.nsites - chunk0, (unsigned)TS);
+  for (unsigned chunk0 = 0; chunk0 < tile.nsites; chunk0 += TSITES) {
+    const unsigned nchunk = min(tile.nsites - chunk0, (unsigned)TSITES);
     if (chunk0) __syncthreads();
     if (tid < 32) {
       const uint32_t bytes = (nchunk + 15u) & ~15u;
@@ -254,19 +271,27 @@ traverse_aa_kernel(const TraverseArgs a)
       for (int e = lo + lane; e < a.count; e += 32) {
         const SEntry &se = ents[e];
         if (se.tipCase < 0) {
-          if (se.ptip_qtip & 1) bulk_g2s(stips + se.poff, gsrc + (size_t)(se.poff / TS) * N, bytes, &mbar);
-          if (se.ptip_qtip & 2) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TS) * N, bytes, &mbar);
+          if (se.ptip_qtip & 1) bulk_g2s(stips + se.poff, gsrc + (size_t)(se.poff / TSITES) * N, bytes, &mbar);
+          if (se.ptip_qtip & 2) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TSITES) * N, bytes, &mbar);
         } else {
-          if (se.tipCase <= 1) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TS) * N, bytes, &mbar);
-          if (se.tipCase == 0) bulk_g2s(stips + se.roff, gsrc + (size_t)(se.roff / TS) * N, bytes, &mbar);
+          if (se.tipCase <= 1) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TSITES) * N, bytes, &mbar);
+          if (se.tipCase == 0) bulk_g2s(stips + se.roff, gsrc + (size_t)(se.roff / TSITES) * N, bytes, &mbar);
         }
       }
     }
 
-    const unsigned i = (unsigned)(warp * 8 + g);          // my site inside the chunk
-    const bool valid = i < nchunk;
-    const int lsite = valid ? (int)i : 0;
-    const size_t soff = ((size_t)tile.site0 + chunk0 + lsite) * SPAN;      // site = soff / SPAN
+    // my row's site in every slot: GAMMA -- the same site four times; CAT -- four sites 8 apart
+    const unsigned i0 = (unsigned)(CAT ? warp * 32 + g : warp * 8 + g);
+    bool valid[4]; int lsite[4], cat[4];
+    #pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const unsigned i = CAT ? i0 + 8u * c : i0;
+      valid[c] = i < nchunk;
+      lsite[c] = valid[c] ? (int)i : 0;
+      cat[c] = CAT ? a.rate_cat[(size_t)tile.site0 + chunk0 + lsite[c]] : c;
+    }
+    const size_t site0 = (size_t)tile.site0 + chunk0 + (CAT ? i0 : lsite[0]);   // CAT: slot c sits at site0 + 8c
+    const size_t soff = site0 * XSPAN;
     double carry[4][3][2];                                // CLV of the entry just computed, C-fragment layout
     long long carry_node = -1;
     #pragma unroll
@@ -283,49 +308,71 @@ traverse_aa_kernel(const TraverseArgs a)
       const bool q_inner = en.tipCase == 2, r_inner = en.tipCase != 0;
       const int qsrc = !q_inner ? SRC_TIP : (en.qoff == carry_node ? SRC_CARRY : SRC_LOAD);
       const int rsrc = !r_inner ? SRC_TIP : (en.roff == carry_node ? SRC_CARRY : SRC_LOAD);
-      // memory sources: a global CLV (category stride 20) or the tip vector in shared memory (stride 0)
-      const int code1 = q_inner ? 0 : stips[en.qoff + lsite], code2 = r_inner ? 0 : stips[en.roff + lsite];
-      const double *x1 = q_inner ? a.clv + en.qoff + soff : &sh.tip[S * code1];
-      const double *x2 = r_inner ? a.clv + en.roff + soff : &sh.tip[S * code2];
-      const int st1 = q_inner ? S : 0, st2 = r_inner ? S : 0;
-      const double *lutE = a.lut ? a.lut + ((size_t)e * a.nparts_cls + tile.part_cls) * 2 * kAaLutRow : nullptr;
-      const double *lut1 = lutE + code1 * SPAN, *lut2 = lutE + kAaLutRow + code2 * SPAN;
+      const double *lutE = a.lut ? a.lut + ((size_t)e * a.nparts_cls + tile.part_cls) * 2 * lutside : nullptr;
+      AaSlots sl;
+      #pragma unroll
+      for (int c = 0; c < 4; c++) {
+        // memory sources: a global CLV or the tip vector in shared memory; tip tables when they exist
+        const int code1 = q_inner ? 0 : stips[en.qoff + lsite[c]], code2 = r_inner ? 0 : stips[en.roff + lsite[c]];
+        sl.xq[c] = q_inner ? a.clv + en.qoff + soff + c * XSLOT : &sh.tip[S * code1];
+        sl.xr[c] = r_inner ? a.clv + en.roff + soff + c * XSLOT : &sh.tip[S * code2];
+        sl.dq[c] = drow + cat[c] * 40;
+        sl.lq[c] = lutE + ((size_t)code1 * ncat + cat[c]) * S;
+        sl.lr[c] = lutE + lutside + ((size_t)code2 * ncat + cat[c]) * S;
+      }
       const bool qlut = !q_inner && lutE, rlut = !r_inner && lutE;
-      if (qlut && rlut)                aa_entry<CH_LUT, CH_LUT>(carry, sh.fragEI, sh.fragEV, x1, st1, x2, st2, lut1, lut2, drow, lane, tq);
-      else if (qlut && rsrc == SRC_CARRY) aa_entry<CH_LUT, CH_CARRY>(carry, sh.fragEI, sh.fragEV, x1, st1, x2, st2, lut1, lut2, drow, lane, tq);
-      else if (qlut)                   aa_entry<CH_LUT, CH_MEM>(carry, sh.fragEI, sh.fragEV, x1, st1, x2, st2, lut1, lut2, drow, lane, tq);
-      else if (rsrc == SRC_CARRY)      aa_entry<CH_MEM, CH_CARRY>(carry, sh.fragEI, sh.fragEV, x1, st1, x2, st2, lut1, lut2, drow, lane, tq);
-      else if (qsrc == SRC_CARRY)      aa_entry<CH_CARRY, CH_MEM>(carry, sh.fragEI, sh.fragEV, x1, st1, x2, st2, lut1, lut2, drow, lane, tq);
-      else                             aa_entry<CH_MEM, CH_MEM>(carry, sh.fragEI, sh.fragEV, x1, st1, x2, st2, lut1, lut2, drow, lane, tq);
+      if (qlut && rlut)                   aa_entry<CH_LUT, CH_LUT>(carry, sh.fragEI, sh.fragEV, sl, lane, tq);
+      else if (qlut && rsrc == SRC_CARRY) aa_entry<CH_LUT, CH_CARRY>(carry, sh.fragEI, sh.fragEV, sl, lane, tq);
+      else if (qlut)                      aa_entry<CH_LUT, CH_MEM>(carry, sh.fragEI, sh.fragEV, sl, lane, tq);
+      else if (rsrc == SRC_CARRY)         aa_entry<CH_MEM, CH_CARRY>(carry, sh.fragEI, sh.fragEV, sl, lane, tq);
+      else if (qsrc == SRC_CARRY)         aa_entry<CH_CARRY, CH_MEM>(carry, sh.fragEI, sh.fragEV, sl, lane, tq);
+      else                                aa_entry<CH_MEM, CH_MEM>(carry, sh.fragEI, sh.fragEV, sl, lane, tq);
 
       if (r_inner) {                            // TIP_TIP is never rescaled (avxLikelihood.c:1393-1440)
-        bool small = true;
-        #pragma unroll
-        for (int c = 0; c < 4; c++)
-          #pragma unroll
-          for (int t = 0; t < 3; t++)            // padding columns hold exact zeros and pass the test
-            small = small && (fabs(carry[c][t][0]) < kMinLikelihood) && (fabs(carry[c][t][1]) < kMinLikelihood);
-        const unsigned int b = __ballot_sync(0xffffffffu, small);
         unsigned int cnt = 0;
-        if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {            // all 80 values of the site are tiny
+        if (!CAT) {
+          bool small = true;
           #pragma unroll
           for (int c = 0; c < 4; c++)
             #pragma unroll
-            for (int t = 0; t < 3; t++) { carry[c][t][0] *= kTwoToThe256; carry[c][t][1] *= kTwoToThe256; }
-          if (tq == 0 && valid) cnt = (unsigned int)a.wgt[soff / SPAN];
+            for (int t = 0; t < 3; t++)            // padding columns hold exact zeros and pass the test
+              small = small && (fabs(carry[c][t][0]) < kMinLikelihood) && (fabs(carry[c][t][1]) < kMinLikelihood);
+          const unsigned int b = __ballot_sync(0xffffffffu, small);
+          if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {            // all 80 values of the site are tiny
+            #pragma unroll
+            for (int c = 0; c < 4; c++)
+              #pragma unroll
+              for (int t = 0; t < 3; t++) { carry[c][t][0] *= kTwoToThe256; carry[c][t][1] *= kTwoToThe256; }
+            if (tq == 0 && valid[0]) cnt = (unsigned int)a.wgt[site0];
+          }
+        } else {
+          #pragma unroll
+          for (int c = 0; c < 4; c++) {            // one site per slot: all 20 values of that site tiny
+            bool small = true;
+            #pragma unroll
+            for (int t = 0; t < 3; t++)
+              small = small && (fabs(carry[c][t][0]) < kMinLikelihood) && (fabs(carry[c][t][1]) < kMinLikelihood);
+            const unsigned int b = __ballot_sync(0xffffffffu, small);
+            if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {
+              #pragma unroll
+              for (int t = 0; t < 3; t++) { carry[c][t][0] *= kTwoToThe256; carry[c][t][1] *= kTwoToThe256; }
+              if (tq == 0 && valid[c]) cnt += (unsigned int)a.wgt[site0 + 8 * c];
+            }
+          }
         }
         if (__any_sync(0xffffffffu, cnt != 0)) {
           const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
           if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
         }
       }
-      if (valid) {
+      {
         double *dst = a.clv + en.poff + soff + 2 * tq;
         #pragma unroll
         for (int c = 0; c < 4; c++) {
-          *reinterpret_cast<double2 *>(dst + c * S) = make_double2(carry[c][0][0], carry[c][0][1]);
-          *reinterpret_cast<double2 *>(dst + c * S + 8) = make_double2(carry[c][1][0], carry[c][1][1]);
-          if (tq < 2) *reinterpret_cast<double2 *>(dst + c * S + 16) = make_double2(carry[c][2][0], carry[c][2][1]);
+          if (!valid[c]) continue;
+          *reinterpret_cast<double2 *>(dst + c * XSLOT) = make_double2(carry[c][0][0], carry[c][0][1]);
+          *reinterpret_cast<double2 *>(dst + c * XSLOT + 8) = make_double2(carry[c][1][0], carry[c][1][1]);
+          if (tq < 2) *reinterpret_cast<double2 *>(dst + c * XSLOT + 16) = make_double2(carry[c][2][0], carry[c][2][1]);
         }
       }
       __syncwarp();
@@ -338,11 +385,11 @@ traverse_aa_kernel(const TraverseArgs a)
     const SEntry br = ents[0];
     const bool ptip = br.ptip_qtip & 1, qtip = br.ptip_qtip & 2;
     const bool p_carry = !ptip && br.poff == carry_node, q_carry = !qtip && br.qoff == carry_node;
-    const double *tpa = ptip ? &sh.tip[S * stips[br.poff + lsite]] : sh.tip;
-    const double *tpb = qtip ? &sh.tip[S * stips[br.qoff + lsite]] : sh.tip;
     double term = 0.0;
     #pragma unroll
     for (int c = 0; c < 4; c++) {
+      const double *tpa = ptip ? &sh.tip[S * stips[br.poff + lsite[c]]] : sh.tip;
+      const double *tpb = qtip ? &sh.tip[S * stips[br.qoff + lsite[c]]] : sh.tip;
       #pragma unroll
       for (int t = 0; t < 3; t++) {
         const int col = 8 * t + 2 * tq;
@@ -350,23 +397,29 @@ traverse_aa_kernel(const TraverseArgs a)
         double2 xa = make_double2(0.0, 0.0), xb = make_double2(0.0, 0.0);
         if (p_carry) xa = make_double2(carry[c][t][0], carry[c][t][1]);
         else if (live) xa = ptip ? *reinterpret_cast<const double2 *>(tpa + col)
-                                 : ld128(a.clv + br.poff + soff + c * S + col);
+                                 : ld128(a.clv + br.poff + soff + c * XSLOT + col);
         if (q_carry) xb = make_double2(carry[c][t][0], carry[c][t][1]);
         else if (live) xb = qtip ? *reinterpret_cast<const double2 *>(tpb + col)
-                                 : ld128(a.clv + br.qoff + soff + c * S + col);
+                                 : ld128(a.clv + br.qoff + soff + c * XSLOT + col);
         if (a.mode == MODE_SUM) {
-          if (valid && live) *reinterpret_cast<double2 *>(a.sum + soff + c * S + col) = make_double2(xa.x * xb.x, xa.y * xb.y);
+          if (valid[c] && live) *reinterpret_cast<double2 *>(a.sum + soff + c * XSLOT + col) = make_double2(xa.x * xb.x, xa.y * xb.y);
         } else if (live) {
-          const double d0 = __ldg(drow0 + c * 40 + col), d1 = __ldg(drow0 + c * 40 + col + 1);   // row 0, q side
+          const double d0 = __ldg(drow0 + cat[c] * 40 + col), d1 = __ldg(drow0 + cat[c] * 40 + col + 1);   // row 0, q side
           term += xa.x * xb.x * d0;
           term += xa.y * xb.y * d1;
         }
       }
+      if (CAT && a.mode == MODE_EVALUATE) {       // one site per slot: its own log (no 1/4: a single category)
+        term += __shfl_xor_sync(0xffffffffu, term, 1);
+        term += __shfl_xor_sync(0xffffffffu, term, 2);
+        if (tq == 0 && valid[c]) acc += (double)a.wgt[site0 + 8 * c] * log(fabs(term));
+        term = 0.0;
+      }
     }
-    if (a.mode == MODE_EVALUATE) {
+    if (!CAT && a.mode == MODE_EVALUATE) {
       term += __shfl_xor_sync(0xffffffffu, term, 1);
       term += __shfl_xor_sync(0xffffffffu, term, 2);
-      if (tq == 0 && valid) acc += (double)a.wgt[soff / SPAN] * log(0.25 * fabs(term));
+      if (tq == 0 && valid[0]) acc += (double)a.wgt[site0] * log(0.25 * fabs(term));
     }
   }
 
@@ -384,21 +437,22 @@ traverse_aa_kernel(const TraverseArgs a)
 __global__ void __launch_bounds__(256)
 aa_lut_kernel(const LutArgs a)
 {
-  __shared__ double EI[400], tip[460], d[80];
+  __shared__ double EI[400], tip[460], d[64 * 20];
   const int side = blockIdx.x & 1;
   const int ep = blockIdx.x >> 1, pc = ep % a.nparts_cls, e = ep / a.nparts_cls;
   if (e < a.first) return;
   const int tc = a.entries[e].tipCase;
   if (!(side == 0 ? tc <= 1 : tc == 0)) return;
+  const int ncat = a.ncat, row = 23 * ncat * 20;
   const double *model = a.models + (size_t)pc * kAaModelDoubles;
-  const double *drow = a.dtab + ((size_t)e * a.nparts_cls + pc) * kAaDtabRow;
+  const double *drow = a.dtab + ((size_t)e * a.nparts_cls + pc) * a.dtab_row;
   for (int i = threadIdx.x; i < 400; i += 256) EI[i] = model[24 + i];
   for (int i = threadIdx.x; i < 460; i += 256) tip[i] = model[824 + i];
-  if (threadIdx.x < 80) d[threadIdx.x] = drow[(threadIdx.x / 20) * 40 + side * 20 + threadIdx.x % 20];
+  for (int i = threadIdx.x; i < ncat * 20; i += 256) d[i] = drow[(i / 20) * 40 + side * 20 + i % 20];
   __syncthreads();
-  double *out = a.lut + ((size_t)ep * 2 + side) * kAaLutRow;
-  for (int i = threadIdx.x; i < kAaLutRow; i += 256) {
-    const int code = i / 80, c = (i % 80) / 20, l = i % 20;
+  double *out = a.lut + ((size_t)ep * 2 + side) * row;
+  for (int i = threadIdx.x; i < row; i += 256) {
+    const int code = i / (ncat * 20), c = (i % (ncat * 20)) / 20, l = i % 20;
     double s = tip[code * 20];                       // j = 0: EI[l][0] = 1, d[0] = 1
     #pragma unroll
     for (int j = 1; j < 20; j++) s += EI[l * 20 + j] * (d[c * 20 + j] * tip[code * 20 + j]);
@@ -415,31 +469,35 @@ void launch_aa_lut(const LutArgs &a, cudaStream_t s)
 __global__ void __launch_bounds__(kThreads, 2)
 core_aa_kernel(const CoreArgs a)
 {
-  __shared__ CoreSmem sh;
+  __shared__ union { CoreSmem g; CoreCatSmem c; } sh;
   const Tile tile = a.tiles[blockIdx.x];
   if (!a.mask[tile.part]) return;
   double t1, t2;
-  core_tile<20>(tile, a.sum, a.wgt, a.models + (size_t)tile.part_cls * kAaModelDoubles,
-                a.lz[a.nbranches > 1 ? tile.part : 0], sh, t1, t2);
+  const double *model = a.models + (size_t)tile.part_cls * kAaModelDoubles;
+  const double lz = a.lz[a.nbranches > 1 ? tile.part : 0];
+  if (a.rate_cat) core_tile_cat<20>(tile, a.sum, a.wgt, model, a.rate_cat, a.cat_rates + (size_t)tile.part_cls * a.max_cats, a.max_cats, lz, sh.c, t1, t2);
+  else            core_tile<20>(tile, a.sum, a.wgt, model, lz, sh.g, t1, t2);
   if (threadIdx.x == 0) { a.tile_out[2 * (size_t)blockIdx.x] = t1; a.tile_out[2 * (size_t)blockIdx.x + 1] = t2; }
 }
 
-static size_t traverse_aa_smem(int count, int mxtips)
+template <bool CAT>
+static void launch_aa_variant(const TraverseArgs &a, int ntiles, cudaStream_t s)
 {
-  return (((size_t)count * sizeof(SEntry) + 15) & ~(size_t)15) + (size_t)mxtips * TS;
+  const size_t smem = (((size_t)a.count * sizeof(SEntry) + 15) & ~(size_t)15) + (size_t)a.mxtips * (CAT ? 384 : 96);
+  static size_t configured = 0;
+  if (smem > configured) {
+    const size_t want = std::min<size_t>(227 * 1024 - 16384, std::max<size_t>(smem, 64 * 1024));
+    cudaFuncSetAttribute(traverse_aa_kernel<CAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    configured = want;
+  }
+  traverse_aa_kernel<CAT><<<ntiles, kAaThreads, smem, s>>>(a);
 }
 
 void launch_traverse_aa(const TraverseArgs &a, const double *, int ntiles, cudaStream_t s)
 {
   if (ntiles <= 0) return;
-  const size_t smem = traverse_aa_smem(a.count, a.mxtips);
-  static size_t configured = 0;
-  if (smem > configured) {
-    const size_t want = std::min<size_t>(227 * 1024 - 8192, std::max<size_t>(smem, 64 * 1024));
-    cudaFuncSetAttribute(traverse_aa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
-    configured = want;
-  }
-  traverse_aa_kernel<<<ntiles, kAaThreads, smem, s>>>(a);
+  if (a.rate_cat) launch_aa_variant<true>(a, ntiles, s);
+  else            launch_aa_variant<false>(a, ntiles, s);
 }
 void launch_core_aa(const CoreArgs &a, int ntiles, cudaStream_t s)
 {

@@ -76,7 +76,8 @@ dtab_kernel(const DtabArgs a)
     const double *model = a.models + (size_t)pc * a.model_doubles;   // EIGN[S] rates[4] ...
     const int slot = a.nbranches > 1 ? a.cls_part_global[pc] : 0;
     const double lz = side ? a.lzr[(size_t)e * a.nbranches + slot] : a.lzq[(size_t)e * a.nbranches + slot];
-    a.dtab[i] = k ? exp(model[S + c] * (model[k] * lz)) : 1.0;
+    const double rate = a.cat_rates ? a.cat_rates[(size_t)pc * a.max_cats + c] : model[S + c];
+    a.dtab[i] = k ? exp(rate * (model[k] * lz)) : 1.0;
   }
 }
 
@@ -326,17 +327,178 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
 }
 
 // ------------------------------------------------------------------------------------------------------
+// CAT / PSR traversal (newviewGTRCAT_AVX avxLikelihood.c:326-485, evaluateGTRCAT evaluateGenericSpecial.c:1988-2083,
+// sumCAT makenewzGenericSpecial.c:1650-1796): one rate category per site, a CLV is 4 doubles = 32 B per site.
+// Same structure as the GAMMA kernel -- descriptor loop inside, carry, staged tips -- with thread = site; a site
+// selects its exponentials through rate_cat[site].  Scaling is decided per thread (all 4 values tiny).
+// ------------------------------------------------------------------------------------------------------
+template <bool PARAM>
+__global__ void __launch_bounds__(kThreads, 3)
+traverse_dna_cat_kernel(const TraverseArgs a, const DnaConsts kc)
+{
+  constexpr int TS = 256;                      // sites per chunk = threads
+  __shared__ DnaShared sh;
+  __shared__ __align__(8) uint64_t mbar;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  SEntry *ents = reinterpret_cast<SEntry *>(dyn);
+  uint8_t *stips = dyn + (((size_t)a.count * sizeof(SEntry) + 15) & ~(size_t)15);   // [mxtips][TS]
+
+  const Tile tile = a.tiles[blockIdx.x];
+  if (!a.mask[tile.part]) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const size_t N = a.N;
+  {
+    const double *model = a.models + (size_t)tile.part_cls * kDnaModelDoubles;
+    if (tid < 64) sh.tip[tid] = model[40 + tid];
+    if (!PARAM && tid < 16) { sh.EI[tid] = model[8 + tid]; sh.EV[tid] = model[24 + tid]; }
+    if (tid == 0) mbar_init(&mbar, 1);
+    for (int e = tid; e < a.count; e += kThreads) {
+      const DevEntry en = a.entries[e];
+      SEntry se;
+      se.tipCase = en.tipCase; se.ptip_qtip = (en.p <= a.mxtips ? 1 : 0) | (en.q <= a.mxtips ? 2 : 0);
+      se.poff = en.p > a.mxtips ? (long long)(en.p - a.mxtips - 1) * (long long)N * 4 : (long long)(en.p - 1) * TS;
+      se.qoff = en.q > a.mxtips ? (long long)(en.q - a.mxtips - 1) * (long long)N * 4 : (long long)(en.q - 1) * TS;
+      se.roff = en.r > a.mxtips ? (long long)(en.r - a.mxtips - 1) * (long long)N * 4 : (long long)(en.r - 1) * TS;
+      ents[e] = se;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+  }
+#define EI_(i) (PARAM ? kc.EI[i] : sh.EI[i])
+#define EV_(i) (PARAM ? kc.EV[i] : sh.EV[i])
+  const size_t dstride = (size_t)a.nparts_cls * a.dtab_row;
+  const int lo = a.mode == MODE_NEWVIEW ? a.first : 0;
+  double acc = 0.0;
+  uint32_t phase = 0;
+
+  for (unsigned chunk0 = 0; chunk0 < tile.nsites; chunk0 += TS) {
+    const unsigned nchunk = min(tile.nsites - chunk0, (unsigned)TS);
+    if (chunk0) __syncthreads();
+    if (tid < 32) {
+      const uint32_t bytes = (nchunk + 15u) & ~15u;
+      const uint8_t *gsrc = a.tips + tile.site0 + chunk0;
+      int mine = 0;
+      for (int e = lo + lane; e < a.count; e += 32) {
+        const SEntry &se = ents[e];
+        if (se.tipCase < 0) mine += (se.ptip_qtip & 1) + ((se.ptip_qtip >> 1) & 1);
+        else                mine += (se.tipCase <= 1) + (se.tipCase == 0);
+      }
+      const int total = __reduce_add_sync(0xffffffffu, mine);
+      if (lane == 0) mbar_expect_tx(&mbar, (uint32_t)total * bytes);
+      __syncwarp();
+      for (int e = lo + lane; e < a.count; e += 32) {
+        const SEntry &se = ents[e];
+        if (se.tipCase < 0) {
+          if (se.ptip_qtip & 1) bulk_g2s(stips + se.poff, gsrc + (size_t)(se.poff / TS) * N, bytes, &mbar);
+          if (se.ptip_qtip & 2) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TS) * N, bytes, &mbar);
+        } else {
+          if (se.tipCase <= 1) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TS) * N, bytes, &mbar);
+          if (se.tipCase == 0) bulk_g2s(stips + se.roff, gsrc + (size_t)(se.roff / TS) * N, bytes, &mbar);
+        }
+      }
+    }
+    const bool valid = (unsigned)tid < nchunk;
+    const int lsite = valid ? tid : 0;
+    const size_t site = (size_t)tile.site0 + chunk0 + lsite;
+    const size_t eoff = site * 4;
+    const int cat = a.rate_cat[site];
+    const double *drow = a.dtab + ((size_t)tile.part_cls * a.max_cats + cat) * 8;    // + e * dstride; q side +0, r side +4
+    double carry[4] = {0.0, 0.0, 0.0, 0.0};
+    long long carry_node = -1;
+
+    mbar_wait(&mbar, phase);
+    phase ^= 1;
+
+    for (int e = a.first; e < a.count; e++) {
+      const SEntry en = ents[e];
+      double dq[4], dr[4];
+      ld256_ro(drow + (size_t)e * dstride, dq);
+      ld256_ro(drow + (size_t)e * dstride + 4, dr);
+      const bool q_inner = en.tipCase == 2, r_inner = en.tipCase != 0;
+      double x1[4], x2[4];
+      if (q_inner && en.qoff == carry_node) { x1[0] = carry[0]; x1[1] = carry[1]; x1[2] = carry[2]; x1[3] = carry[3]; }
+      else if (q_inner) ld256(a.clv + en.qoff + eoff, x1);
+      else { const double *tv = &sh.tip[4 * stips[en.qoff + lsite]]; x1[0] = tv[0]; x1[1] = tv[1]; x1[2] = tv[2]; x1[3] = tv[3]; }
+      if (r_inner && en.roff == carry_node) { x2[0] = carry[0]; x2[1] = carry[1]; x2[2] = carry[2]; x2[3] = carry[3]; }
+      else if (r_inner) ld256(a.clv + en.roff + eoff, x2);
+      else { const double *tv = &sh.tip[4 * stips[en.roff + lsite]]; x2[0] = tv[0]; x2[1] = tv[1]; x2[2] = tv[2]; x2[3] = tv[3]; }
+
+      const double tq1 = dq[1] * x1[1], tq2 = dq[2] * x1[2], tq3 = dq[3] * x1[3];
+      const double tr1 = dr[1] * x2[1], tr2 = dr[2] * x2[2], tr3 = dr[3] * x2[3];
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+      #pragma unroll
+      for (int l = 0; l < 4; l++) {
+        const double al = x1[0] + EI_(l * 4 + 1) * tq1 + EI_(l * 4 + 2) * tq2 + EI_(l * 4 + 3) * tq3;
+        const double ar = x2[0] + EI_(l * 4 + 1) * tr1 + EI_(l * 4 + 2) * tr2 + EI_(l * 4 + 3) * tr3;
+        const double ab = al * ar;
+        #pragma unroll
+        for (int m = 0; m < 4; m++) v[m] += ab * EV_(l * 4 + m);
+      }
+      unsigned int cnt = 0;
+      if (r_inner) {
+        const bool small = fabs(v[0]) < kMinLikelihood && fabs(v[1]) < kMinLikelihood &&
+                           fabs(v[2]) < kMinLikelihood && fabs(v[3]) < kMinLikelihood;
+        if (small) {
+          #pragma unroll
+          for (int m = 0; m < 4; m++) v[m] *= kTwoToThe256;
+          if (valid) cnt = (unsigned int)a.wgt[site];
+        }
+        if (__any_sync(0xffffffffu, cnt != 0)) {
+          const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
+          if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
+        }
+      }
+      if (valid) st256(a.clv + en.poff + eoff, v);
+      carry[0] = v[0]; carry[1] = v[1]; carry[2] = v[2]; carry[3] = v[3];
+      carry_node = en.poff;
+    }
+    if (a.mode == MODE_NEWVIEW) continue;
+
+    const SEntry br = ents[0];
+    const bool ptip = br.ptip_qtip & 1, qtip = br.ptip_qtip & 2;
+    double xa[4], xb[4];
+    if (!ptip && br.poff == carry_node) { xa[0] = carry[0]; xa[1] = carry[1]; xa[2] = carry[2]; xa[3] = carry[3]; }
+    else if (!ptip) ld256(a.clv + br.poff + eoff, xa);
+    else { const double *tv = &sh.tip[4 * stips[br.poff + lsite]]; xa[0] = tv[0]; xa[1] = tv[1]; xa[2] = tv[2]; xa[3] = tv[3]; }
+    if (!qtip && br.qoff == carry_node) { xb[0] = carry[0]; xb[1] = carry[1]; xb[2] = carry[2]; xb[3] = carry[3]; }
+    else if (!qtip) ld256(a.clv + br.qoff + eoff, xb);
+    else { const double *tv = &sh.tip[4 * stips[br.qoff + lsite]]; xb[0] = tv[0]; xb[1] = tv[1]; xb[2] = tv[2]; xb[3] = tv[3]; }
+    if (a.mode == MODE_SUM) {
+      double sm[4];
+      #pragma unroll
+      for (int k = 0; k < 4; k++) sm[k] = xa[k] * xb[k];
+      if (valid) st256(a.sum + eoff, sm);
+    } else {
+      double diag[4];
+      ld256_ro(drow, diag);                    // row 0, q side
+      double term = xa[0] * xb[0];
+      #pragma unroll
+      for (int k = 1; k < 4; k++) term += xa[k] * xb[k] * diag[k];
+      if (valid) acc += (double)a.wgt[site] * log(fabs(term));     // no 1/4: a single category (evaluateGenericSpecial.c:289)
+    }
+  }
+#undef EI_
+#undef EV_
+  if (a.mode == MODE_EVALUATE) {
+    const double tot = block_sum(acc, sh.red);
+    if (tid == 0) { a.tile_out[2 * (size_t)blockIdx.x] = tot; a.tile_out[2 * (size_t)blockIdx.x + 1] = 0.0; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // core: first and second derivative of lnL w.r.t. lz over the sum table (one launch per NR iteration).
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 4)
 core_dna_kernel(const CoreArgs a)
 {
-  __shared__ CoreSmem sh;
+  __shared__ union { CoreSmem g; CoreCatSmem c; } sh;
   const Tile tile = a.tiles[blockIdx.x];
   if (!a.mask[tile.part]) return;
   double t1, t2;
-  core_tile<4>(tile, a.sum, a.wgt, a.models + (size_t)tile.part_cls * kDnaModelDoubles,
-               a.lz[a.nbranches > 1 ? tile.part : 0], sh, t1, t2);
+  const double *model = a.models + (size_t)tile.part_cls * kDnaModelDoubles;
+  const double lz = a.lz[a.nbranches > 1 ? tile.part : 0];
+  if (a.rate_cat) core_tile_cat<4>(tile, a.sum, a.wgt, model, a.rate_cat, a.cat_rates + (size_t)tile.part_cls * a.max_cats, a.max_cats, lz, sh.c, t1, t2);
+  else            core_tile<4>(tile, a.sum, a.wgt, model, lz, sh.g, t1, t2);
   if (threadIdx.x == 0) { a.tile_out[2 * (size_t)blockIdx.x] = t1; a.tile_out[2 * (size_t)blockIdx.x + 1] = t2; }
 }
 
@@ -387,6 +549,25 @@ void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *kc, int ntiles,
   if (ns == 1) launch_ns<1>(a, kc, ntiles, s);
   else if (ns == 2) launch_ns<2>(a, kc, ntiles, s);
   else launch_ns<4>(a, kc, ntiles, s);
+}
+void launch_traverse_dna_cat(const TraverseArgs &a, const DnaConsts *kc, int ntiles, cudaStream_t s)
+{
+  if (ntiles <= 0) return;
+  const size_t smem = (((size_t)a.count * sizeof(SEntry) + 15) & ~(size_t)15) + (size_t)a.mxtips * 256;
+  static size_t configured[2] = {0, 0};
+  const int v = kc ? 1 : 0;
+  if (smem > configured[v]) {
+    const size_t want = std::min<size_t>(227 * 1024 - 2048, std::max<size_t>(smem, 64 * 1024));
+    if (kc) cudaFuncSetAttribute(traverse_dna_cat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    else    cudaFuncSetAttribute(traverse_dna_cat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    configured[v] = want;
+  }
+  if (kc) traverse_dna_cat_kernel<true><<<ntiles, kThreads, smem, s>>>(a, *kc);
+  else {
+    DnaConsts none;
+    memset(&none, 0, sizeof none);
+    traverse_dna_cat_kernel<false><<<ntiles, kThreads, smem, s>>>(a, none);
+  }
 }
 void launch_core_dna(const CoreArgs &a, int ntiles, cudaStream_t s)
 {

@@ -39,7 +39,8 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
 __global__ void __launch_bounds__(kThreads, 2)
 newton_raphson_kernel(const NrArgs a)
 {
-  __shared__ CoreSmem sh;
+  __shared__ union { CoreSmem g; CoreCatSmem c; double red[32]; } shu;
+  CoreSmem &sh = shu.g;
   NrState *st = a.state;
   unsigned int gen = 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -77,8 +78,12 @@ newton_raphson_kernel(const NrArgs a)
         if (!a.mask[tile.part]) continue;
         double t1, t2;
         const double lz = st->lz[nb > 1 ? tile.part : 0];
-        if (c == CLS_DNA) core_tile<4>(tile, a.sum[c], a.wgt[c], a.models[c] + (size_t)tile.part_cls * kDnaModelDoubles, lz, sh, t1, t2);
-        else              core_tile<20>(tile, a.sum[c], a.wgt[c], a.models[c] + (size_t)tile.part_cls * kAaModelDoubles, lz, sh, t1, t2);
+        if (a.rate_cat[c]) {
+          const double *rates = a.cat_rates[c] + (size_t)tile.part_cls * a.max_cats;
+          if (c == CLS_DNA) core_tile_cat<4>(tile, a.sum[c], a.wgt[c], a.models[c] + (size_t)tile.part_cls * kDnaModelDoubles, a.rate_cat[c], rates, a.max_cats, lz, shu.c, t1, t2);
+          else              core_tile_cat<20>(tile, a.sum[c], a.wgt[c], a.models[c] + (size_t)tile.part_cls * kAaModelDoubles, a.rate_cat[c], rates, a.max_cats, lz, shu.c, t1, t2);
+        } else if (c == CLS_DNA) core_tile<4>(tile, a.sum[c], a.wgt[c], a.models[c] + (size_t)tile.part_cls * kDnaModelDoubles, lz, sh, t1, t2);
+        else                     core_tile<20>(tile, a.sum[c], a.wgt[c], a.models[c] + (size_t)tile.part_cls * kAaModelDoubles, lz, sh, t1, t2);
         if (tid == 0) { a.tile_out[c][2 * (size_t)t] = t1; a.tile_out[c][2 * (size_t)t + 1] = t2; }
       }
     }
@@ -97,8 +102,8 @@ newton_raphson_kernel(const NrArgs a)
         }
         for (; t < n; t += kThreads) { const double2 v = to[t]; s0 += v.x; s1 += v.y; }
       }
-      s0 = block_sum(s0, sh.red);
-      s1 = block_sum(s1, sh.red);
+      s0 = block_sum(s0, shu.g.red);
+      s1 = block_sum(s1, shu.g.red);
       if (tid == 0) { a.part_out[part] = s0; a.part_out[P + part] = s1; }
     }
     grid_barrier(a.barrier, gen);

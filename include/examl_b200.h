@@ -92,6 +92,13 @@ const char *exb_last_error(void);
 int  exb_set_partition(exb_engine *e, int model, int states, size_t width,
                        const int *wgt, const unsigned char *yResource);
 
+/* Rate heterogeneity model of the run (tr->rateHetModel, axml.h:349-350): EXB_GAMMA (default; four discrete GAMMA
+ * categories per site, CLV = 4*states doubles) or EXB_CAT (-m PSR: ONE rate category per site, CLV = states
+ * doubles; maxCategories = tr->maxCategories <= 64).  Call before exb_set_partition. */
+#define EXB_CAT    0
+#define EXB_GAMMA  1
+int  exb_set_rate_model(exb_engine *e, int rateHetModel, int maxCategories);
+
 /* Freeze the layout, allocate the device arenas (CLVs for mxtips-2 inner nodes, sum table,
  * scalers) and upload tips and weights. */
 int  exb_commit(exb_engine *e);
@@ -103,6 +110,11 @@ int  exb_commit(exb_engine *e);
  * unchanged (host-side compare). */
 int  exb_set_model(exb_engine *e, int model, const double *EIGN, const double *EV,
                    const double *EI, const double *tipVector, const double *gammaRates);
+
+/* EXB_CAT only: pInfo.numberOfCategories, pInfo.perSiteRates[numberOfCategories], pInfo.rateCategory[width]
+ * (rewritten by optimizeRateCategories, optimizeModel.c:2403).  Cheap when unchanged (host-side compare). */
+int  exb_set_categories(exb_engine *e, int model, int numberOfCategories, const double *perSiteRates,
+                        const int *rateCategory);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
 

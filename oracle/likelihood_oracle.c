@@ -13,6 +13,9 @@
  *   sum table           makenewzGenericSpecial.c:251-319 (sumGAMMA_FLEX)
  *   core                makenewzGenericSpecial.c:2309-2393 (coreGTRGAMMA; coreGAMMA_FLEX :523
  *                       does not compile in the reference)
+ *   CAT / PSR           newviewCAT_FLEX newviewGenericSpecial.c:217-427, evaluateCAT_FLEX
+ *                       evaluateGenericSpecial.c:232-330, sumCAT_FLEX makenewzGenericSpecial.c:170-249,
+ *                       coreCAT_FLEX makenewzGenericSpecial.c:394-519 (one rate category per site)
  *   partition plumbing  newviewGenericSpecial.c:1114 (executeModel && width>0), :972-981
  *                       (branch slot), evaluateGenericSpecial.c:845-860 (masked partitions),
  *                       makenewzGenericSpecial.c:921-946 (derivative slots)
@@ -37,8 +40,13 @@
 
 typedef struct { int tipCase, pNumber, qNumber, rNumber; } orc_entry;
 
+#define ORC_MAX_CATS 64
+
 typedef struct {
   int states, codes;
+  int ncat;                     /* CAT: numberOfCategories */
+  double catRates[ORC_MAX_CATS];/* CAT: perSiteRates */
+  int *rateCategory;            /* CAT: per-site category index [width] */
   size_t width;
   int *wgt;
   unsigned char *tips;          /* [mxtips][width] */
@@ -50,8 +58,14 @@ typedef struct {
 
 typedef struct {
   int mxtips, nparts, nbranches;
+  int cat;                      /* 0: GAMMA (4 categories per site), 1: CAT/PSR (one category per site) */
   orc_part *parts;
 } orc_engine;
+
+/* rate categories a site carries / the rate table they index:
+   GAMMA: R = 4, rates = gammaRates; CAT: R = 1, rates = perSiteRates[rateCategory[i]]
+   (newviewGenericSpecial.c:958-968, discreteRateCategories axml.c:301) */
+static int orc_R(const orc_engine *e) { return e->cat ? 1 : 4; }
 
 int orc_create(orc_engine **out, int mxtips, int nparts, int nbranches)
 {
@@ -68,7 +82,7 @@ void orc_destroy(orc_engine *e)
   if (!e) return;
   for (m = 0; m < e->nparts; m++) {
     free(e->parts[m].wgt); free(e->parts[m].tips); free(e->parts[m].clv);
-    free(e->parts[m].sum); free(e->parts[m].scaler);
+    free(e->parts[m].sum); free(e->parts[m].scaler); free(e->parts[m].rateCategory);
   }
   free(e->parts); free(e);
 }
@@ -76,8 +90,10 @@ void orc_destroy(orc_engine *e)
 int orc_set_partition(orc_engine *e, int model, int states, size_t width, const int *wgt, const unsigned char *y)
 {
   orc_part *p = &e->parts[model];
-  size_t span = 4 * (size_t)states;
+  size_t span = (size_t)orc_R(e) * (size_t)states;
   p->states = states; p->codes = states == 20 ? 23 : 16; p->width = width;
+  p->rateCategory = (int *)calloc(width + 1, sizeof(int));
+  p->ncat = 1; p->catRates[0] = 1.0;
   p->wgt = (int *)malloc((width + 1) * sizeof(int));
   p->tips = (unsigned char *)malloc((size_t)e->mxtips * width + 1);
   memcpy(p->wgt, wgt, width * sizeof(int));
@@ -101,24 +117,32 @@ int orc_set_model(orc_engine *e, int model, const double *EIGN, const double *EV
   return 0;
 }
 
-/* P(z) for the four GAMMA categories: P[c][j][k] = exp(EIGN[k] r_c lz) EI[j][k], P[c][j][0] = 1. */
-static void orc_make_p(double z, const orc_part *p, double *P)
+/* Number of distinct P matrices of a partition and the rate of each (makeP's rptr / numberOfCategories,
+   newviewGenericSpecial.c:958-968). */
+static int orc_np(const orc_engine *e, const orc_part *p) { return e->cat ? p->ncat : 4; }
+static const double *orc_rates(const orc_engine *e, const orc_part *p) { return e->cat ? p->catRates : p->gammaRates; }
+/* index of the P matrix of (site i, category slot c) */
+static int orc_pidx(const orc_engine *e, const orc_part *p, size_t i, int c) { return e->cat ? p->rateCategory[i] : c; }
+
+/* P(z): P[n][j][k] = exp(EIGN[k] r_n lz) EI[j][k], P[n][j][0] = 1 for every rate r_n of the partition. */
+static void orc_make_p(const orc_engine *e, double z, const orc_part *p, double *P)
 {
-  int S = p->states, c, j, k;
+  int S = p->states, n, j, k, np = orc_np(e, p);
+  const double *rates = orc_rates(e, p);
   double lz = (z > ORC_ZMIN) ? log(z) : log(ORC_ZMIN);
   double d[20];
-  for (c = 0; c < 4; c++) {
-    for (k = 1; k < S; k++) d[k] = exp(p->gammaRates[c] * (p->EIGN[k] * lz));
+  for (n = 0; n < np; n++) {
+    for (k = 1; k < S; k++) d[k] = exp(rates[n] * (p->EIGN[k] * lz));
     for (j = 0; j < S; j++) {
-      P[c * S * S + j * S] = 1.0;
-      for (k = 1; k < S; k++) P[c * S * S + j * S + k] = d[k] * p->EI[j * S + k];
+      P[n * S * S + j * S] = 1.0;
+      for (k = 1; k < S; k++) P[n * S * S + j * S + k] = d[k] * p->EI[j * S + k];
     }
   }
 }
 
 static double *clv_of(const orc_engine *e, const orc_part *p, int number)
 {
-  return p->clv + (size_t)(number - e->mxtips - 1) * p->width * 4 * (size_t)p->states;
+  return p->clv + (size_t)(number - e->mxtips - 1) * p->width * (size_t)orc_R(e) * (size_t)p->states;
 }
 static const unsigned char *tip_of(const orc_engine *e, const orc_part *p, int number)
 {
@@ -126,20 +150,20 @@ static const unsigned char *tip_of(const orc_engine *e, const orc_part *p, int n
   return p->tips + (size_t)(number - 1) * p->width;
 }
 
-/* One traversal entry for one partition. */
+/* One traversal entry for one partition (GAMMA: newviewGAMMA_FLEX :430-682; CAT: newviewCAT_FLEX :217-427). */
 static void orc_newview_entry(orc_engine *e, orc_part *p, const orc_entry *t, double qz, double rz)
 {
-  int S = p->states, span = 4 * S, c, j, l;
+  int S = p->states, R = orc_R(e), span = R * S, c, j, l, np = orc_np(e, p);
   size_t i;
-  double *left = (double *)malloc(sizeof(double) * 4 * S * S), *right = (double *)malloc(sizeof(double) * 4 * S * S);
+  double *left = (double *)malloc(sizeof(double) * np * S * S), *right = (double *)malloc(sizeof(double) * np * S * S);
   double a[20], b[20], v1[20], v2[20];
   double *x3 = clv_of(e, p, t->pNumber);
   const double *x1 = NULL, *x2 = NULL;
   const unsigned char *tip1 = NULL, *tip2 = NULL;
   unsigned int addScale = 0;
 
-  orc_make_p(qz, p, left);
-  orc_make_p(rz, p, right);
+  orc_make_p(e, qz, p, left);
+  orc_make_p(e, rz, p, right);
 
   switch (t->tipCase) {
   case 0: tip1 = tip_of(e, p, t->qNumber); tip2 = tip_of(e, p, t->rNumber); break;
@@ -150,7 +174,8 @@ static void orc_newview_entry(orc_engine *e, orc_part *p, const orc_entry *t, do
   for (i = 0; i < p->width; i++) {
     double *v = x3 + i * span;
     int scale = 1;
-    for (c = 0; c < 4; c++) {
+    for (c = 0; c < R; c++) {
+      const double *L = left + (size_t)orc_pidx(e, p, i, c) * S * S, *Rm = right + (size_t)orc_pidx(e, p, i, c) * S * S;
       /* child vectors in the eigenvector basis; a tip's vector is the same for every category */
       if (tip1) memcpy(v1, p->tipVector + (size_t)S * tip1[i], S * sizeof(double));
       else      memcpy(v1, x1 + i * span + c * S, S * sizeof(double));
@@ -159,8 +184,8 @@ static void orc_newview_entry(orc_engine *e, orc_part *p, const orc_entry *t, do
       for (l = 0; l < S; l++) {
         double al = 0.0, ar = 0.0;
         for (j = 0; j < S; j++) {
-          al += v1[j] * left[c * S * S + l * S + j];
-          ar += v2[j] * right[c * S * S + l * S + j];
+          al += v1[j] * L[l * S + j];
+          ar += v2[j] * Rm[l * S + j];
         }
         a[l] = al; b[l] = ar;
       }
@@ -170,7 +195,7 @@ static void orc_newview_entry(orc_engine *e, orc_part *p, const orc_entry *t, do
         for (j = 0; j < S; j++) v[c * S + j] += x1px2 * p->EV[l * S + j];
       }
     }
-    if (t->tipCase != 0) {           /* TIP_TIP is never rescaled (newviewGenericSpecial.c:496-523) */
+    if (t->tipCase != 0) {           /* TIP_TIP is never rescaled (newviewGenericSpecial.c:496-523, 270-313) */
       for (l = 0; scale && l < span; l++) scale = fabs(v[l]) < ORC_MINLIKELIHOOD;
       if (scale) {
         for (l = 0; l < span; l++) v[l] *= ORC_TWOTOTHE256;
@@ -220,34 +245,38 @@ static void branch_ends(const orc_engine *e, const orc_part *p, const orc_entry 
   else { *xa = clv_of(e, p, P); *xb = clv_of(e, p, Q); }
 }
 
+/* GAMMA: evaluateGAMMA_FLEX eval:154-228 (log(0.25 |term|)); CAT: evaluateCAT_FLEX eval:232-330 (log |term|). */
 int orc_evaluate(orc_engine *e, const orc_entry *ti, int count, const double *qz, const double *rz,
                  const unsigned char *mask, double *perPartitionLH)
 {
-  int m, c, k, nb = e->nbranches;
+  int m, c, k, n, nb = e->nbranches, R = orc_R(e);
   orc_run_newviews(e, ti, 1, count, qz, rz, mask);
   for (m = 0; m < e->nparts; m++) {
     orc_part *p = &e->parts[m];
-    int S = p->states, span = 4 * S;
-    double diag[80], z, lz, sum = 0.0;
+    int S = p->states, span = R * S, np = orc_np(e, p);
+    const double *rates = orc_rates(e, p);
+    double diag[ORC_MAX_CATS * 20], z, lz, sum = 0.0;
     const unsigned char *tipA, *tipB; const double *xa, *xb;
     size_t i;
     if (!executes(e, mask, m)) { if (p->width == 0) perPartitionLH[m] = 0.0; continue; }
     z = qz[nb > 1 ? m : 0];
     lz = (z < ORC_ZMIN) ? log(ORC_ZMIN) : log(z);
-    for (c = 0; c < 4; c++) {
-      diag[c * S] = 1.0;
-      for (k = 1; k < S; k++) diag[c * S + k] = exp(p->gammaRates[c] * (p->EIGN[k] * lz));
+    for (n = 0; n < np; n++) {
+      diag[n * S] = 1.0;
+      for (k = 1; k < S; k++) diag[n * S + k] = exp(rates[n] * (p->EIGN[k] * lz));
     }
     branch_ends(e, p, &ti[0], &tipA, &tipB, &xa, &xb);
     for (i = 0; i < p->width; i++) {
       double term = 0.0;
-      for (c = 0; c < 4; c++)
+      for (c = 0; c < R; c++) {
+        const double *dg = diag + (size_t)orc_pidx(e, p, i, c) * S;
         for (k = 0; k < S; k++) {
           double l = tipA ? p->tipVector[(size_t)S * tipA[i] + k] : xa[i * span + c * S + k];
           double r = tipB ? p->tipVector[(size_t)S * tipB[i] + k] : xb[i * span + c * S + k];
-          term += l * r * diag[c * S + k];
+          term += l * r * dg[k];
         }
-      sum += p->wgt[i] * log(0.25 * fabs(term));
+      }
+      sum += p->wgt[i] * (e->cat ? log(fabs(term)) : log(0.25 * fabs(term)));
     }
     sum += (double)(p->scaler[ti[0].pNumber] + p->scaler[ti[0].qNumber]) * log(ORC_MINLIKELIHOOD);
     perPartitionLH[m] = sum;
@@ -258,17 +287,17 @@ int orc_evaluate(orc_engine *e, const orc_entry *ti, int count, const double *qz
 int orc_makenewz_prepare(orc_engine *e, const orc_entry *ti, int count, const double *qz, const double *rz,
                          const unsigned char *mask)
 {
-  int m, c, k;
+  int m, c, k, R = orc_R(e);
   orc_run_newviews(e, ti, 1, count, qz, rz, mask);
   for (m = 0; m < e->nparts; m++) {
     orc_part *p = &e->parts[m];
-    int S = p->states, span = 4 * S;
+    int S = p->states, span = R * S;
     const unsigned char *tipA, *tipB; const double *xa, *xb;
     size_t i;
     if (!executes(e, mask, m)) continue;
     branch_ends(e, p, &ti[0], &tipA, &tipB, &xa, &xb);
     for (i = 0; i < p->width; i++)
-      for (c = 0; c < 4; c++)
+      for (c = 0; c < R; c++)
         for (k = 0; k < S; k++) {
           double l = tipA ? p->tipVector[(size_t)S * tipA[i] + k] : xa[i * span + c * S + k];
           double r = tipB ? p->tipVector[(size_t)S * tipB[i] + k] : xb[i * span + c * S + k];
@@ -278,37 +307,49 @@ int orc_makenewz_prepare(orc_engine *e, const orc_entry *ti, int count, const do
   return 0;
 }
 
+/* GAMMA: coreGTRGAMMA mkz:2309-2393; CAT: coreCAT_FLEX mkz:394-519 (the site's rate multiplies the weight,
+   not the table: wr1 = r w, wr2 = r^2 w). */
 int orc_core(orc_engine *e, const double *lzv, const unsigned char *mask, double *dlnLdlz, double *d2lnLdlz2)
 {
-  int m, c, k, nb = e->nbranches;
+  int m, c, k, n, nb = e->nbranches, R = orc_R(e);
   for (m = 0; m < nb; m++) { dlnLdlz[m] = 0.0; d2lnLdlz2[m] = 0.0; }
   for (m = 0; m < e->nparts; m++) {
     orc_part *p = &e->parts[m];
-    int S = p->states, span = 4 * S, slot = nb > 1 ? m : 0;
-    double d0[80], d1[80], d2[80], lz = lzv[slot], dl = 0.0, d2l = 0.0;
+    int S = p->states, span = R * S, slot = nb > 1 ? m : 0, np = orc_np(e, p);
+    const double *rates = orc_rates(e, p);
+    double d0[ORC_MAX_CATS * 20], d1[ORC_MAX_CATS * 20], d2[ORC_MAX_CATS * 20], lz = lzv[slot], dl = 0.0, d2l = 0.0;
     size_t i;
     if (!executes(e, mask, m)) continue;
-    for (c = 0; c < 4; c++) {
-      double ki = p->gammaRates[c];
-      d0[c * S] = 1.0; d1[c * S] = 0.0; d2[c * S] = 0.0;
+    for (n = 0; n < np; n++) {
+      double ki = rates[n];
+      d0[n * S] = 1.0; d1[n * S] = 0.0; d2[n * S] = 0.0;
       for (k = 1; k < S; k++) {
-        d0[c * S + k] = exp(p->EIGN[k] * ki * lz);
-        d1[c * S + k] = p->EIGN[k] * ki;
-        d2[c * S + k] = p->EIGN[k] * p->EIGN[k] * ki * ki;
+        if (e->cat) {
+          d0[n * S + k] = exp((p->EIGN[k] * lz) * ki);
+          d1[n * S + k] = p->EIGN[k];
+          d2[n * S + k] = p->EIGN[k] * p->EIGN[k];
+        } else {
+          d0[n * S + k] = exp(p->EIGN[k] * ki * lz);
+          d1[n * S + k] = p->EIGN[k] * ki;
+          d2[n * S + k] = p->EIGN[k] * p->EIGN[k] * ki * ki;
+        }
       }
     }
     for (i = 0; i < p->width; i++) {
       const double *s = p->sum + i * span;
-      double L = 0.0, L1 = 0.0, L2 = 0.0, inv;
-      for (c = 0; c < 4; c++)
+      double L = 0.0, L1 = 0.0, L2 = 0.0, inv, w1 = p->wgt[i], w2 = p->wgt[i];
+      for (c = 0; c < R; c++) {
+        int pi = orc_pidx(e, p, i, c);
         for (k = 0; k < S; k++) {
-          double t = d0[c * S + k] * s[c * S + k];
-          L += t; L1 += t * d1[c * S + k]; L2 += t * d2[c * S + k];
+          double t = d0[pi * S + k] * s[c * S + k];
+          L += t; L1 += t * d1[pi * S + k]; L2 += t * d2[pi * S + k];
         }
+      }
+      if (e->cat) { double r = rates[p->rateCategory[i]]; w1 = r * p->wgt[i]; w2 = r * r * p->wgt[i]; }
       inv = 1.0 / fabs(L);
       L1 *= inv; L2 *= inv;
-      dl += p->wgt[i] * L1;
-      d2l += p->wgt[i] * (L2 - L1 * L1);
+      dl += w1 * L1;
+      d2l += w2 * (L2 - L1 * L1);
     }
     dlnLdlz[slot] += dl;
     d2lnLdlz2[slot] += d2l;
@@ -316,10 +357,28 @@ int orc_core(orc_engine *e, const double *lzv, const unsigned char *mask, double
   return 0;
 }
 
+/* CAT/PSR: switch the engine to one rate category per site (before orc_set_partition) and hand over
+   pInfo.numberOfCategories / perSiteRates / rateCategory (axml.h:533-629). */
+int orc_set_rate_model(orc_engine *e, int rateHetModel, int maxCategories)
+{
+  (void)maxCategories;
+  e->cat = rateHetModel == 0;          /* CAT = 0, GAMMA = 1 (axml.h:349-350) */
+  return 0;
+}
+int orc_set_categories(orc_engine *e, int model, int ncat, const double *perSiteRates, const int *rateCategory)
+{
+  orc_part *p = &e->parts[model];
+  if (ncat > ORC_MAX_CATS) return -1;
+  p->ncat = ncat;
+  memcpy(p->catRates, perSiteRates, (size_t)ncat * sizeof(double));
+  memcpy(p->rateCategory, rateCategory, p->width * sizeof(int));
+  return 0;
+}
+
 int orc_read_clv(orc_engine *e, int model, int number, double *out)
 {
   orc_part *p = &e->parts[model];
-  memcpy(out, clv_of(e, p, number), p->width * 4 * (size_t)p->states * sizeof(double));
+  memcpy(out, clv_of(e, p, number), p->width * (size_t)orc_R(e) * (size_t)p->states * sizeof(double));
   return 0;
 }
 int orc_read_scaler(orc_engine *e, int model, int number, unsigned int *out)
@@ -330,6 +389,6 @@ int orc_read_scaler(orc_engine *e, int model, int number, unsigned int *out)
 int orc_read_sumtable(orc_engine *e, int model, double *out)
 {
   orc_part *p = &e->parts[model];
-  memcpy(out, p->sum, p->width * 4 * (size_t)p->states * sizeof(double));
+  memcpy(out, p->sum, p->width * (size_t)orc_R(e) * (size_t)p->states * sizeof(double));
   return 0;
 }

@@ -55,7 +55,8 @@ static void dump_state(tree *tr, const char *path, int with_alignment, const cha
   int m, i, b, nb = tr->numBranches;
   int notips = !with_alignment || getenv("EXAML_PROBE_NOTIPS") != NULL, first_entry = 1;
   if (!f) { perror(path); return; }
-  fprintf(f, "{\n\"mxtips\": %d, \"numBranches\": %d, \"NumberOfModels\": %d,\n", tr->mxtips, nb, tr->NumberOfModels);
+  fprintf(f, "{\n\"mxtips\": %d, \"numBranches\": %d, \"NumberOfModels\": %d, \"rateHetModel\": %d, \"maxCategories\": %d,\n",
+          tr->mxtips, nb, tr->NumberOfModels, tr->rateHetModel, tr->maxCategories);
   fprintf(f, "\"likelihood\": %.17g,\n", tr->likelihood);
   put_darr(f, "perPartitionLH", tr->perPartitionLH, (size_t)tr->NumberOfModels);
   fprintf(f, ",\n");
@@ -78,6 +79,13 @@ static void dump_state(tree *tr, const char *path, int with_alignment, const cha
     put_darr(f, "tipVector", p->tipVector, (size_t)codes * S); fprintf(f, ",\n");
     put_darr(f, "frequencies", p->frequencies, (size_t)S); fprintf(f, ",\n");
     put_darr(f, "gammaRates", p->gammaRates, 4); fprintf(f, ",\n");
+    if (tr->rateHetModel == CAT) {
+      fprintf(f, "\"numberOfCategories\": %d,\n", p->numberOfCategories);
+      put_darr(f, "perSiteRates", p->perSiteRates, (size_t)p->numberOfCategories); fprintf(f, ",\n");
+      fprintf(f, "\"rateCategory\": [");
+      for (w = 0; w < p->width; w++) fprintf(f, "%s%d", w ? "," : "", p->rateCategory[w]);
+      fprintf(f, "],\n");
+    }
     fprintf(f, "\"rootScaler\": %u", p->width ?
             p->globalScaler[tr->td[0].ti[0].pNumber] + p->globalScaler[tr->td[0].ti[0].qNumber] : 0u);
     if (!notips) {

@@ -45,11 +45,11 @@ def write_inputs(tag: str, tmp: str, partition_lines=None):
     return os.path.join(tmp, f"{tag}.binary"), tree, first
 
 
-def run_dropin(binary: str, tree: str, tmp: str, extra_args, env=None, exe=DROPIN):
+def run_dropin(binary: str, tree: str, tmp: str, extra_args, env=None, exe=DROPIN, model="GAMMA"):
     e = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
     e["EXAML_PROBE_DUMP"] = os.path.join(tmp, "dump")
     e.update(env or {})
-    r = subprocess.run([exe, "-s", binary, "-t", tree, "-m", "GAMMA", "-n", "RUN", "-w", tmp + "/"] + extra_args,
+    r = subprocess.run([exe, "-s", binary, "-t", tree, "-m", model, "-n", "RUN", "-w", tmp + "/"] + extra_args,
                        cwd=tmp, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
     dumps = {}
     for d in ("first", "mkz", "final"):

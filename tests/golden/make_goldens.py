@@ -48,13 +48,13 @@ def store(name, obj):
     print(f"  wrote {os.path.relpath(path, ROOT)} ({os.path.getsize(path)} bytes)  lnL={obj['likelihood']!r}")
 
 
-def case(tag, alignment, tree_file, parser_args, examl_args, dumps=("first", "mkz", "final"), exit_first=False):
+def case(tag, alignment, tree_file, parser_args, examl_args, dumps=("first", "mkz", "final"), exit_first=False, model="GAMMA"):
     with tempfile.TemporaryDirectory() as tmp:
         run([os.path.join(BIN, "parse-examl"), "-s", alignment, "-n", "aln"] + parser_args, tmp)
         env = {"EXAML_PROBE_DUMP": os.path.join(tmp, "dump")}
         if exit_first:
             env["EXAML_PROBE_EXIT_FIRST"] = "1"
-        out = run([os.path.join(BIN, "examl-AVX"), "-s", "aln.binary", "-t", tree_file, "-m", "GAMMA",
+        out = run([os.path.join(BIN, "examl-AVX"), "-s", "aln.binary", "-t", tree_file, "-m", model,
                    "-n", "G", "-w", tmp + "/"] + examl_args, tmp, env)
         newick = open(tree_file).read().strip()
         for d in dumps:
@@ -98,6 +98,10 @@ def main():
         lg2 = os.path.join(tmp, "lg2.model")
         open(lg2, "w").write("LG, p0 = 1-300\n")
         case("aa60", phy, tf, ["-m", "PROT", "-q", lg2], ["-f", "e"], ("first", "mkz", "final"))
+        print("PSR (per-site rate categories, -m PSR): the same AA set, and testData/49")
+        case("aa60psr", phy, tf, ["-m", "PROT", "-q", lg2], ["-f", "e"], ("first", "mkz", "final"), model="PSR")
+        case("dna49psr", f"{td}/49", f"{td}/49.tree", ["-m", "DNA"], ["-f", "e"], ("first", "mkz", "final"), model="PSR")
+        case("dna49ppsr", f"{td}/49", f"{td}/49.tree", ["-m", "DNA", "-q", f"{td}/49.model"], ["-f", "e"], ("first", "final"), model="PSR")
 
 
 if __name__ == "__main__":

@@ -48,6 +48,8 @@ def load_engine(make_engine, state: dict, alignment_state: dict | None = None, *
     src = alignment_state or state
     mxtips, nparts, nb = state["mxtips"], state["NumberOfModels"], state["numBranches"]
     eng = make_engine(mxtips, nparts, nb, **kw)
+    if state.get("rateHetModel", 1) == 0:
+        eng.set_rate_model(0, state.get("maxCategories", 25))
     for m, part in enumerate(src["partitions"]):
         tips, wgt = alignment_of(part, mxtips)
         eng.set_partition(m, part["states"], wgt, tips)
@@ -59,3 +61,5 @@ def load_engine(make_engine, state: dict, alignment_state: dict | None = None, *
 def set_models(eng, state: dict) -> None:
     for m, part in enumerate(state["partitions"]):
         eng.set_model(m, constants_of(part))
+        if state.get("rateHetModel", 1) == 0:
+            eng.set_categories(m, part["perSiteRates"], part["rateCategory"])

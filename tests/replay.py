@@ -23,6 +23,10 @@ CASES = {
     "aa140": (True, True),
     "dnaiid200": (False, False),
     "aa60": (True, True),
+    # -m PSR: one rate category per site (CAT kernels); the end state carries the optimised per-site categories
+    "dna49psr": (True, True),
+    "dna49ppsr": (False, True),
+    "aa60psr": (True, True),
 }
 
 

@@ -43,11 +43,27 @@ def random_case(mxtips, widths, kinds, seed=0, mode="signal", num_branches=1, co
     return tree, parts, random_models(kinds, seed)
 
 
-def build_engine(factory, tree, parts, models, **kw):
+def random_categories(parts, max_cats=25, seed=0):
+    """PSR-style per-site rate categories: (perSiteRates[ncat], rateCategory[width]) per partition."""
+    rng = np.random.default_rng(seed + 77)
+    out = []
+    for i, (s, tips, wgt) in enumerate(parts):
+        ncat = int(rng.integers(1, max_cats + 1))
+        rates = np.sort(rng.gamma(2.0, 0.5, ncat)) + 0.01
+        out.append((rates, rng.integers(0, ncat, wgt.shape[0]).astype(np.int32)))
+    return out
+
+
+def build_engine(factory, tree, parts, models, cats=None, max_cats=25, **kw):
+    """cats: None for GAMMA, else the list from random_categories (CAT / PSR)."""
     eng = factory(tree.mxtips, len(parts), tree.numBranches, **kw)
+    if cats is not None:
+        eng.set_rate_model(0, max_cats)
     for m, (s, tips, wgt) in enumerate(parts):
         eng.set_partition(m, s, wgt, tips)
     eng.commit()
     for m, mc in enumerate(models):
         eng.set_model(m, mc)
+        if cats is not None:
+            eng.set_categories(m, cats[m][0], cats[m][1])
     return eng

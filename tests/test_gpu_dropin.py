@@ -24,6 +24,9 @@ def _rel(a, b):
     ("dna49p", "from-fixture", []),
     ("dna49pM", "from-fixture", ["-M"]),
     ("aa60", ["LG, p0 = 1-300"], []),
+    ("dna49psr", None, ["PSR"]),
+    ("dna49ppsr", "from-fixture", ["PSR"]),
+    ("aa60psr", ["LG, p0 = 1-300"], ["PSR"]),
 ])
 def test_tree_evaluation_matches_reference(tag, lines, extra):
     """`-f e`: model + branch-length optimisation on a fixed tree (treeEvaluate, modOpt: thousands of
@@ -39,7 +42,8 @@ def test_tree_evaluation_matches_reference(tag, lines, extra):
             lo += n
     with tempfile.TemporaryDirectory() as tmp:
         binary, tree, _ = write_inputs(tag, tmp, lines)
-        r, dumps = run_dropin(binary, tree, tmp, ["-f", "e"] + extra)
+        psr = "PSR" in extra
+        r, dumps = run_dropin(binary, tree, tmp, ["-f", "e"] + [x for x in extra if x != "PSR"], model="PSR" if psr else "GAMMA")
         assert r.returncode == 0, r.stdout[-3000:]
         assert _rel(dumps["first"]["likelihood"], first_gold["likelihood"]) < 1e-11, (dumps["first"]["likelihood"], first_gold["likelihood"])
         got, want = dumps["final"]["likelihood"], final_gold["likelihood"]

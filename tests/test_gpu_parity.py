@@ -8,7 +8,7 @@ import pytest
 
 from examl_b200.likelihood import Likelihood
 from replay import CASES, replay_case
-from synth import build_engine, random_case
+from synth import build_engine, random_case, random_categories
 
 pytestmark = pytest.mark.gpu
 
@@ -197,3 +197,48 @@ def test_device_newton_raphson_matches_host_loop(cuda_factory, oracle_factory, w
         a2.z[:] = z2
     l1, l2 = lk.evaluateGeneric(tree.start, True), lk2.evaluateGeneric(tree2.start, True)
     assert abs(l1 - l2) <= 1e-10 * abs(l2)
+
+
+@pytest.mark.parametrize("widths,kinds,nb", [([1], [4], 1), ([700], [4], 1), ([50], [20], 1), ([500], [20], 1),
+                                             ([300, 0, 420, 33], [4, 4, 20, 20], 1), ([130, 400], [4, 20], 2)])
+def test_psr_cat_model_vs_oracle(cuda_factory, oracle_factory, widths, kinds, nb):
+    """-m PSR: one rate category per site (CAT kernels): CLVs, scalers, lnL, sum table, derivatives and the
+    device-resident Newton-Raphson against the oracle's CAT restatement."""
+    tree, parts, models = random_case(22, widths, kinds, seed=41 + len(widths), num_branches=nb)
+    tree2, parts2, models2 = random_case(22, widths, kinds, seed=41 + len(widths), num_branches=nb)
+    cats = random_categories(parts, max_cats=25, seed=5)
+    gpu = build_engine(cuda_factory, tree, parts, models, cats=cats, tile_sites=64)
+    cpu = build_engine(oracle_factory, tree2, parts2, models2, cats=cats)
+    _compare_engines(gpu, cpu, tree, parts)
+    lk = Likelihood(tree, gpu, len(widths), device_newton_raphson=True)
+    lk2 = Likelihood(tree2, cpu, len(widths))
+    lk.evaluateGeneric(tree.start, True)
+    lk2.evaluateGeneric(tree2.start, True)
+    for (a, b), (a2, b2) in list(zip(tree.branches(), tree2.branches()))[:8]:
+        ti = tree.partial_traversal(a)
+        ti2 = tree2.partial_traversal(a2)
+        gpu.makenewzIterative(ti); cpu.makenewzIterative(ti2)
+        for m, (s, tips, wgt) in enumerate(parts):
+            if wgt.shape[0]:
+                x, y = gpu.read_sumtable(m), cpu.read_sumtable(m)
+                assert np.all(np.abs(x - y) <= CLV_RTOL * np.abs(y).max(axis=(1, 2), keepdims=True))
+        lz = [np.log(0.7)] * nb
+        g1, g2 = gpu.execCore(lz); c1, c2 = cpu.execCore(lz)
+        np.testing.assert_allclose(g1, c1, rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(g2, c2, rtol=1e-10, atol=1e-10)
+        z = lk.makenewzGeneric(a, b, a.z, 10)
+        z2 = lk2.makenewzGeneric(a2, b2, a2.z, 10)
+        for u, v in zip(z, z2):
+            assert abs(u - v) <= 1e-9 * v
+        a.z[:] = z; a2.z[:] = z2
+    l1, l2 = lk.evaluateGeneric(tree.start, True), lk2.evaluateGeneric(tree2.start, True)
+    assert abs(l1 - l2) <= 1e-10 * abs(l2)
+
+
+def test_psr_scaling_path(cuda_factory, oracle_factory):
+    tree, parts, models = random_case(150, [400, 300], [4, 20], seed=3, mode="iid")
+    cats = random_categories(parts, max_cats=12, seed=2)
+    gpu = build_engine(cuda_factory, tree, parts, models, cats=cats, max_cats=12)
+    cpu = build_engine(oracle_factory, tree, parts, models, cats=cats, max_cats=12)
+    ti = _compare_engines(gpu, cpu, tree, parts)
+    assert gpu.read_scaler(0, ti[0].pNumber) + gpu.read_scaler(0, ti[0].qNumber) > 0
