@@ -58,9 +58,16 @@ def model_for(workload: str, alpha: float = 0.5):
     return exmodel.poisson_aa(alpha=alpha, seed=4)     # generic 20-state GTR-like matrix (LG-shaped work)
 
 
-def algorithmic_bytes(ti, n_sites: int, states: int) -> float:
+def psr_categories(n_sites: int, lower: int = 0):
+    """25 per-site rate categories, assigned pseudo-randomly but reproducibly per global site index."""
+    rates = np.linspace(0.05, 3.0, 25)
+    idx = ((np.arange(lower, lower + n_sites, dtype=np.int64) * 2654435761) >> 7) % 25
+    return rates, idx.astype(np.int32)
+
+
+def algorithmic_bytes(ti, n_sites: int, states: int, cats_per_site: int = 4) -> float:
     """bytes a perfect implementation must move for this traversal."""
-    span = 4 * states * 8
+    span = cats_per_site * states * 8
     per = {0: 2 + span, 1: span + 1 + span, 2: 3 * span}
     b = sum(per[e.tipCase] for e in ti[1:]) * n_sites
     b += (span + 5) * n_sites            # evaluate at a tip branch (start is a tip): span + 1 B tip + 4 B weight
@@ -151,7 +158,7 @@ def usable_cores() -> int:
     return n
 
 
-def run_reference(tree: Tree, workload: str, sample_sites: int, steps: int, warmup: int):
+def run_reference(tree: Tree, workload: str, sample_sites: int, steps: int, warmup: int, model: str = "gamma"):
     cores = usable_cores()
     tips = make_sites(tree, 0, sample_sites, workload)
     exe = os.path.join(REF_DIR, "examl-OMP-AVX")
@@ -168,7 +175,7 @@ def run_reference(tree: Tree, workload: str, sample_sites: int, steps: int, warm
                            stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
             env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}   # a single process
             env.update(OMP_NUM_THREADS=str(cores), EXAML_PROBE_BENCH=str(steps), EXAML_PROBE_WARMUP=str(warmup))
-            r = subprocess.run([exe, "-s", "a.binary", "-t", "a.tree", "-m", "GAMMA", "-n", "B", "-f", "e", "-w", tmp + "/"],
+            r = subprocess.run([exe, "-s", "a.binary", "-t", "a.tree", "-m", "PSR" if model == "psr" else "GAMMA", "-n", "B", "-f", "e", "-w", tmp + "/"],
                                cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             for line in r.stdout.splitlines():
                 if line.startswith("PROBE_BENCH "):
@@ -182,8 +189,12 @@ def run_reference(tree: Tree, workload: str, sample_sites: int, steps: int, warm
     from oracle.oracle import OracleEngine
     mc = model_for(workload)
     eng = OracleEngine(tree.mxtips, 1, 1)
+    if model == "psr":
+        eng.set_rate_model(0, 25)
     eng.set_partition(0, mc.states, np.ones(sample_sites, dtype=np.int32), tips)
     eng.set_model(0, mc)
+    if model == "psr":
+        eng.set_categories(0, *psr_categories(sample_sites))
     ti = tree.full_traversal()
     for _ in range(warmup):
         eng.evaluateIterative(ti)
@@ -203,6 +214,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dna", choices=["dna", "aa"])
+    ap.add_argument("--model", default="gamma", choices=["gamma", "psr"],
+                    help="rate heterogeneity: GAMMA (the headline config) or PSR/CAT (one rate category per site, 25 categories)")
     ap.add_argument("--sites", type=int, default=None)
     ap.add_argument("--taxa", type=int, default=None)
     ap.add_argument("--tile", type=int, default=None)
@@ -219,7 +232,7 @@ def main():
     taxa = args.taxa or (200 if args.workload == "dna" else 500)
     states = 4 if args.workload == "dna" else 20
     metric = "million site-lnL updates/sec (newview)"
-    workload_name = (f"synthetic {'DNA GTR' if states == 4 else 'AA (20-state GTR-like, LG-shaped)'}+GAMMA4, "
+    workload_name = (f"synthetic {'DNA GTR' if states == 4 else 'AA (20-state GTR-like, LG-shaped)'}+{'GAMMA4' if args.model == 'gamma' else 'PSR (25 per-site rate categories)'}, "
                      f"{sites} sites x {taxa} taxa, 1 partition, full-traversal evaluateGeneric")
     tree = Tree.random(taxa, seed=TREE_SEED)
     ti = tree.full_traversal()
@@ -230,7 +243,7 @@ def main():
         if rank != 0:
             return 0
         sample = args.cpu_sample_sites or min(sites, 200_000 if states == 4 else 10_000)
-        ref = run_reference(tree, args.workload, sample, max(args.steps, 1), args.warmup)
+        ref = run_reference(tree, args.workload, sample, max(args.steps, 1), args.warmup, args.model)
         line = {"impl": "reference", "metric": metric, "value": ref["value"], "unit": "M site-updates/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * ref["seconds"] / max(args.steps, 1), "higher_is_better": True,
@@ -261,9 +274,13 @@ def main():
     mc = model_for(args.workload)
 
     eng = Engine(taxa, 1, 1, device=local_rank, tile_sites=args.tile)
+    if args.model == "psr":
+        eng.set_rate_model(0, 25)
     eng.set_partition(0, states, wgt, tips)
     eng.commit()
     eng.set_model(0, mc)
+    if args.model == "psr":
+        eng.set_categories(0, *psr_categories(upper - lower, lower))
     if world > 1:
         uid = [eng.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -334,12 +351,12 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
         n_local = upper - lower
-        abytes = algorithmic_bytes(ti, n_local, states)
+        abytes = algorithmic_bytes(ti, n_local, states, 4 if args.model == "gamma" else 1)
         achieved = abytes / (dev_s / args.steps) / 1e9
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{sites}x{taxa}")
-            if tj and world == 1:
+            if tj and world == 1 and args.model == "gamma":
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
@@ -381,9 +398,9 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             sample = args.cpu_sample_sites or min(sites, 200_000 if states == 4 else 10_000)
             try:
-                ref = run_reference(tree, args.workload, sample, 3, 1)
+                ref = run_reference(tree, args.workload, sample, 3, 1, args.model)
                 line["cpu_baseline"] = {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample")}
-                if states == 4:
+                if states == 4 and args.model == "gamma":
                     # proof of work: the same sample through the CUDA engine must give the reference's lnL
                     e2 = Engine(taxa, 1, 1, device=local_rank)
                     e2.set_partition(0, states, np.ones(sample, dtype=np.int32), make_sites(tree, 0, sample, args.workload))

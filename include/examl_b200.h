@@ -15,12 +15,15 @@
  *   reading pInfo.{EIGN,EV,EI,tipVector,gammaRates} on every   exb_set_model
  *     call (newviewGenericSpecial.c:939-1045,
  *     evaluateGenericSpecial.c:433-480)
+ *   tr->rateHetModel, pInfo.{numberOfCategories,              exb_set_rate_model,
+ *     perSiteRates,rateCategory} (-m PSR)                       exb_set_categories
  *   newviewIterative      (newviewGenericSpecial.c:917)        exb_newview
  *   evaluateIterative     (evaluateGenericSpecial.c:403)       exb_evaluate
  *     + MPI_Allreduce     (evaluateGenericSpecial.c:968-975)     (all-reduce inside, NCCL)
  *   makenewzIterative     (makenewzGenericSpecial.c:628)       exb_makenewz_prepare
  *   execCore              (makenewzGenericSpecial.c:849)       exb_core
  *     + MPI_Allreduce     (makenewzGenericSpecial.c:1241-1248)   (all-reduce inside, NCCL)
+ *   topLevelMakenewz      (makenewzGenericSpecial.c:1133)      exb_makenewz (single rank: whole NR loop on the device)
  *
  * The three public axml.h entry points (evaluateGeneric axml.h:1223, newviewGeneric :1232,
  * makenewzGeneric :1241) are exported by the companion translation unit
