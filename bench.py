@@ -74,12 +74,12 @@ def algorithmic_bytes(ti, n_sites: int, states: int, cats_per_site: int = 4) -> 
     return float(b)
 
 
-def algorithmic_flops(ti, n_sites: int, states: int) -> float:
+def algorithmic_flops(ti, n_sites: int, states: int, cats_per_site: int = 4) -> float:
     """FP64 flops a tip-table implementation (the reference's, and ours) needs: per site update and category two
     SxS matrix-vector products for inner children (a table look-up for tips), the element-wise product and the SxS
     back-transformation (~9 440 flop per INNER_INNER AA site update, ~352 for DNA)."""
-    mv = 2 * states * states * 4                       # one child, four categories
-    per = {0: mv + 4 * states, 1: 2 * mv + 4 * states, 2: 3 * mv + 4 * states}
+    mv = 2 * states * states * cats_per_site           # one child, all categories of a site
+    per = {0: mv + cats_per_site * states, 1: 2 * mv + cats_per_site * states, 2: 3 * mv + cats_per_site * states}
     return float(sum(per[e.tipCase] for e in ti[1:]) * n_sites)
 
 
@@ -368,7 +368,7 @@ def main():
                         "note": "child CLVs are consumed from registers / L2, so DRAM traffic is ~half of the algorithmic bytes "
                                 "and frac can exceed 1; the design's own ceiling is the CLV write stream (see DESIGN.md 5)"}
         else:
-            aflops = algorithmic_flops(ti, n_local, states)
+            aflops = algorithmic_flops(ti, n_local, states, 4 if args.model == "gamma" else 1)
             tf = aflops / (dev_s / args.steps) / 1e12
             roofline = {"bound": "tensor", "achieved": tf, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / DMMA_PEAK_TFLOPS,
                         "traffic": traffic, "kernel": "traverse_aa_kernel",

@@ -17,7 +17,9 @@
 // are broadcast from shared memory.
 #include "engine.cuh"
 #include "core_tile.cuh"
+#include "stage.cuh"
 #include <algorithm>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -34,12 +36,6 @@ struct AaShared {
   double fragEI[15][32];  // B fragments of EI^T, [k-step * 3 + n-tile][lane]: conflict-free LDS.64
   double fragEV[15][32];  // B fragments of EV
   double red[32];
-};
-
-struct SEntry {
-  int tipCase;
-  int ptip_qtip;
-  long long poff, qoff, roff;
 };
 
 __device__ __forceinline__ void ld256(const double *p, double *v)
@@ -63,32 +59,6 @@ __device__ __forceinline__ void st256(double *p, const double *v)
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}"
-      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 enum Src : int { SRC_TIP = 0, SRC_CARRY = 1, SRC_LOAD = 2 };
 
 // D(8x8) += A(8x4) * B(4x8), FP64 tensor pipe (SASS: DMMA.8x8x4).
@@ -146,21 +116,35 @@ __device__ __forceinline__ void child_y(double (&y)[3][2], const double (&carry)
 
 // Per-slot operands of one entry.  A "slot" is a Gamma category of the warp's 8 sites (GAMMA) or one of the
 // warp's four 8-site groups (CAT / PSR, one category per site).
-struct AaSlots {
-  const double *xq[4], *xr[4];     // child vectors (memory mode): 20 doubles of my row
-  const double *lq[4], *lr[4];     // tip table rows (LUT mode): 20 doubles
-  const double *dq[4];             // exponentials of the q side; the r side follows at +20
+struct AaSlotsCat {                // CAT: everything differs per slot (four different sites)
+  const double *xq_[4], *xr_[4];   // child vectors (memory mode): 20 doubles of my row
+  const double *lq_[4], *lr_[4];   // tip table rows (LUT mode): 20 doubles
+  const double *dq_[4];            // exponentials of the q side; the r side follows at +20
+  __device__ __forceinline__ const double *xq(int c) const { return xq_[c]; }
+  __device__ __forceinline__ const double *xr(int c) const { return xr_[c]; }
+  __device__ __forceinline__ const double *lq(int c) const { return lq_[c]; }
+  __device__ __forceinline__ const double *lr(int c) const { return lr_[c]; }
+  __device__ __forceinline__ const double *dq(int c) const { return dq_[c]; }
+};
+struct AaSlotsGamma {              // GAMMA: one site, slot = category: a base and a constant stride
+  const double *x1, *x2, *lut1, *lut2, *drow;
+  int st1, st2;                    // 20 for a CLV, 0 for the tip vector (the same for every category)
+  __device__ __forceinline__ const double *xq(int c) const { return x1 + c * st1; }
+  __device__ __forceinline__ const double *xr(int c) const { return x2 + c * st2; }
+  __device__ __forceinline__ const double *lq(int c) const { return lut1 + c * S; }
+  __device__ __forceinline__ const double *lr(int c) const { return lut2 + c * S; }
+  __device__ __forceinline__ const double *dq(int c) const { return drow + c * 40; }
 };
 
-template <int QM, int RM>
+template <int QM, int RM, class Slots>
 __device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const double (*fEI)[32], const double (*fEV)[32],
-                                         const AaSlots &sl, int lane, int tq)
+                                         const Slots &sl, int lane, int tq)
 {
   #pragma unroll
   for (int c = 0; c < 4; c++) {
     double y1[3][2], y2[3][2];
-    child_y<QM>(y1, carry, fEI, sl.xq[c], sl.lq[c], sl.dq[c], c, lane, tq);
-    child_y<RM>(y2, carry, fEI, sl.xr[c], sl.lr[c], sl.dq[c] + S, c, lane, tq);
+    child_y<QM>(y1, carry, fEI, sl.xq(c), sl.lq(c), sl.dq(c), c, lane, tq);
+    child_y<RM>(y2, carry, fEI, sl.xr(c), sl.lr(c), sl.dq(c) + S, c, lane, tq);
     // Z = Y1 (.) Y2 in C layout, then X3 = Z * EV
     #pragma unroll
     for (int t = 0; t < 3; t++) { y1[t][0] *= y2[t][0]; y1[t][1] *= y2[t][1]; }
@@ -211,8 +195,8 @@ traverse_aa_kernel(const TraverseArgs a)
   __shared__ AaShared sh;
   __shared__ __align__(8) uint64_t mbar;
   extern __shared__ __align__(16) unsigned char dyn[];
-  SEntry *ents = reinterpret_cast<SEntry *>(dyn);
-  uint8_t *stips = dyn + (((size_t)a.count * sizeof(SEntry) + 15) & ~(size_t)15);   // [mxtips][TSITES]
+  const SEntry *ents = reinterpret_cast<const SEntry *>(dyn);                     // window entries; slot kWindow = branch entry
+  const uint8_t *stips = dyn + (size_t)(kWindow + 1) * sizeof(SEntry);             // [2*kWindow + 2][TSITES] staged tip rows
 
   const Tile tile = a.tiles[blockIdx.x];
   if (!a.mask[tile.part]) return;
@@ -231,55 +215,20 @@ traverse_aa_kernel(const TraverseArgs a)
       sh.fragEV[f][ln] = n < S ? model[424 + k * S + n] : 0.0;
     }
     if (tid == 0) mbar_init(&mbar, 1);
-    for (int e = tid; e < a.count; e += kAaThreads) {
-      const DevEntry en = a.entries[e];
-      SEntry se;
-      se.tipCase = en.tipCase;
-      se.ptip_qtip = (en.p <= a.mxtips ? 1 : 0) | (en.q <= a.mxtips ? 2 : 0);
-      se.poff = en.p > a.mxtips ? (long long)(en.p - a.mxtips - 1) * (long long)N * XSPAN : (long long)(en.p - 1) * TSITES;
-      se.qoff = en.q > a.mxtips ? (long long)(en.q - a.mxtips - 1) * (long long)N * XSPAN : (long long)(en.q - 1) * TSITES;
-      se.roff = en.r > a.mxtips ? (long long)(en.r - a.mxtips - 1) * (long long)N * XSPAN : (long long)(en.r - 1) * TSITES;
-      ents[e] = se;
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
   }
 
   const int ncat = CAT ? a.max_cats : 4;                                  // blocks per d-table / tip-table row
-  const double *drow0 = a.dtab + (size_t)tile.part_cls * a.dtab_row;      // + e * dstride + cat*40 + side*20 + k
-  const size_t dstride = (size_t)a.nparts_cls * a.dtab_row;
-  const size_t lutside = (size_t)23 * ncat * S;                           // doubles per (entry, partition, side)
-  const int lo = a.mode == MODE_NEWVIEW ? a.first : 0;
+  const int drowlen = CAT ? a.dtab_row : kAaDtabRow;                      // (compile-time constants under GAMMA)
+  const double *drow0 = a.dtab + (size_t)tile.part_cls * drowlen;         // + e * dstride + cat*40 + side*20 + k
+  const size_t dstride = (size_t)a.nparts_cls * drowlen;
+  const size_t lutside = CAT ? (size_t)23 * ncat * S : (size_t)kAaLutRow; // doubles per (entry, partition, side)
   double acc = 0.0;
   uint32_t phase = 0;
 
   for (unsigned chunk0 = 0; chunk0 < tile.nsites; chunk0 += TSITES) {
     const unsigned nchunk = min(tile.nsites - chunk0, (unsigned)TSITES);
-    if (chunk0) __syncthreads();
-    if (tid < 32) {
-      const uint32_t bytes = (nchunk + 15u) & ~15u;
-      const uint8_t *gsrc = a.tips + tile.site0 + chunk0;
-      int mine = 0;
-      for (int e = lo + lane; e < a.count; e += 32) {
-        const SEntry &se = ents[e];
-        if (se.tipCase < 0) mine += (se.ptip_qtip & 1) + ((se.ptip_qtip >> 1) & 1);
-        else                mine += (se.tipCase <= 1) + (se.tipCase == 0);
-      }
-      const int total = __reduce_add_sync(0xffffffffu, mine);
-      if (lane == 0) mbar_expect_tx(&mbar, (uint32_t)total * bytes);
-      __syncwarp();
-      for (int e = lo + lane; e < a.count; e += 32) {
-        const SEntry &se = ents[e];
-        if (se.tipCase < 0) {
-          if (se.ptip_qtip & 1) bulk_g2s(stips + se.poff, gsrc + (size_t)(se.poff / TSITES) * N, bytes, &mbar);
-          if (se.ptip_qtip & 2) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TSITES) * N, bytes, &mbar);
-        } else {
-          if (se.tipCase <= 1) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TSITES) * N, bytes, &mbar);
-          if (se.tipCase == 0) bulk_g2s(stips + se.roff, gsrc + (size_t)(se.roff / TSITES) * N, bytes, &mbar);
-        }
-      }
-    }
-
     // my row's site in every slot: GAMMA -- the same site four times; CAT -- four sites 8 apart
     const unsigned i0 = (unsigned)(CAT ? warp * 32 + g : warp * 8 + g);
     bool valid[4]; int lsite[4], cat[4];
@@ -299,26 +248,37 @@ traverse_aa_kernel(const TraverseArgs a)
       #pragma unroll
       for (int t = 0; t < 3; t++) carry[c][t][0] = carry[c][t][1] = 0.0;
 
-    mbar_wait(&mbar, phase);
-    phase ^= 1;
-
-    for (int e = a.first; e < a.count; e++) {
-      const SEntry en = ents[e];
+    int w0 = a.first;
+    do {
+    const int w1 = min(w0 + kWindow, a.count);
+    stage_window<TSITES>(dyn, &mbar, phase, a, N, XSPAN, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
+                         w0 == a.first && a.mode != MODE_NEWVIEW);
+    for (int e = w0; e < w1; e++) {
+      const SEntry en = ents[e - w0];
       const double *drow = drow0 + (size_t)e * dstride;
       const bool q_inner = en.tipCase == 2, r_inner = en.tipCase != 0;
       const int qsrc = !q_inner ? SRC_TIP : (en.qoff == carry_node ? SRC_CARRY : SRC_LOAD);
       const int rsrc = !r_inner ? SRC_TIP : (en.roff == carry_node ? SRC_CARRY : SRC_LOAD);
       const double *lutE = a.lut ? a.lut + ((size_t)e * a.nparts_cls + tile.part_cls) * 2 * lutside : nullptr;
-      AaSlots sl;
-      #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        // memory sources: a global CLV or the tip vector in shared memory; tip tables when they exist
-        const int code1 = q_inner ? 0 : stips[en.qoff + lsite[c]], code2 = r_inner ? 0 : stips[en.roff + lsite[c]];
-        sl.xq[c] = q_inner ? a.clv + en.qoff + soff + c * XSLOT : &sh.tip[S * code1];
-        sl.xr[c] = r_inner ? a.clv + en.roff + soff + c * XSLOT : &sh.tip[S * code2];
-        sl.dq[c] = drow + cat[c] * 40;
-        sl.lq[c] = lutE + ((size_t)code1 * ncat + cat[c]) * S;
-        sl.lr[c] = lutE + lutside + ((size_t)code2 * ncat + cat[c]) * S;
+      // memory sources: a global CLV or the tip vector in shared memory; tip tables when they exist
+      typename std::conditional<CAT, AaSlotsCat, AaSlotsGamma>::type sl;
+      if constexpr (CAT) {
+        #pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int code1 = q_inner ? 0 : stips[en.qoff + lsite[c]], code2 = r_inner ? 0 : stips[en.roff + lsite[c]];
+          sl.xq_[c] = q_inner ? a.clv + en.qoff + soff + c * XSLOT : &sh.tip[S * code1];
+          sl.xr_[c] = r_inner ? a.clv + en.roff + soff + c * XSLOT : &sh.tip[S * code2];
+          sl.dq_[c] = drow + cat[c] * 40;
+          sl.lq_[c] = lutE + ((size_t)code1 * ncat + cat[c]) * S;
+          sl.lr_[c] = lutE + lutside + ((size_t)code2 * ncat + cat[c]) * S;
+        }
+      } else {
+        const int code1 = q_inner ? 0 : stips[en.qoff + lsite[0]], code2 = r_inner ? 0 : stips[en.roff + lsite[0]];
+        sl.x1 = q_inner ? a.clv + en.qoff + soff : &sh.tip[S * code1];
+        sl.x2 = r_inner ? a.clv + en.roff + soff : &sh.tip[S * code2];
+        sl.st1 = q_inner ? S : 0; sl.st2 = r_inner ? S : 0;
+        sl.lut1 = lutE + (size_t)code1 * SPAN; sl.lut2 = lutE + lutside + (size_t)code2 * SPAN;
+        sl.drow = drow;
       }
       const bool qlut = !q_inner && lutE, rlut = !r_inner && lutE;
       if (qlut && rlut)                   aa_entry<CH_LUT, CH_LUT>(carry, sh.fragEI, sh.fragEV, sl, lane, tq);
@@ -365,11 +325,11 @@ traverse_aa_kernel(const TraverseArgs a)
           if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
         }
       }
-      {
+      if (CAT || valid[0]) {
         double *dst = a.clv + en.poff + soff + 2 * tq;
         #pragma unroll
         for (int c = 0; c < 4; c++) {
-          if (!valid[c]) continue;
+          if (CAT && !valid[c]) continue;
           *reinterpret_cast<double2 *>(dst + c * XSLOT) = make_double2(carry[c][0][0], carry[c][0][1]);
           *reinterpret_cast<double2 *>(dst + c * XSLOT + 8) = make_double2(carry[c][1][0], carry[c][1][1]);
           if (tq < 2) *reinterpret_cast<double2 *>(dst + c * XSLOT + 16) = make_double2(carry[c][2][0], carry[c][2][1]);
@@ -378,11 +338,12 @@ traverse_aa_kernel(const TraverseArgs a)
       __syncwarp();
       carry_node = en.poff;
     }
+    } while ((w0 += kWindow) < a.count);
 
     if (a.mode == MODE_NEWVIEW) continue;
 
     // ---------------- branch (entry 0): evaluate or sum table (C-fragment layout on both ends) ----------------
-    const SEntry br = ents[0];
+    const SEntry br = ents[kWindow];
     const bool ptip = br.ptip_qtip & 1, qtip = br.ptip_qtip & 2;
     const bool p_carry = !ptip && br.poff == carry_node, q_carry = !qtip && br.qoff == carry_node;
     double term = 0.0;
@@ -483,7 +444,7 @@ core_aa_kernel(const CoreArgs a)
 template <bool CAT>
 static void launch_aa_variant(const TraverseArgs &a, int ntiles, cudaStream_t s)
 {
-  const size_t smem = (((size_t)a.count * sizeof(SEntry) + 15) & ~(size_t)15) + (size_t)a.mxtips * (CAT ? 384 : 96);
+  const size_t smem = window_smem_bytes<(CAT ? 384 : 96)>();
   static size_t configured = 0;
   if (smem > configured) {
     const size_t want = std::min<size_t>(227 * 1024 - 16384, std::max<size_t>(smem, 64 * 1024));

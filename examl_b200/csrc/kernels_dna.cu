@@ -25,6 +25,7 @@
 // entry loop).
 #include "engine.cuh"
 #include "core_tile.cuh"
+#include "stage.cuh"
 #include <algorithm>
 #include <stdlib.h>
 #include <string.h>
@@ -98,45 +99,6 @@ void launch_dtab(const DtabArgs &a, cudaStream_t s)
 // (TMA, 1-D) per row, all completing on a single mbarrier -- the only cold HBM reads of the kernel
 // are issued up front and in bulk instead of one dependent byte load per entry.
 // ------------------------------------------------------------------------------------------------------
-namespace {
-
-struct SEntry {            // a traversal entry as the threads consume it (32 B)
-  int tipCase;             // -1 for the branch entry
-  int ptip_qtip;           // branch entry only: bit0 = p is a tip, bit1 = q is a tip
-  long long poff, qoff, roff;   // inner node: element offset of its CLV (node_index * N * 16, unique per node);
-                                // tip: row * TS inside the staged tip rows
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}"
-      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-}  // namespace
-
 template <int NS, bool PARAM, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
@@ -145,8 +107,8 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
   __shared__ DnaShared sh;
   __shared__ __align__(8) uint64_t mbar;
   extern __shared__ __align__(16) unsigned char dyn[];
-  SEntry *ents = reinterpret_cast<SEntry *>(dyn);                          // [count]
-  uint8_t *stips = dyn + (((size_t)a.count * sizeof(SEntry) + 15) & ~(size_t)15);   // [mxtips][TS]
+  const SEntry *ents = reinterpret_cast<const SEntry *>(dyn);                  // window entries; slot kWindow = branch entry
+  const uint8_t *stips = dyn + (size_t)(kWindow + 1) * sizeof(SEntry);          // [2*kWindow + 2][TS] staged tip rows
 
   const Tile tile = a.tiles[blockIdx.x];
   if (!a.mask[tile.part]) return;
@@ -159,16 +121,6 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
     if (tid < 64) sh.tip[tid] = model[40 + tid];
     if (!PARAM && tid < 16) { sh.EI[tid] = model[8 + tid]; sh.EV[tid] = model[24 + tid]; }
     if (tid == 0) mbar_init(&mbar, 1);
-    // expand the descriptor: node numbers -> offsets
-    for (int e = tid; e < a.count; e += kThreads) {
-      const DevEntry en = a.entries[e];
-      SEntry se;
-      se.tipCase = en.tipCase; se.ptip_qtip = (en.p <= a.mxtips ? 1 : 0) | (en.q <= a.mxtips ? 2 : 0);
-      se.poff = en.p > a.mxtips ? (long long)(en.p - a.mxtips - 1) * (long long)N * 16 : (long long)(en.p - 1) * TS;
-      se.qoff = en.q > a.mxtips ? (long long)(en.q - a.mxtips - 1) * (long long)N * 16 : (long long)(en.q - 1) * TS;
-      se.roff = en.r > a.mxtips ? (long long)(en.r - a.mxtips - 1) * (long long)N * 16 : (long long)(en.r - 1) * TS;
-      ents[e] = se;
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
   }
@@ -177,38 +129,11 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
 
   const double *drow = a.dtab + ((size_t)tile.part_cls * 4 + c) * 8;       // + e * nparts_cls * 32
   const size_t dstride = (size_t)a.nparts_cls * kDnaDtabRow;
-  const int lo = a.mode == MODE_NEWVIEW ? a.first : 0;                     // entry 0 = branch (may have tip ends)
   double acc = 0.0;
   uint32_t phase = 0;
 
   for (unsigned chunk0 = 0; chunk0 < tile.nsites; chunk0 += TS) {
     const unsigned nchunk = min(tile.nsites - chunk0, (unsigned)TS);
-    // ---- stage the tip rows of this chunk (warp 0 issues, everybody waits on the mbarrier) ----
-    if (chunk0) __syncthreads();               // previous chunk's readers are done with stips
-    if (tid < 32) {
-      const uint32_t bytes = (nchunk + 15u) & ~15u;
-      const uint8_t *gsrc = a.tips + tile.site0 + chunk0;
-      int mine = 0;
-      for (int e = lo + lane; e < a.count; e += 32) {
-        const SEntry &se = ents[e];
-        if (se.tipCase < 0) mine += (se.ptip_qtip & 1) + ((se.ptip_qtip >> 1) & 1);
-        else                mine += (se.tipCase <= 1) + (se.tipCase == 0);
-      }
-      const int total = __reduce_add_sync(0xffffffffu, mine);
-      if (lane == 0) mbar_expect_tx(&mbar, (uint32_t)total * bytes);
-      __syncwarp();
-      for (int e = lo + lane; e < a.count; e += 32) {
-        const SEntry &se = ents[e];
-        if (se.tipCase < 0) {
-          if (se.ptip_qtip & 1) bulk_g2s(stips + se.poff, gsrc + (size_t)(se.poff / TS) * N, bytes, &mbar);
-          if (se.ptip_qtip & 2) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TS) * N, bytes, &mbar);
-        } else {
-          if (se.tipCase <= 1) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TS) * N, bytes, &mbar);
-          if (se.tipCase == 0) bulk_g2s(stips + se.roff, gsrc + (size_t)(se.roff / TS) * N, bytes, &mbar);
-        }
-      }
-    }
-
     size_t eoff[NS];                           // element offset of (site, category) inside a CLV; site = eoff >> 4
     bool valid[NS];
     int lsite[NS];
@@ -224,12 +149,14 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
     #pragma unroll
     for (int s = 0; s < NS; s++) { carry[s][0] = carry[s][1] = carry[s][2] = carry[s][3] = 0.0; }
 
-    mbar_wait(&mbar, phase);
-    phase ^= 1;
-
-    // ---------------- newview entries ----------------
-    for (int e = a.first; e < a.count; e++) {
-      const SEntry en = ents[e];
+    // ---------------- newview entries, one window at a time ----------------
+    int w0 = a.first;
+    do {
+    const int w1 = min(w0 + kWindow, a.count);
+    stage_window<TS>(dyn, &mbar, phase, a, N, 16, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
+                     w0 == a.first && a.mode != MODE_NEWVIEW);
+    for (int e = w0; e < w1; e++) {
+      const SEntry en = ents[e - w0];
       double dq[4], dr[4];
       ld256_ro(drow + (size_t)e * dstride, dq);
       ld256_ro(drow + (size_t)e * dstride + 4, dr);
@@ -283,11 +210,12 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
         if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
       }
     }
+    } while ((w0 += kWindow) < a.count);
 
     if (a.mode == MODE_NEWVIEW) continue;
 
     // ---------------- branch (entry 0): evaluate or sum table ----------------
-    const SEntry br = ents[0];
+    const SEntry br = ents[kWindow];
     const bool ptip = br.ptip_qtip & 1, qtip = br.ptip_qtip & 2;
     const bool p_carry = !ptip && br.poff == carry_node, q_carry = !qtip && br.qoff == carry_node;
     double diag[4];
@@ -340,8 +268,8 @@ traverse_dna_cat_kernel(const TraverseArgs a, const DnaConsts kc)
   __shared__ DnaShared sh;
   __shared__ __align__(8) uint64_t mbar;
   extern __shared__ __align__(16) unsigned char dyn[];
-  SEntry *ents = reinterpret_cast<SEntry *>(dyn);
-  uint8_t *stips = dyn + (((size_t)a.count * sizeof(SEntry) + 15) & ~(size_t)15);   // [mxtips][TS]
+  const SEntry *ents = reinterpret_cast<const SEntry *>(dyn);                  // window entries; slot kWindow = branch entry
+  const uint8_t *stips = dyn + (size_t)(kWindow + 1) * sizeof(SEntry);          // [2*kWindow + 2][TS] staged tip rows
 
   const Tile tile = a.tiles[blockIdx.x];
   if (!a.mask[tile.part]) return;
@@ -352,51 +280,17 @@ traverse_dna_cat_kernel(const TraverseArgs a, const DnaConsts kc)
     if (tid < 64) sh.tip[tid] = model[40 + tid];
     if (!PARAM && tid < 16) { sh.EI[tid] = model[8 + tid]; sh.EV[tid] = model[24 + tid]; }
     if (tid == 0) mbar_init(&mbar, 1);
-    for (int e = tid; e < a.count; e += kThreads) {
-      const DevEntry en = a.entries[e];
-      SEntry se;
-      se.tipCase = en.tipCase; se.ptip_qtip = (en.p <= a.mxtips ? 1 : 0) | (en.q <= a.mxtips ? 2 : 0);
-      se.poff = en.p > a.mxtips ? (long long)(en.p - a.mxtips - 1) * (long long)N * 4 : (long long)(en.p - 1) * TS;
-      se.qoff = en.q > a.mxtips ? (long long)(en.q - a.mxtips - 1) * (long long)N * 4 : (long long)(en.q - 1) * TS;
-      se.roff = en.r > a.mxtips ? (long long)(en.r - a.mxtips - 1) * (long long)N * 4 : (long long)(en.r - 1) * TS;
-      ents[e] = se;
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
   }
 #define EI_(i) (PARAM ? kc.EI[i] : sh.EI[i])
 #define EV_(i) (PARAM ? kc.EV[i] : sh.EV[i])
   const size_t dstride = (size_t)a.nparts_cls * a.dtab_row;
-  const int lo = a.mode == MODE_NEWVIEW ? a.first : 0;
   double acc = 0.0;
   uint32_t phase = 0;
 
   for (unsigned chunk0 = 0; chunk0 < tile.nsites; chunk0 += TS) {
     const unsigned nchunk = min(tile.nsites - chunk0, (unsigned)TS);
-    if (chunk0) __syncthreads();
-    if (tid < 32) {
-      const uint32_t bytes = (nchunk + 15u) & ~15u;
-      const uint8_t *gsrc = a.tips + tile.site0 + chunk0;
-      int mine = 0;
-      for (int e = lo + lane; e < a.count; e += 32) {
-        const SEntry &se = ents[e];
-        if (se.tipCase < 0) mine += (se.ptip_qtip & 1) + ((se.ptip_qtip >> 1) & 1);
-        else                mine += (se.tipCase <= 1) + (se.tipCase == 0);
-      }
-      const int total = __reduce_add_sync(0xffffffffu, mine);
-      if (lane == 0) mbar_expect_tx(&mbar, (uint32_t)total * bytes);
-      __syncwarp();
-      for (int e = lo + lane; e < a.count; e += 32) {
-        const SEntry &se = ents[e];
-        if (se.tipCase < 0) {
-          if (se.ptip_qtip & 1) bulk_g2s(stips + se.poff, gsrc + (size_t)(se.poff / TS) * N, bytes, &mbar);
-          if (se.ptip_qtip & 2) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TS) * N, bytes, &mbar);
-        } else {
-          if (se.tipCase <= 1) bulk_g2s(stips + se.qoff, gsrc + (size_t)(se.qoff / TS) * N, bytes, &mbar);
-          if (se.tipCase == 0) bulk_g2s(stips + se.roff, gsrc + (size_t)(se.roff / TS) * N, bytes, &mbar);
-        }
-      }
-    }
     const bool valid = (unsigned)tid < nchunk;
     const int lsite = valid ? tid : 0;
     const size_t site = (size_t)tile.site0 + chunk0 + lsite;
@@ -406,11 +300,13 @@ traverse_dna_cat_kernel(const TraverseArgs a, const DnaConsts kc)
     double carry[4] = {0.0, 0.0, 0.0, 0.0};
     long long carry_node = -1;
 
-    mbar_wait(&mbar, phase);
-    phase ^= 1;
-
-    for (int e = a.first; e < a.count; e++) {
-      const SEntry en = ents[e];
+    int w0 = a.first;
+    do {
+    const int w1 = min(w0 + kWindow, a.count);
+    stage_window<TS>(dyn, &mbar, phase, a, N, 4, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
+                     w0 == a.first && a.mode != MODE_NEWVIEW);
+    for (int e = w0; e < w1; e++) {
+      const SEntry en = ents[e - w0];
       double dq[4], dr[4];
       ld256_ro(drow + (size_t)e * dstride, dq);
       ld256_ro(drow + (size_t)e * dstride + 4, dr);
@@ -452,9 +348,10 @@ traverse_dna_cat_kernel(const TraverseArgs a, const DnaConsts kc)
       carry[0] = v[0]; carry[1] = v[1]; carry[2] = v[2]; carry[3] = v[3];
       carry_node = en.poff;
     }
+    } while ((w0 += kWindow) < a.count);
     if (a.mode == MODE_NEWVIEW) continue;
 
-    const SEntry br = ents[0];
+    const SEntry br = ents[kWindow];
     const bool ptip = br.ptip_qtip & 1, qtip = br.ptip_qtip & 2;
     double xa[4], xb[4];
     if (!ptip && br.poff == carry_node) { xa[0] = carry[0]; xa[1] = carry[1]; xa[2] = carry[2]; xa[3] = carry[3]; }
@@ -502,15 +399,15 @@ core_dna_kernel(const CoreArgs a)
   if (threadIdx.x == 0) { a.tile_out[2 * (size_t)blockIdx.x] = t1; a.tile_out[2 * (size_t)blockIdx.x + 1] = t2; }
 }
 
-size_t traverse_dna_smem(int count, int mxtips, int ns)
+size_t traverse_dna_smem(int ns)
 {
-  return (((size_t)count * sizeof(SEntry) + 15) & ~(size_t)15) + (size_t)mxtips * 64 * ns;
+  return (size_t)(kWindow + 1) * sizeof(SEntry) + (size_t)(2 * kWindow + 2) * 64 * ns;
 }
 
 template <int NS, bool PARAM, int MINB>
 static void launch_minb(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
 {
-  const size_t smem = traverse_dna_smem(a.count, a.mxtips, NS);
+  const size_t smem = traverse_dna_smem(NS);
   static size_t configured = 0;
   if (smem > configured) {
     cudaFuncSetAttribute(traverse_dna_kernel<NS, PARAM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(227 * 1024 - 2048, std::max<size_t>(smem, 64 * 1024)));
@@ -542,10 +439,9 @@ static void launch_ns(const TraverseArgs &a, const DnaConsts *kc, int ntiles, cu
 void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *kc, int ntiles, cudaStream_t s)
 {
   if (ntiles <= 0) return;
-  // chunk = 64*NS sites; the staged tip rows (mxtips * 64 * NS bytes) must fit in shared memory
+  // chunk = 64*NS sites
   int ns = a.tile_sites <= 64 ? 1 : (a.tile_sites <= 128 ? 2 : 4);
   if (!kc) ns = 1;                               // shared-memory constants: one site per thread keeps the registers in budget
-  while (ns > 1 && traverse_dna_smem(a.count, a.mxtips, ns) > 96 * 1024) ns >>= 1;
   if (ns == 1) launch_ns<1>(a, kc, ntiles, s);
   else if (ns == 2) launch_ns<2>(a, kc, ntiles, s);
   else launch_ns<4>(a, kc, ntiles, s);
@@ -553,7 +449,7 @@ void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *kc, int ntiles,
 void launch_traverse_dna_cat(const TraverseArgs &a, const DnaConsts *kc, int ntiles, cudaStream_t s)
 {
   if (ntiles <= 0) return;
-  const size_t smem = (((size_t)a.count * sizeof(SEntry) + 15) & ~(size_t)15) + (size_t)a.mxtips * 256;
+  const size_t smem = window_smem_bytes<256>();
   static size_t configured[2] = {0, 0};
   const int v = kc ? 1 : 0;
   if (smem > configured[v]) {

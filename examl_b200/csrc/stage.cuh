@@ -1,0 +1,117 @@
+// stage.cuh -- entry windows: how the traverse kernels bring the descriptor and the tip codes on chip.
+//
+// A traversal descriptor can be long (one entry per inner node: tens of thousands on the trees ExaML is used for)
+// and every entry may touch one or two tip rows, so neither fits in shared memory as a whole.  The kernels therefore
+// walk the descriptor in WINDOWS of kWindow entries.  Per window and per site chunk
+//   1. all threads expand the window's entries (node numbers -> CLV element offsets / tip-row slots) into smem,
+//   2. warp 0 issues one cp.async.bulk (TMA, 1-D; SASS UBLKCP) per tip row the window touches -- the chunk's
+//      slice of that taxon's tip codes -- all completing on one mbarrier,
+//   3. everybody waits on the mbarrier, then the window's entries are processed without any further barrier.
+// The cold HBM reads of tip codes are thus issued up front and in bulk; the carry registers live across windows.
+// Shared memory is bounded by the window, not by the tree: (kWindow + 1) entries + (2 kWindow + 2) tip rows.
+#pragma once
+#include "engine.cuh"
+
+namespace exb {
+
+constexpr int kWindow = 96;                  // entries per window
+
+struct SEntry {            // a traversal entry as the threads consume it (32 B)
+  int tipCase;             // -1 for the branch entry
+  int ptip_qtip;           // branch entry only: bit0 = p is a tip, bit1 = q is a tip
+  long long poff, qoff, roff;   // inner node: element offset of its CLV (node_index * N * span, unique per node);
+                                // tip: byte offset of its staged row inside the window's tip area
+};
+
+__device__ __forceinline__ uint32_t stage_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(stage_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(stage_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      :: "r"(stage_smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(stage_smem_u32(dst)), "l"(src), "r"(bytes), "r"(stage_smem_u32(bar)) : "memory");
+}
+
+template <int TSB>          // bytes per staged tip row = sites per chunk
+__host__ __device__ constexpr size_t window_smem_bytes()
+{
+  return (size_t)(kWindow + 1) * sizeof(SEntry) + (size_t)(2 * kWindow + 2) * TSB;
+}
+
+// Stage entries [w0, w1) (slots 0 .. w1-w0-1) and, when `with_branch`, the branch entry 0 (slot kWindow).
+// Must be called by every thread of the CTA; ends with all staged data visible to all threads.
+//   dyn      : dynamic shared memory base (window_smem_bytes<TSB>() bytes, 16-byte aligned)
+//   span_el  : doubles per site in a CLV (node stride = N * span_el)
+template <int TSB>
+__device__ __noinline__ void stage_window(unsigned char *dyn, uint64_t *mbar, uint32_t &phase, const TraverseArgs &a,
+                                             size_t N, int span_el, size_t chunk_site0, unsigned nchunk,
+                                             int w0, int w1, bool with_branch)
+{
+  SEntry *ents = reinterpret_cast<SEntry *>(dyn);
+  uint8_t *stips = dyn + (size_t)(kWindow + 1) * sizeof(SEntry);
+  const int tid = threadIdx.x, lane = tid & 31;
+  __syncthreads();                             // the previous window's readers are done with ents / stips
+  for (int j = tid; j < (w1 - w0) + (with_branch ? 1 : 0); j += blockDim.x) {
+    const bool is_branch = j == (w1 - w0);
+    const DevEntry en = a.entries[is_branch ? 0 : w0 + j];
+    const int slot = is_branch ? kWindow : j;
+    SEntry se;
+    se.tipCase = is_branch ? -1 : en.tipCase;
+    se.ptip_qtip = (en.p <= a.mxtips ? 1 : 0) | (en.q <= a.mxtips ? 2 : 0);
+    // tips: q uses row 2*slot, r (or a tip p of the branch entry) row 2*slot+1
+    se.poff = en.p > a.mxtips ? (long long)(en.p - a.mxtips - 1) * (long long)N * span_el : (long long)(2 * slot + 1) * TSB;
+    se.qoff = en.q > a.mxtips ? (long long)(en.q - a.mxtips - 1) * (long long)N * span_el : (long long)(2 * slot) * TSB;
+    se.roff = en.r > a.mxtips ? (long long)(en.r - a.mxtips - 1) * (long long)N * span_el : (long long)(2 * slot + 1) * TSB;
+    ents[slot] = se;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const uint32_t bytes = (nchunk + 15u) & ~15u;
+    const uint8_t *gsrc = a.tips + chunk_site0;
+    const int n = (w1 - w0) + (with_branch ? 1 : 0);
+    int mine = 0;
+    for (int j = lane; j < n; j += 32) {
+      const bool is_branch = j == (w1 - w0);
+      const DevEntry en = a.entries[is_branch ? 0 : w0 + j];
+      if (is_branch) mine += (en.p <= a.mxtips) + (en.q <= a.mxtips);
+      else           mine += (en.tipCase <= 1) + (en.tipCase == 0);
+    }
+    const int total = __reduce_add_sync(0xffffffffu, mine);
+    if (lane == 0) mbar_expect_tx(mbar, (uint32_t)total * bytes);
+    __syncwarp();
+    for (int j = lane; j < n; j += 32) {
+      const bool is_branch = j == (w1 - w0);
+      const DevEntry en = a.entries[is_branch ? 0 : w0 + j];
+      const int slot = is_branch ? kWindow : j;
+      if (is_branch) {
+        if (en.p <= a.mxtips) bulk_g2s(stips + (size_t)(2 * slot + 1) * TSB, gsrc + (size_t)(en.p - 1) * N, bytes, mbar);
+        if (en.q <= a.mxtips) bulk_g2s(stips + (size_t)(2 * slot) * TSB, gsrc + (size_t)(en.q - 1) * N, bytes, mbar);
+      } else {
+        if (en.tipCase <= 1) bulk_g2s(stips + (size_t)(2 * slot) * TSB, gsrc + (size_t)(en.q - 1) * N, bytes, mbar);
+        if (en.tipCase == 0) bulk_g2s(stips + (size_t)(2 * slot + 1) * TSB, gsrc + (size_t)(en.r - 1) * N, bytes, mbar);
+      }
+    }
+  }
+  mbar_wait(mbar, phase);
+  phase ^= 1;
+}
+
+}  // namespace exb

@@ -242,3 +242,30 @@ def test_psr_scaling_path(cuda_factory, oracle_factory):
     cpu = build_engine(oracle_factory, tree, parts, models, cats=cats, max_cats=12)
     ti = _compare_engines(gpu, cpu, tree, parts)
     assert gpu.read_scaler(0, ti[0].pNumber) + gpu.read_scaler(0, ti[0].qNumber) > 0
+
+
+@pytest.mark.parametrize("cat", [False, True])
+def test_large_tree_entry_windows(cuda_factory, oracle_factory, cat):
+    """700 taxa: the descriptor (698 entries) spans eight staging windows of 96 entries; the tip rows and the
+    descriptor are staged per window, the carry registers live across windows.  GAMMA and PSR, DNA and AA."""
+    tree, parts, models = random_case(700, [70, 40], [4, 20], seed=77)
+    cats = random_categories(parts, max_cats=9, seed=1) if cat else None
+    gpu = build_engine(cuda_factory, tree, parts, models, cats=cats, max_cats=9, tile_sites=64)
+    cpu = build_engine(oracle_factory, tree, parts, models, cats=cats, max_cats=9)
+    ti = tree.full_traversal()
+    lg, lc = gpu.evaluateIterative(ti), cpu.evaluateIterative(ti)
+    assert np.all(np.abs(lg - lc) <= 5e-12 * np.abs(lc)), (lg, lc)
+    for e in ti[1::37]:
+        for m in range(2):
+            a, b = gpu.read_clv(m, e.pNumber), cpu.read_clv(m, e.pNumber)
+            assert np.all(np.abs(a - b) <= CLV_RTOL * np.abs(b).max(axis=(1, 2), keepdims=True))
+            assert gpu.read_scaler(m, e.pNumber) == cpu.read_scaler(m, e.pNumber)
+    # evaluate with no newview at all, and a partial traversal whose length is not a multiple of the window
+    lg0, lc0 = gpu.evaluateIterative(ti[:1]), cpu.evaluateIterative(ti[:1])
+    assert np.all(np.abs(lg0 - lc0) <= 5e-12 * np.abs(lc0))
+    sub = ti[:1] + ti[-200:]
+    lg1, lc1 = gpu.evaluateIterative(sub), cpu.evaluateIterative(sub)
+    assert np.all(np.abs(lg1 - lc1) <= 5e-12 * np.abs(lc1))
+    gpu.makenewzIterative(sub); cpu.makenewzIterative(sub)
+    g1, g2 = gpu.execCore([np.log(0.5)]); c1, c2 = cpu.execCore([np.log(0.5)])
+    np.testing.assert_allclose(g1, c1, rtol=1e-10); np.testing.assert_allclose(g2, c2, rtol=1e-10)
