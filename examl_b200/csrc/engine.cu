@@ -243,7 +243,10 @@ struct exb_engine {
   // per-call staging (pinned host + device mirror): entries | lzq | lzr | mask | lz(core)
   size_t stage_bytes = 0;
   unsigned char *stage_h = nullptr, *stage_d = nullptr;
-  size_t off_entries = 0, off_lzq = 0, off_lzr = 0, off_mask = 0, off_corelz = 0;
+  size_t off_entries = 0, off_lzq = 0, off_lzr = 0, off_mask = 0, off_corelz = 0;   // capacity layout (exb_core uses the tail)
+  // per traversal call: the descriptor is packed compactly and only the bytes in use are copied
+  size_t o_entries = 0, o_lzq = 0, o_lzr = 0, o_mask = 0, o_dtab[2] = {0, 0};
+  bool host_dtab[2] = {false, false};  // short descriptors: the exponentials are computed on the host and ride along
   int max_entries = 0;
   // partition tables
   int *part_has_sites = nullptr, *part_tile_begin = nullptr, *part_tile_count = nullptr, *part_cls = nullptr;
@@ -267,6 +270,8 @@ struct exb_engine {
 };
 
 constexpr int kMaxParamPartitions = 16;
+constexpr size_t kHostDtabBytes = 16 * 1024;     // per class
+constexpr int kHostDtabMaxExps = 256;            // ~25 ns each on the host: cheaper than a kernel launch below this
 
 static int class_of(int states) { return states == 4 ? CLS_DNA : (states == 20 ? CLS_AA : -1); }
 
@@ -530,6 +535,7 @@ extern "C" int exb_commit(exb_engine *e)
   e->off_lzr = off;     off = align16(off + (size_t)e->max_entries * e->nb * sizeof(double));
   e->off_corelz = off;  off = align16(off + (size_t)e->nb * sizeof(double));
   e->off_mask = off;    off = align16(off + (size_t)e->P);
+  off += 2 * (kHostDtabBytes + 128);              // room for host-built d-tables of short descriptors
   e->stage_bytes = off;
   CUDA_TRY(cudaMallocHost(&e->stage_h, off));
   CUDA_TRY(cudaMalloc(&e->stage_d, off));
@@ -589,15 +595,21 @@ static int check_models(exb_engine *e, const unsigned char *mask)
 struct exb_engine;
 static void set_finish_outputs(exb_engine *e, FinishArgs &f);
 
-// Validate and stage a traversal descriptor; one H2D copy.
+// Validate and stage a traversal descriptor; one H2D copy of exactly the bytes in use.
 static int stage_traversal(exb_engine *e, const exb_entry *ti, int count, int first, const double *qz, const double *rz,
                            const unsigned char *mask)
 {
   if (count < first || count > e->max_entries)
     return fail(EXB_ERR_ARG, "traversal of %d entries (max %d)", count, e->max_entries);
   const int lo = e->mxtips + 1, hi = 2 * e->mxtips - 2;
-  DevEntry *de = (DevEntry *)(e->stage_h + e->off_entries);
-  double *lq = (double *)(e->stage_h + e->off_lzq), *lr = (double *)(e->stage_h + e->off_lzr);
+  auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  size_t off = 0;
+  e->o_entries = off; off = align16(off + (size_t)count * sizeof(DevEntry));
+  e->o_lzq = off;     off = align16(off + (size_t)count * e->nb * sizeof(double));
+  e->o_lzr = off;     off = align16(off + (size_t)count * e->nb * sizeof(double));
+  e->o_mask = off;    off = align16(off + (size_t)e->P);
+  DevEntry *de = (DevEntry *)(e->stage_h + e->o_entries);
+  double *lq = (double *)(e->stage_h + e->o_lzq), *lr = (double *)(e->stage_h + e->o_lzr);
   const double logzmin = log(kZmin);
   for (int i = 0; i < count; i++) {
     const exb_entry &t = ti[i];
@@ -624,12 +636,43 @@ static int stage_traversal(exb_engine *e, const exb_entry *ti, int count, int fi
       lr[(size_t)i * e->nb + b] = (zr > kZmin) ? log(zr) : logzmin;
     }
   }
-  unsigned char *mk = e->stage_h + e->off_mask;
+  unsigned char *mk = e->stage_h + e->o_mask;
   for (int m = 0; m < e->P; m++) mk[m] = mask ? (mask[m] != 0) : 1;
-  // (Reading the descriptor zero-copy from the pinned area was measured slower: three kernels each pay the PCIe
-  //  round trip on their critical path; one small async copy is cheaper.)
+
+  // Short descriptors (the partial traversals of a tree search): the few exponentials of the d-table are computed
+  // here and travel with the descriptor -- one kernel launch less on the critical path of the call.
+  for (int c = 0; c < 2; c++) {
+    ClassState &k = e->cls[c];
+    e->host_dtab[c] = false;
+    if (k.tiles_h.empty() || k.nparts == 0) continue;
+    const int R = e->cat ? e->max_cats : 4;
+    const size_t doubles = (size_t)count * k.nparts * k.dtab_row;
+    const size_t exps = (size_t)count * k.nparts * R * 2 * (k.S - 1);
+    if (exps > (size_t)kHostDtabMaxExps || doubles * sizeof(double) > kHostDtabBytes) continue;
+    e->host_dtab[c] = true;
+    off = (off + 127) & ~(size_t)127;               // the kernels read the table with 256-bit loads
+    e->o_dtab[c] = off;
+    double *dt = (double *)(e->stage_h + off);
+    off = align16(off + doubles * sizeof(double));
+    for (int i = 0; i < count; i++)
+      for (int pc = 0; pc < k.nparts; pc++) {
+        const double *model = &k.models_h[(size_t)pc * k.model_doubles];     // EIGN[S] rates[4] ...
+        const HostPart &hp = e->parts[k.cp_global[pc]];
+        const int slot = e->nb > 1 ? k.cp_global[pc] : 0;
+        double *row = dt + ((size_t)i * k.nparts + pc) * k.dtab_row;
+        for (int cc = 0; cc < R; cc++) {
+          const double rate = e->cat ? (cc < (int)hp.cat_rates.size() ? hp.cat_rates[cc] : 0.0) : model[k.S + cc];
+          for (int side = 0; side < 2; side++) {
+            const double lz = side ? lr[(size_t)i * e->nb + slot] : lq[(size_t)i * e->nb + slot];
+            double *d = row + ((size_t)cc * 2 + side) * k.S;
+            d[0] = 1.0;
+            for (int kk = 1; kk < k.S; kk++) d[kk] = exp(rate * (model[kk] * lz));     // same association as makeP
+          }
+        }
+      }
+  }
   e->stage_use = e->stage_d;
-  CUDA_TRY(cudaMemcpyAsync(e->stage_d, e->stage_h, e->stage_bytes, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->stage_d, e->stage_h, off, cudaMemcpyHostToDevice, e->stream));
   return EXB_OK;
 }
 
@@ -650,38 +693,42 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   for (int c = 0; c < 2; c++) {
     ClassState &k = e->cls[c];
     if (k.tiles_h.empty()) continue;
-    DtabArgs d;
-    d.dtab = k.dtab; d.models = k.models; d.cls_part_global = k.part_global;
-    d.lzq = (const double *)(e->stage_use + e->off_lzq); d.lzr = (const double *)(e->stage_use + e->off_lzr);
-    d.count = count; d.nparts_cls = k.nparts; d.nbranches = e->nb; d.states = k.S;
-    d.model_doubles = k.model_doubles; d.row = k.dtab_row;
-    d.cat_rates = e->cat ? k.cat_rates : nullptr; d.max_cats = e->max_cats;
-    launch_dtab(d, e->stream);
-    e->launches++;
+    const double *dtab_use = k.dtab;
+    if (e->host_dtab[c]) dtab_use = (const double *)(e->stage_use + e->o_dtab[c]);
+    else {
+      DtabArgs d;
+      d.dtab = k.dtab; d.models = k.models; d.cls_part_global = k.part_global;
+      d.lzq = (const double *)(e->stage_use + e->o_lzq); d.lzr = (const double *)(e->stage_use + e->o_lzr);
+      d.count = count; d.nparts_cls = k.nparts; d.nbranches = e->nb; d.states = k.S;
+      d.model_doubles = k.model_doubles; d.row = k.dtab_row;
+      d.cat_rates = e->cat ? k.cat_rates : nullptr; d.max_cats = e->max_cats;
+      launch_dtab(d, e->stream);
+      e->launches++;
+    }
     if (k.lut) {
       LutArgs l;
-      l.lut = k.lut; l.models = k.models; l.dtab = k.dtab;
-      l.entries = (const DevEntry *)(e->stage_use + e->off_entries);
+      l.lut = k.lut; l.models = k.models; l.dtab = dtab_use;
+      l.entries = (const DevEntry *)(e->stage_use + e->o_entries);
       l.count = count; l.first = first; l.nparts_cls = k.nparts;
       l.ncat = e->cat ? e->max_cats : 4; l.dtab_row = k.dtab_row;
       launch_aa_lut(l, e->stream);
       e->launches++;
     }
     TraverseArgs a;
-    a.dtab = k.dtab; a.lut = k.lut; a.nparts_cls = k.nparts; a.tile_sites = e->tile_sites;
+    a.dtab = dtab_use; a.lut = k.lut; a.nparts_cls = k.nparts; a.tile_sites = e->tile_sites;
     a.rate_cat = e->cat ? k.rate_cat : nullptr; a.max_cats = e->max_cats; a.dtab_row = k.dtab_row;
     a.tiles = k.tiles; a.clv = k.clv; a.tips = k.tips; a.wgt = k.wgt; a.sum = k.sum; a.models = k.models;
     a.N = k.N; a.mxtips = e->mxtips; a.nparts = e->P; a.nbranches = e->nb;
-    a.entries = (const DevEntry *)(e->stage_use + e->off_entries);
-    a.lzq = (const double *)(e->stage_use + e->off_lzq);
-    a.lzr = (const double *)(e->stage_use + e->off_lzr);
-    a.mask = e->stage_use + e->off_mask;
+    a.entries = (const DevEntry *)(e->stage_use + e->o_entries);
+    a.lzq = (const double *)(e->stage_use + e->o_lzq);
+    a.lzr = (const double *)(e->stage_use + e->o_lzr);
+    a.mask = e->stage_use + e->o_mask;
     a.count = count; a.first = first; a.mode = mode;
     a.scale_inc = e->scale_inc; a.tile_out = k.tile_out;
     if (c == CLS_DNA && k.nparts <= kMaxParamPartitions) {
       // few partitions: one launch per partition, its EI/EV travel as kernel parameters (constant bank)
       for (int pc = 0; pc < k.nparts; pc++) {
-        if (k.cp_tile_count[pc] == 0 || !(e->stage_h + e->off_mask)[k.cp_global[pc]]) continue;   // empty or masked
+        if (k.cp_tile_count[pc] == 0 || !(e->stage_h + e->o_mask)[k.cp_global[pc]]) continue;   // empty or masked
         DnaConsts kc;
         memcpy(kc.EI, &k.models_h[(size_t)pc * k.model_doubles + 8], sizeof kc.EI);
         memcpy(kc.EV, &k.models_h[(size_t)pc * k.model_doubles + 24], sizeof kc.EV);
@@ -702,9 +749,9 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   }
   FinishArgs f;
   f.gs = e->gs; f.scale_inc = e->scale_inc;
-  f.entries = (const DevEntry *)(e->stage_use + e->off_entries);
+  f.entries = (const DevEntry *)(e->stage_use + e->o_entries);
   f.count = count; f.first = first; f.mxtips = e->mxtips; f.nparts = e->P;
-  f.mask = e->stage_use + e->off_mask; f.part_has_sites = e->part_has_sites;
+  f.mask = e->stage_use + e->o_mask; f.part_has_sites = e->part_has_sites;
   f.tile_out[0] = e->cls[0].tile_out; f.tile_out[1] = e->cls[1].tile_out;
   f.part_tile_begin = e->part_tile_begin; f.part_tile_count = e->part_tile_count; f.part_cls = e->part_cls;
   f.mode = mode; f.log_minlikelihood = log(kMinLikelihood); f.out = e->out_d;
@@ -861,7 +908,7 @@ extern "C" int exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const
   memset(h, 0, sizeof *h);
   for (int b = 0; b < e->nb; b++) { h->z[b] = z0[b]; h->z0[b] = z0[b]; h->budget[b] = maxiter; h->done[b] = 0; h->curvatOK[b] = 1; }
   CUDA_TRY(cudaMemcpyAsync(e->nr_state_d, h, sizeof *h, cudaMemcpyHostToDevice, e->stream));
-  CUDA_TRY(cudaMemcpyAsync(e->nr_mask, e->stage_h + e->off_mask, (size_t)e->P, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->nr_mask, e->stage_h + e->o_mask, (size_t)e->P, cudaMemcpyHostToDevice, e->stream));
   CUDA_TRY(cudaMemsetAsync(e->nr_barrier, 0, sizeof(unsigned int), e->stream));
   NrArgs a;
   memset(&a, 0, sizeof a);
