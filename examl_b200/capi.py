@@ -23,7 +23,7 @@ EXPORTS = [
     "exb_set_model", "exb_newview", "exb_evaluate", "exb_makenewz_prepare", "exb_core", "exb_makenewz",
     "exb_comm_unique_id", "exb_comm_init", "exb_read_clv", "exb_read_scaler",
     "exb_read_sumtable", "exb_last_kernel_ms", "exb_launch_count", "exb_set_tile_sites", "exb_set_timing",
-    "exb_set_rate_model", "exb_set_categories",
+    "exb_set_rate_model", "exb_set_categories", "exb_set_model_lg4",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -159,6 +159,12 @@ class Engine:
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in
                 (mc.EIGN, mc.EV, mc.EI, mc.tipVector, mc.gammaRates)]
         self._check(self._f("set_model")(self._h, C.c_int(model), *[_dptr(a) for a in arrs]))
+
+    def set_model_lg4(self, model: int, EIGN, EV, EI, tipVector, gammaRates, weights) -> None:
+        """LG4M / LG4X: per-category eigen-systems, flattened [4][20], [4][400], [4][400], [4][460], and category weights."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (EIGN, EV, EI, tipVector, gammaRates, weights)]
+        assert [a.size for a in arrs] == [80, 1600, 1600, 1840, 4, 4]
+        self._check(self._f("set_model_lg4")(self._h, C.c_int(model), *[_dptr(a) for a in arrs]))
 
     # ---- hot path ---------------------------------------------------------------------------
     @staticmethod

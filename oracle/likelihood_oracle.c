@@ -54,6 +54,9 @@ typedef struct {
   double *sum;                  /* [width][4][S] */
   unsigned int *scaler;         /* [2*mxtips] (axml.c:1966-1971) */
   double EIGN[20], EV[400], EI[400], tipVector[23 * 20], gammaRates[4];
+  /* LG4M / LG4X: one eigen-system per GAMMA category and category weights (axml.h:560-575) */
+  int lg4;
+  double EIGN4[4][20], EV4[4][400], EI4[4][400], tip4[4][23 * 20], weights[4];
 } orc_part;
 
 typedef struct {
@@ -117,6 +120,12 @@ int orc_set_model(orc_engine *e, int model, const double *EIGN, const double *EV
   return 0;
 }
 
+/* constants of category slot c (LG4: per category; otherwise shared) */
+static const double *orc_EIGN(const orc_part *p, int c) { return p->lg4 ? p->EIGN4[c] : p->EIGN; }
+static const double *orc_EI(const orc_part *p, int c) { return p->lg4 ? p->EI4[c] : p->EI; }
+static const double *orc_EV(const orc_part *p, int c) { return p->lg4 ? p->EV4[c] : p->EV; }
+static const double *orc_tipv(const orc_part *p, int c) { return p->lg4 ? p->tip4[c] : p->tipVector; }
+
 /* Number of distinct P matrices of a partition and the rate of each (makeP's rptr / numberOfCategories,
    newviewGenericSpecial.c:958-968). */
 static int orc_np(const orc_engine *e, const orc_part *p) { return e->cat ? p->ncat : 4; }
@@ -132,10 +141,12 @@ static void orc_make_p(const orc_engine *e, double z, const orc_part *p, double 
   double lz = (z > ORC_ZMIN) ? log(z) : log(ORC_ZMIN);
   double d[20];
   for (n = 0; n < np; n++) {
-    for (k = 1; k < S; k++) d[k] = exp(rates[n] * (p->EIGN[k] * lz));
+    const double *EIGN = orc_EIGN(p, n), *EI = orc_EI(p, n);
+    for (k = 1; k < S; k++) d[k] = p->lg4 ? exp(rates[n] * EIGN[k] * lz)        /* makeP_FlexLG4 newview:170-205 */
+                                          : exp(rates[n] * (EIGN[k] * lz));
     for (j = 0; j < S; j++) {
       P[n * S * S + j * S] = 1.0;
-      for (k = 1; k < S; k++) P[n * S * S + j * S + k] = d[k] * p->EI[j * S + k];
+      for (k = 1; k < S; k++) P[n * S * S + j * S + k] = d[k] * EI[j * S + k];
     }
   }
 }
@@ -177,9 +188,9 @@ static void orc_newview_entry(orc_engine *e, orc_part *p, const orc_entry *t, do
     for (c = 0; c < R; c++) {
       const double *L = left + (size_t)orc_pidx(e, p, i, c) * S * S, *Rm = right + (size_t)orc_pidx(e, p, i, c) * S * S;
       /* child vectors in the eigenvector basis; a tip's vector is the same for every category */
-      if (tip1) memcpy(v1, p->tipVector + (size_t)S * tip1[i], S * sizeof(double));
+      if (tip1) memcpy(v1, orc_tipv(p, c) + (size_t)S * tip1[i], S * sizeof(double));
       else      memcpy(v1, x1 + i * span + c * S, S * sizeof(double));
-      if (tip2) memcpy(v2, p->tipVector + (size_t)S * tip2[i], S * sizeof(double));
+      if (tip2) memcpy(v2, orc_tipv(p, c) + (size_t)S * tip2[i], S * sizeof(double));
       else      memcpy(v2, x2 + i * span + c * S, S * sizeof(double));
       for (l = 0; l < S; l++) {
         double al = 0.0, ar = 0.0;
@@ -192,7 +203,7 @@ static void orc_newview_entry(orc_engine *e, orc_part *p, const orc_entry *t, do
       for (j = 0; j < S; j++) v[c * S + j] = 0.0;
       for (l = 0; l < S; l++) {
         double x1px2 = a[l] * b[l];
-        for (j = 0; j < S; j++) v[c * S + j] += x1px2 * p->EV[l * S + j];
+        for (j = 0; j < S; j++) v[c * S + j] += x1px2 * orc_EV(p, c)[l * S + j];
       }
     }
     if (t->tipCase != 0) {           /* TIP_TIP is never rescaled (newviewGenericSpecial.c:496-523, 270-313) */
@@ -263,20 +274,23 @@ int orc_evaluate(orc_engine *e, const orc_entry *ti, int count, const double *qz
     lz = (z < ORC_ZMIN) ? log(ORC_ZMIN) : log(z);
     for (n = 0; n < np; n++) {
       diag[n * S] = 1.0;
-      for (k = 1; k < S; k++) diag[n * S + k] = exp(rates[n] * (p->EIGN[k] * lz));
+      for (k = 1; k < S; k++) diag[n * S + k] = p->lg4 ? exp(rates[n] * orc_EIGN(p, n)[k] * lz)   /* eval:122-145 */
+                                                       : exp(rates[n] * (p->EIGN[k] * lz));
     }
     branch_ends(e, p, &ti[0], &tipA, &tipB, &xa, &xb);
     for (i = 0; i < p->width; i++) {
       double term = 0.0;
       for (c = 0; c < R; c++) {
         const double *dg = diag + (size_t)orc_pidx(e, p, i, c) * S;
+        double t = 0.0;
         for (k = 0; k < S; k++) {
-          double l = tipA ? p->tipVector[(size_t)S * tipA[i] + k] : xa[i * span + c * S + k];
-          double r = tipB ? p->tipVector[(size_t)S * tipB[i] + k] : xb[i * span + c * S + k];
-          term += l * r * dg[k];
+          double l = tipA ? orc_tipv(p, c)[(size_t)S * tipA[i] + k] : xa[i * span + c * S + k];
+          double r = tipB ? orc_tipv(p, c)[(size_t)S * tipB[i] + k] : xb[i * span + c * S + k];
+          t += l * r * dg[k];
         }
+        term += p->lg4 ? p->weights[c] * t : t;          /* evaluateGTRGAMMAPROT_LG4 eval:1164-1287 */
       }
-      sum += p->wgt[i] * (e->cat ? log(fabs(term)) : log(0.25 * fabs(term)));
+      sum += p->wgt[i] * ((e->cat || p->lg4) ? log(fabs(term)) : log(0.25 * fabs(term)));
     }
     sum += (double)(p->scaler[ti[0].pNumber] + p->scaler[ti[0].qNumber]) * log(ORC_MINLIKELIHOOD);
     perPartitionLH[m] = sum;
@@ -299,8 +313,8 @@ int orc_makenewz_prepare(orc_engine *e, const orc_entry *ti, int count, const do
     for (i = 0; i < p->width; i++)
       for (c = 0; c < R; c++)
         for (k = 0; k < S; k++) {
-          double l = tipA ? p->tipVector[(size_t)S * tipA[i] + k] : xa[i * span + c * S + k];
-          double r = tipB ? p->tipVector[(size_t)S * tipB[i] + k] : xb[i * span + c * S + k];
+          double l = tipA ? orc_tipv(p, c)[(size_t)S * tipA[i] + k] : xa[i * span + c * S + k];
+          double r = tipB ? orc_tipv(p, c)[(size_t)S * tipB[i] + k] : xb[i * span + c * S + k];
           p->sum[i * span + c * S + k] = l * r;
         }
   }
@@ -329,9 +343,10 @@ int orc_core(orc_engine *e, const double *lzv, const unsigned char *mask, double
           d1[n * S + k] = p->EIGN[k];
           d2[n * S + k] = p->EIGN[k] * p->EIGN[k];
         } else {
-          d0[n * S + k] = exp(p->EIGN[k] * ki * lz);
-          d1[n * S + k] = p->EIGN[k] * ki;
-          d2[n * S + k] = p->EIGN[k] * p->EIGN[k] * ki * ki;
+          const double ek = orc_EIGN(p, n)[k];             /* LG4: coreGTRGAMMAPROT_LG4 mkz:2489-2578 */
+          d0[n * S + k] = exp(ek * ki * lz);
+          d1[n * S + k] = ek * ki;
+          d2[n * S + k] = ek * ek * ki * ki;
         }
       }
     }
@@ -340,10 +355,13 @@ int orc_core(orc_engine *e, const double *lzv, const unsigned char *mask, double
       double L = 0.0, L1 = 0.0, L2 = 0.0, inv, w1 = p->wgt[i], w2 = p->wgt[i];
       for (c = 0; c < R; c++) {
         int pi = orc_pidx(e, p, i, c);
+        double l0 = 0.0, l1 = 0.0, l2 = 0.0;
         for (k = 0; k < S; k++) {
           double t = d0[pi * S + k] * s[c * S + k];
-          L += t; L1 += t * d1[pi * S + k]; L2 += t * d2[pi * S + k];
+          l0 += t; l1 += t * d1[pi * S + k]; l2 += t * d2[pi * S + k];
         }
+        if (p->lg4) { L += p->weights[c] * l0; L1 += p->weights[c] * l1; L2 += p->weights[c] * l2; }
+        else { L += l0; L1 += l1; L2 += l2; }
       }
       if (e->cat) { double r = rates[p->rateCategory[i]]; w1 = r * p->wgt[i]; w2 = r * r * p->wgt[i]; }
       inv = 1.0 / fabs(L);
@@ -372,6 +390,19 @@ int orc_set_categories(orc_engine *e, int model, int ncat, const double *perSite
   p->ncat = ncat;
   memcpy(p->catRates, perSiteRates, (size_t)ncat * sizeof(double));
   memcpy(p->rateCategory, rateCategory, p->width * sizeof(int));
+  return 0;
+}
+
+/* LG4M / LG4X: flattened pInfo.{EIGN,EV,EI,tipVector}_LG4[4] + gammaRates + weights. */
+int orc_set_model_lg4(orc_engine *e, int model, const double *EIGN, const double *EV, const double *EI,
+                      const double *tipVector, const double *gammaRates, const double *weights)
+{
+  orc_part *p = &e->parts[model];
+  if (p->states != 20) return -1;
+  p->lg4 = 1;
+  memcpy(p->EIGN4, EIGN, sizeof p->EIGN4); memcpy(p->EV4, EV, sizeof p->EV4); memcpy(p->EI4, EI, sizeof p->EI4);
+  memcpy(p->tip4, tipVector, sizeof p->tip4);
+  memcpy(p->gammaRates, gammaRates, 4 * sizeof(double)); memcpy(p->weights, weights, 4 * sizeof(double));
   return 0;
 }
 

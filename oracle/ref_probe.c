@@ -79,6 +79,24 @@ static void dump_state(tree *tr, const char *path, int with_alignment, const cha
     put_darr(f, "tipVector", p->tipVector, (size_t)codes * S); fprintf(f, ",\n");
     put_darr(f, "frequencies", p->frequencies, (size_t)S); fprintf(f, ",\n");
     put_darr(f, "gammaRates", p->gammaRates, 4); fprintf(f, ",\n");
+    if (p->protModels == LG4M || p->protModels == LG4X) {
+      int c;
+      const char *names[4] = {"EIGN_LG4", "EV_LG4", "EI_LG4", "tipVector_LG4"};
+      double **arrs[4] = {p->EIGN_LG4, p->EV_LG4, p->EI_LG4, p->tipVector_LG4};
+      size_t lens[4] = {20, 400, 400, 460};
+      int a;
+      for (a = 0; a < 4; a++) {
+        fprintf(f, "\"%s\": [", names[a]);
+        for (c = 0; c < 4; c++) {
+          size_t q;
+          fprintf(f, "%s[", c ? "," : "");
+          for (q = 0; q < lens[a]; q++) fprintf(f, "%s%.17g", q ? "," : "", arrs[a][c][q]);
+          fprintf(f, "]");
+        }
+        fprintf(f, "],\n");
+      }
+      put_darr(f, "weights", p->weights, 4); fprintf(f, ",\n");
+    }
     if (tr->rateHetModel == CAT) {
       fprintf(f, "\"numberOfCategories\": %d,\n", p->numberOfCategories);
       put_darr(f, "perSiteRates", p->perSiteRates, (size_t)p->numberOfCategories); fprintf(f, ",\n");

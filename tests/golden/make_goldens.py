@@ -98,6 +98,11 @@ def main():
         lg2 = os.path.join(tmp, "lg2.model")
         open(lg2, "w").write("LG, p0 = 1-300\n")
         case("aa60", phy, tf, ["-m", "PROT", "-q", lg2], ["-f", "e"], ("first", "mkz", "final"))
+        print("LG4X / LG4M (one eigen-system per GAMMA category + category weights) on the same AA set")
+        for mname in ("LG4X", "LG4M"):
+            q = os.path.join(tmp, mname + ".model")
+            open(q, "w").write(f"{mname}, p0 = 1-300\n")
+            case("aa60" + mname.lower(), phy, tf, ["-m", "PROT", "-q", q], ["-f", "e"], ("first", "mkz", "final"))
         print("PSR (per-site rate categories, -m PSR): the same AA set, and testData/49")
         case("aa60psr", phy, tf, ["-m", "PROT", "-q", lg2], ["-f", "e"], ("first", "mkz", "final"), model="PSR")
         case("dna49psr", f"{td}/49", f"{td}/49.tree", ["-m", "DNA"], ["-f", "e"], ("first", "mkz", "final"), model="PSR")

@@ -60,6 +60,10 @@ def load_engine(make_engine, state: dict, alignment_state: dict | None = None, *
 
 def set_models(eng, state: dict) -> None:
     for m, part in enumerate(state["partitions"]):
-        eng.set_model(m, constants_of(part))
+        if "EIGN_LG4" in part:
+            eng.set_model_lg4(m, part["EIGN_LG4"], part["EV_LG4"], part["EI_LG4"], part["tipVector_LG4"],
+                              part["gammaRates"], part["weights"])
+        else:
+            eng.set_model(m, constants_of(part))
         if state.get("rateHetModel", 1) == 0:
             eng.set_categories(m, part["perSiteRates"], part["rateCategory"])

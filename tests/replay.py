@@ -27,6 +27,9 @@ CASES = {
     "dna49psr": (True, True),
     "dna49ppsr": (False, True),
     "aa60psr": (True, True),
+    # LG4X / LG4M: per-category eigen-systems and category weights
+    "aa60lg4x": (True, True),
+    "aa60lg4m": (True, True),
 }
 
 
