@@ -30,8 +30,8 @@
  * makenewzGenericSpecial.c:1241-1248) become one ncclAllReduce inside exb_evaluate / exb_core.
  *
  * Unsupported modes are refused loudly, the way the reference's MIC back-end does
- * (axml.c:2645-2657): the -S memory saving option, binary data and LG4M/LG4X.  Both rate models are
- * implemented: GAMMA and PSR/CAT (-m PSR; its per-site rate optimisation, evaluatePartialGeneric, stays the
+ * (axml.c:2645-2657): the -S memory saving option and binary data.  Both rate models are
+ * implemented: GAMMA (including the LG4M / LG4X protein models) and PSR/CAT (-m PSR; its per-site rate optimisation, evaluatePartialGeneric, stays the
  * reference's host code).  There is no CPU fallback.
  */
 #include <assert.h>
@@ -107,7 +107,8 @@ static void backend_init(tree *tr)
   for (m = 0; m < tr->NumberOfModels; m++) {
     const pInfo *p = &tr->partitionData[m];
     if (p->states != 4 && p->states != 20) refuse("binary or multi-state data");
-    if (p->protModels == LG4M || p->protModels == LG4X) refuse("the LG4M / LG4X protein models");
+    if ((p->protModels == LG4M || p->protModels == LG4X) && tr->rateHetModel == CAT)
+      refuse("the LG4M / LG4X protein models under PSR");
   }
   if (exb_create(&g_engine, local_device(), tr->mxtips, tr->NumberOfModels, tr->numBranches) != EXB_OK)
     backend_fail("exb_create");
@@ -140,7 +141,19 @@ static void backend_sync(tree *tr)
   if (!g_engine) backend_init(tr);
   for (m = 0; m < tr->NumberOfModels; m++) {
     const pInfo *p = &tr->partitionData[m];
-    if (exb_set_model(g_engine, m, p->EIGN, p->EV, p->EI, p->tipVector, p->gammaRates) != EXB_OK)
+    if (p->protModels == LG4M || p->protModels == LG4X) {
+      /* one eigen-system per GAMMA category: flatten pInfo's four pointers each */
+      static double eign[4 * 20], ev[4 * 400], ei[4 * 400], tipv[4 * 460];
+      int c;
+      for (c = 0; c < 4; c++) {
+        memcpy(eign + c * 20, p->EIGN_LG4[c], 20 * sizeof(double));
+        memcpy(ev + c * 400, p->EV_LG4[c], 400 * sizeof(double));
+        memcpy(ei + c * 400, p->EI_LG4[c], 400 * sizeof(double));
+        memcpy(tipv + c * 460, p->tipVector_LG4[c], 460 * sizeof(double));
+      }
+      if (exb_set_model_lg4(g_engine, m, eign, ev, ei, tipv, p->gammaRates, p->weights) != EXB_OK)
+        backend_fail("exb_set_model_lg4");
+    } else if (exb_set_model(g_engine, m, p->EIGN, p->EV, p->EI, p->tipVector, p->gammaRates) != EXB_OK)
       backend_fail("exb_set_model");
     /* PSR: rateCategory[] / perSiteRates[] are rewritten by optimizeRateCategories (optimizeModel.c:2403) and at
        start-up / restart only, and each of those is followed by a full-traversal evaluateGeneric; comparing a

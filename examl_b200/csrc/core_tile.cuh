@@ -9,6 +9,11 @@ namespace exb {
 
 struct CoreSmem { double d0[80], d1[80], d2[80], red[32]; };
 
+// model-block accessors (layouts in engine.cuh): AA keeps one eigen-system per category
+template <int S> __device__ __forceinline__ double m_eign(const double *m, int c, int k) { return S == 20 ? m[kAaEign + c * 20 + k] : m[k]; }
+template <int S> __device__ __forceinline__ double m_rate(const double *m, int c) { return S == 20 ? m[kAaRates + c] : m[S + c]; }
+template <int S> __device__ __forceinline__ double m_weight(const double *m, int c) { return S == 20 ? m[kAaWeights + c] : 1.0; }
+
 __device__ __forceinline__ void core_ld256(const double *p, double *v)
 {
   asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
@@ -25,13 +30,14 @@ __device__ __forceinline__ void core_tile(const Tile &tile, const double *sum, c
   __syncthreads();                                 // the tables may still be read by the previous tile
   if (tid < SPAN) {
     const int cc = tid / S, k = tid % S;
-    const double ki = model[S + cc], ek = model[k];
+    const double ki = m_rate<S>(model, cc), ek = m_eign<S>(model, cc, k);
     sh.d0[tid] = k ? exp(ek * ki * lz) : 1.0;
     sh.d1[tid] = k ? ek * ki : 0.0;
     sh.d2[tid] = k ? ek * ek * (ki * ki) : 0.0;
   }
   __syncthreads();
   double acc1 = 0.0, acc2 = 0.0;
+  const double wc = m_weight<S>(model, c);
   const int npass = (tile.nsites + 63) >> 6;
   for (int u = 0; u < npass; u++) {
     const int i = (u << 6) + (tid >> 2);
@@ -49,6 +55,7 @@ __device__ __forceinline__ void core_tile(const Tile &tile, const double *sum, c
         L += t; L1 += t * sh.d1[c * S + j + k]; L2 += t * sh.d2[c * S + j + k];
       }
     }
+    if (S == 20) { const double w = wc; L *= w; L1 *= w; L2 *= w; }     // LG4X category weights (1.0 otherwise)
     L  += __shfl_xor_sync(0xffffffffu, L, 1);   L  += __shfl_xor_sync(0xffffffffu, L, 2);
     L1 += __shfl_xor_sync(0xffffffffu, L1, 1);  L1 += __shfl_xor_sync(0xffffffffu, L1, 2);
     L2 += __shfl_xor_sync(0xffffffffu, L2, 1);  L2 += __shfl_xor_sync(0xffffffffu, L2, 2);
@@ -78,7 +85,7 @@ __device__ __forceinline__ void core_tile_cat(const Tile &tile, const double *su
   __syncthreads();
   for (int i = tid; i < max_cats * S; i += blockDim.x) {
     const int n = i / S, k = i % S;
-    sh.d[i] = k ? exp((model[k] * lz) * rates[n]) : 1.0;
+    sh.d[i] = k ? exp((m_eign<S>(model, 0, k) * lz) * rates[n]) : 1.0;
   }
   __syncthreads();
   double acc1 = 0.0, acc2 = 0.0;
@@ -95,7 +102,7 @@ __device__ __forceinline__ void core_tile_cat(const Tile &tile, const double *su
       #pragma unroll
       for (int k = 0; k < 4; k++) {
         if (j + k == 0) { L = s[0]; continue; }
-        const double ek = model[j + k], t = d[j + k] * s[k];
+        const double ek = m_eign<S>(model, 0, j + k), t = d[j + k] * s[k];
         L += t; L1 += t * ek; L2 += t * (ek * ek);
       }
     }

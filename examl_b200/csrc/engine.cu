@@ -543,6 +543,18 @@ extern "C" int exb_commit(exb_engine *e)
   return EXB_OK;
 }
 
+// Store a partition's constants in its class layout and mark them for upload when they changed.
+static int commit_model(exb_engine *e, HostPart &p, ClassState &k, const std::vector<double> &m)
+{
+  if (p.model_set && memcmp(m.data(), p.model.data(), m.size() * sizeof(double)) == 0) return EXB_OK;
+  p.model = m;
+  p.model_set = true;
+  memcpy(&k.models_h[(size_t)p.part_cls * k.model_doubles], m.data(), m.size() * sizeof(double));
+  k.dirty_lo = std::min(k.dirty_lo, p.part_cls);
+  k.dirty_hi = std::max(k.dirty_hi, p.part_cls);
+  return EXB_OK;
+}
+
 extern "C" int exb_set_model(exb_engine *e, int model, const double *EIGN, const double *EV,
                              const double *EI, const double *tipVector, const double *gammaRates)
 {
@@ -551,20 +563,46 @@ extern "C" int exb_set_model(exb_engine *e, int model, const double *EIGN, const
   HostPart &p = e->parts[model];
   ClassState &k = e->cls[p.cls];
   const int S = k.S;
-  std::vector<double> m((size_t)k.model_doubles);
-  double *w = m.data();
-  memcpy(w, EIGN, S * sizeof(double)); w += S;
-  memcpy(w, gammaRates, 4 * sizeof(double)); w += 4;
-  memcpy(w, EI, (size_t)S * S * sizeof(double)); w += S * S;
-  memcpy(w, EV, (size_t)S * S * sizeof(double)); w += S * S;
-  memcpy(w, tipVector, (size_t)k.codes * S * sizeof(double));
-  if (p.model_set && memcmp(m.data(), p.model.data(), m.size() * sizeof(double)) == 0) return EXB_OK;
-  p.model = m;
-  p.model_set = true;
-  memcpy(&k.models_h[(size_t)p.part_cls * k.model_doubles], m.data(), m.size() * sizeof(double));
-  k.dirty_lo = std::min(k.dirty_lo, p.part_cls);
-  k.dirty_hi = std::max(k.dirty_hi, p.part_cls);
-  return EXB_OK;
+  std::vector<double> m((size_t)k.model_doubles, 0.0);
+  if (p.cls == CLS_DNA) {
+    double *w = m.data();
+    memcpy(w, EIGN, S * sizeof(double)); w += S;
+    memcpy(w, gammaRates, 4 * sizeof(double)); w += 4;
+    memcpy(w, EI, (size_t)S * S * sizeof(double)); w += S * S;
+    memcpy(w, EV, (size_t)S * S * sizeof(double)); w += S * S;
+    memcpy(w, tipVector, (size_t)k.codes * S * sizeof(double));
+  } else {                                           // AA: the same eigen-system for all four categories
+    for (int c = 0; c < 4; c++) {
+      memcpy(&m[kAaEign + c * 20], EIGN, 20 * sizeof(double));
+      memcpy(&m[kAaEI + c * 400], EI, 400 * sizeof(double));
+      memcpy(&m[kAaEV + c * 400], EV, 400 * sizeof(double));
+      memcpy(&m[kAaTip + c * 460], tipVector, 460 * sizeof(double));
+      m[kAaWeights + c] = 1.0;
+    }
+    memcpy(&m[kAaRates], gammaRates, 4 * sizeof(double));
+    m[kAaLg4] = 0.0;
+  }
+  return commit_model(e, p, k, m);
+}
+
+extern "C" int exb_set_model_lg4(exb_engine *e, int model, const double *EIGN, const double *EV, const double *EI,
+                                 const double *tipVector, const double *gammaRates, const double *weights)
+{
+  if (!e || !e->committed) return fail(EXB_ERR_STATE, "exb_set_model_lg4: call exb_commit first");
+  if (model < 0 || model >= e->P) return fail(EXB_ERR_ARG, "exb_set_model_lg4: partition %d out of range", model);
+  HostPart &p = e->parts[model];
+  if (p.cls != CLS_AA) return fail(EXB_ERR_ARG, "exb_set_model_lg4: partition %d is not protein data", model);
+  if (e->cat) return fail(EXB_ERR_ARG, "exb_set_model_lg4: LG4M / LG4X are GAMMA-only models");
+  ClassState &k = e->cls[p.cls];
+  std::vector<double> m((size_t)k.model_doubles, 0.0);
+  memcpy(&m[kAaEign], EIGN, 80 * sizeof(double));
+  memcpy(&m[kAaRates], gammaRates, 4 * sizeof(double));
+  memcpy(&m[kAaWeights], weights, 4 * sizeof(double));
+  m[kAaLg4] = 1.0;
+  memcpy(&m[kAaEI], EI, 1600 * sizeof(double));
+  memcpy(&m[kAaEV], EV, 1600 * sizeof(double));
+  memcpy(&m[kAaTip], tipVector, 1840 * sizeof(double));
+  return commit_model(e, p, k, m);
 }
 
 // Upload whatever the host changed since the last call.
@@ -660,13 +698,17 @@ static int stage_traversal(exb_engine *e, const exb_entry *ti, int count, int fi
         const HostPart &hp = e->parts[k.cp_global[pc]];
         const int slot = e->nb > 1 ? k.cp_global[pc] : 0;
         double *row = dt + ((size_t)i * k.nparts + pc) * k.dtab_row;
+        const int rates_off = c == CLS_AA ? kAaRates : k.S, estride = c == CLS_AA ? 20 : 0;
+        const bool lg4 = c == CLS_AA && model[kAaLg4] != 0.0;
         for (int cc = 0; cc < R; cc++) {
-          const double rate = e->cat ? (cc < (int)hp.cat_rates.size() ? hp.cat_rates[cc] : 0.0) : model[k.S + cc];
+          const double rate = e->cat ? (cc < (int)hp.cat_rates.size() ? hp.cat_rates[cc] : 0.0) : model[rates_off + cc];
+          const double *eign = model + (e->cat ? 0 : cc) * estride;
           for (int side = 0; side < 2; side++) {
             const double lz = side ? lr[(size_t)i * e->nb + slot] : lq[(size_t)i * e->nb + slot];
             double *d = row + ((size_t)cc * 2 + side) * k.S;
             d[0] = 1.0;
-            for (int kk = 1; kk < k.S; kk++) d[kk] = exp(rate * (model[kk] * lz));     // same association as makeP
+            for (int kk = 1; kk < k.S; kk++)               // same association as makeP / makeP_FlexLG4
+              d[kk] = lg4 ? exp(rate * eign[kk] * lz) : exp(rate * (eign[kk] * lz));
           }
         }
       }
@@ -702,6 +744,7 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
       d.count = count; d.nparts_cls = k.nparts; d.nbranches = e->nb; d.states = k.S;
       d.model_doubles = k.model_doubles; d.row = k.dtab_row;
       d.cat_rates = e->cat ? k.cat_rates : nullptr; d.max_cats = e->max_cats;
+      d.eign_cat_stride = c == CLS_AA ? 20 : 0; d.rates_off = c == CLS_AA ? kAaRates : k.S; d.lg4_off = c == CLS_AA ? kAaLg4 : -1;
       launch_dtab(d, e->stream);
       e->launches++;
     }
@@ -710,7 +753,7 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
       l.lut = k.lut; l.models = k.models; l.dtab = dtab_use;
       l.entries = (const DevEntry *)(e->stage_use + e->o_entries);
       l.count = count; l.first = first; l.nparts_cls = k.nparts;
-      l.ncat = e->cat ? e->max_cats : 4; l.dtab_row = k.dtab_row;
+      l.ncat = e->cat ? e->max_cats : 4; l.dtab_row = k.dtab_row; l.cat = e->cat ? 1 : 0;
       launch_aa_lut(l, e->stream);
       e->launches++;
     }

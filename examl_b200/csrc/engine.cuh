@@ -19,9 +19,13 @@ constexpr int CLS_AA  = 1;   // 20 states, 23 tip codes, span 80 doubles (640 B 
 
 // Per-partition model constants as laid out in HBM (doubles).
 //   DNA: EIGN[4] rates[4] EI[16] EV[16] tip[16*4]            = 104 doubles
-//   AA : EIGN[20] rates[4] EI[400] EV[400] tip[23*20]        = 1284 doubles
+//   AA : one eigen-system PER GAMMA CATEGORY (LG4M / LG4X, axml.h:560-575; ordinary models store four copies):
+//        EIGN[4][20] rates[4] weights[4] lg4-flag pad | EI[4][400] | EV[4][400] | tip[4][23*20]   = 5136 doubles
+//        weights = category weights of LG4X, 1.0 otherwise (they cancel in the derivative ratios); the flag selects
+//        log(|sum w_c t_c|) (LG4, evaluateGenericSpecial.c:1164-1287) vs log(0.25 |sum t_c|) in evaluate.
 constexpr int kDnaModelDoubles = 4 + 4 + 16 + 16 + 64;
-constexpr int kAaModelDoubles  = 20 + 4 + 400 + 400 + 460;
+constexpr int kAaEign = 0, kAaRates = 80, kAaWeights = 84, kAaLg4 = 88, kAaEI = 96, kAaEV = 1696, kAaTip = 3296;
+constexpr int kAaModelDoubles  = 5136;
 
 // A work tile: a run of sites of ONE partition, processed by one CTA for the whole traversal.
 struct Tile {
@@ -50,6 +54,8 @@ struct DtabArgs {
   const double *lzq, *lzr;   // [count][nbranches]
   const double *cat_rates;   // CAT: [parts_in_class][max_cats] perSiteRates; null under GAMMA
   int count, nparts_cls, nbranches, states, model_doubles, row, max_cats;
+  int eign_cat_stride;       // doubles between the EIGN of consecutive categories (0: shared, DNA; 20: AA)
+  int rates_off, lg4_off;    // offsets of gammaRates[4] / the LG4 flag inside a model block (lg4_off < 0: none)
 };
 
 // Everything a traversal kernel needs.  Passed by value (fits the 4 KB parameter space).
@@ -134,6 +140,7 @@ struct LutArgs {
   int count, first, nparts_cls;
   int ncat;        // categories per table row: 4 (GAMMA) or max_cats (CAT)
   int dtab_row;
+  int cat;         // CAT: every category uses the (single) eigen-system 0
 };
 void launch_aa_lut(const LutArgs &a, cudaStream_t s);
 // ---- device-resident Newton-Raphson (kernels_nr.cu) ----

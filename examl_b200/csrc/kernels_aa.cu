@@ -31,11 +31,13 @@ constexpr int S = 20;
 constexpr int SPAN = 80;
 constexpr int kAaThreads = 384;  // 12 warps, one CTA per SM (the register budget of the DMMA pipeline)
 
-struct AaShared {
-  double tip[460];        // tipVector[23 codes][20]
-  double fragEI[15][32];  // B fragments of EI^T, [k-step * 3 + n-tile][lane]: conflict-free LDS.64
-  double fragEV[15][32];  // B fragments of EV
-  double red[32];
+struct AaShared { double red[32]; };
+
+// per-category constants in dynamic shared memory, behind the window area (45.4 KB):
+struct AaConstsSmem {
+  double fragEI[4][15][32];  // B fragments of EI_c^T, [category][k-step * 3 + n-tile][lane]: conflict-free LDS.64
+  double fragEV[4][15][32];  // B fragments of EV_c
+  double tip[4][460];        // tipVector_c[23 codes][20]
 };
 
 __device__ __forceinline__ void ld256(const double *p, double *v)
@@ -128,7 +130,7 @@ struct AaSlotsCat {                // CAT: everything differs per slot (four dif
 };
 struct AaSlotsGamma {              // GAMMA: one site, slot = category: a base and a constant stride
   const double *x1, *x2, *lut1, *lut2, *drow;
-  int st1, st2;                    // 20 for a CLV, 0 for the tip vector (the same for every category)
+  int st1, st2;                    // 20 for a CLV, 460 for the tip vector of the next category's eigen-system
   __device__ __forceinline__ const double *xq(int c) const { return x1 + c * st1; }
   __device__ __forceinline__ const double *xr(int c) const { return x2 + c * st2; }
   __device__ __forceinline__ const double *lq(int c) const { return lut1 + c * S; }
@@ -136,12 +138,15 @@ struct AaSlotsGamma {              // GAMMA: one site, slot = category: a base a
   __device__ __forceinline__ const double *dq(int c) const { return drow + c * 40; }
 };
 
-template <int QM, int RM, class Slots>
-__device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const double (*fEI)[32], const double (*fEV)[32],
+// KC: true -> slot c uses the eigen-system of category c (GAMMA; LG4 makes them differ); false -> system 0 (CAT)
+template <int QM, int RM, bool KC, class Slots>
+__device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const AaConstsSmem &K,
                                          const Slots &sl, int lane, int tq)
 {
   #pragma unroll
   for (int c = 0; c < 4; c++) {
+    const double (*fEI)[32] = K.fragEI[KC ? c : 0];
+    const double (*fEV)[32] = K.fragEV[KC ? c : 0];
     double y1[3][2], y2[3][2];
     child_y<QM>(y1, carry, fEI, sl.xq(c), sl.lq(c), sl.dq(c), c, lane, tq);
     child_y<RM>(y2, carry, fEI, sl.xr(c), sl.lr(c), sl.dq(c) + S, c, lane, tq);
@@ -197,6 +202,7 @@ traverse_aa_kernel(const TraverseArgs a)
   extern __shared__ __align__(16) unsigned char dyn[];
   const SEntry *ents = reinterpret_cast<const SEntry *>(dyn);                     // window entries; slot kWindow = branch entry
   const uint8_t *stips = dyn + (size_t)(kWindow + 1) * sizeof(SEntry);             // [2*kWindow + 2][TSITES] staged tip rows
+  AaConstsSmem &K = *reinterpret_cast<AaConstsSmem *>(dyn + ((window_smem_bytes<TSITES>() + 127) & ~(size_t)127));
 
   const Tile tile = a.tiles[blockIdx.x];
   if (!a.mask[tile.part]) return;
@@ -206,13 +212,13 @@ traverse_aa_kernel(const TraverseArgs a)
   const size_t N = a.N;
   const double *model = a.models + (size_t)tile.part_cls * kAaModelDoubles;   // EIGN[20] rates[4] EI[400] EV[400] tip[460]
   {
-    for (int i = tid; i < 460; i += kAaThreads) sh.tip[i] = model[824 + i];
-    // B fragments: EI^T[k = 4s+tq][n = 8t+g] = EI[n][k];  EV[k][n];  zero padding for n >= 20
-    for (int i = tid; i < 15 * 32; i += kAaThreads) {
-      const int f = i >> 5, ln = i & 31, fs = f / 3, ft = f % 3;
+    for (int i = tid; i < 4 * 460; i += kAaThreads) K.tip[i / 460][i % 460] = model[kAaTip + i];
+    // B fragments per category: EI_c^T[k = 4s+tq][n = 8t+g] = EI_c[n][k];  EV_c[k][n];  zero padding for n >= 20
+    for (int i = tid; i < 4 * 15 * 32; i += kAaThreads) {
+      const int kc = i / 480, f = (i % 480) >> 5, ln = i & 31, fs = f / 3, ft = f % 3;
       const int k = 4 * fs + (ln & 3), n = 8 * ft + (ln >> 2);
-      sh.fragEI[f][ln] = n < S ? model[24 + n * S + k] : 0.0;
-      sh.fragEV[f][ln] = n < S ? model[424 + k * S + n] : 0.0;
+      K.fragEI[kc][f][ln] = n < S ? model[kAaEI + kc * 400 + n * S + k] : 0.0;
+      K.fragEV[kc][f][ln] = n < S ? model[kAaEV + kc * 400 + k * S + n] : 0.0;
     }
     if (tid == 0) mbar_init(&mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -266,27 +272,27 @@ traverse_aa_kernel(const TraverseArgs a)
         #pragma unroll
         for (int c = 0; c < 4; c++) {
           const int code1 = q_inner ? 0 : stips[en.qoff + lsite[c]], code2 = r_inner ? 0 : stips[en.roff + lsite[c]];
-          sl.xq_[c] = q_inner ? a.clv + en.qoff + soff + c * XSLOT : &sh.tip[S * code1];
-          sl.xr_[c] = r_inner ? a.clv + en.roff + soff + c * XSLOT : &sh.tip[S * code2];
+          sl.xq_[c] = q_inner ? a.clv + en.qoff + soff + c * XSLOT : &K.tip[0][S * code1];
+          sl.xr_[c] = r_inner ? a.clv + en.roff + soff + c * XSLOT : &K.tip[0][S * code2];
           sl.dq_[c] = drow + cat[c] * 40;
           sl.lq_[c] = lutE + ((size_t)code1 * ncat + cat[c]) * S;
           sl.lr_[c] = lutE + lutside + ((size_t)code2 * ncat + cat[c]) * S;
         }
       } else {
         const int code1 = q_inner ? 0 : stips[en.qoff + lsite[0]], code2 = r_inner ? 0 : stips[en.roff + lsite[0]];
-        sl.x1 = q_inner ? a.clv + en.qoff + soff : &sh.tip[S * code1];
-        sl.x2 = r_inner ? a.clv + en.roff + soff : &sh.tip[S * code2];
-        sl.st1 = q_inner ? S : 0; sl.st2 = r_inner ? S : 0;
+        sl.x1 = q_inner ? a.clv + en.qoff + soff : &K.tip[0][S * code1];
+        sl.x2 = r_inner ? a.clv + en.roff + soff : &K.tip[0][S * code2];
+        sl.st1 = q_inner ? S : 460; sl.st2 = r_inner ? S : 460;
         sl.lut1 = lutE + (size_t)code1 * SPAN; sl.lut2 = lutE + lutside + (size_t)code2 * SPAN;
         sl.drow = drow;
       }
       const bool qlut = !q_inner && lutE, rlut = !r_inner && lutE;
-      if (qlut && rlut)                   aa_entry<CH_LUT, CH_LUT>(carry, sh.fragEI, sh.fragEV, sl, lane, tq);
-      else if (qlut && rsrc == SRC_CARRY) aa_entry<CH_LUT, CH_CARRY>(carry, sh.fragEI, sh.fragEV, sl, lane, tq);
-      else if (qlut)                      aa_entry<CH_LUT, CH_MEM>(carry, sh.fragEI, sh.fragEV, sl, lane, tq);
-      else if (rsrc == SRC_CARRY)         aa_entry<CH_MEM, CH_CARRY>(carry, sh.fragEI, sh.fragEV, sl, lane, tq);
-      else if (qsrc == SRC_CARRY)         aa_entry<CH_CARRY, CH_MEM>(carry, sh.fragEI, sh.fragEV, sl, lane, tq);
-      else                                aa_entry<CH_MEM, CH_MEM>(carry, sh.fragEI, sh.fragEV, sl, lane, tq);
+      if (qlut && rlut)                   aa_entry<CH_LUT, CH_LUT, !CAT>(carry, K, sl, lane, tq);
+      else if (qlut && rsrc == SRC_CARRY) aa_entry<CH_LUT, CH_CARRY, !CAT>(carry, K, sl, lane, tq);
+      else if (qlut)                      aa_entry<CH_LUT, CH_MEM, !CAT>(carry, K, sl, lane, tq);
+      else if (rsrc == SRC_CARRY)         aa_entry<CH_MEM, CH_CARRY, !CAT>(carry, K, sl, lane, tq);
+      else if (qsrc == SRC_CARRY)         aa_entry<CH_CARRY, CH_MEM, !CAT>(carry, K, sl, lane, tq);
+      else                                aa_entry<CH_MEM, CH_MEM, !CAT>(carry, K, sl, lane, tq);
 
       if (r_inner) {                            // TIP_TIP is never rescaled (avxLikelihood.c:1393-1440)
         unsigned int cnt = 0;
@@ -346,11 +352,13 @@ traverse_aa_kernel(const TraverseArgs a)
     const SEntry br = ents[kWindow];
     const bool ptip = br.ptip_qtip & 1, qtip = br.ptip_qtip & 2;
     const bool p_carry = !ptip && br.poff == carry_node, q_carry = !qtip && br.qoff == carry_node;
+    const bool lg4 = !CAT && model[kAaLg4] != 0.0;
     double term = 0.0;
     #pragma unroll
     for (int c = 0; c < 4; c++) {
-      const double *tpa = ptip ? &sh.tip[S * stips[br.poff + lsite[c]]] : sh.tip;
-      const double *tpb = qtip ? &sh.tip[S * stips[br.qoff + lsite[c]]] : sh.tip;
+      const double *tpa = ptip ? &K.tip[CAT ? 0 : c][S * stips[br.poff + lsite[c]]] : K.tip[0];
+      const double *tpb = qtip ? &K.tip[CAT ? 0 : c][S * stips[br.qoff + lsite[c]]] : K.tip[0];
+      double tc = 0.0;                            // this category's share (weighted under LG4X)
       #pragma unroll
       for (int t = 0; t < 3; t++) {
         const int col = 8 * t + 2 * tq;
@@ -366,10 +374,11 @@ traverse_aa_kernel(const TraverseArgs a)
           if (valid[c] && live) *reinterpret_cast<double2 *>(a.sum + soff + c * XSLOT + col) = make_double2(xa.x * xb.x, xa.y * xb.y);
         } else if (live) {
           const double d0 = __ldg(drow0 + cat[c] * 40 + col), d1 = __ldg(drow0 + cat[c] * 40 + col + 1);   // row 0, q side
-          term += xa.x * xb.x * d0;
-          term += xa.y * xb.y * d1;
+          tc += xa.x * xb.x * d0;
+          tc += xa.y * xb.y * d1;
         }
       }
+      term += lg4 ? model[kAaWeights + c] * tc : tc;
       if (CAT && a.mode == MODE_EVALUATE) {       // one site per slot: its own log (no 1/4: a single category)
         term += __shfl_xor_sync(0xffffffffu, term, 1);
         term += __shfl_xor_sync(0xffffffffu, term, 2);
@@ -380,7 +389,7 @@ traverse_aa_kernel(const TraverseArgs a)
     if (!CAT && a.mode == MODE_EVALUATE) {
       term += __shfl_xor_sync(0xffffffffu, term, 1);
       term += __shfl_xor_sync(0xffffffffu, term, 2);
-      if (tq == 0 && valid[0]) acc += (double)a.wgt[site0] * log(0.25 * fabs(term));
+      if (tq == 0 && valid[0]) acc += (double)a.wgt[site0] * (lg4 ? log(fabs(term)) : log(0.25 * fabs(term)));
     }
   }
 
@@ -398,7 +407,8 @@ traverse_aa_kernel(const TraverseArgs a)
 __global__ void __launch_bounds__(256)
 aa_lut_kernel(const LutArgs a)
 {
-  __shared__ double EI[400], tip[460], d[64 * 20];
+  extern __shared__ double lsm[];                 // EI[4][400] | tip[4][460] | d[ncat][20]
+  double *EI = lsm, *tip = lsm + 1600, *d = lsm + 1600 + 1840;
   const int side = blockIdx.x & 1;
   const int ep = blockIdx.x >> 1, pc = ep % a.nparts_cls, e = ep / a.nparts_cls;
   if (e < a.first) return;
@@ -407,16 +417,18 @@ aa_lut_kernel(const LutArgs a)
   const int ncat = a.ncat, row = 23 * ncat * 20;
   const double *model = a.models + (size_t)pc * kAaModelDoubles;
   const double *drow = a.dtab + ((size_t)e * a.nparts_cls + pc) * a.dtab_row;
-  for (int i = threadIdx.x; i < 400; i += 256) EI[i] = model[24 + i];
-  for (int i = threadIdx.x; i < 460; i += 256) tip[i] = model[824 + i];
+  for (int i = threadIdx.x; i < 1600; i += 256) EI[i] = model[kAaEI + i];
+  for (int i = threadIdx.x; i < 1840; i += 256) tip[i] = model[kAaTip + i];
   for (int i = threadIdx.x; i < ncat * 20; i += 256) d[i] = drow[(i / 20) * 40 + side * 20 + i % 20];
   __syncthreads();
   double *out = a.lut + ((size_t)ep * 2 + side) * row;
   for (int i = threadIdx.x; i < row; i += 256) {
     const int code = i / (ncat * 20), c = (i % (ncat * 20)) / 20, l = i % 20;
-    double s = tip[code * 20];                       // j = 0: EI[l][0] = 1, d[0] = 1
+    const int kc = a.cat ? 0 : c;                    // the eigen-system of the category (CAT: a single one)
+    const double *E = EI + kc * 400, *tv = tip + kc * 460 + code * 20;
+    double s = tv[0];                                // j = 0: EI[l][0] = 1, d[0] = 1
     #pragma unroll
-    for (int j = 1; j < 20; j++) s += EI[l * 20 + j] * (d[c * 20 + j] * tip[code * 20 + j]);
+    for (int j = 1; j < 20; j++) s += E[l * 20 + j] * (d[c * 20 + j] * tv[j]);
     out[i] = s;
   }
 }
@@ -424,7 +436,11 @@ aa_lut_kernel(const LutArgs a)
 void launch_aa_lut(const LutArgs &a, cudaStream_t s)
 {
   const int blocks = a.count * a.nparts_cls * 2;
-  if (blocks > 0) aa_lut_kernel<<<blocks, 256, 0, s>>>(a);
+  if (blocks <= 0) return;
+  const size_t smem = (size_t)(1600 + 1840 + a.ncat * 20) * sizeof(double);
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(aa_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); configured = true; }
+  aa_lut_kernel<<<blocks, 256, smem, s>>>(a);
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
@@ -444,7 +460,7 @@ core_aa_kernel(const CoreArgs a)
 template <bool CAT>
 static void launch_aa_variant(const TraverseArgs &a, int ntiles, cudaStream_t s)
 {
-  const size_t smem = window_smem_bytes<(CAT ? 384 : 96)>();
+  const size_t smem = ((window_smem_bytes<(CAT ? 384 : 96)>() + 127) & ~(size_t)127) + sizeof(AaConstsSmem);
   static size_t configured = 0;
   if (smem > configured) {
     const size_t want = std::min<size_t>(227 * 1024 - 16384, std::max<size_t>(smem, 64 * 1024));

@@ -77,8 +77,11 @@ dtab_kernel(const DtabArgs a)
     const double *model = a.models + (size_t)pc * a.model_doubles;   // EIGN[S] rates[4] ...
     const int slot = a.nbranches > 1 ? a.cls_part_global[pc] : 0;
     const double lz = side ? a.lzr[(size_t)e * a.nbranches + slot] : a.lzq[(size_t)e * a.nbranches + slot];
-    const double rate = a.cat_rates ? a.cat_rates[(size_t)pc * a.max_cats + c] : model[S + c];
-    a.dtab[i] = k ? exp(rate * (model[k] * lz)) : 1.0;
+    const double rate = a.cat_rates ? a.cat_rates[(size_t)pc * a.max_cats + c] : model[a.rates_off + c];
+    const double ek = model[(a.cat_rates ? 0 : c) * a.eign_cat_stride + k];
+    const bool lg4 = a.lg4_off >= 0 && model[a.lg4_off] != 0.0;
+    a.dtab[i] = !k ? 1.0 : (lg4 ? exp(rate * ek * lz)          // makeP_FlexLG4 newviewGenericSpecial.c:189-190
+                                : exp(rate * (ek * lz)));       // makeP :95-112
   }
 }
 

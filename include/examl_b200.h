@@ -114,6 +114,13 @@ int  exb_commit(exb_engine *e);
 int  exb_set_model(exb_engine *e, int model, const double *EIGN, const double *EV,
                    const double *EI, const double *tipVector, const double *gammaRates);
 
+/* LG4M / LG4X protein models (pInfo.protModels, axml.h:262-263): one eigen-system per GAMMA category and, for LG4X,
+ * free category weights -- pInfo.{EIGN,EV,EI,tipVector}_LG4[4] flattened to [4][20], [4][400], [4][400], [4][460],
+ * gammaRates[4], weights[4] (newviewGTRGAMMAPROT_LG4 avxLikelihood.c:814, evaluateGenericSpecial.c:1164-1287,
+ * makenewzGenericSpecial.c:2489-2578).  GAMMA only. */
+int  exb_set_model_lg4(exb_engine *e, int model, const double *EIGN, const double *EV, const double *EI,
+                       const double *tipVector, const double *gammaRates, const double *weights);
+
 /* EXB_CAT only: pInfo.numberOfCategories, pInfo.perSiteRates[numberOfCategories], pInfo.rateCategory[width]
  * (rewritten by optimizeRateCategories, optimizeModel.c:2403).  Cheap when unchanged (host-side compare). */
 int  exb_set_categories(exb_engine *e, int model, int numberOfCategories, const double *perSiteRates,

@@ -24,6 +24,8 @@ def _rel(a, b):
     ("dna49p", "from-fixture", []),
     ("dna49pM", "from-fixture", ["-M"]),
     ("aa60", ["LG, p0 = 1-300"], []),
+    ("aa60lg4x", ["LG4X, p0 = 1-300"], []),
+    ("aa60lg4m", ["LG4M, p0 = 1-300"], []),
     ("dna49psr", None, ["PSR"]),
     ("dna49ppsr", "from-fixture", ["PSR"]),
     ("aa60psr", ["LG, p0 = 1-300"], ["PSR"]),
