@@ -23,7 +23,7 @@ EXPORTS = [
     "exb_set_model", "exb_newview", "exb_evaluate", "exb_makenewz_prepare", "exb_core", "exb_makenewz",
     "exb_comm_unique_id", "exb_comm_init", "exb_read_clv", "exb_read_scaler",
     "exb_read_sumtable", "exb_last_kernel_ms", "exb_launch_count", "exb_set_tile_sites", "exb_set_timing",
-    "exb_set_rate_model", "exb_set_categories", "exb_set_model_lg4",
+    "exb_set_rate_model", "exb_set_categories", "exb_set_model_lg4", "exb_evaluate_partial",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -213,6 +213,20 @@ class Engine:
         self._check(self._f("makenewz")(self._h, arr, C.c_int(t.count), _dptr(qz), _dptr(rz), _dptr(m), _dptr(z0v),
                                         C.c_int(maxiter), _dptr(res), _dptr(cok), C.byref(it)))
         return res, cok, int(it.value)
+
+    def evaluatePartial(self, ti, models, sites, rates) -> np.ndarray:
+        """Batched evaluatePartialGeneric (evaluatePartialGenericSpecial.c:259): for every (partition, site, rate)
+        triple the site's log likelihood (times its pattern weight) with that single rate, recomputed from the
+        tips along the full traversal `ti` (ti[0] = root branch whose pNumber is a tip).  CAT / PSR engines only."""
+        t = self.pack(ti)
+        mo = np.ascontiguousarray(models, dtype=np.int32)
+        si = np.ascontiguousarray(sites, dtype=np.int32)
+        ra = np.ascontiguousarray(rates, dtype=np.float64)
+        assert mo.shape == si.shape == ra.shape
+        out = np.zeros(ra.shape[0])
+        self._check(self._f("evaluate_partial")(self._h, t.arr, C.c_int(t.count), _dptr(t.qz), _dptr(t.rz),
+                                                C.c_size_t(ra.shape[0]), _dptr(mo), _dptr(si), _dptr(ra), _dptr(out)))
+        return out
 
     # ---- multi-GPU -------------------------------------------------------------------------
     def comm_unique_id(self) -> bytes:

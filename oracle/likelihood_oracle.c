@@ -16,6 +16,9 @@
  *   CAT / PSR           newviewCAT_FLEX newviewGenericSpecial.c:217-427, evaluateCAT_FLEX
  *                       evaluateGenericSpecial.c:232-330, sumCAT_FLEX makenewzGenericSpecial.c:170-249,
  *                       coreCAT_FLEX makenewzGenericSpecial.c:394-519 (one rate category per site)
+ *   orc_evaluate_partial evaluatePartialGenericSpecial.c:259 (evaluatePartialGeneric) ->
+ *                       :190-255 (evaluatePartialCAT_FLEX) + :92-187 (computeVectorCAT_FLEX): one site,
+ *                       one explicit rate, the whole traversal recomputed from the tips
  *   partition plumbing  newviewGenericSpecial.c:1114 (executeModel && width>0), :972-981
  *                       (branch slot), evaluateGenericSpecial.c:845-860 (masked partitions),
  *                       makenewzGenericSpecial.c:921-946 (derivative slots)
@@ -403,6 +406,59 @@ int orc_set_model_lg4(orc_engine *e, int model, const double *EIGN, const double
   memcpy(p->EIGN4, EIGN, sizeof p->EIGN4); memcpy(p->EV4, EV, sizeof p->EV4); memcpy(p->EI4, EI, sizeof p->EI4);
   memcpy(p->tip4, tipVector, sizeof p->tip4);
   memcpy(p->gammaRates, gammaRates, 4 * sizeof(double)); memcpy(p->weights, weights, 4 * sizeof(double));
+  return 0;
+}
+
+/* evaluatePartialGeneric (evaluatePartialGenericSpecial.c:259), batched over n (partition, site, rate) triples.
+ * Follows evaluatePartialCAT_FLEX (:190-255): entries[0] is the root branch, its pNumber a tip; entries
+ * [1..count) are recomputed for this one site with rate ki by computeVectorCAT_FLEX (:92-187), x3 kept
+ * per inner node; every entry's branch lengths are clamped to zmin before the logarithm (:220-221), the
+ * root branch's is not (:232-234 overwrite the clamp); the result is w * (log|sum| + scale*log(minlikelihood)). */
+int orc_evaluate_partial(orc_engine *e, const orc_entry *ti, int count, const double *qz, const double *rz,
+                         size_t n, const int *models, const int *sites, const double *rates, double *out)
+{
+  size_t j;
+  if (!e->cat || count < 1 || ti[0].pNumber > e->mxtips) return 1;
+  for (j = 0; j < n; j++) {
+    const orc_part *p = &e->parts[models[j]];
+    const int S = p->states, slot = e->nbranches > 1 ? models[j] : 0;
+    const size_t i = (size_t)sites[j];
+    const double ki = rates[j];
+    double *lVector = (double *)calloc((size_t)S * e->mxtips, sizeof(double)), d1[20], d2[20], x1px2[20], d[20], lz, term;
+    const double *x1, *x2;
+    int scale = 0, k, a, b;
+    for (k = 1; k < count; k++) {
+      const orc_entry *t = &ti[k];
+      const double zq = qz[(size_t)k * e->nbranches + slot], zr = rz[(size_t)k * e->nbranches + slot];
+      const double lz1 = ((zq > ORC_ZMIN) ? log(zq) : log(ORC_ZMIN)) * ki, lz2 = ((zr > ORC_ZMIN) ? log(zr) : log(ORC_ZMIN)) * ki;
+      double *x3 = &lVector[S * (t->pNumber - e->mxtips)];
+      int sc;
+      x1 = t->tipCase == 2 ? &lVector[S * (t->qNumber - e->mxtips)] : &p->tipVector[S * tip_of(e, p, t->qNumber)[i]];
+      x2 = t->tipCase == 0 ? &p->tipVector[S * tip_of(e, p, t->rNumber)[i]] : &lVector[S * (t->rNumber - e->mxtips)];
+      d1[0] = x1[0]; d2[0] = x2[0];
+      for (a = 1; a < S; a++) { d1[a] = x1[a] * exp(p->EIGN[a] * lz1); d2[a] = x2[a] * exp(p->EIGN[a] * lz2); }
+      for (a = 0; a < S; a++) {
+        double u1 = 0.0, u2 = 0.0;
+        for (b = 0; b < S; b++) { u1 += d1[b] * p->EI[a * S + b]; u2 += d2[b] * p->EI[a * S + b]; }
+        x1px2[a] = u1 * u2;
+      }
+      for (a = 0; a < S; a++) x3[a] = 0.0;
+      for (a = 0; a < S; a++)
+        for (b = 0; b < S; b++) x3[b] += x1px2[a] * p->EV[S * a + b];
+      sc = 1;
+      for (a = 0; sc && a < S; a++) sc = (x3[a] < ORC_MINLIKELIHOOD) && (x3[a] > -ORC_MINLIKELIHOOD);
+      if (sc) { for (a = 0; a < S; a++) x3[a] *= ORC_TWOTOTHE256; scale++; }
+    }
+    x1 = &p->tipVector[S * tip_of(e, p, ti[0].pNumber)[i]];
+    x2 = &lVector[S * (ti[0].qNumber - e->mxtips)];
+    lz = log(qz[slot]) * ki;
+    d[0] = 1.0;
+    for (a = 1; a < S; a++) d[a] = exp(p->EIGN[a] * lz);
+    term = 0.0;
+    for (a = 0; a < S; a++) term += x1[a] * x2[a] * d[a];
+    out[j] = (log(fabs(term)) + scale * log(ORC_MINLIKELIHOOD)) * p->wgt[i];
+    free(lVector);
+  }
   return 0;
 }
 

@@ -1,6 +1,6 @@
 /* ref_probe.c -- TEST INFRASTRUCTURE.  Linked into the UNMODIFIED reference build
  * (oracle/Makefile, outputs in oracle/_ref/) with
- *      -Wl,--wrap=evaluateGeneric -Wl,--wrap=makenewzGeneric
+ *      -Wl,--wrap=evaluateGeneric -Wl,--wrap=makenewzGeneric -Wl,--wrap=evaluatePartialGeneric
  * so that the reference's own binary can (a) dump golden states for the parity tests
  * and (b) time its CPU likelihood path for bench.py's reference arm -- without editing or
  * copying a single reference source line.
@@ -9,7 +9,11 @@
  *   EXAML_PROBE_DUMP=<prefix>   write <prefix>.first.json after the first evaluateGeneric
  *                               (axml.c:2317 / :2760), <prefix>.mkz.json after the first
  *                               makenewzGeneric, <prefix>.final.json at process exit
- *                               (after one more full evaluateGeneric on the final tree).
+ *                               (after one more full evaluateGeneric on the final tree);
+ *                               under -m PSR also <prefix>.partial.json: the state during the first
+ *                               optimizeRateCategories (optimizeModel.c:2403) and the first
+ *                               PARTIAL_REC evaluatePartialGeneric calls of every partition
+ *                               (partition, site, rate, returned value).
  *   EXAML_PROBE_BENCH=<K>       after the first evaluateGeneric: W warm-up (EXAML_PROBE_WARMUP,
  *                               default 1) then K timed full-traversal evaluateGeneric calls;
  *                               print one JSON line "PROBE_BENCH {...}" and exit(0).
@@ -25,6 +29,7 @@
 
 void __real_evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal);
 void __real_makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxiter, double *result, boolean mask);
+double __real_evaluatePartialGeneric(tree *tr, int i, double ki, int _model);
 #ifdef _USE_OMP
 void allocateXVectors(tree *tr);
 #endif
@@ -132,6 +137,41 @@ static void dump_state(tree *tr, const char *path, int with_alignment, const cha
   fclose(f);
 }
 
+/* ---- evaluatePartialGeneric: record the first calls of every partition, dump before the next evaluateGeneric ---- */
+#define PARTIAL_REC 160
+#define PARTIAL_MODELS 8
+static struct { int model, site; double rate, value; } g_partial[PARTIAL_REC * PARTIAL_MODELS];
+static int g_partial_n = 0, g_partial_per_model[PARTIAL_MODELS], g_partial_dumped = 0;
+
+double __wrap_evaluatePartialGeneric(tree *tr, int i, double ki, int _model)
+{
+  const double v = __real_evaluatePartialGeneric(tr, i, ki, _model);
+#ifndef _USE_OMP
+  if (!g_partial_dumped && getenv("EXAML_PROBE_DUMP") && _model < PARTIAL_MODELS && g_partial_per_model[_model] < PARTIAL_REC) {
+    g_partial_per_model[_model]++;
+    g_partial[g_partial_n].model = _model; g_partial[g_partial_n].site = i;
+    g_partial[g_partial_n].rate = ki;      g_partial[g_partial_n].value = v;
+    g_partial_n++;
+  }
+#endif
+  return v;
+}
+
+static void dump_partial(tree *tr)
+{
+  const char *prefix = getenv("EXAML_PROBE_DUMP");
+  char path[4096], *extra = (char *)malloc((size_t)g_partial_n * 96 + 64);
+  int off = 0, j;
+  off += sprintf(extra + off, "\"partial\": [");
+  for (j = 0; j < g_partial_n; j++)
+    off += sprintf(extra + off, "%s[%d,%d,%.17g,%.17g]", j ? "," : "", g_partial[j].model, g_partial[j].site, g_partial[j].rate, g_partial[j].value);
+  off += sprintf(extra + off, "]");
+  snprintf(path, sizeof path, "%s.partial.json", prefix);
+  dump_state(tr, path, 0, extra);      /* td[0] is still the full traversal the calls were made with */
+  free(extra);
+  g_partial_dumped = 1;
+}
+
 static void dump_final(void)
 {
   const char *prefix = getenv("EXAML_PROBE_DUMP");
@@ -149,6 +189,7 @@ void __wrap_evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal)
   if (g_eval_calls == 0 && tr->partitionData[0].xVector[0] == NULL)
     allocateXVectors(tr);     /* the reference's -f e path forgets this under OMP (only axml.c:2752 calls it) */
 #endif
+  if (g_partial_n > 0 && !g_partial_dumped && prefix) dump_partial(tr);
   __real_evaluateGeneric(tr, p, fullTraversal);
   g_eval_calls++;
   if (g_eval_calls == 1) {

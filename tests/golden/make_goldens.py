@@ -10,6 +10,8 @@ alignments, and dumps, with %.17g:
            as the reference holds it (pattern-compressed tip codes + weights)
   *.mkz    state after the first makenewzGeneric (descriptor, z0, resulting z)
   *.final  state at exit of `-f e` (optimised model + branch lengths) and its lnL
+  *.partial (PSR) state during the first optimizeRateCategories and the first 160 evaluatePartialGeneric
+           calls of every partition: (partition, site, rate, value)
 The parity tests replay those states through the oracle and the CUDA engine.
 
 Usage: python tests/golden/make_goldens.py            (about a minute)
@@ -104,9 +106,9 @@ def main():
             open(q, "w").write(f"{mname}, p0 = 1-300\n")
             case("aa60" + mname.lower(), phy, tf, ["-m", "PROT", "-q", q], ["-f", "e"], ("first", "mkz", "final"))
         print("PSR (per-site rate categories, -m PSR): the same AA set, and testData/49")
-        case("aa60psr", phy, tf, ["-m", "PROT", "-q", lg2], ["-f", "e"], ("first", "mkz", "final"), model="PSR")
-        case("dna49psr", f"{td}/49", f"{td}/49.tree", ["-m", "DNA"], ["-f", "e"], ("first", "mkz", "final"), model="PSR")
-        case("dna49ppsr", f"{td}/49", f"{td}/49.tree", ["-m", "DNA", "-q", f"{td}/49.model"], ["-f", "e"], ("first", "final"), model="PSR")
+        case("aa60psr", phy, tf, ["-m", "PROT", "-q", lg2], ["-f", "e"], ("first", "mkz", "final", "partial"), model="PSR")
+        case("dna49psr", f"{td}/49", f"{td}/49.tree", ["-m", "DNA"], ["-f", "e"], ("first", "mkz", "final", "partial"), model="PSR")
+        case("dna49ppsr", f"{td}/49", f"{td}/49.tree", ["-m", "DNA", "-q", f"{td}/49.model"], ["-f", "e"], ("first", "final", "partial"), model="PSR")
 
 
 if __name__ == "__main__":

@@ -72,3 +72,21 @@ def replay_case(factory, tag, rtol=TIGHT_RTOL, **kw):
             assert rel(lh[m], final["perPartitionLH"][m]) < rtol, (tag, m, lh[m], final["perPartitionLH"][m])
         assert rel(float(np.sum(lh)), final["likelihood"]) < rtol
     eng.close()
+
+
+PARTIAL_CASES = ("dna49psr", "dna49ppsr", "aa60psr")
+
+
+def replay_partial(factory, tag, rtol=1e-11, **kw):
+    """evaluatePartialGeneric: the reference's recorded (partition, site, rate) -> value calls during its first
+    optimizeRateCategories, replayed as one batch."""
+    first = load_json(f"{tag}.first.json")
+    part = load_json(f"{tag}.partial.json")
+    eng = load_engine(factory, part, alignment_state=first, **kw)
+    calls = np.array(part["partial"])
+    got = eng.evaluatePartial(traversal_of(part), calls[:, 0].astype(np.int32), calls[:, 1].astype(np.int32), calls[:, 2])
+    want = calls[:, 3]
+    err = np.abs(got - want) / np.maximum(1.0, np.abs(want))
+    assert err.max() < rtol, (tag, int(err.argmax()), got[err.argmax()], want[err.argmax()])
+    eng.close()
+    return len(want)

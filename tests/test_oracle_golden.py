@@ -3,12 +3,17 @@ from the reference's own AVX build must be reproduced -- lnL and per-partition l
 evaluation and of the optimised `-f e` end state, root scaler counts, the first makenewz result."""
 import pytest
 
-from replay import CASES, replay_case
+from replay import CASES, PARTIAL_CASES, replay_case, replay_partial
 
 
 @pytest.mark.parametrize("tag", list(CASES))
 def test_oracle_reproduces_reference(oracle_factory, tag):
     replay_case(oracle_factory, tag)
+
+
+@pytest.mark.parametrize("tag", PARTIAL_CASES)
+def test_oracle_reproduces_reference_evaluate_partial(oracle_factory, tag):
+    assert replay_partial(oracle_factory, tag) >= 160
 
 
 def test_golden_headline_values():
