@@ -5,8 +5,8 @@
     bin/examl-b200-probe   the same with oracle/ref_probe.c attached through ld --wrap (golden dumps and
                            the evaluateGeneric timing loop; used by tests and bench only)
 
-The four objects newviewGenericSpecial.o, evaluateGenericSpecial.o, makenewzGenericSpecial.o and
-avxLikelihood.o of the reference are NOT linked: axml_backend.c provides their entry points.
+The five objects newviewGenericSpecial.o, evaluateGenericSpecial.o, makenewzGenericSpecial.o,
+evaluatePartialGenericSpecial.o and avxLikelihood.o of the reference are NOT linked: axml_backend.c provides their entry points.
 Only possible where /root/reference exists (the reference objects are compiled there by
 oracle/Makefile into oracle/_ref/obj/); elsewhere the prebuilt binaries are used as they are.
 """
@@ -20,7 +20,7 @@ ROOT = os.path.dirname(HERE)
 REF = "/root/reference"
 OBJ = os.path.join(ROOT, "oracle", "_ref", "obj")
 BIN = os.path.join(ROOT, "bin")
-KEEP = ["axml", "optimizeModel", "trash", "searchAlgo", "topologies", "treeIO", "evaluatePartialGenericSpecial",
+KEEP = ["axml", "optimizeModel", "trash", "searchAlgo", "topologies", "treeIO",
         "bipartitionList", "restartHashTable", "byteFile", "partitionAssignment", "communication", "quartets", "models"]
 CFLAGS = ["-D__SIM_SSE3", "-D__AVX", "-D_OPTIMIZED_FUNCTIONS", "-msse3", "-mavx", "-D_GNU_SOURCE", "-D_USE_ALLREDUCE",
           "-O2", "-w"]
@@ -42,7 +42,7 @@ def build(force: bool = False) -> bool:
     link = ["-L" + HERE, "-lexaml_b200", "-Wl,-rpath,$ORIGIN/../examl_b200", "-lm"]
     subprocess.check_call(["gcc", "-o", exe] + objs + link)
     subprocess.check_call(["gcc", "-o", exe + "-probe"] + objs + [os.path.join(OBJ, "avx", "ref_probe.o")] +
-                          ["-Wl,--wrap=evaluateGeneric", "-Wl,--wrap=makenewzGeneric"] + link)
+                          ["-Wl,--wrap=evaluateGeneric", "-Wl,--wrap=makenewzGeneric", "-Wl,--wrap=evaluatePartialGeneric"] + link)
     return True
 
 

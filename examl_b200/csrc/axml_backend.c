@@ -1,16 +1,18 @@
 /* axml_backend.c -- the B200 back-end of ExaML's likelihood API.
  *
  * This translation unit is compiled against the reference's own, unmodified axml.h and REPLACES
- * the four reference objects newviewGenericSpecial.o, evaluateGenericSpecial.o,
- * makenewzGenericSpecial.o and avxLikelihood.o (object list: examl/Makefile.AVX.gcc:18).  Every
+ * the five reference objects newviewGenericSpecial.o, evaluateGenericSpecial.o,
+ * makenewzGenericSpecial.o, evaluatePartialGenericSpecial.o and avxLikelihood.o (object list:
+ * examl/Makefile.AVX.gcc:18).  Every
  * other reference file (axml.c, searchAlgo.c, optimizeModel.c, models.c, byteFile.c, ...) is
- * compiled as it is and links against the three entry points it calls (nm on the reference
+ * compiled as it is and links against the four entry points it calls (nm on the reference
  * objects: only these are imported from the replaced files):
  *
  *     void evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal);                    axml.h:1223
  *     void newviewGeneric (tree *tr, nodeptr p, boolean masked);                           axml.h:1232
  *     void makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxiter,
  *                          double *result, boolean mask);                                  axml.h:1241
+ *     double evaluatePartialGeneric(tree *tr, int i, double ki, int _model);               axml.h:1222
  *
  * plus the internal-but-global helpers of the replaced files, kept for API completeness:
  * computeTraversalInfo, newviewIterative, evaluateIterative, makenewzIterative, execCore,
@@ -31,8 +33,8 @@
  *
  * Unsupported modes are refused loudly, the way the reference's MIC back-end does
  * (axml.c:2645-2657): the -S memory saving option and binary data.  Both rate models are
- * implemented: GAMMA (including the LG4M / LG4X protein models) and PSR/CAT (-m PSR; its per-site rate optimisation, evaluatePartialGeneric, stays the
- * reference's host code).  There is no CPU fallback.
+ * implemented: GAMMA (including the LG4M / LG4X protein models) and PSR/CAT (-m PSR, including the per-site
+ * rate scan of optimizeRateCategories: evaluatePartialGeneric below).  There is no CPU fallback.
  */
 #include <assert.h>
 #include <math.h>
@@ -134,11 +136,13 @@ static void backend_init(tree *tr)
    notice); hand the current ones over before every launch.  exb_set_model compares and only
    uploads what changed. */
 static int g_categories_stale = 1;      /* PSR: per-site categories must be handed over (again) */
+static int g_scan_valid = 0;            /* evaluatePartialGeneric: the batched rate scan below is current */
 
 static void backend_sync(tree *tr)
 {
   int m;
   if (!g_engine) backend_init(tr);
+  g_scan_valid = 0;                     /* any other likelihood call ends a rate scan */
   for (m = 0; m < tr->NumberOfModels; m++) {
     const pInfo *p = &tr->partitionData[m];
     if (p->protModels == LG4M || p->protModels == LG4X) {
@@ -470,4 +474,178 @@ void makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxiter, do
     newton_raphson(tr, z0, maxiter, result);
 
   for (i = 0; i < tr->numBranches; i++) tr->executeModel[i] = TRUE;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* evaluatePartialGeneric: the per-site rate scan of -m PSR                                        */
+/* ---------------------------------------------------------------------------------------------- */
+/* optimizeRateCategories (optimizeModel.c:2403) walks over the sites one by one (optRateCatPthreads,
+ * optimizeModel.c:1792-1922): evaluatePartialGeneric at the site's current rate, then at rate - k*lower_spacing
+ * for k = 1, 2, ... while that improves, then at rate + k*upper_spacing likewise.  Each call is a whole
+ * traversal for ONE site -- far too little work for a GPU.  But the questions are predictable: the first call
+ * of a scan tells us that every site will be asked for its current rate, the first call on each side tells us
+ * the spacing, and the caller's stopping rule depends only on the values we return.  So the answers are
+ * computed ahead, for all sites of all partitions at once, round by round (round k = step k of every site whose
+ * scan is still running), through exb_evaluate_partial; the calls of the caller are then served from that table.
+ * A question that is not in the table (it never happened in our runs) is answered by a single-pair launch.
+ * Nothing here touches patrat / lhs: the caller's loop still takes every decision itself. */
+typedef struct {
+  double *rate0, *v0;           /* [width] rate of the site when the scan began, value there */
+  size_t *off[2];               /* [width + 1] CSR offsets into val[side] */
+  double *val[2];               /* values at rate0 -/+ k * spacing, k = 1 ..  */
+} scan_part;
+static scan_part *g_scan = NULL;
+static int g_scan_models = 0, g_scan_side_ready[2] = {0, 0};
+static double g_scan_spacing[2] = {0.0, 0.0};
+static int g_scan_count = 0;     /* packed descriptor of the scan (g_entries / g_qz / g_rz) */
+
+static double scan_rate(double r0, int side, int k, double spacing)
+{
+  return side == 0 ? r0 - k * spacing : r0 + k * spacing;        /* optimizeModel.c:1876, 1892 */
+}
+
+static void scan_eval(size_t n, const int *models, const int *sites, const double *rates, double *out)
+{
+  if (exb_evaluate_partial(g_engine, g_entries, g_scan_count, g_qz, g_rz, n, models, sites, rates, out) != EXB_OK)
+    backend_fail("exb_evaluate_partial");
+}
+
+static void scan_begin(tree *tr)
+{
+  int m, s;
+  size_t total = 0, at = 0, i;
+  int *models, *sites;
+  double *rates, *vals;
+  backend_sync(tr);                                   /* current model constants; also marks the old scan invalid */
+  g_scan_count = pack_descriptor(tr, 0);              /* td[0] still holds the full traversal of evaluateGeneric(tr, start, TRUE) */
+  if (!g_scan || g_scan_models != tr->NumberOfModels) {
+    g_scan = (scan_part *)calloc((size_t)tr->NumberOfModels, sizeof(scan_part));
+    g_scan_models = tr->NumberOfModels;
+  }
+  for (m = 0; m < tr->NumberOfModels; m++) total += tr->partitionData[m].width;
+  models = (int *)malloc((total + 1) * sizeof(int)); sites = (int *)malloc((total + 1) * sizeof(int));
+  rates = (double *)malloc((total + 1) * sizeof(double)); vals = (double *)malloc((total + 1) * sizeof(double));
+  for (m = 0; m < tr->NumberOfModels; m++) {
+    const pInfo *p = &tr->partitionData[m];
+    scan_part *sp = &g_scan[m];
+    free(sp->rate0); free(sp->v0);
+    for (s = 0; s < 2; s++) { free(sp->off[s]); free(sp->val[s]); sp->off[s] = NULL; sp->val[s] = NULL; }
+    sp->rate0 = (double *)malloc((p->width + 1) * sizeof(double));
+    sp->v0 = (double *)malloc((p->width + 1) * sizeof(double));
+    for (i = 0; i < p->width; i++, at++) {
+      sp->rate0[i] = p->patrat[i];
+      models[at] = m; sites[at] = (int)i; rates[at] = p->patrat[i];
+    }
+  }
+  scan_eval(total, models, sites, rates, vals);
+  for (m = 0, at = 0; m < tr->NumberOfModels; m++) {
+    memcpy(g_scan[m].v0, vals + at, tr->partitionData[m].width * sizeof(double));
+    at += tr->partitionData[m].width;
+  }
+  free(models); free(sites); free(rates); free(vals);
+  g_scan_side_ready[0] = g_scan_side_ready[1] = 0;
+  g_scan_spacing[0] = g_scan_spacing[1] = 0.0;
+  g_scan_valid = 1;
+}
+
+/* Which spacing turns r0 into ki in one step?  The caller's choices are 0.5 / 1.0 on its first invocation and
+   0.05/n / 0.1/n afterwards, never below 0.001 (optimizeModel.c:2429-2444). */
+static double scan_infer_spacing(int side, double r0, double ki)
+{
+  int n;
+  for (n = 1; n <= 256; n++) {
+    double sp = side == 0 ? (n == 1 ? 0.5 : 0.05) / ((double)n) : (n == 1 ? 1.0 : 0.1) / ((double)n);
+    if (sp < 0.001) sp = 0.001;
+    if (scan_rate(r0, side, 1, sp) == ki) return sp;
+  }
+  return 0.0;
+}
+
+/* All remaining steps of one side, for every site, in rounds. */
+static void scan_side(tree *tr, int side, double spacing)
+{
+  const double epsilon = 0.00001;                     /* optimizeModel.c:1861 */
+  size_t total = 0, nact = 0, at, i, j, rounds = 0, rcap = 0;
+  int m, *models, *sites, **rsites_m = NULL, **rsites_i = NULL;
+  double *rates, *vals, *best, **rvals = NULL;
+  size_t *rn = NULL;
+  for (m = 0; m < tr->NumberOfModels; m++) total += tr->partitionData[m].width;
+  models = (int *)malloc((total + 1) * sizeof(int)); sites = (int *)malloc((total + 1) * sizeof(int));
+  rates = (double *)malloc((total + 1) * sizeof(double)); vals = (double *)malloc((total + 1) * sizeof(double));
+  best = (double *)malloc((total + 1) * sizeof(double));
+  for (m = 0, at = 0; m < tr->NumberOfModels; m++) {
+    g_scan[m].off[side] = (size_t *)calloc(tr->partitionData[m].width + 2, sizeof(size_t));
+    for (i = 0; i < tr->partitionData[m].width; i++, at++) { models[at] = m; sites[at] = (int)i; best[at] = g_scan[m].v0[i]; }
+  }
+  nact = total;
+  while (nact > 0) {
+    const int k = (int)rounds + 1;
+    size_t keep = 0;
+    /* who takes step k?  left: only while the rate stays above 0.0001 (optimizeModel.c:1875) */
+    for (j = 0, at = 0; j < nact; j++) {
+      const double r = scan_rate(g_scan[models[j]].rate0[sites[j]], side, k, spacing);
+      if (side == 0 && !(r > 0.0001)) continue;
+      models[at] = models[j]; sites[at] = sites[j]; best[at] = best[j]; rates[at] = r; at++;
+    }
+    nact = at;
+    if (nact == 0) break;
+    scan_eval(nact, models, sites, rates, vals);
+    if (rounds == rcap) {
+      rcap = rcap ? 2 * rcap : 16;
+      rsites_m = (int **)realloc(rsites_m, rcap * sizeof(int *)); rsites_i = (int **)realloc(rsites_i, rcap * sizeof(int *));
+      rvals = (double **)realloc(rvals, rcap * sizeof(double *)); rn = (size_t *)realloc(rn, rcap * sizeof(size_t));
+    }
+    rsites_m[rounds] = (int *)malloc(nact * sizeof(int)); rsites_i[rounds] = (int *)malloc(nact * sizeof(int));
+    rvals[rounds] = (double *)malloc(nact * sizeof(double)); rn[rounds] = nact;
+    memcpy(rsites_m[rounds], models, nact * sizeof(int)); memcpy(rsites_i[rounds], sites, nact * sizeof(int));
+    memcpy(rvals[rounds], vals, nact * sizeof(double));
+    for (j = 0; j < nact; j++) {
+      g_scan[models[j]].off[side][sites[j] + 1] += 1;            /* counts first, prefix sums below */
+      if (vals[j] > best[j] && fabs(best[j] - vals[j]) > epsilon) {   /* the caller goes on (optimizeModel.c:1876-1878, 1892-1893) */
+        models[keep] = models[j]; sites[keep] = sites[j]; best[keep] = vals[j]; keep++;
+      }
+    }
+    nact = keep;
+    rounds++;
+  }
+  for (m = 0; m < tr->NumberOfModels; m++) {
+    scan_part *sp = &g_scan[m];
+    const size_t w = tr->partitionData[m].width;
+    for (i = 0; i < w; i++) sp->off[side][i + 1] += sp->off[side][i];
+    sp->val[side] = (double *)malloc((sp->off[side][w] + 1) * sizeof(double));
+  }
+  for (i = 0; i < rounds; i++) {                       /* round i holds step i+1 of its sites */
+    for (j = 0; j < rn[i]; j++) {
+      scan_part *sp = &g_scan[rsites_m[i][j]];
+      sp->val[side][sp->off[side][rsites_i[i][j]] + i] = rvals[i][j];
+    }
+    free(rsites_m[i]); free(rsites_i[i]); free(rvals[i]);
+  }
+  free(rsites_m); free(rsites_i); free(rvals); free(rn);
+  free(models); free(sites); free(rates); free(vals); free(best);
+}
+
+double evaluatePartialGeneric(tree *tr, int i, double ki, int _model)
+{
+  const scan_part *sp;
+  double r0, v;
+  int side, k, nsteps;
+  assert(tr->rateHetModel == CAT);                    /* evaluatePartialGenericSpecial.c:326 */
+  if (!g_scan_valid) scan_begin(tr);
+  sp = &g_scan[_model];
+  r0 = sp->rate0[i];
+  if (ki == r0) return sp->v0[i];
+  side = ki < r0 ? 0 : 1;
+  if (!g_scan_side_ready[side]) {
+    g_scan_spacing[side] = scan_infer_spacing(side, r0, ki);
+    if (g_scan_spacing[side] > 0.0) scan_side(tr, side, g_scan_spacing[side]);
+    g_scan_side_ready[side] = 1;
+  }
+  if (g_scan_spacing[side] > 0.0) {
+    nsteps = (int)(sp->off[side][i + 1] - sp->off[side][i]);
+    for (k = 1; k <= nsteps; k++)
+      if (scan_rate(r0, side, k, g_scan_spacing[side]) == ki) return sp->val[side][sp->off[side][i] + k - 1];
+  }
+  scan_eval(1, &_model, &i, &ki, &v);                 /* not anticipated: answer this one question */
+  return v;
 }

@@ -267,6 +267,11 @@ struct exb_engine {
   unsigned int *nr_barrier = nullptr;
   unsigned char *nr_mask = nullptr;
   int nr_max_blocks = 0;
+  // exb_evaluate_partial: growable device buffers (descriptor + pairs | results | slot stacks)
+  unsigned char *pp_in = nullptr; size_t pp_in_cap = 0;
+  double *pp_out = nullptr; size_t pp_out_cap = 0;
+  double *pp_scratch = nullptr; size_t pp_scratch_cap = 0;
+  int pp_max_blocks[2] = {0, 0};
 };
 
 constexpr int kMaxParamPartitions = 16;
@@ -320,6 +325,7 @@ extern "C" void exb_destroy(exb_engine *e)
   cudaFree(e->gs); cudaFree(e->scale_inc); cudaFree(e->out_d); cudaFreeHost(e->out_h);
   cudaFree(e->nr_state_d); cudaFreeHost(e->nr_state_h); cudaFree(e->nr_barrier); cudaFree(e->nr_mask);
   cudaFree(e->ticket); cudaFreeHost((void *)e->done_flag);
+  cudaFree(e->pp_in); cudaFree(e->pp_out); cudaFree(e->pp_scratch);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -980,6 +986,160 @@ extern "C" int exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const
     if (curvatOK) curvatOK[b] = h->curvatOK[b];
   }
   if (iterations) *iterations = h->iterations;
+  return EXB_OK;
+}
+
+// ---- per-site likelihood at explicit rates (evaluatePartialGeneric, evaluatePartialGenericSpecial.c:259) ----
+template <class T>
+static cudaError_t grow(T **p, size_t *cap, size_t need)
+{
+  if (need <= *cap) return cudaSuccess;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  const size_t want = need + need / 4;
+  cudaError_t r = cudaMalloc((void **)p, want);
+  if (r == cudaSuccess) *cap = want;
+  return r;
+}
+
+extern "C" int exb_evaluate_partial(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
+                                    size_t n, const int *models, const int *sites, const double *rates, double *out)
+{
+  if (!e || !e->committed) return fail(EXB_ERR_STATE, "engine not committed");
+  if (!e->cat) return fail(EXB_ERR_STATE, "exb_evaluate_partial: only under the CAT / PSR rate model (evaluatePartialGenericSpecial.c:326)");
+  if (!ti || !qz || !rz || count < 1) return fail(EXB_ERR_ARG, "exb_evaluate_partial: null traversal arguments");
+  if (n == 0) return EXB_OK;
+  if (!models || !sites || !rates || !out) return fail(EXB_ERR_ARG, "exb_evaluate_partial: null pair arrays");
+  if (n >= ((size_t)1 << 31)) return fail(EXB_ERR_ARG, "exb_evaluate_partial: more than 2^31 pairs in one call");
+  if (ti[0].pNumber < 1 || ti[0].pNumber > e->mxtips || ti[0].qNumber <= e->mxtips)
+    return fail(EXB_ERR_ARG, "exb_evaluate_partial: the root branch must join a tip (pNumber=%d) and an inner node (qNumber=%d), "
+                "evaluatePartialGenericSpecial.c:210", ti[0].pNumber, ti[0].qNumber);
+  CUDA_TRY(cudaSetDevice(e->device));
+  int rc = stage_traversal(e, ti, count, 1, qz, rz, nullptr);      // validation, lzq / lzr on the device
+  if (rc) return rc;
+  rc = flush_models(e);
+  if (rc) return rc;
+
+  // slot program: a post-order traversal keeps few vectors alive; give every inner node a slot for its lifetime
+  std::vector<PartialEntry> prog((size_t)count);
+  std::vector<int> slot_of((size_t)2 * e->mxtips, -1), free_slots;
+  int nslots = 0;
+  for (int k = 1; k < count; k++) {
+    const exb_entry &t = ti[k];
+    int q = t.qNumber, r = t.rNumber;
+    if (t.tipCase == EXB_INNER_INNER) {
+      if (slot_of[q] < 0) return fail(EXB_ERR_ARG, "exb_evaluate_partial: entry %d reads inner node %d which this traversal does not compute "
+                                      "(a FULL traversal is required, evaluatePartialGenericSpecial.c:214-226)", k, q);
+      const int sq = slot_of[q]; slot_of[q] = -1; free_slots.push_back(sq); q = sq;
+    }
+    if (t.tipCase != EXB_TIP_TIP) {
+      if (slot_of[r] < 0) return fail(EXB_ERR_ARG, "exb_evaluate_partial: entry %d reads inner node %d which this traversal does not compute "
+                                      "(a FULL traversal is required, evaluatePartialGenericSpecial.c:214-226)", k, r);
+      const int sr = slot_of[r]; slot_of[r] = -1; free_slots.push_back(sr); r = sr;
+    }
+    int sp;                                        // may reuse a child's slot: the thread holds both children in registers
+    if (!free_slots.empty()) { sp = free_slots.back(); free_slots.pop_back(); } else sp = nslots++;
+    slot_of[t.pNumber] = sp;
+    prog[k] = PartialEntry{t.tipCase, sp, q, r};
+  }
+  if (slot_of[ti[0].qNumber] < 0)
+    return fail(EXB_ERR_ARG, "exb_evaluate_partial: the traversal does not compute the root's inner node %d", ti[0].qNumber);
+  prog[0] = PartialEntry{-1, ti[0].pNumber, slot_of[ti[0].qNumber], 0};
+  if (nslots < 1) nslots = 1;
+
+  // group the pairs by class and partition (counting sort, stable), cut each partition's run into chunks
+  std::vector<size_t> pstart((size_t)e->P + 1, 0);
+  for (size_t j = 0; j < n; j++) {
+    const int m = models[j];
+    if (m < 0 || m >= e->P) return fail(EXB_ERR_ARG, "exb_evaluate_partial: pair %zu names partition %d", j, m);
+    if (sites[j] < 0 || (size_t)sites[j] >= e->parts[m].width)
+      return fail(EXB_ERR_ARG, "exb_evaluate_partial: pair %zu names site %d of partition %d (width %zu)", j, sites[j], m, e->parts[m].width);
+    if (!e->parts[m].model_set) return fail(EXB_ERR_STATE, "partition %d has no model constants (exb_set_model)", m);
+    pstart[m + 1]++;
+  }
+  // order: class 0 partitions first, then class 1, each in partition order
+  std::vector<int> porder;
+  for (int c = 0; c < 2; c++) for (int m = 0; m < e->P; m++) if (e->parts[m].cls == c) porder.push_back(m);
+  std::vector<size_t> pbase((size_t)e->P, 0);
+  size_t run = 0, cls_begin[3] = {0, 0, 0};
+  {
+    int ci = 0;
+    for (int m : porder) {
+      while (ci < e->parts[m].cls) cls_begin[++ci] = run;
+      pbase[m] = run; run += pstart[m + 1];
+    }
+    while (ci < 2) cls_begin[++ci] = run;
+  }
+  std::vector<PartialPair> pairs(n);
+  std::vector<uint32_t> origin(n);
+  {
+    std::vector<size_t> fill = pbase;
+    for (size_t j = 0; j < n; j++) {
+      const HostPart &p = e->parts[models[j]];
+      const size_t at = fill[models[j]]++;
+      pairs[at] = PartialPair{rates[j], (uint32_t)(p.site0 + (size_t)sites[j]), 0u};
+      origin[at] = (uint32_t)j;
+    }
+  }
+  std::vector<PartialChunk> chunks[2];
+  for (int m : porder) {
+    const HostPart &p = e->parts[m];
+    const size_t cnt = pstart[m + 1];
+    for (size_t o = 0; o < cnt; o += kPartialThreads)
+      chunks[p.cls].push_back(PartialChunk{(uint32_t)(pbase[m] + o - cls_begin[p.cls]), (uint32_t)std::min<size_t>(kPartialThreads, cnt - o),
+                                           p.part_cls, e->nb > 1 ? m : 0});
+  }
+  std::vector<double> root_lz((size_t)e->nb);
+  for (int b = 0; b < e->nb; b++) root_lz[b] = log(qz[b]);        // not clamped, :232-234
+
+  // device image: prog | root_lz | pairs | chunks[0] | chunks[1]
+  auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  size_t off = 0;
+  const size_t o_prog = off;  off = align16(off + prog.size() * sizeof(PartialEntry));
+  const size_t o_root = off;  off = align16(off + root_lz.size() * sizeof(double));
+  const size_t o_pairs = off; off = align16(off + pairs.size() * sizeof(PartialPair));
+  size_t o_chunks[2];
+  for (int c = 0; c < 2; c++) { o_chunks[c] = off; off = align16(off + chunks[c].size() * sizeof(PartialChunk)); }
+  CUDA_TRY(grow(&e->pp_in, &e->pp_in_cap, off));
+  CUDA_TRY(grow(&e->pp_out, &e->pp_out_cap, n * sizeof(double)));
+  CUDA_TRY(cudaMemcpyAsync(e->pp_in + o_prog, prog.data(), prog.size() * sizeof(PartialEntry), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->pp_in + o_root, root_lz.data(), root_lz.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->pp_in + o_pairs, pairs.data(), pairs.size() * sizeof(PartialPair), cudaMemcpyHostToDevice, e->stream));
+  for (int c = 0; c < 2; c++)
+    if (!chunks[c].empty())
+      CUDA_TRY(cudaMemcpyAsync(e->pp_in + o_chunks[c], chunks[c].data(), chunks[c].size() * sizeof(PartialChunk), cudaMemcpyHostToDevice, e->stream));
+  int blocks[2] = {0, 0};
+  size_t scratch_need = 0;
+  for (int c = 0; c < 2; c++) {
+    if (chunks[c].empty()) continue;
+    if (!e->pp_max_blocks[c]) e->pp_max_blocks[c] = partial_max_blocks(e->cls[c].S, e->device);
+    blocks[c] = (int)std::min<size_t>(chunks[c].size(), (size_t)e->pp_max_blocks[c]);
+    scratch_need = std::max(scratch_need, (size_t)blocks[c] * nslots * e->cls[c].S * kPartialThreads * sizeof(double));
+  }
+  CUDA_TRY(grow(&e->pp_scratch, &e->pp_scratch_cap, scratch_need));
+  if (e->timing) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+  for (int c = 0; c < 2; c++) {
+    if (chunks[c].empty()) continue;
+    ClassState &k = e->cls[c];
+    PartialArgs a;
+    a.chunks = (const PartialChunk *)(e->pp_in + o_chunks[c]); a.nchunks = (int)chunks[c].size();
+    a.pairs = (const PartialPair *)(e->pp_in + o_pairs) + cls_begin[c];
+    a.entries = (const PartialEntry *)(e->pp_in + o_prog); a.count = count;
+    a.lzq = (const double *)(e->stage_d + e->o_lzq); a.lzr = (const double *)(e->stage_d + e->o_lzr);
+    a.root_lz = (const double *)(e->pp_in + o_root); a.nbranches = e->nb;
+    a.models = k.models; a.model_doubles = k.model_doubles; a.tips = k.tips; a.N = k.N; a.wgt = k.wgt;
+    a.scratch = e->pp_scratch; a.nslots = nslots; a.log_minlikelihood = log(kMinLikelihood);
+    a.out = e->pp_out + cls_begin[c];
+    launch_partial(a, k.S, blocks[c], e->stream);       // the two classes share the scratch area: same stream, in order
+    e->launches++;
+  }
+  if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+  CUDA_TRY(cudaGetLastError());
+  std::vector<double> res(n);
+  CUDA_TRY(cudaMemcpyAsync(res.data(), e->pp_out, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if (e->timing) cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
+  for (size_t j = 0; j < n; j++) out[origin[j]] = res[j];
   return EXB_OK;
 }
 

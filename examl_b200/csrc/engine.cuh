@@ -167,6 +167,28 @@ struct NrArgs {
 int launch_newton_raphson(const NrArgs &a, int blocks, cudaStream_t s);
 int newton_raphson_max_blocks(int device);
 
+// ---- per-site likelihood at an explicit rate (kernels_partial.cu; evaluatePartialGeneric) ----
+constexpr int kPartialThreads = 128;
+struct PartialPair  { double rate; uint32_t site; uint32_t pad; };        // site on the class axis
+struct PartialChunk { uint32_t begin, count; int part_cls, branch_slot; };  // <= kPartialThreads pairs of ONE partition
+struct PartialEntry { int tipCase, p, q, r; };                             // tips: node number; inner nodes: slot index
+struct PartialArgs {
+  const PartialChunk *chunks; int nchunks;
+  const PartialPair  *pairs;
+  const PartialEntry *entries; int count;
+  const double *lzq, *lzr;     // [count][nbranches] log(max(z, zmin))
+  const double *root_lz;       // [nbranches] log(z) of the root branch, NOT clamped (evaluatePartialGenericSpecial.c:232-234)
+  int nbranches;
+  const double *models; int model_doubles;
+  const uint8_t *tips; size_t N;
+  const int *wgt;
+  double *scratch; int nslots;   // [grid][nslots][S][kPartialThreads]
+  double log_minlikelihood;
+  double *out;                   // [npairs], in pair order
+};
+void launch_partial(const PartialArgs &a, int states, int blocks, cudaStream_t s);
+int partial_max_blocks(int states, int device);
+
 void launch_dtab(const DtabArgs &a, cudaStream_t s);
 void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
 void launch_traverse_dna_cat(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);

@@ -24,6 +24,7 @@
  *   execCore              (makenewzGenericSpecial.c:849)       exb_core
  *     + MPI_Allreduce     (makenewzGenericSpecial.c:1241-1248)   (all-reduce inside, NCCL)
  *   topLevelMakenewz      (makenewzGenericSpecial.c:1133)      exb_makenewz (single rank: whole NR loop on the device)
+ *   evaluatePartialGeneric (evaluatePartialGenericSpecial.c:259) exb_evaluate_partial (batched over sites and rates)
  *
  * The three public axml.h entry points (evaluateGeneric axml.h:1223, newviewGeneric :1232,
  * makenewzGeneric :1241) are exported by the companion translation unit
@@ -161,6 +162,18 @@ int  exb_core(exb_engine *e, const double *lz, const unsigned char *executeModel
 int  exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
                   const unsigned char *executeModel, const double *z0, int maxiter,
                   double *result, int *curvatOK, int *iterationsDone);
+
+/* evaluatePartialGeneric(tr, i, ki, model)  evaluatePartialGenericSpecial.c:259 -- batched.
+ * Under CAT / PSR, optimizeRateCategories (optimizeModel.c:1792-1922) asks, site by site and candidate rate by
+ * candidate rate, for the log likelihood of ONE site with ONE explicit rate, recomputed from the tips along the
+ * full traversal td[0].  This entry point answers n such questions at once: for pair j the value
+ *     wgt[site] * ( log|x_tip . x_inner . exp(EIGN * ki * log z_root)| + scale * log(minlikelihood) )
+ * of site sites[j] (index inside partition models[j]) at rate rates[j] is written to out[j].
+ * entries[0] is the root branch, its pNumber a tip (evaluatePartialGenericSpecial.c:210); entries[1..count)
+ * must be a full traversal (every inner node read is computed earlier in the list).  The engine's CLVs,
+ * scalers and categories are neither read nor changed.  Local: no collective is involved. */
+int  exb_evaluate_partial(exb_engine *e, const exb_entry *entries, int count, const double *qz, const double *rz,
+                          size_t n, const int *models, const int *sites, const double *rates, double *out);
 
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------------ */
 

@@ -52,7 +52,7 @@ def run_dropin(binary: str, tree: str, tmp: str, extra_args, env=None, exe=DROPI
     r = subprocess.run([exe, "-s", binary, "-t", tree, "-m", model, "-n", "RUN", "-w", tmp + "/"] + extra_args,
                        cwd=tmp, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
     dumps = {}
-    for d in ("first", "mkz", "final"):
+    for d in ("first", "mkz", "final", "partial"):
         p = os.path.join(tmp, f"dump.{d}.json")
         if os.path.exists(p):
             dumps[d] = json.load(open(p))

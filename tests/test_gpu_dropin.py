@@ -51,6 +51,13 @@ def test_tree_evaluation_matches_reference(tag, lines, extra):
         got, want = dumps["final"]["likelihood"], final_gold["likelihood"]
         assert _rel(got, want) < NORTH_STAR_RTOL, (got, want)
         print(f"{tag}: drop-in final lnL {got!r} vs reference {want!r} (rel {_rel(got, want):.2e})")
+        if psr:
+            # the per-site rate scan: optimizeModel.c asked the back-end the very questions it asked the reference
+            # (same sites, same rates, same stopping points) and got the same answers
+            import numpy as np
+            a, b = np.array(dumps["partial"]["partial"]), np.array(load_json(f"{tag}.partial.json")["partial"])
+            assert a.shape == b.shape and np.array_equal(a[:, :3], b[:, :3]), "the rate scan took a different path"
+            assert np.all(np.abs(a[:, 3] - b[:, 3]) <= 1e-9 * np.maximum(1.0, np.abs(b[:, 3])))
 
 
 @pytest.mark.skipif(not have_binaries(), reason="bin/examl-b200-probe / oracle/_ref/parse-examl not built")

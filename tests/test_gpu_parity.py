@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from examl_b200.likelihood import Likelihood
-from replay import CASES, replay_case
+from replay import CASES, PARTIAL_CASES, replay_case, replay_partial
 from synth import build_engine, random_case, random_categories
 
 pytestmark = pytest.mark.gpu
@@ -302,3 +302,63 @@ def test_lg4_mixed_with_ordinary_partitions(cuda_factory, oracle_factory):
         a.z[:] = z; a2.z[:] = z2
     l1, l2 = lk.evaluateGeneric(tree.start, True), lk2.evaluateGeneric(tree2.start, True)
     assert abs(l1 - l2) <= 1e-10 * abs(l2)
+
+
+# ---- evaluatePartialGeneric (the per-site rate scan of -m PSR) --------------------------------------------
+@pytest.mark.parametrize("tag", PARTIAL_CASES)
+def test_evaluate_partial_reference_goldens(cuda_factory, tag):
+    """The reference's own evaluatePartialGeneric calls (partition, site, rate) -> value, recorded during its first
+    optimizeRateCategories, answered in one batch."""
+    assert replay_partial(cuda_factory, tag) >= 160
+
+
+@pytest.mark.parametrize("mxtips,widths,kinds,nb,mode", [
+    (22, [300, 0, 420, 33], [4, 4, 20, 20], 1, "signal"),
+    (30, [130, 400], [4, 20], 2, "signal"),
+    (150, [500, 200], [4, 20], 1, "iid"),        # every vector is rescaled several times
+    (700, [70, 40], [4, 20], 1, "signal"),       # deep descriptor, many live slots
+])
+def test_evaluate_partial_vs_oracle(cuda_factory, oracle_factory, mxtips, widths, kinds, nb, mode):
+    tree, parts, models = random_case(mxtips, widths, kinds, seed=91, num_branches=nb, mode=mode)
+    cats = random_categories(parts, max_cats=8, seed=4)
+    gpu = build_engine(cuda_factory, tree, parts, models, cats=cats, max_cats=8)
+    cpu = build_engine(oracle_factory, tree, parts, models, cats=cats, max_cats=8)
+    ti = tree.full_traversal()
+    rng = np.random.default_rng(12)
+    mo, si, ra = [], [], []
+    for m, w in enumerate(widths):
+        for rep in range(3):                       # every site, several rates, shuffled across partitions
+            mo += [m] * w; si += list(range(w)); ra += list(rng.gamma(2.0, 0.6, w) + 1e-3)
+    perm = rng.permutation(len(mo))
+    mo, si, ra = np.array(mo)[perm], np.array(si)[perm], np.array(ra)[perm]
+    g = gpu.evaluatePartial(ti, mo, si, ra)
+    c = cpu.evaluatePartial(ti, mo, si, ra)
+    assert np.all(np.isfinite(g))
+    assert np.all(np.abs(g - c) <= 1e-11 * np.maximum(1.0, np.abs(c))), np.abs(g - c).max()
+    # consistency with the ordinary evaluate: the sum over the sites at their categories' rates is the partition's lnL
+    lh = gpu.evaluateIterative(ti)
+    for m, w in enumerate(widths):
+        if w:
+            own = gpu.evaluatePartial(ti, [m] * w, np.arange(w), np.asarray(cats[m][0])[cats[m][1]])
+            assert abs(own.sum() - lh[m]) <= 1e-10 * abs(lh[m]), (m, own.sum(), lh[m])
+    # an empty batch is legal, the CLVs of the engine were not disturbed
+    assert gpu.evaluatePartial(ti, [], [], []).shape == (0,)
+    lh2 = gpu.evaluateIterative(ti[:1])
+    assert np.array_equal(lh, lh2)
+
+
+def test_evaluate_partial_errors(cuda_factory):
+    from examl_b200.capi import EngineError
+    tree, parts, models = random_case(12, [40], [4], seed=5)
+    gam = build_engine(cuda_factory, tree, parts, models)
+    with pytest.raises(EngineError, match="CAT"):
+        gam.evaluatePartial(tree.full_traversal(), [0], [0], [1.0])
+    cats = random_categories(parts, max_cats=4, seed=1)
+    psr = build_engine(cuda_factory, tree, parts, models, cats=cats, max_cats=4)
+    ti = tree.full_traversal()
+    with pytest.raises(EngineError, match="FULL traversal"):
+        psr.evaluatePartial(ti[:1] + ti[3:], [0], [0], [1.0])
+    with pytest.raises(EngineError, match="site"):
+        psr.evaluatePartial(ti, [0], [40], [1.0])
+    with pytest.raises(EngineError, match="partition"):
+        psr.evaluatePartial(ti, [1], [0], [1.0])

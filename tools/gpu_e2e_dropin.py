@@ -1,6 +1,6 @@
 """Whole-program comparison on a mid-size data set: ExaML's own `-f e` (model + branch-length optimisation on a fixed
 tree: thousands of evaluateGeneric / makenewzGeneric / newviewGeneric calls) through the drop-in binary on one B200 vs
-the unmodified reference (OMP-AVX, all usable cores).   usage: tools/gpu_e2e_dropin.py [taxa] [sites] [mode]"""
+the unmodified reference (OMP-AVX, all usable cores).   usage: tools/gpu_e2e_dropin.py [taxa] [sites] [mode] [GAMMA|PSR]"""
 import os, sys, time, subprocess, tempfile, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -11,6 +11,7 @@ sys.path.insert(0, ROOT); import bench
 taxa = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 sites = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
 mode = sys.argv[3] if len(sys.argv) > 3 else "e"
+rate_model = sys.argv[4] if len(sys.argv) > 4 else "GAMMA"
 tree = Tree.random(taxa, seed=3)
 tips = exdata.synthetic_dna(tree, sites, seed=9, mode="signal", p_change=0.08)
 with tempfile.TemporaryDirectory() as tmp:
@@ -24,12 +25,12 @@ with tempfile.TemporaryDirectory() as tmp:
                                  ("reference", os.path.join(ROOT, "oracle/_ref/examl-OMP-AVX"), {"OMP_NUM_THREADS": str(bench.usable_cores())})) if not (x[0] == "reference" and os.environ.get("E2E_SKIP_REF"))]:
         e = dict(env); e.update(extra_env); e["EXAML_PROBE_DUMP"] = os.path.join(tmp, name); e["EXAML_PROBE_NOTIPS"] = "1"
         t0 = time.time()
-        r = subprocess.run([exe, "-s", "a.binary", "-t", "a.tree", "-m", "GAMMA", "-n", name, "-f", mode, "-w", tmp + "/"], cwd=tmp, env=e,
+        r = subprocess.run([exe, "-s", "a.binary", "-t", "a.tree", "-m", rate_model, "-n", name, "-f", mode, "-w", tmp + "/"], cwd=tmp, env=e,
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         dt = time.time() - t0
         lnl = json.load(open(os.path.join(tmp, name + ".final.json")))["likelihood"] if r.returncode == 0 else None
         res[name] = (dt, lnl)
-        print(f"{name:10s} -f {mode}: wall {dt:8.1f} s  final lnL {lnl!r}  rc={r.returncode}", flush=True)
+        print(f"{name:10s} -m {rate_model} -f {mode}: wall {dt:8.1f} s  final lnL {lnl!r}  rc={r.returncode}", flush=True)
         if r.returncode: print(r.stdout[-1500:])
     if all(v[1] for v in res.values()):
         print("speed-up %.1fx (reference on %d cores), lnL rel diff %.2e" % (res["reference"][0] / res["b200"][0], bench.usable_cores(),
