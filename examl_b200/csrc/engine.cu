@@ -792,7 +792,9 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
       if (e->cat) launch_traverse_dna_cat(a, nullptr, (int)k.tiles_h.size(), e->stream);
       else        launch_traverse_dna(a, nullptr, (int)k.tiles_h.size(), e->stream);   // many partitions: constants via shared memory
     } else {
-      launch_traverse_aa(a, k.nparts == 1 ? k.models_h.data() : nullptr, (int)k.tiles_h.size(), e->stream);
+      bool any_lg4 = false;                        // per-category eigen-systems anywhere in the class?
+      for (int pc = 0; pc < k.nparts; pc++) any_lg4 = any_lg4 || k.models_h[(size_t)pc * k.model_doubles + kAaLg4] != 0.0;
+      launch_traverse_aa(a, any_lg4, (int)k.tiles_h.size(), e->stream);
     }
     e->launches++;
   }

@@ -193,7 +193,7 @@ void launch_dtab(const DtabArgs &a, cudaStream_t s);
 void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
 void launch_traverse_dna_cat(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
 void launch_core_dna(const CoreArgs &a, int ntiles, cudaStream_t s);
-void launch_traverse_aa(const TraverseArgs &a, const double *single_partition_model, int ntiles, cudaStream_t s);
+void launch_traverse_aa(const TraverseArgs &a, bool any_lg4, int ntiles, cudaStream_t s);
 void launch_core_aa(const CoreArgs &a, int ntiles, cudaStream_t s);
 void launch_finish(const FinishArgs &a, cudaStream_t s);
 

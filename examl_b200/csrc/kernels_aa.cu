@@ -190,10 +190,13 @@ __device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const AaConst
 //              slot = one of four 8-site groups of the warp (32 sites per warp, 384 per chunk), CLV = 20 doubles per
 //              site, every row scales its A operand with the exponentials of ITS site's category; scaling and the
 //              log are per site.
-template <bool CAT>
+// LG4 = true : every Gamma category has its own eigen-system (LG4M / LG4X partitions in the class): per-category B
+//              fragments and tip vectors.  false: one system -- fragment and tip addresses do not depend on the category.
+template <bool CAT, bool LG4>
 __global__ void __launch_bounds__(kAaThreads, 1)
 traverse_aa_kernel(const TraverseArgs a)
 {
+  constexpr int NSYS = LG4 ? 4 : 1;            // eigen-systems kept in shared memory
   constexpr int TSITES = CAT ? 384 : 96;       // sites per chunk = bytes per staged tip row
   constexpr int XSPAN = CAT ? 20 : 80;         // doubles per site in a CLV
   constexpr int XSLOT = CAT ? 8 * 20 : 20;     // distance between consecutive slots of my row in a CLV
@@ -212,9 +215,9 @@ traverse_aa_kernel(const TraverseArgs a)
   const size_t N = a.N;
   const double *model = a.models + (size_t)tile.part_cls * kAaModelDoubles;   // EIGN[20] rates[4] EI[400] EV[400] tip[460]
   {
-    for (int i = tid; i < 4 * 460; i += kAaThreads) K.tip[i / 460][i % 460] = model[kAaTip + i];
+    for (int i = tid; i < NSYS * 460; i += kAaThreads) K.tip[i / 460][i % 460] = model[kAaTip + i];
     // B fragments per category: EI_c^T[k = 4s+tq][n = 8t+g] = EI_c[n][k];  EV_c[k][n];  zero padding for n >= 20
-    for (int i = tid; i < 4 * 15 * 32; i += kAaThreads) {
+    for (int i = tid; i < NSYS * 15 * 32; i += kAaThreads) {
       const int kc = i / 480, f = (i % 480) >> 5, ln = i & 31, fs = f / 3, ft = f % 3;
       const int k = 4 * fs + (ln & 3), n = 8 * ft + (ln >> 2);
       K.fragEI[kc][f][ln] = n < S ? model[kAaEI + kc * 400 + n * S + k] : 0.0;
@@ -282,17 +285,17 @@ traverse_aa_kernel(const TraverseArgs a)
         const int code1 = q_inner ? 0 : stips[en.qoff + lsite[0]], code2 = r_inner ? 0 : stips[en.roff + lsite[0]];
         sl.x1 = q_inner ? a.clv + en.qoff + soff : &K.tip[0][S * code1];
         sl.x2 = r_inner ? a.clv + en.roff + soff : &K.tip[0][S * code2];
-        sl.st1 = q_inner ? S : 460; sl.st2 = r_inner ? S : 460;
+        sl.st1 = q_inner ? S : (LG4 ? 460 : 0); sl.st2 = r_inner ? S : (LG4 ? 460 : 0);
         sl.lut1 = lutE + (size_t)code1 * SPAN; sl.lut2 = lutE + lutside + (size_t)code2 * SPAN;
         sl.drow = drow;
       }
       const bool qlut = !q_inner && lutE, rlut = !r_inner && lutE;
-      if (qlut && rlut)                   aa_entry<CH_LUT, CH_LUT, !CAT>(carry, K, sl, lane, tq);
-      else if (qlut && rsrc == SRC_CARRY) aa_entry<CH_LUT, CH_CARRY, !CAT>(carry, K, sl, lane, tq);
-      else if (qlut)                      aa_entry<CH_LUT, CH_MEM, !CAT>(carry, K, sl, lane, tq);
-      else if (rsrc == SRC_CARRY)         aa_entry<CH_MEM, CH_CARRY, !CAT>(carry, K, sl, lane, tq);
-      else if (qsrc == SRC_CARRY)         aa_entry<CH_CARRY, CH_MEM, !CAT>(carry, K, sl, lane, tq);
-      else                                aa_entry<CH_MEM, CH_MEM, !CAT>(carry, K, sl, lane, tq);
+      if (qlut && rlut)                   aa_entry<CH_LUT, CH_LUT, LG4>(carry, K, sl, lane, tq);
+      else if (qlut && rsrc == SRC_CARRY) aa_entry<CH_LUT, CH_CARRY, LG4>(carry, K, sl, lane, tq);
+      else if (qlut)                      aa_entry<CH_LUT, CH_MEM, LG4>(carry, K, sl, lane, tq);
+      else if (rsrc == SRC_CARRY)         aa_entry<CH_MEM, CH_CARRY, LG4>(carry, K, sl, lane, tq);
+      else if (qsrc == SRC_CARRY)         aa_entry<CH_CARRY, CH_MEM, LG4>(carry, K, sl, lane, tq);
+      else                                aa_entry<CH_MEM, CH_MEM, LG4>(carry, K, sl, lane, tq);
 
       if (r_inner) {                            // TIP_TIP is never rescaled (avxLikelihood.c:1393-1440)
         unsigned int cnt = 0;
@@ -352,12 +355,12 @@ traverse_aa_kernel(const TraverseArgs a)
     const SEntry br = ents[kWindow];
     const bool ptip = br.ptip_qtip & 1, qtip = br.ptip_qtip & 2;
     const bool p_carry = !ptip && br.poff == carry_node, q_carry = !qtip && br.qoff == carry_node;
-    const bool lg4 = !CAT && model[kAaLg4] != 0.0;
+    const bool lg4 = LG4 && model[kAaLg4] != 0.0;       // an ordinary partition next to LG4 ones keeps log(0.25 |sum|)
     double term = 0.0;
     #pragma unroll
     for (int c = 0; c < 4; c++) {
-      const double *tpa = ptip ? &K.tip[CAT ? 0 : c][S * stips[br.poff + lsite[c]]] : K.tip[0];
-      const double *tpb = qtip ? &K.tip[CAT ? 0 : c][S * stips[br.qoff + lsite[c]]] : K.tip[0];
+      const double *tpa = ptip ? &K.tip[LG4 ? c : 0][S * stips[br.poff + lsite[c]]] : K.tip[0];
+      const double *tpb = qtip ? &K.tip[LG4 ? c : 0][S * stips[br.qoff + lsite[c]]] : K.tip[0];
       double tc = 0.0;                            // this category's share (weighted under LG4X)
       #pragma unroll
       for (int t = 0; t < 3; t++) {
@@ -457,24 +460,25 @@ core_aa_kernel(const CoreArgs a)
   if (threadIdx.x == 0) { a.tile_out[2 * (size_t)blockIdx.x] = t1; a.tile_out[2 * (size_t)blockIdx.x + 1] = t2; }
 }
 
-template <bool CAT>
+template <bool CAT, bool LG4>
 static void launch_aa_variant(const TraverseArgs &a, int ntiles, cudaStream_t s)
 {
   const size_t smem = ((window_smem_bytes<(CAT ? 384 : 96)>() + 127) & ~(size_t)127) + sizeof(AaConstsSmem);
   static size_t configured = 0;
   if (smem > configured) {
     const size_t want = std::min<size_t>(227 * 1024 - 16384, std::max<size_t>(smem, 64 * 1024));
-    cudaFuncSetAttribute(traverse_aa_kernel<CAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    cudaFuncSetAttribute(traverse_aa_kernel<CAT, LG4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
     configured = want;
   }
-  traverse_aa_kernel<CAT><<<ntiles, kAaThreads, smem, s>>>(a);
+  traverse_aa_kernel<CAT, LG4><<<ntiles, kAaThreads, smem, s>>>(a);
 }
 
-void launch_traverse_aa(const TraverseArgs &a, const double *, int ntiles, cudaStream_t s)
+void launch_traverse_aa(const TraverseArgs &a, bool any_lg4, int ntiles, cudaStream_t s)
 {
   if (ntiles <= 0) return;
-  if (a.rate_cat) launch_aa_variant<true>(a, ntiles, s);
-  else            launch_aa_variant<false>(a, ntiles, s);
+  if (a.rate_cat)   launch_aa_variant<true, false>(a, ntiles, s);
+  else if (any_lg4) launch_aa_variant<false, true>(a, ntiles, s);
+  else              launch_aa_variant<false, false>(a, ntiles, s);
 }
 void launch_core_aa(const CoreArgs &a, int ntiles, cudaStream_t s)
 {
