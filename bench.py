@@ -383,6 +383,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name, "tip_cases_TT_TI_II": [ntt, nti, nii],
                        "sites_per_gpu": n_local, "parallelism": f"site-sharded dp{world}",
+                       "allreduce": ("none (1 GPU)" if world == 1 else
+                                     "inside finish_kernel over CUDA-IPC peer buffers (NVLink)" if eng.comm_is_p2p() else "ncclAllReduce after the kernel"),
                        "l2": "inputs_larger_than_L2 (CLV arena %.1f GB per GPU)" % ((taxa - 2) * n_local * states * 32 / 1e9),
                        "value_timing": "CUDA events around the kernels of each step (engine stream), max over ranks",
                        "lnl": lnl_resident},

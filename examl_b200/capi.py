@@ -23,7 +23,7 @@ EXPORTS = [
     "exb_set_model", "exb_newview", "exb_evaluate", "exb_makenewz_prepare", "exb_core", "exb_makenewz",
     "exb_comm_unique_id", "exb_comm_init", "exb_read_clv", "exb_read_scaler",
     "exb_read_sumtable", "exb_last_kernel_ms", "exb_launch_count", "exb_set_tile_sites", "exb_set_timing",
-    "exb_set_rate_model", "exb_set_categories", "exb_set_model_lg4", "exb_evaluate_partial",
+    "exb_set_rate_model", "exb_set_categories", "exb_set_model_lg4", "exb_evaluate_partial", "exb_comm_is_p2p",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -237,6 +237,9 @@ class Engine:
     def comm_init(self, rank: int, nranks: int, uid: bytes) -> None:
         buf = C.create_string_buffer(uid, UNIQUE_ID_BYTES)
         self._check(self._f("comm_init")(self._h, C.c_int(rank), C.c_int(nranks), buf))
+
+    def comm_is_p2p(self) -> bool:
+        return bool(self._f("comm_is_p2p")(self._h))
 
     # ---- introspection ------------------------------------------------------------------------
     def read_clv(self, model: int, node_number: int) -> np.ndarray:

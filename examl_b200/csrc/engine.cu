@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <string>
 #include <vector>
@@ -91,32 +92,66 @@ finish_kernel(const FinishArgs a)
     if (tid == 0) {
       s0 = ((red0[0] + red0[1]) + (red0[2] + red0[3]));
       s1 = ((red1[0] + red1[1]) + (red1[2] + red1[3]));
-      if (a.mode == MODE_EVALUATE) {
-        if (exec) {
-          const DevEntry br = a.entries[0];
-          s0 += (double)(gs[br.p] + gs[br.q]) * a.log_minlikelihood;   // evaluateGenericSpecial.c:830
+      if (a.mode == MODE_EVALUATE && exec) {
+        const DevEntry br = a.entries[0];
+        s0 += (double)(gs[br.p] + gs[br.q]) * a.log_minlikelihood;   // evaluateGenericSpecial.c:830
+      }
+      if (a.nranks > 1) {          // my contribution goes straight into every rank's receive buffer
+        const size_t at = ((size_t)(a.xseq & 1u) * a.nranks + a.rank) * 2 * a.nparts + part;
+        for (int r = 0; r < a.nranks; r++) {
+          a.peer_buf[r][at] = s0;
+          if (a.mode == MODE_CORE) a.peer_buf[r][at + a.nparts] = s1;
         }
+      } else {
         a.out[part] = s0;
         if (a.out_host) a.out_host[part] = s0;
-      } else {           // MODE_CORE
-        a.out[part] = s0;
-        a.out[a.nparts + part] = s1;
-        if (a.out_host) { a.out_host[part] = s0; a.out_host[a.nparts + part] = s1; }
+        if (a.mode == MODE_CORE) {
+          a.out[a.nparts + part] = s1;
+          if (a.out_host) a.out_host[a.nparts + part] = s1;
+        }
       }
     }
     __syncthreads();
   }
   if (a.done_flag_host) {
     // the last block to arrive publishes the completion flag after everybody's results are visible to the host
+    __shared__ int last, peer_lost;
     __threadfence_system();
     __syncthreads();
-    if (tid == 0) {
-      const unsigned int t = atomicAdd(a.ticket, 1u);
-      if (t == gridDim.x - 1) {
-        *a.ticket = 0;
-        __threadfence_system();
-        *a.done_flag_host = a.seq;
+    if (tid == 0) { last = atomicAdd(a.ticket, 1u) == gridDim.x - 1; peer_lost = 0; }
+    __syncthreads();
+    if (!last) return;
+    if (a.nranks > 1 && a.mode != MODE_NEWVIEW && a.mode != MODE_SUM) {
+      __threadfence_system();                        // every block's remote stores are ordered before the flags
+      if (tid < a.nranks) {
+        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.peer_flags[tid] + a.rank), "r"(a.xseq) : "memory");
+        // wait for rank tid's contribution to arrive in MY buffer
+        const unsigned int *f = a.peer_flags[a.rank] + tid;
+        unsigned int v;
+        const long long t0 = clock64();
+        for (;;) {
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+          if ((int)(v - a.xseq) >= 0) break;
+          if (clock64() - t0 > 40000000000LL) { peer_lost = 1; break; }     // ~20 s: a peer is gone
+          __nanosleep(200);
+        }
       }
+      __syncthreads();
+      const int nvals = (a.mode == MODE_CORE ? 2 : 1) * a.nparts;
+      const double *mine = a.peer_buf[a.rank] + (size_t)(a.xseq & 1u) * a.nranks * 2 * a.nparts;
+      for (int i = tid; i < nvals; i += blockDim.x) {
+        double t = 0.0;
+        for (int r = 0; r < a.nranks; r++) t += mine[(size_t)r * 2 * a.nparts + i];   // rank order: same bits everywhere
+        a.out[i] = t;
+        a.out_host[i] = t;
+      }
+      __threadfence_system();
+      __syncthreads();
+    }
+    if (tid == 0) {
+      *a.ticket = 0;
+      __threadfence_system();
+      *a.done_flag_host = peer_lost ? 0xFFFFFFFFu : a.seq;       // 0xFFFFFFFF: the host reports the lost peer
     }
   }
 }
@@ -172,11 +207,13 @@ struct NcclApi {
   int (*GetUniqueId)(NcclUniqueId *) = nullptr;
   int (*CommInitRank)(ncclComm_t *, int, NcclUniqueId, int) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 } g_nccl;
 constexpr int kNcclFloat64 = 8;   // ncclDouble
 constexpr int kNcclSum = 0;       // ncclSum
+constexpr int kNcclInt8 = 0;      // ncclInt8 / ncclChar
 
 int load_nccl()
 {
@@ -187,6 +224,7 @@ int load_nccl()
   g_nccl.GetUniqueId = (int (*)(NcclUniqueId *))dlsym(g_nccl.handle, "ncclGetUniqueId");
   g_nccl.CommInitRank = (int (*)(ncclComm_t *, int, NcclUniqueId, int))dlsym(g_nccl.handle, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(g_nccl.handle, "ncclAllReduce");
+  g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))dlsym(g_nccl.handle, "ncclAllGather");
   g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(g_nccl.handle, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.handle, "ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce)
@@ -261,7 +299,13 @@ struct exb_engine {
   unsigned char *stage_use = nullptr;    // what the kernels of the current call read: stage_d, or stage_h (zero copy)
   int total_tiles = 0;
   ncclComm_t comm = nullptr;
-  int nranks = 1;
+  int nranks = 1, rank = 0;
+  // all GPUs on one node: the all-reduce is fused into finish_kernel over CUDA-IPC mapped peer buffers (NVLink)
+  bool p2p = false;
+  unsigned char *xbuf = nullptr;                 // my receive buffer: [2][nranks][2P] doubles, then [nranks] flags
+  double *peer_buf[kMaxP2pRanks] = {};
+  unsigned int *peer_flags[kMaxP2pRanks] = {};
+  unsigned int xseq = 0;
   // device-resident Newton-Raphson
   NrState *nr_state_d = nullptr, *nr_state_h = nullptr;
   unsigned int *nr_barrier = nullptr;
@@ -313,6 +357,10 @@ extern "C" void exb_destroy(exb_engine *e)
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->p2p)
+    for (int r = 0; r < e->nranks; r++)
+      if (r != e->rank && e->peer_buf[r]) cudaIpcCloseMemHandle(e->peer_buf[r]);
+  cudaFree(e->xbuf);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (int c = 0; c < 2; c++) {
     ClassState &k = e->cls[c];
@@ -818,17 +866,26 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
 static void set_finish_outputs(exb_engine *e, FinishArgs &f)
 {
   f.ticket = e->ticket;
-  if (e->comm) { f.out_host = nullptr; f.done_flag_host = nullptr; f.seq = 0; return; }
-  e->seq += 1;
+  f.nranks = 1; f.rank = 0; f.xseq = 0;
+  if (e->comm && !e->p2p) { f.out_host = nullptr; f.done_flag_host = nullptr; f.seq = 0; return; }   // NCCL after the kernel
+  if (++e->seq == 0xFFFFFFFFu) e->seq = 1;          // 0xFFFFFFFF is the kernel's "peer lost" marker
   f.out_host = e->out_h; f.done_flag_host = e->done_flag; f.seq = e->seq;
+  if (e->p2p) {
+    f.nranks = e->nranks; f.rank = e->rank;
+    for (int r = 0; r < e->nranks; r++) { f.peer_buf[r] = e->peer_buf[r]; f.peer_flags[r] = e->peer_flags[r]; }
+    if (f.mode == MODE_EVALUATE || f.mode == MODE_CORE) e->xseq += 1;
+    f.xseq = e->xseq;
+  }
 }
 
 static int wait_done(exb_engine *e)
 {
-  if (e->comm) { CUDA_TRY(cudaStreamSynchronize(e->stream)); }
+  if (e->comm && !e->p2p) { CUDA_TRY(cudaStreamSynchronize(e->stream)); }
   else {
     unsigned long spins = 0;
     while (*e->done_flag != e->seq) {
+      if (*e->done_flag == 0xFFFFFFFFu)
+        return fail(EXB_ERR_NCCL, "a peer rank did not deliver its partial sums within 20 s (all-reduce inside finish_kernel)");
       if ((++spins & 0xFFFF) == 0) {                 // a faulting kernel must not hang the host
         const cudaError_t q = cudaStreamQuery(e->stream);
         if (q != cudaSuccess && q != cudaErrorNotReady)
@@ -846,7 +903,7 @@ static int wait_done(exb_engine *e)
 // all-reduce (if a communicator exists), copy n doubles of out_d to the pinned mirror, wait.
 static int collect(exb_engine *e, size_t n)
 {
-  if (!e->comm) return wait_done(e);                 // results already sit in out_h
+  if (!e->comm || e->p2p) return wait_done(e);       // (globally reduced) results already sit in out_h
   if (e->comm) {
     const int r = g_nccl.AllReduce(e->out_d, e->out_d, n, kNcclFloat64, kNcclSum, e->comm, e->stream);
     if (r != 0) return fail(EXB_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
@@ -884,7 +941,7 @@ extern "C" int exb_makenewz_prepare(exb_engine *e, const exb_entry *ti, int coun
   int rc = run_traversal(e, ti, count, 1, qz, rz, executeModel, MODE_SUM);
   if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(e->stream));
-  cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
+  if (e->timing) cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
   return EXB_OK;
 }
 
@@ -903,7 +960,7 @@ extern "C" int exb_core(exb_engine *e, const double *lz, const unsigned char *ex
                            cudaMemcpyHostToDevice, e->stream));
   int rc = flush_models(e);
   if (rc) return rc;
-  CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+  if (e->timing) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
   for (int c = 0; c < 2; c++) {
     ClassState &k = e->cls[c];
     if (k.tiles_h.empty()) continue;
@@ -1157,6 +1214,61 @@ extern "C" int exb_comm_unique_id(void *id_out)
   return EXB_OK;
 }
 
+// One node, every GPU can map every other GPU's memory: exchange CUDA-IPC handles of the receive buffers (through
+// NCCL, once) so that finish_kernel can do the all-reduce itself.  Any rank that cannot -> everybody stays on NCCL.
+static int setup_p2p(exb_engine *e)
+{
+  const int n = e->nranks;
+  if (n > kMaxP2pRanks || getenv("EXB_NO_P2P") || !g_nccl.AllGather) return EXB_OK;
+  struct Card { cudaIpcMemHandle_t h; int ok; int device; char host[64]; };
+  const size_t data_bytes = (size_t)2 * n * 2 * e->P * sizeof(double);
+  const size_t flag_off = (data_bytes + 255) & ~(size_t)255;
+  Card mine;
+  memset(&mine, 0, sizeof mine);
+  mine.device = e->device;
+  gethostname(mine.host, sizeof mine.host - 1);
+  mine.ok = cudaMalloc(&e->xbuf, flag_off + (size_t)n * sizeof(unsigned int)) == cudaSuccess &&
+            cudaMemset(e->xbuf, 0, flag_off + (size_t)n * sizeof(unsigned int)) == cudaSuccess &&
+            cudaIpcGetMemHandle(&mine.h, e->xbuf) == cudaSuccess;
+  cudaGetLastError();
+  std::vector<Card> cards((size_t)n);
+  Card *cards_d = nullptr;
+  CUDA_TRY(cudaMalloc(&cards_d, (size_t)n * sizeof(Card)));
+  CUDA_TRY(cudaMemcpyAsync(cards_d + e->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, e->stream));
+  int r = g_nccl.AllGather(cards_d + e->rank, cards_d, sizeof(Card), kNcclInt8, e->comm, e->stream);
+  if (r != 0) { cudaFree(cards_d); return fail(EXB_ERR_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); }
+  CUDA_TRY(cudaMemcpyAsync(cards.data(), cards_d, (size_t)n * sizeof(Card), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  bool all = true;
+  for (int i = 0; i < n; i++) all = all && cards[i].ok && strncmp(cards[i].host, mine.host, sizeof mine.host) == 0;
+  double bad = 0.0;
+  if (all) {
+    for (int i = 0; i < n && bad == 0.0; i++) {
+      void *ptr = e->xbuf;
+      if (i != e->rank && cudaIpcOpenMemHandle(&ptr, cards[i].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); bad = 1.0; break; }
+      e->peer_buf[i] = (double *)ptr;
+      e->peer_flags[i] = (unsigned int *)((unsigned char *)ptr + flag_off);
+    }
+  } else bad = 1.0;
+  // agree: one failure anywhere keeps everybody on the NCCL path
+  double *bad_d = (double *)cards_d;
+  CUDA_TRY(cudaMemcpyAsync(bad_d, &bad, sizeof bad, cudaMemcpyHostToDevice, e->stream));
+  r = g_nccl.AllReduce(bad_d, bad_d, 1, kNcclFloat64, kNcclSum, e->comm, e->stream);
+  if (r != 0) { cudaFree(cards_d); return fail(EXB_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); }
+  CUDA_TRY(cudaMemcpyAsync(&bad, bad_d, sizeof bad, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  cudaFree(cards_d);
+  if (bad != 0.0) {
+    for (int i = 0; i < n; i++) {
+      if (i != e->rank && e->peer_buf[i]) cudaIpcCloseMemHandle(e->peer_buf[i]);
+      e->peer_buf[i] = nullptr; e->peer_flags[i] = nullptr;
+    }
+    return EXB_OK;
+  }
+  e->p2p = true;
+  return EXB_OK;
+}
+
 extern "C" int exb_comm_init(exb_engine *e, int rank, int nranks, const void *id)
 {
   if (!e) return fail(EXB_ERR_ARG, "exb_comm_init: null engine");
@@ -1170,8 +1282,11 @@ extern "C" int exb_comm_init(exb_engine *e, int rank, int nranks, const void *id
   memcpy(&uid, id, sizeof uid);
   const int r = g_nccl.CommInitRank(&e->comm, nranks, uid, rank);
   if (r != 0) return fail(EXB_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
-  return EXB_OK;
+  e->rank = rank;
+  return setup_p2p(e);
 }
+
+extern "C" int exb_comm_is_p2p(exb_engine *e) { return e && e->p2p ? 1 : 0; }
 
 // ---- introspection ---------------------------------------------------------------------------------------
 extern "C" int exb_read_clv(exb_engine *e, int model, int nodeNumber, double *out)

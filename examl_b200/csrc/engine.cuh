@@ -108,6 +108,7 @@ struct CoreArgs {
   double       *tile_out;    // [ntiles][2]
 };
 
+constexpr int kMaxP2pRanks = 16;
 struct FinishArgs {
   // scaler fix-up: gs[p] = gs[q] + gs[r] + inc  for every newview entry, in order
   unsigned int *gs;          // [P][2*mxtips]
@@ -131,6 +132,14 @@ struct FinishArgs {
   unsigned int *ticket;           // block arrival counter (self-resetting)
   unsigned int  seq;              // value to publish in *done_flag_host
   int           gs_in_smem;       // scaler chain staged in shared memory (set by launch_finish)
+  // several GPUs on one node: the all-reduce of evaluateGeneric / topLevelMakenewz (evaluateGenericSpecial.c:968-975,
+  // makenewzGenericSpecial.c:1241-1248) is part of this kernel.  Every rank stores its per-partition sums straight
+  // into every peer's receive buffer over NVLink (CUDA IPC mappings), raises a sequence flag there, waits for
+  // the peers' flags in its own memory and adds the nranks contributions in rank order -- the same bits on every rank.
+  int           nranks, rank;     // nranks <= 1: no exchange
+  double       *peer_buf[kMaxP2pRanks];          // receive buffers: [2 slots][nranks][2*P] doubles (entry `rank` is mine)
+  unsigned int *peer_flags[kMaxP2pRanks];        // [nranks] sequence flags in each receive buffer
+  unsigned int  xseq;             // exchange number (slot = xseq & 1)
 };
 
 // AA tip look-up table: what precomputeTips / umpX do in the reference (avxLikelihood.c:1353-1389, mic_native_aa.c:97)

@@ -184,6 +184,11 @@ int  exb_evaluate_partial(exb_engine *e, const exb_entry *entries, int count, co
 #define EXB_UNIQUE_ID_BYTES 128
 int  exb_comm_unique_id(void *id_out);
 int  exb_comm_init(exb_engine *e, int rank, int nranks, const void *id);
+/* 1 when the ranks found each other on one node and mapped each other's receive buffers (CUDA IPC over NVLink):
+ * the all-reduce then happens inside the finish kernel -- partial sums stored straight into every peer's memory,
+ * summed in rank order on every GPU -- and no NCCL call remains on the per-call path.  0: NCCL all-reduce after
+ * the kernel (several nodes, no peer access, or EXB_NO_P2P set). */
+int  exb_comm_is_p2p(exb_engine *e);
 
 /* ---- introspection (tests, benchmarks) ----------------------------------------------------- */
 

@@ -61,6 +61,18 @@ def test_tree_evaluation_matches_reference(tag, lines, extra):
 
 
 @pytest.mark.skipif(not have_binaries(), reason="bin/examl-b200-probe / oracle/_ref/parse-examl not built")
+def test_host_newton_raphson_path():
+    """The multi-rank form of makenewzGeneric (host state machine, exb_makenewz_prepare + one exb_core per iteration)
+    on a single GPU: EXAML_B200_HOST_NR=1 selects it."""
+    final_gold = load_json("dna49.final.json")
+    with tempfile.TemporaryDirectory() as tmp:
+        binary, tree, _ = write_inputs("dna49", tmp)
+        r, dumps = run_dropin(binary, tree, tmp, ["-f", "e"], env={"EXAML_B200_HOST_NR": "1"})
+        assert r.returncode == 0, r.stdout[-3000:]
+        assert _rel(dumps["final"]["likelihood"], final_gold["likelihood"]) < NORTH_STAR_RTOL
+
+
+@pytest.mark.skipif(not have_binaries(), reason="bin/examl-b200-probe / oracle/_ref/parse-examl not built")
 def test_aa140_lg_tree_evaluation():
     """testData/140 (protein, LG): the other north_star data set."""
     first_gold = load_json("aa140.first.json")
