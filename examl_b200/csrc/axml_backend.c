@@ -32,7 +32,7 @@
  * makenewzGenericSpecial.c:1241-1248) become one ncclAllReduce inside exb_evaluate / exb_core.
  *
  * Unsupported modes are refused loudly, the way the reference's MIC back-end does
- * (axml.c:2645-2657): the -S memory saving option and binary data.  Both rate models are
+ * (axml.c:2645-2657): binary data.  -S is accepted but not applied (dense CLVs in HBM, identical results).  Both rate models are
  * implemented: GAMMA (including the LG4M / LG4X protein models) and PSR/CAT (-m PSR, including the per-site
  * rate scan of optimizeRateCategories: evaluatePartialGeneric below).  There is no CPU fallback.
  */
@@ -65,7 +65,7 @@ static void refuse(const char *why)
 {
   if (processID == 0)
     fprintf(stderr, "\nThe B200 back-end of ExaML does not implement %s.\n"
-                    "Supported: DNA and protein data under the GAMMA and PSR models of rate heterogeneity (with or without -M).\n\n", why);
+                    "Supported: DNA and protein data under the GAMMA and PSR models of rate heterogeneity (with or without -M, -S).\n\n", why);
   MPI_Barrier(MPI_COMM_WORLD);
   MPI_Finalize();
   exit(-1);
@@ -105,7 +105,12 @@ static void backend_init(tree *tr)
   int m;
   size_t nb = (size_t)tr->numBranches, slots = (size_t)tr->mxtips + 1;
 
-  if (tr->saveMemory) refuse("the memory saving option -S");
+  /* -S (SEV memory saving, *_GAPPED_SAVE kernels): the reference's -S runs produce bit-identical likelihoods to
+     its dense runs (all-gap subtrees share one column instead of storing it per site; checked on testData/49).
+     The engine keeps dense CLVs in HBM, so the option is accepted and changes nothing but the host-side gap
+     bookkeeping the reference sets up for itself (axml.c:2085-2168); exb_commit reports the HBM it needs. */
+  if (tr->saveMemory && processID == 0)
+    printf("\nB200 back-end: -S accepted; CLVs stay dense in HBM (results are identical, the memory saving is not applied)\n");
   for (m = 0; m < tr->NumberOfModels; m++) {
     const pInfo *p = &tr->partitionData[m];
     if (p->states != 4 && p->states != 20) refuse("binary or multi-state data");
