@@ -264,6 +264,10 @@ class Engine:
         self._check(self._f("last_kernel_ms")(self._h, C.byref(v)))
         return float(v.value)
 
+    def set_timing(self, on: bool) -> None:
+        """CUDA events around the kernels of every hot-path call (last_kernel_ms); off on latency-critical paths."""
+        self._check(self._f("set_timing")(self._h, C.c_int(1 if on else 0)))
+
     def launch_count(self) -> int:
         f = self.lib.exb_launch_count
         f.restype = C.c_long

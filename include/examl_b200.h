@@ -186,8 +186,9 @@ int  exb_comm_unique_id(void *id_out);
 int  exb_comm_init(exb_engine *e, int rank, int nranks, const void *id);
 /* 1 when the ranks found each other on one node and mapped each other's receive buffers (CUDA IPC over NVLink):
  * the all-reduce then happens inside the finish kernel -- partial sums stored straight into every peer's memory,
- * summed in rank order on every GPU -- and no NCCL call remains on the per-call path.  0: NCCL all-reduce after
- * the kernel (several nodes, no peer access, or EXB_NO_P2P set). */
+ * summed in rank order on every GPU -- and no NCCL call remains on the per-call path (selected with EXB_P2P=1 in
+ * the environment of every rank).  0: NCCL all-reduce after the kernel (the default; also several nodes or no
+ * peer access). */
 int  exb_comm_is_p2p(exb_engine *e);
 
 /* ---- introspection (tests, benchmarks) ----------------------------------------------------- */
