@@ -371,18 +371,21 @@ def main():
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
+        dram_frac = (traffic / (dev_s / args.steps) / 1e9 / peak) if traffic else None
         if states == 4:
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "kernel": "traverse_dna_kernel",
+                        "traffic": traffic, "dram_frac": dram_frac, "kernel": "traverse_dna_kernel",
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
                         "algorithmic_bytes_per_launch": abytes,
                         "note": "child CLVs are consumed from registers / L2, so DRAM traffic is ~half of the algorithmic bytes "
-                                "and frac can exceed 1; the design's own ceiling is the CLV write stream (see DESIGN.md 5)"}
+                                "and frac can exceed 1; dram_frac = measured DRAM bytes per launch (ncu, profiles/traffic.json) / "
+                                "kernel time / peak is the physical utilisation; the design's own ceiling is the CLV write "
+                                "stream (see DESIGN.md 5)"}
         else:
             aflops = algorithmic_flops(ti, n_local, states, 4 if args.model == "gamma" else 1)
             tf = aflops / (dev_s / args.steps) / 1e12
             roofline = {"bound": "tensor", "achieved": tf, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / DMMA_PEAK_TFLOPS,
-                        "traffic": traffic, "kernel": "traverse_aa_kernel",
+                        "traffic": traffic, "dram_frac": dram_frac, "kernel": "traverse_aa_kernel",
                         "peak_source": "FP64 tensor pipe (DMMA.8x8x4) measured on this pool with tools/microbench/fp64_rates.cu; "
                                        "MEASURED_PEAKS.json has no FP64 figure",
                         "algorithmic_flops_per_launch": aflops, "hbm_gbs_algorithmic": achieved,
