@@ -1,0 +1,74 @@
+"""CPU coverage of the drop-in's HOST logic (examl_b200/csrc/axml_backend.c): the reference's unchanged host
+objects + the back-end, linked against the C ABI implemented on the CPU oracle (tests/hostcheck/exb_on_oracle.c)
+instead of libexaml_b200.so.  Runs ExaML's own workflows without a GPU and must land on the reference's results:
+traversal descriptors and x flags, the host Newton-Raphson loop, -M masks, the anticipated PSR rate scan, and the
+multi-rank plumbing over mpi_tcp.c.  (The same workflows run on the GPU in tests/test_gpu_dropin.py.)"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from dropin_util import PARSER, ROOT, run_dropin, write_inputs
+from golden_util import load_json
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "hostcheck"))
+import build as hostcheck_build  # noqa: E402
+
+EXE = hostcheck_build.build()
+pytestmark = pytest.mark.skipif(EXE is None or not os.path.exists(PARSER),
+                                reason="tests/hostcheck/_build/examl-hostcheck or oracle/_ref/parse-examl not built")
+ENV = {"EXAML_B200_HOST_NR": "1"}
+
+
+def _rel(a, b):
+    return abs(a - b) / abs(b)
+
+
+def _partition_lines(first):
+    lo, lines = 1, []
+    for i, part in enumerate(first["partitions"]):
+        n = int(np.sum(part["wgt"]))
+        lines.append(f"DNA, p{i} = {lo}-{lo + n - 1}")
+        lo += n
+    return lines
+
+
+@pytest.mark.parametrize("tag,partitioned,extra,model", [
+    ("dna49", False, [], "GAMMA"),
+    ("dna49pM", True, ["-M"], "GAMMA"),
+    ("dna49psr", False, [], "PSR"),
+    ("dna49ppsr", True, [], "PSR"),
+])
+def test_tree_evaluation_host_logic(tag, partitioned, extra, model):
+    first_gold, final_gold = load_json(f"{tag}.first.json"), load_json(f"{tag}.final.json")
+    with tempfile.TemporaryDirectory() as tmp:
+        binary, tree, _ = write_inputs(tag, tmp, _partition_lines(first_gold) if partitioned else None)
+        r, dumps = run_dropin(binary, tree, tmp, ["-f", "e"] + extra, env=ENV, exe=EXE, model=model)
+        assert r.returncode == 0, r.stdout[-3000:]
+        assert _rel(dumps["first"]["likelihood"], first_gold["likelihood"]) < 1e-11
+        assert _rel(dumps["final"]["likelihood"], final_gold["likelihood"]) < 1e-6, (dumps["final"]["likelihood"], final_gold["likelihood"])
+        if model == "PSR":
+            # optimizeRateCategories asked the back-end exactly what it asked the reference, and stopped where it stopped
+            a, b = np.array(dumps["partial"]["partial"]), np.array(load_json(f"{tag}.partial.json")["partial"])
+            assert a.shape == b.shape and np.array_equal(a[:, :3], b[:, :3])
+            assert np.all(np.abs(a[:, 3] - b[:, 3]) <= 1e-9 * np.maximum(1.0, np.abs(b[:, 3])))
+
+
+def test_two_ranks_host_logic():
+    """ExaML's own site sharding over two ranks (mpi_tcp.c), PSR: per-rank rate scans, gathered and re-categorised on rank 0."""
+    tag = "dna49ppsr"
+    first_gold, final_gold = load_json(f"{tag}.first.json"), load_json(f"{tag}.final.json")
+    with tempfile.TemporaryDirectory() as tmp:
+        binary, tree, _ = write_inputs(tag, tmp, _partition_lines(first_gold))
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+        env.update(ENV, EXAML_PROBE_DUMP=os.path.join(tmp, "dump"), EXAML_PROBE_NOTIPS="1", PYTHONPATH=ROOT)
+        r = subprocess.run([sys.executable, "-m", "examl_b200.launch", "-np", "2", "--", EXE, "-s", binary, "-t", tree,
+                            "-m", "PSR", "-n", "R", "-f", "e", "-w", tmp + "/"],
+                           cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-3000:]
+        got = json.load(open(os.path.join(tmp, "dump.final.json")))["likelihood"]
+        assert _rel(got, final_gold["likelihood"]) < 1e-6, (got, final_gold["likelihood"])
