@@ -57,3 +57,34 @@ def run_dropin(binary: str, tree: str, tmp: str, extra_args, env=None, exe=DROPI
         if os.path.exists(p):
             dumps[d] = json.load(open(p))
     return r, dumps
+
+
+REFERENCE = os.path.join(ROOT, "oracle", "_ref", "examl-AVX")
+
+
+def small_dna_case(tmp: str, taxa: int = 10, sites: int = 300, seed: int = 5):
+    """A seeded synthetic alignment small enough for the reference's search / quartet modes to run in well under a
+    second; returns (binary alignment, start tree)."""
+    from examl_b200.phylo import Tree
+    tree = Tree.random(taxa, seed=seed)
+    tips = exdata.synthetic_dna(tree, sites, seed=seed + 1, mode="signal", p_change=0.15, gap_frac=0.02)
+    exdata.write_phylip(os.path.join(tmp, "s.phy"), tree.names, tips, 4)
+    open(os.path.join(tmp, "s.tree"), "w").write(tree.to_newick() + "\n")
+    subprocess.run([PARSER, "-s", "s.phy", "-n", "s", "-m", "DNA"], cwd=tmp, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
+    return os.path.join(tmp, "s.binary"), os.path.join(tmp, "s.tree")
+
+
+def run_mode(exe: str, binary: str, tree: str, tmp: str, run_id: str, args, env=None, timeout=900):
+    """Run one ExaML workflow; returns (CompletedProcess, 'Likelihood of best tree' or None, quartet table or None)."""
+    import re
+    e = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    e.update(env or {})
+    r = subprocess.run([exe, "-s", binary, "-t", tree, "-n", run_id, "-w", tmp + "/"] + args, cwd=tmp, env=e,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    m = re.findall(r"Likelihood of best tree: (-?[0-9.]+)", r.stdout)
+    quartets = None
+    qf = os.path.join(tmp, f"ExaML_quartets.{run_id}")
+    if os.path.exists(qf):
+        quartets = [[float(x) for x in re.findall(r"-[0-9]+\.[0-9]+", line)] for line in open(qf) if "|" in line]
+        quartets = [q for q in quartets if q]
+    return r, (float(m[-1]) if m else None), quartets

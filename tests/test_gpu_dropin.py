@@ -7,7 +7,7 @@ import tempfile
 
 import pytest
 
-from dropin_util import have_binaries, run_dropin, write_inputs
+from dropin_util import DROPIN_PLAIN, REFERENCE, have_binaries, run_dropin, run_mode, small_dna_case, write_inputs
 from golden_util import load_json
 
 pytestmark = pytest.mark.gpu
@@ -129,3 +129,24 @@ def test_two_ranks_two_gpus():
         got = json.load(open(os.path.join(tmp, "dump.final.json")))["likelihood"]
         assert _rel(got, final_gold["likelihood"]) < NORTH_STAR_RTOL, (got, final_gold["likelihood"])
         print("2 ranks / 2 GPUs final lnL", got, "reference", final_gold["likelihood"])
+
+
+@pytest.mark.skipif(not have_binaries(), reason="bin/examl-b200 / oracle/_ref not built")
+@pytest.mark.parametrize("args", [["-m", "GAMMA", "-f", "d"], ["-m", "GAMMA", "-f", "o"], ["-m", "PSR", "-f", "d"],
+                                  ["-m", "GAMMA", "-f", "q"], ["-m", "GAMMA", "-f", "d", "-M"]])
+def test_search_and_quartet_workflows(args):
+    """-f d / -f o searches, PSR search, -f q quartets, -M search on a small seeded alignment: the reference binary
+    (CPU, run beside it) and the drop-in on the GPU must agree."""
+    import numpy as np
+    with tempfile.TemporaryDirectory() as tmp:
+        binary, tree = small_dna_case(tmp)
+        r0, best0, q0 = run_mode(REFERENCE, binary, tree, tmp, "REF", args)
+        r1, best1, q1 = run_mode(DROPIN_PLAIN, binary, tree, tmp, "GPU", args)
+        assert r0.returncode == 0 and r1.returncode == 0, (r0.stdout[-1500:], r1.stdout[-1500:])
+        if "q" in args:
+            a, b = np.array(q0), np.array(q1)
+            assert a.shape == b.shape and a.shape[0] == 630
+            assert np.all(np.abs(a - b) <= 2e-6 * np.abs(a))
+        else:
+            assert best0 is not None and best1 is not None
+            assert _rel(best1, best0) < NORTH_STAR_RTOL, (best1, best0)

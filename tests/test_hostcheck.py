@@ -12,7 +12,7 @@ import tempfile
 import numpy as np
 import pytest
 
-from dropin_util import PARSER, ROOT, run_dropin, write_inputs
+from dropin_util import PARSER, REFERENCE, ROOT, run_dropin, run_mode, small_dna_case, write_inputs
 from golden_util import load_json
 
 sys.path.insert(0, os.path.join(ROOT, "tests", "hostcheck"))
@@ -72,3 +72,41 @@ def test_two_ranks_host_logic():
         assert r.returncode == 0, r.stdout[-3000:]
         got = json.load(open(os.path.join(tmp, "dump.final.json")))["likelihood"]
         assert _rel(got, final_gold["likelihood"]) < 1e-6, (got, final_gold["likelihood"])
+
+
+@pytest.mark.parametrize("args", [["-m", "GAMMA", "-f", "d"], ["-m", "GAMMA", "-f", "o"], ["-m", "PSR", "-f", "d"],
+                                  ["-m", "GAMMA", "-f", "q"], ["-m", "GAMMA", "-f", "d", "-M"]])
+def test_search_and_quartet_workflows(args):
+    """The other workflows of axml.c (-f d new rapid hill climbing, -f o the old search, -f q quartets; PSR search,
+    -M) on a small seeded alignment: the reference binary and the back-end behind the same host code must agree."""
+    with tempfile.TemporaryDirectory() as tmp:
+        binary, tree = small_dna_case(tmp)
+        r0, best0, q0 = run_mode(REFERENCE, binary, tree, tmp, "REF", args)
+        r1, best1, q1 = run_mode(EXE, binary, tree, tmp, "HC", args, env=ENV)
+        assert r0.returncode == 0 and r1.returncode == 0, (r0.stdout[-1500:], r1.stdout[-1500:])
+        if "q" in args:
+            a, b = np.array(q0), np.array(q1)
+            assert a.shape == b.shape and a.shape[0] == 630            # 210 quartets x 3 topologies
+            assert np.all(np.abs(a - b) <= 2e-6 * np.abs(a))           # the file prints 6 decimals
+        else:
+            assert best0 is not None and best1 is not None
+            assert _rel(best1, best0) < 1e-6, (best1, best0)
+
+
+def test_restart_from_checkpoint():
+    """-R: the search state comes back from ExaML_binaryCheckpoint (searchAlgo.c:1726); CLVs are not part of it, so the
+    back-end must rebuild everything from the first full traversal after the restart."""
+    with tempfile.TemporaryDirectory() as tmp:
+        binary, tree = small_dna_case(tmp, taxa=14, sites=400, seed=9)
+        r0, best0, _ = run_mode(EXE, binary, tree, tmp, "A", ["-m", "GAMMA", "-f", "d"], env=ENV)
+        assert r0.returncode == 0, r0.stdout[-1500:]
+        ckpt = os.path.join(tmp, "ExaML_binaryCheckpoint.A_0")
+        assert os.path.exists(ckpt)
+        e = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+        e.update(ENV)
+        r1 = subprocess.run([EXE, "-s", binary, "-R", ckpt, "-m", "GAMMA", "-n", "B", "-f", "d", "-w", tmp + "/"], cwd=tmp, env=e,
+                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert r1.returncode == 0, r1.stdout[-1500:]
+        import re
+        m = re.findall(r"Likelihood of best tree: (-?[0-9.]+)", r1.stdout)
+        assert m and _rel(float(m[-1]), best0) < 1e-6, (m, best0)
