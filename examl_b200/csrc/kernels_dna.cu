@@ -60,6 +60,59 @@ __device__ __forceinline__ void st256(double *p, const double v[4])
 
 }  // namespace
 
+// One traversal entry for the NS sites of a thread, compiled once per combination of child sources so that the
+// NS loop carries no branch on tip case / carry / scaling.
+//   source: 0 = tip (staged tip row + shared tip vector), 1 = carry registers, 2 = CLV load
+template <int QS, int RS, int NS, bool PARAM>
+__device__ __forceinline__ unsigned int dna_entry(double (&carry)[NS][4], const TraverseArgs &a, const DnaConsts &kc, const DnaShared &sh,
+                                                  const uint8_t *stips, const SEntry &en, const double (&dq)[4], const double (&dr)[4],
+                                                  const size_t (&eoff)[NS], const bool (&valid)[NS], const int (&lsite)[NS], int c, int lane)
+{
+#define EI_(i) (PARAM ? kc.EI[i] : sh.EI[i])
+#define EV_(i) (PARAM ? kc.EV[i] : sh.EV[i])
+  double x1[NS][4], x2[NS][4];
+  #pragma unroll
+  for (int s = 0; s < NS; s++) {
+    if (QS == 1) { x1[s][0] = carry[s][0]; x1[s][1] = carry[s][1]; x1[s][2] = carry[s][2]; x1[s][3] = carry[s][3]; }
+    else if (QS == 2) ld256(a.clv + en.qoff + eoff[s], x1[s]);
+    else { const double *tv = &sh.tip[4 * stips[en.qoff + lsite[s]]]; x1[s][0] = tv[0]; x1[s][1] = tv[1]; x1[s][2] = tv[2]; x1[s][3] = tv[3]; }
+    if (RS == 1) { x2[s][0] = carry[s][0]; x2[s][1] = carry[s][1]; x2[s][2] = carry[s][2]; x2[s][3] = carry[s][3]; }
+    else if (RS == 2) ld256(a.clv + en.roff + eoff[s], x2[s]);
+    else { const double *tv = &sh.tip[4 * stips[en.roff + lsite[s]]]; x2[s][0] = tv[0]; x2[s][1] = tv[1]; x2[s][2] = tv[2]; x2[s][3] = tv[3]; }
+  }
+  unsigned int cnt = 0;
+  double *const dst = a.clv + en.poff;
+  #pragma unroll
+  for (int s = 0; s < NS; s++) {
+    const double tq1 = dq[1] * x1[s][1], tq2 = dq[2] * x1[s][2], tq3 = dq[3] * x1[s][3];
+    const double tr1 = dr[1] * x2[s][1], tr2 = dr[2] * x2[s][2], tr3 = dr[3] * x2[s][3];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    #pragma unroll
+    for (int l = 0; l < 4; l++) {
+      const double al = x1[s][0] + EI_(l * 4 + 1) * tq1 + EI_(l * 4 + 2) * tq2 + EI_(l * 4 + 3) * tq3;
+      const double ar = x2[s][0] + EI_(l * 4 + 1) * tr1 + EI_(l * 4 + 2) * tr2 + EI_(l * 4 + 3) * tr3;
+      const double ab = al * ar;
+      #pragma unroll
+      for (int m = 0; m < 4; m++) v[m] += ab * EV_(l * 4 + m);
+    }
+    if (RS != 0) {                           // TIP_TIP is never rescaled (avxLikelihood.c:87-160)
+      const bool small = fabs(v[0]) < kMinLikelihood && fabs(v[1]) < kMinLikelihood &&
+                         fabs(v[2]) < kMinLikelihood && fabs(v[3]) < kMinLikelihood;
+      const unsigned int b = __ballot_sync(0xffffffffu, small);
+      if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {            // all 16 values of the site are tiny
+        #pragma unroll
+        for (int m = 0; m < 4; m++) v[m] *= kTwoToThe256;
+        if (c == 0 && valid[s]) cnt += (unsigned int)a.wgt[eoff[s] >> 4];
+      }
+    }
+    if (valid[s]) st256(dst + eoff[s], v);
+    carry[s][0] = v[0]; carry[s][1] = v[1]; carry[s][2] = v[2]; carry[s][3] = v[3];
+  }
+  return cnt;
+#undef EI_
+#undef EV_
+}
+
 // ------------------------------------------------------------------------------------------------------
 // d-table: exp(EIGN[k] * rate[c] * lz) for every (entry, partition of the class, side, category, k).
 // Same association as makeP / calcDiagptable: rate * (EIGN * lz).
@@ -102,7 +155,7 @@ void launch_dtab(const DtabArgs &a, cudaStream_t s)
 // (TMA, 1-D) per row, all completing on a single mbarrier -- the only cold HBM reads of the kernel
 // are issued up front and in bulk instead of one dependent byte load per entry.
 // ------------------------------------------------------------------------------------------------------
-template <int NS, bool PARAM, int MINB>
+template <int NS, bool PARAM, int MINB, bool SPEC>
 __global__ void __launch_bounds__(kThreads, MINB)
 traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
 {
@@ -167,6 +220,24 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
       const bool q_inner = en.tipCase == 2, r_inner = en.tipCase != 0;
       const bool q_carry = q_inner && en.qoff == carry_node, r_carry = r_inner && en.roff == carry_node;
 
+      if constexpr (SPEC) {
+        const int qs = !q_inner ? 0 : (q_carry ? 1 : 2), rs = !r_inner ? 0 : (r_carry ? 1 : 2);
+        unsigned int cnt;
+        switch (qs * 3 + rs) {                   // block-uniform
+        case 0:  cnt = dna_entry<0, 0, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane); break;
+        case 1:  cnt = dna_entry<0, 1, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane); break;
+        case 2:  cnt = dna_entry<0, 2, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane); break;
+        case 5:  cnt = dna_entry<1, 2, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane); break;
+        case 7:  cnt = dna_entry<2, 1, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane); break;
+        default: cnt = dna_entry<2, 2, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane); break;
+        }
+        carry_node = en.poff;
+        if (r_inner && __any_sync(0xffffffffu, cnt != 0)) {
+          const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
+          if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
+        }
+        continue;
+      }
       // gather the children of all NS sites first (independent loads in flight together)
       double x1[NS][4], x2[NS][4];
       #pragma unroll
@@ -407,16 +478,28 @@ size_t traverse_dna_smem(int ns)
   return (size_t)(kWindow + 1) * sizeof(SEntry) + (size_t)(2 * kWindow + 2) * 64 * ns;
 }
 
-template <int NS, bool PARAM, int MINB>
-static void launch_minb(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
+template <int NS, bool PARAM, int MINB, bool SPEC>
+static void launch_spec(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
 {
   const size_t smem = traverse_dna_smem(NS);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaFuncSetAttribute(traverse_dna_kernel<NS, PARAM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(227 * 1024 - 2048, std::max<size_t>(smem, 64 * 1024)));
+    cudaFuncSetAttribute(traverse_dna_kernel<NS, PARAM, MINB, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(227 * 1024 - 2048, std::max<size_t>(smem, 64 * 1024)));
     configured = std::max<size_t>(smem, 64 * 1024);
   }
-  traverse_dna_kernel<NS, PARAM, MINB><<<ntiles, kThreads, smem, s>>>(a, kc);
+  traverse_dna_kernel<NS, PARAM, MINB, SPEC><<<ntiles, kThreads, smem, s>>>(a, kc);
+}
+
+template <int NS, bool PARAM, int MINB>
+static void launch_minb(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
+{
+  // default: the entry body compiled once per child-source combination (dna_entry<QS,RS>): ~460 instead of ~600
+  // instructions per warp and entry, 6.0 -> 5.5 ms per traversal on the bench workload.  EXB_DNA_SPEC=0 selects the
+  // single body with run-time source selection (kept for comparison).
+  static int spec = -1;
+  if (spec < 0) { const char *v = getenv("EXB_DNA_SPEC"); spec = v ? atoi(v) : 1; }
+  if (spec) launch_spec<NS, PARAM, MINB, true>(a, kc, ntiles, s);
+  else      launch_spec<NS, PARAM, MINB, false>(a, kc, ntiles, s);
 }
 
 template <int NS, bool PARAM>

@@ -362,3 +362,17 @@ def test_evaluate_partial_errors(cuda_factory):
         psr.evaluatePartial(ti, [0], [40], [1.0])
     with pytest.raises(EngineError, match="partition"):
         psr.evaluatePartial(ti, [1], [0], [1.0])
+
+
+def test_many_partitions_shared_memory_constants(cuda_factory, oracle_factory):
+    """More than 16 DNA partitions in one class: one launch for all of them, EI / EV from shared memory instead of
+    kernel parameters (the C5 shape: thousands of small partitions per GPU), with -M style per-partition branches
+    exercised through the mask."""
+    widths = [40 + 7 * (i % 5) for i in range(24)] + [0, 64]
+    kinds = [4] * len(widths)
+    tree, parts, models = random_case(20, widths, kinds, seed=123)
+    gpu = build_engine(cuda_factory, tree, parts, models)
+    cpu = build_engine(oracle_factory, tree, parts, models)
+    _compare_engines(gpu, cpu, tree, parts)
+    mask = np.array([i % 3 != 0 for i in range(len(widths))], dtype=np.uint8)
+    _compare_engines(gpu, cpu, tree, parts, mask=mask)
