@@ -88,3 +88,16 @@ def run_mode(exe: str, binary: str, tree: str, tmp: str, run_id: str, args, env=
         quartets = [[float(x) for x in re.findall(r"-[0-9]+\.[0-9]+", line)] for line in open(qf) if "|" in line]
         quartets = [q for q in quartets if q]
     return r, (float(m[-1]) if m else None), quartets
+
+
+def small_aa_case(tmp: str, partition_lines, taxa: int = 8, sites: int = 120, seed: int = 4):
+    """Small seeded protein alignment with a partition file (e.g. ["AUTO, p0 = 1-60", "LG4X, p1 = 61-120"])."""
+    from examl_b200.phylo import Tree
+    tree = Tree.random(taxa, seed=seed)
+    tips = exdata.synthetic_aa(tree, sites, seed=seed - 1, mode="signal", p_change=0.2, gap_frac=0.02)
+    exdata.write_phylip(os.path.join(tmp, "s.phy"), tree.names, tips, 20)
+    open(os.path.join(tmp, "s.tree"), "w").write(tree.to_newick() + "\n")
+    open(os.path.join(tmp, "q.model"), "w").write("\n".join(partition_lines) + "\n")
+    subprocess.run([PARSER, "-s", "s.phy", "-n", "s", "-m", "PROT", "-q", "q.model"], cwd=tmp, check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
+    return os.path.join(tmp, "s.binary"), os.path.join(tmp, "s.tree")

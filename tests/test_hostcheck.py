@@ -12,7 +12,7 @@ import tempfile
 import numpy as np
 import pytest
 
-from dropin_util import PARSER, REFERENCE, ROOT, run_dropin, run_mode, small_dna_case, write_inputs
+from dropin_util import PARSER, REFERENCE, ROOT, run_dropin, run_mode, small_aa_case, small_dna_case, write_inputs
 from golden_util import load_json
 
 sys.path.insert(0, os.path.join(ROOT, "tests", "hostcheck"))
@@ -110,3 +110,20 @@ def test_restart_from_checkpoint():
         import re
         m = re.findall(r"Likelihood of best tree: (-?[0-9.]+)", r1.stdout)
         assert m and _rel(float(m[-1]), best0) < 1e-6, (m, best0)
+
+
+def test_auto_protein_model_next_to_lg4x():
+    """--auto-prot=ml: optimizeModel.c tries every empirical AA matrix on the AUTO partition (the host rewrites EIGN / EV /
+    EI / tipVector without notice, the back-end must pick every change up) while the neighbour partition runs LG4X
+    (four eigen-systems per partition)."""
+    import re
+    with tempfile.TemporaryDirectory() as tmp:
+        binary, tree = small_aa_case(tmp, ["AUTO, p0 = 1-60", "LG4X, p1 = 61-120"])
+        args = ["-m", "GAMMA", "-f", "e", "--auto-prot=ml"]
+        r0, _, _ = run_mode(REFERENCE, binary, tree, tmp, "REF", args)
+        r1, _, _ = run_mode(EXE, binary, tree, tmp, "HC", args, env=ENV)
+        assert r0.returncode == 0 and r1.returncode == 0, (r0.stdout[-1500:], r1.stdout[-1500:])
+        pick = lambda out: re.findall(r"best-scoring AA model: (\S+) likelihood (-?[0-9.]+)", out)
+        final = lambda out: float(re.findall(r"Likelihood tree 0: (-?[0-9.]+)", out)[-1])
+        assert pick(r0.stdout) and [m for m, _ in pick(r0.stdout)] == [m for m, _ in pick(r1.stdout)]
+        assert _rel(final(r1.stdout), final(r0.stdout)) < 1e-6
