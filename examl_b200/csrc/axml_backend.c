@@ -137,10 +137,14 @@ static void backend_init(tree *tr)
   if (!g_entries || !g_qz || !g_rz || !g_mask) { fprintf(stderr, "out of memory\n"); MPI_Abort(MPI_COMM_WORLD, -1); }
 }
 
-/* The host may have rewritten the model constants at any time (optimizeModel.c:419-462 gives no
-   notice); hand the current ones over before every launch.  exb_set_model compares and only
-   uploads what changed. */
-static int g_categories_stale = 1;      /* PSR: per-site categories must be handed over (again) */
+/* The host rewrites the model constants without notice (optimizeModel.c:419-462).  But every such change
+   invalidates all CLVs, so the host code itself always follows it with a FULL traversal (evaluateGeneric(tr,
+   tr->start, TRUE)) before it does anything else with the tree -- a partial traversal after a model change would
+   read stale CLVs in the reference too.  The constants (and, under PSR, the per-site categories, rewritten by
+   optimizeRateCategories optimizeModel.c:2403 and at start-up / restart) are therefore handed over on full traversals
+   and on the first call only: the thousands of small calls of a tree search cost nothing per partition.
+   exb_set_model compares and only uploads what changed. */
+static int g_constants_stale = 1;       /* model constants / PSR categories must be handed over (again) */
 static int g_scan_valid = 0;            /* evaluatePartialGeneric: the batched rate scan below is current */
 
 static void backend_sync(tree *tr)
@@ -148,6 +152,8 @@ static void backend_sync(tree *tr)
   int m;
   if (!g_engine) backend_init(tr);
   g_scan_valid = 0;                     /* any other likelihood call ends a rate scan */
+  for (m = 0; m < tr->NumberOfModels; m++) g_mask[m] = tr->td[0].executeModel[m] ? 1 : 0;
+  if (!g_constants_stale) return;
   for (m = 0; m < tr->NumberOfModels; m++) {
     const pInfo *p = &tr->partitionData[m];
     if (p->protModels == LG4M || p->protModels == LG4X) {
@@ -164,15 +170,11 @@ static void backend_sync(tree *tr)
         backend_fail("exb_set_model_lg4");
     } else if (exb_set_model(g_engine, m, p->EIGN, p->EV, p->EI, p->tipVector, p->gammaRates) != EXB_OK)
       backend_fail("exb_set_model");
-    /* PSR: rateCategory[] / perSiteRates[] are rewritten by optimizeRateCategories (optimizeModel.c:2403) and at
-       start-up / restart only, and each of those is followed by a full-traversal evaluateGeneric; comparing a
-       per-site array on every small call would cost more than the call, so it is done on full traversals. */
-    if (tr->rateHetModel == CAT && g_categories_stale &&
+    if (tr->rateHetModel == CAT &&
         exb_set_categories(g_engine, m, p->numberOfCategories, p->perSiteRates, p->rateCategory) != EXB_OK)
       backend_fail("exb_set_categories");
-    g_mask[m] = tr->td[0].executeModel[m] ? 1 : 0;
   }
-  g_categories_stale = 0;
+  g_constants_stale = 0;
 }
 
 /* Flatten td[0].ti[first .. count) into the C-ABI form; returns the number of entries. */
@@ -322,7 +324,7 @@ void evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal)
 
   if (fullTraversal) {
     assert(isTip(p->number, tr->mxtips));
-    g_categories_stale = 1;
+    g_constants_stale = 1;
     computeTraversalInfo(q, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, FALSE);
   } else {
     if (!p->x) computeTraversalInfo(p, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);

@@ -34,7 +34,15 @@ double __real_evaluatePartialGeneric(tree *tr, int i, double ki, int _model);
 void allocateXVectors(tree *tr);
 #endif
 
+extern int processID;            /* axml.c: the MPI rank */
 static tree *g_tr = NULL;
+
+/* <prefix>.<kind>.json on rank 0, <prefix>.r<rank>.<kind>.json elsewhere (every rank dumps its own slice) */
+static void dump_path(char *path, size_t n, const char *prefix, const char *kind)
+{
+  if (processID == 0) snprintf(path, n, "%s.%s.json", prefix, kind);
+  else snprintf(path, n, "%s.r%d.%s.json", prefix, processID, kind);
+}
 static int g_eval_calls = 0, g_mkz_calls = 0;
 
 static double now_s(void)
@@ -166,7 +174,7 @@ static void dump_partial(tree *tr)
   for (j = 0; j < g_partial_n; j++)
     off += sprintf(extra + off, "%s[%d,%d,%.17g,%.17g]", j ? "," : "", g_partial[j].model, g_partial[j].site, g_partial[j].rate, g_partial[j].value);
   off += sprintf(extra + off, "]");
-  snprintf(path, sizeof path, "%s.partial.json", prefix);
+  dump_path(path, sizeof path, prefix, "partial");
   dump_state(tr, path, 0, extra);      /* td[0] is still the full traversal the calls were made with */
   free(extra);
   g_partial_dumped = 1;
@@ -178,7 +186,7 @@ static void dump_final(void)
   char path[4096];
   if (!prefix || !g_tr) return;
   __real_evaluateGeneric(g_tr, g_tr->start, TRUE);
-  snprintf(path, sizeof path, "%s.final.json", prefix);
+  dump_path(path, sizeof path, prefix, "final");
   dump_state(g_tr, path, 0, NULL);
 }
 
@@ -196,7 +204,7 @@ void __wrap_evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal)
     g_tr = tr;
     if (prefix) {
       char path[4096];
-      snprintf(path, sizeof path, "%s.first.json", prefix);
+      dump_path(path, sizeof path, prefix, "first");
       dump_state(tr, path, 1, NULL);
       atexit(dump_final);
     }
@@ -237,7 +245,7 @@ void __wrap_makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxi
     off += snprintf(extra + off, sizeof extra - off, "], \"result\": [");
     for (b = 0; b < tr->numBranches; b++) off += snprintf(extra + off, sizeof extra - off, "%s%.17g", b ? "," : "", result[b]);
     off += snprintf(extra + off, sizeof extra - off, "]}");
-    snprintf(path, sizeof path, "%s.mkz.json", prefix);
+    dump_path(path, sizeof path, prefix, "mkz");
     dump_state(tr, path, 0, extra);
   }
 }
