@@ -113,6 +113,75 @@ __device__ __forceinline__ unsigned int dna_entry(double (&carry)[NS][4], const 
 #undef EV_
 }
 
+// The same entry with the loops interchanged: every EI / EV constant is fetched once per entry and used for all NS
+// sites (constant-outer, site-inner) instead of once per site.  In the site-outer form above the compiler re-loads the
+// 28 constants for every site (LDC: 29 of the ~105 instructions per site).  Stages keep the live set inside the
+// register budget: (A) d (.) x for all sites, (B) row l of EI -> ab[s][l], (C) v[s][:] += ab[s][l] * EV[l][:].
+// Opt-in (EXB_DNA_SPEC=2) until it has been run against the parity tests on a GPU.
+template <int QS, int RS, int NS, bool PARAM>
+__device__ __forceinline__ unsigned int dna_entry_staged(double (&carry)[NS][4], const TraverseArgs &a, const DnaConsts &kc, const DnaShared &sh,
+                                                         const uint8_t *stips, const SEntry &en, const double (&dq)[4], const double (&dr)[4],
+                                                         const size_t (&eoff)[NS], const bool (&valid)[NS], const int (&lsite)[NS], int c, int lane)
+{
+#define EI_(i) (PARAM ? kc.EI[i] : sh.EI[i])
+#define EV_(i) (PARAM ? kc.EV[i] : sh.EV[i])
+  double q0[NS], q1[NS], q2[NS], q3[NS], r0[NS], r1[NS], r2[NS], r3[NS];
+  #pragma unroll
+  for (int s = 0; s < NS; s++) {                      // (A) gather + exponentials
+    double x1[4], x2[4];
+    if (QS == 1) { x1[0] = carry[s][0]; x1[1] = carry[s][1]; x1[2] = carry[s][2]; x1[3] = carry[s][3]; }
+    else if (QS == 2) ld256(a.clv + en.qoff + eoff[s], x1);
+    else { const double *tv = &sh.tip[4 * stips[en.qoff + lsite[s]]]; x1[0] = tv[0]; x1[1] = tv[1]; x1[2] = tv[2]; x1[3] = tv[3]; }
+    if (RS == 1) { x2[0] = carry[s][0]; x2[1] = carry[s][1]; x2[2] = carry[s][2]; x2[3] = carry[s][3]; }
+    else if (RS == 2) ld256(a.clv + en.roff + eoff[s], x2);
+    else { const double *tv = &sh.tip[4 * stips[en.roff + lsite[s]]]; x2[0] = tv[0]; x2[1] = tv[1]; x2[2] = tv[2]; x2[3] = tv[3]; }
+    q0[s] = x1[0]; q1[s] = dq[1] * x1[1]; q2[s] = dq[2] * x1[2]; q3[s] = dq[3] * x1[3];
+    r0[s] = x2[0]; r1[s] = dr[1] * x2[1]; r2[s] = dr[2] * x2[2]; r3[s] = dr[3] * x2[3];
+  }
+  double ab[NS][4];
+  #pragma unroll
+  for (int l = 0; l < 4; l++) {                       // (B) one row of EI for all sites
+    const double e1 = EI_(l * 4 + 1), e2 = EI_(l * 4 + 2), e3 = EI_(l * 4 + 3);
+    #pragma unroll
+    for (int s = 0; s < NS; s++) {
+      const double al = q0[s] + e1 * q1[s] + e2 * q2[s] + e3 * q3[s];
+      const double ar = r0[s] + e1 * r1[s] + e2 * r2[s] + e3 * r3[s];
+      ab[s][l] = al * ar;
+    }
+  }
+  double v[NS][4];
+  #pragma unroll
+  for (int m = 0; m < 4; m++) {                       // (C) one column of EV for all sites; same summation order over l
+    const double f0 = EV_(0 * 4 + m), f1 = EV_(1 * 4 + m), f2 = EV_(2 * 4 + m), f3 = EV_(3 * 4 + m);
+    #pragma unroll
+    for (int s = 0; s < NS; s++) {
+      double t = 0.0;
+      t += ab[s][0] * f0; t += ab[s][1] * f1; t += ab[s][2] * f2; t += ab[s][3] * f3;
+      v[s][m] = t;
+    }
+  }
+  unsigned int cnt = 0;
+  double *const dst = a.clv + en.poff;
+  #pragma unroll
+  for (int s = 0; s < NS; s++) {
+    if (RS != 0) {
+      const bool small = fabs(v[s][0]) < kMinLikelihood && fabs(v[s][1]) < kMinLikelihood &&
+                         fabs(v[s][2]) < kMinLikelihood && fabs(v[s][3]) < kMinLikelihood;
+      const unsigned int b = __ballot_sync(0xffffffffu, small);
+      if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {
+        #pragma unroll
+        for (int m = 0; m < 4; m++) v[s][m] *= kTwoToThe256;
+        if (c == 0 && valid[s]) cnt += (unsigned int)a.wgt[eoff[s] >> 4];
+      }
+    }
+    if (valid[s]) st256(dst + eoff[s], v[s]);
+    carry[s][0] = v[s][0]; carry[s][1] = v[s][1]; carry[s][2] = v[s][2]; carry[s][3] = v[s][3];
+  }
+  return cnt;
+#undef EI_
+#undef EV_
+}
+
 // ------------------------------------------------------------------------------------------------------
 // d-table: exp(EIGN[k] * rate[c] * lz) for every (entry, partition of the class, side, category, k).
 // Same association as makeP / calcDiagptable: rate * (EIGN * lz).
@@ -155,7 +224,7 @@ void launch_dtab(const DtabArgs &a, cudaStream_t s)
 // (TMA, 1-D) per row, all completing on a single mbarrier -- the only cold HBM reads of the kernel
 // are issued up front and in bulk instead of one dependent byte load per entry.
 // ------------------------------------------------------------------------------------------------------
-template <int NS, bool PARAM, int MINB, bool SPEC>
+template <int NS, bool PARAM, int MINB, int SPEC>
 __global__ void __launch_bounds__(kThreads, MINB)
 traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
 {
@@ -220,17 +289,20 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
       const bool q_inner = en.tipCase == 2, r_inner = en.tipCase != 0;
       const bool q_carry = q_inner && en.qoff == carry_node, r_carry = r_inner && en.roff == carry_node;
 
-      if constexpr (SPEC) {
+      if constexpr (SPEC != 0) {
         const int qs = !q_inner ? 0 : (q_carry ? 1 : 2), rs = !r_inner ? 0 : (r_carry ? 1 : 2);
         unsigned int cnt;
+#define DNA_ENTRY(QS, RS) (SPEC == 2 ? dna_entry_staged<QS, RS, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane) \
+                                     : dna_entry<QS, RS, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane))
         switch (qs * 3 + rs) {                   // block-uniform
-        case 0:  cnt = dna_entry<0, 0, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane); break;
-        case 1:  cnt = dna_entry<0, 1, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane); break;
-        case 2:  cnt = dna_entry<0, 2, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane); break;
-        case 5:  cnt = dna_entry<1, 2, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane); break;
-        case 7:  cnt = dna_entry<2, 1, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane); break;
-        default: cnt = dna_entry<2, 2, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane); break;
+        case 0:  cnt = DNA_ENTRY(0, 0); break;
+        case 1:  cnt = DNA_ENTRY(0, 1); break;
+        case 2:  cnt = DNA_ENTRY(0, 2); break;
+        case 5:  cnt = DNA_ENTRY(1, 2); break;
+        case 7:  cnt = DNA_ENTRY(2, 1); break;
+        default: cnt = DNA_ENTRY(2, 2); break;
         }
+#undef DNA_ENTRY
         carry_node = en.poff;
         if (r_inner && __any_sync(0xffffffffu, cnt != 0)) {
           const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
@@ -478,7 +550,7 @@ size_t traverse_dna_smem(int ns)
   return (size_t)(kWindow + 1) * sizeof(SEntry) + (size_t)(2 * kWindow + 2) * 64 * ns;
 }
 
-template <int NS, bool PARAM, int MINB, bool SPEC>
+template <int NS, bool PARAM, int MINB, int SPEC>
 static void launch_spec(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
 {
   const size_t smem = traverse_dna_smem(NS);
@@ -498,8 +570,9 @@ static void launch_minb(const TraverseArgs &a, const DnaConsts &kc, int ntiles, 
   // single body with run-time source selection (kept for comparison).
   static int spec = -1;
   if (spec < 0) { const char *v = getenv("EXB_DNA_SPEC"); spec = v ? atoi(v) : 1; }
-  if (spec) launch_spec<NS, PARAM, MINB, true>(a, kc, ntiles, s);
-  else      launch_spec<NS, PARAM, MINB, false>(a, kc, ntiles, s);
+  if (spec == 2)  launch_spec<NS, PARAM, MINB, 2>(a, kc, ntiles, s);     // staged body, opt-in (see dna_entry_staged)
+  else if (spec)  launch_spec<NS, PARAM, MINB, 1>(a, kc, ntiles, s);
+  else            launch_spec<NS, PARAM, MINB, 0>(a, kc, ntiles, s);
 }
 
 template <int NS, bool PARAM>

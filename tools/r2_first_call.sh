@@ -1,11 +1,14 @@
 #!/bin/bash
 # First GPU call of the next round (1 GPU, ~4 min): everything that could not be measured at the end of round 1.
 #   1. full GPU test suite (includes test_many_partitions_shared_memory_constants, never run on a GPU yet)
-#   2. DNA kernel sweep: body (EXB_DNA_SPEC) x registers budget (EXB_DNA_MINB) x sites per thread (--tile 128 -> NS=2)
+#   2. DNA kernel sweep: body (EXB_DNA_SPEC 0 run-time selection | 1 specialised | 2 specialised + staged) x registers budget (EXB_DNA_MINB) x sites per thread (--tile 128 -> NS=2)
 #   3. ncu --set full of the specialised DNA body and of partial_kernel -> gpurun_out/prof_dna_v5 / prof_partial
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for cfg in "1 2 256" "0 2 256" "1 3 256" "1 3 128" "1 2 128"; do
+# the staged DNA entry body (constant-outer / site-inner loops, EXB_DNA_SPEC=2) has never run on a GPU: parity first
+EXB_DNA_SPEC=2 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -2
+EXB_DNA_SPEC=2 EXB_DNA_MINB=3 python -m pytest tests/test_gpu_parity.py -x -q -k "goldens or clv_scaler or large_tree or many_partitions" 2>&1 | tail -2
+for cfg in "1 2 256" "2 2 256" "2 3 256" "0 2 256" "1 3 256" "2 3 128" "2 2 128"; do
   set -- $cfg
   EXB_DNA_SPEC=$1 EXB_DNA_MINB=$2 python bench.py --steps 20 --warmup 3 --tile $3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
 import json,sys
