@@ -6,15 +6,15 @@
 //   sumGAMMAPROT             makenewzGenericSpecial.c:2083-2153
 //   coreGTRGAMMAPROT         makenewzGenericSpecial.c:2581-2655
 //
-// Same structure as kernels_dna.cu: the traversal loop is inside the kernel, thread t owns
-// (site = t/4, Gamma category = t%4) of a 64-site chunk for every entry, keeps the CLV it just
-// produced in registers for the parent ("carry"), writes every CLV to HBM once.
-// All arithmetic is FP64 -- the reference's precision; tcgen05 has no f64 kind.
-// P(t) is never materialised: a = EI * (d (.) x); d comes from the per-call d-table.  With a single
-// AA partition the 800 EI / EV constants travel as kernel parameters, so each of the ~1 200 DFMAs
-// per (site, category, entry) takes its matrix element as an immediate constant-bank operand: no
-// load instruction, no shared-memory traffic in the contraction.  Several AA partitions: EI^T / EV
-// are broadcast from shared memory.
+// Same structure as kernels_dna.cu: the traversal loop is inside the kernel, a CTA owns a tile of sites for the whole
+// descriptor, the CLV just produced stays in registers for the parent ("carry"), every CLV is written to HBM once.
+// The arithmetic runs on the FP64 tensor pipe: a warp owns 8 sites (GAMMA: all four categories of each; PSR: four
+// groups of 8 sites), and the three 20x20 contractions of an entry
+//     Y1 = (d_q (.) X1) * EI^T        Y2 = (d_r (.) X2) * EI^T        X3 = (Y1 (.) Y2) * EV
+// are [8 x 20] x [20 x 24] GEMMs on mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  All arithmetic is FP64 -- the
+// reference's precision; tcgen05 has no f64 kind.  P(t) is never materialised: the exponentials of
+// the per-call d-table are folded into the A operand.  EI^T / EV sit in shared memory as ready-made B fragments (one
+// set per eigen-system: LG4M / LG4X have four), tip children come from a per-call look-up table (aa_lut_kernel).
 #include "engine.cuh"
 #include "core_tile.cuh"
 #include "stage.cuh"
