@@ -195,15 +195,15 @@ __device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const AaConst
 // ------------------------------------------------------------------------------------------------------
 // Fused traversal on the FP64 tensor pipe.
 //
-// A warp owns 8 sites (one per "row" g = lane/4) for all four Gamma categories; a CTA of 8 warps owns a
-// 64-site chunk.  For every (entry, category) the three 20x20 contractions
+// A warp owns 8 sites (one per "row" g = lane/4) for all four Gamma categories; a CTA of 12 warps owns a
+// 96-site chunk.  For every (entry, category) the three 20x20 contractions
 //     Y1 = (d_q (.) X1) * EI^T        Y2 = (d_r (.) X2) * EI^T        X3 = (Y1 (.) Y2) * EV
-// are [8 sites x 20] x [20 x 20(24)] GEMMs = 15 DMMA.8x8x4 each.  EI^T and EV live in registers as
-// B fragments for the whole kernel (they do not depend on entry, side or category because the
-// exponentials are folded into the A operand).  The result stays in registers in C-fragment layout
-// ("carry") and is converted to an A operand for the parent with warp shuffles; it is written to HBM
-// once, 16 B per thread.  Scaling (all 80 values of a site < 2^-256) is decided after the four
-// categories are done, from the 24 register values of the 4 lanes that share a site.
+// are [8 sites x 20] x [20 x 20(24)] GEMMs = 15 DMMA.8x8x4 each.  EI^T and EV are read from shared memory as B
+// fragments (they do not depend on entry or side because the exponentials are folded into the A operand; they
+// depend on the category only under LG4M / LG4X).  The result stays in registers in C-fragment layout ("carry") and
+// is converted to an A operand for the parent (c_to_a); it is written to HBM once, 16 B per thread.  Scaling (all 80
+// values of a site < 2^-256) is decided after the four categories are done, from the 24 register values of the 4
+// lanes that share a site.
 // ------------------------------------------------------------------------------------------------------
 // CAT = false: GAMMA, slot = category, 8 sites per warp, 96 per chunk, CLV = 80 doubles per site.
 // CAT = true : PSR (newviewGTRCATPROT_AVX avxLikelihood.c:487-812, evaluateGTRCATPROT evaluateGenericSpecial.c:1308-1391):
