@@ -24,6 +24,7 @@ EXPORTS = [
     "exb_comm_unique_id", "exb_comm_init", "exb_read_clv", "exb_read_scaler",
     "exb_read_sumtable", "exb_last_kernel_ms", "exb_launch_count", "exb_set_tile_sites", "exb_set_timing",
     "exb_set_rate_model", "exb_set_categories", "exb_set_model_lg4", "exb_evaluate_partial", "exb_comm_is_p2p",
+    "exb_last_phase_ms",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -263,6 +264,12 @@ class Engine:
         v = C.c_float(0)
         self._check(self._f("last_kernel_ms")(self._h, C.byref(v)))
         return float(v.value)
+
+    def last_phase_ms(self):
+        """(tables, traverse, finish) milliseconds of the most recent traversal call (timing must be on)."""
+        v = (C.c_float * 3)()
+        self._check(self._f("last_phase_ms")(self._h, v))
+        return float(v[0]), float(v[1]), float(v[2])
 
     def set_timing(self, on: bool) -> None:
         """CUDA events around the kernels of every hot-path call (last_kernel_ms); off on latency-critical paths."""

@@ -147,13 +147,70 @@ static void backend_init(tree *tr)
 static int g_constants_stale = 1;       /* model constants / PSR categories must be handed over (again) */
 static int g_scan_valid = 0;            /* evaluatePartialGeneric: the batched rate scan below is current */
 
+/* Guard for the caller invariant above (EXAML_B200_CHECK_CONSTANTS=1): a fingerprint of everything that is handed
+   over, taken at hand-over time and re-computed on EVERY call.  A host that changed a constant and then issued a
+   partial traversal without a full one in between is reported instead of silently computing with the old values. */
+static int g_check_constants = -1;
+static unsigned long long *g_fingerprint = NULL;     /* [NumberOfModels] */
+
+static unsigned long long fp_mix(unsigned long long h, const void *data, size_t bytes)
+{
+  const unsigned char *b = (const unsigned char *)data;
+  size_t i;
+  for (i = 0; i < bytes; i++) { h ^= b[i]; h *= 1099511628211ULL; }     /* FNV-1a */
+  return h;
+}
+
+static unsigned long long fingerprint_of(const tree *tr, int m)
+{
+  const pInfo *p = &tr->partitionData[m];
+  const size_t S = (size_t)p->states, codes = S == 4 ? 16 : 23;
+  unsigned long long h = 1469598103934665603ULL;
+  if (p->protModels == LG4M || p->protModels == LG4X) {
+    int c;
+    for (c = 0; c < 4; c++) {
+      h = fp_mix(h, p->EIGN_LG4[c], S * sizeof(double));
+      h = fp_mix(h, p->EV_LG4[c], S * S * sizeof(double));
+      h = fp_mix(h, p->EI_LG4[c], S * S * sizeof(double));
+      h = fp_mix(h, p->tipVector_LG4[c], codes * S * sizeof(double));
+    }
+    h = fp_mix(h, p->weights, 4 * sizeof(double));
+  } else {
+    h = fp_mix(h, p->EIGN, S * sizeof(double));
+    h = fp_mix(h, p->EV, S * S * sizeof(double));
+    h = fp_mix(h, p->EI, S * S * sizeof(double));
+    h = fp_mix(h, p->tipVector, codes * S * sizeof(double));
+  }
+  h = fp_mix(h, p->gammaRates, 4 * sizeof(double));
+  if (tr->rateHetModel == CAT) {
+    h = fp_mix(h, p->perSiteRates, (size_t)p->numberOfCategories * sizeof(double));
+    h = fp_mix(h, p->rateCategory, (size_t)p->width * sizeof(int));
+  }
+  return h;
+}
+
 static void backend_sync(tree *tr)
 {
   int m;
   if (!g_engine) backend_init(tr);
   g_scan_valid = 0;                     /* any other likelihood call ends a rate scan */
   for (m = 0; m < tr->NumberOfModels; m++) g_mask[m] = tr->td[0].executeModel[m] ? 1 : 0;
-  if (!g_constants_stale) return;
+  if (g_check_constants < 0) {
+    const char *v = getenv("EXAML_B200_CHECK_CONSTANTS");
+    g_check_constants = v && atoi(v) != 0;
+    if (g_check_constants) g_fingerprint = (unsigned long long *)calloc((size_t)tr->NumberOfModels, sizeof *g_fingerprint);
+  }
+  if (!g_constants_stale) {
+    if (g_check_constants)
+      for (m = 0; m < tr->NumberOfModels; m++)
+        if (fingerprint_of(tr, m) != g_fingerprint[m]) {
+          fprintf(stderr, "\nB200 back-end: the model constants of partition %d changed without a full traversal "
+                          "(EXAML_B200_CHECK_CONSTANTS)\n", m);
+          MPI_Abort(MPI_COMM_WORLD, -1);
+          exit(-1);
+        }
+    return;
+  }
   for (m = 0; m < tr->NumberOfModels; m++) {
     const pInfo *p = &tr->partitionData[m];
     if (p->protModels == LG4M || p->protModels == LG4X) {
@@ -173,6 +230,7 @@ static void backend_sync(tree *tr)
     if (tr->rateHetModel == CAT &&
         exb_set_categories(g_engine, m, p->numberOfCategories, p->perSiteRates, p->rateCategory) != EXB_OK)
       backend_fail("exb_set_categories");
+    if (g_check_constants) g_fingerprint[m] = fingerprint_of(tr, m);
   }
   g_constants_stale = 0;
 }
@@ -467,7 +525,8 @@ void makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxiter, do
   if (!p->x) computeTraversalInfo(p, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
   if (!q->x) computeTraversalInfo(q, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
 
-  if (g_ranks == 1 && !getenv("EXAML_B200_HOST_NR")) {
+  /* the whole Newton-Raphson loop on the device: single rank, or all ranks on one node (in-kernel all-reduce) */
+  if ((g_ranks == 1 || exb_comm_is_p2p(g_engine)) && !getenv("EXAML_B200_HOST_NR")) {
     /* single rank: the whole Newton-Raphson loop runs on the device (exb_makenewz) */
     int cok[NUM_BRANCHES], n, m;
     storeExecuteMaskInTraversalDescriptor(tr);

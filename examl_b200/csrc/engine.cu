@@ -6,6 +6,7 @@
 // one fused kernel launch per data-type class plus one small "finish" launch.
 #include "../../include/examl_b200.h"
 #include "engine.cuh"
+#include "p2p.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -96,11 +97,11 @@ finish_kernel(const FinishArgs a)
         const DevEntry br = a.entries[0];
         s0 += (double)(gs[br.p] + gs[br.q]) * a.log_minlikelihood;   // evaluateGenericSpecial.c:830
       }
-      if (a.nranks > 1) {          // my contribution goes straight into every rank's receive buffer
-        const size_t at = ((size_t)(a.xseq & 1u) * a.nranks + a.rank) * 2 * a.nparts + part;
-        for (int r = 0; r < a.nranks; r++) {
-          a.peer_buf[r][at] = s0;
-          if (a.mode == MODE_CORE) a.peer_buf[r][at + a.nparts] = s1;
+      if (a.x.nranks > 1) {        // my contribution goes straight into every rank's receive buffer
+        const size_t at = p2p_row(a.x, a.xseq, a.x.rank, 2 * a.nparts) + part;
+        for (int r = 0; r < a.x.nranks; r++) {
+          a.x.peer_buf[r][at] = s0;
+          if (a.mode == MODE_CORE) a.x.peer_buf[r][at + a.nparts] = s1;
         }
       } else {
         a.out[part] = s0;
@@ -121,30 +122,9 @@ finish_kernel(const FinishArgs a)
     if (tid == 0) { last = atomicAdd(a.ticket, 1u) == gridDim.x - 1; peer_lost = 0; }
     __syncthreads();
     if (!last) return;
-    if (a.nranks > 1 && a.mode != MODE_NEWVIEW && a.mode != MODE_SUM) {
-      __threadfence_system();                        // every block's remote stores are ordered before the flags
-      if (tid < a.nranks) {
-        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.peer_flags[tid] + a.rank), "r"(a.xseq) : "memory");
-        // wait for rank tid's contribution to arrive in MY buffer
-        const unsigned int *f = a.peer_flags[a.rank] + tid;
-        unsigned int v;
-        const long long t0 = clock64();
-        for (;;) {
-          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-          if ((int)(v - a.xseq) >= 0) break;
-          if (clock64() - t0 > 40000000000LL) { peer_lost = 1; break; }     // ~20 s: a peer is gone
-          __nanosleep(200);
-        }
-      }
-      __syncthreads();
-      const int nvals = (a.mode == MODE_CORE ? 2 : 1) * a.nparts;
-      const double *mine = a.peer_buf[a.rank] + (size_t)(a.xseq & 1u) * a.nranks * 2 * a.nparts;
-      for (int i = tid; i < nvals; i += blockDim.x) {
-        double t = 0.0;
-        for (int r = 0; r < a.nranks; r++) t += mine[(size_t)r * 2 * a.nparts + i];   // rank order: same bits everywhere
-        a.out[i] = t;
-        a.out_host[i] = t;
-      }
+    if (a.x.nranks > 1 && a.mode != MODE_NEWVIEW && a.mode != MODE_SUM) {
+      const bool ok = p2p_finish_exchange(a.x, a.xseq, (a.mode == MODE_CORE ? 2 : 1) * a.nparts, 2 * a.nparts, a.out, a.out_host);
+      if (tid == 0 && !ok) peer_lost = 1;
       __threadfence_system();
       __syncthreads();
     }
@@ -154,6 +134,17 @@ finish_kernel(const FinishArgs a)
       *a.done_flag_host = peer_lost ? 0xFFFFFFFFu : a.seq;       // 0xFFFFFFFF: the host reports the lost peer
     }
   }
+}
+
+// first touch of every peer mapping: an all-reduce of one zero
+__global__ void p2p_warmup_kernel(const P2pArgs x, unsigned int xseq, int stride)
+{
+  if ((int)threadIdx.x < x.nranks) x.peer_buf[threadIdx.x][p2p_row(x, xseq, x.rank, stride)] = 0.0;
+  p2p_finish_exchange(x, xseq, 1, stride, nullptr, nullptr);
+}
+void launch_p2p_warmup(const P2pArgs &x, unsigned int xseq, int stride, cudaStream_t s)
+{
+  p2p_warmup_kernel<<<1, 32, 0, s>>>(x, xseq, stride);
 }
 
 void launch_finish(const FinishArgs &a0, cudaStream_t s)
@@ -277,7 +268,7 @@ struct exb_engine {
   bool cat = false;                    // CAT / PSR: one rate category per site (span = S)
   int max_cats = 4;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_a = nullptr, ev_b = nullptr;   // call start / end, traverse start / end
   // per-call staging (pinned host + device mirror): entries | lzq | lzr | mask | lz(core)
   size_t stage_bytes = 0;
   unsigned char *stage_h = nullptr, *stage_d = nullptr;
@@ -292,6 +283,8 @@ struct exb_engine {
   double *out_d = nullptr, *out_h = nullptr;     // [2*P]
   long launches = 0;
   float last_ms = 0.f;
+  float phase_ms[3] = {0.f, 0.f, 0.f};   // tables (d-table, tip look-up) | traverse kernels | finish kernel of the last traversal call
+  bool phases_valid = false;
   bool timing = true;                    // CUDA events around the kernels of every call (exb_last_kernel_ms)
   unsigned int *ticket = nullptr;        // finish-kernel arrival counter
   volatile unsigned int *done_flag = nullptr;   // pinned, written by the finish kernel on the single-rank path
@@ -348,6 +341,8 @@ extern "C" int exb_create(exb_engine **out, int device, int mxtips, int numParti
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&e->ev0));
   CUDA_TRY(cudaEventCreate(&e->ev1));
+  CUDA_TRY(cudaEventCreate(&e->ev_a));
+  CUDA_TRY(cudaEventCreate(&e->ev_b));
   *out = e;
   return EXB_OK;
 }
@@ -376,6 +371,8 @@ extern "C" void exb_destroy(exb_engine *e)
   cudaFree(e->pp_in); cudaFree(e->pp_out); cudaFree(e->pp_scratch);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->ev_a) cudaEventDestroy(e->ev_a);
+  if (e->ev_b) cudaEventDestroy(e->ev_b);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -516,6 +513,9 @@ extern "C" int exb_commit(exb_engine *e)
       // AA tip look-up table (optional: skipped when it would not fit comfortably, e.g. thousands of AA partitions)
       const size_t lbytes = (size_t)(e->mxtips + 1) * idx * 2 * 23 * 20 * (e->cat ? e->max_cats : 4) * sizeof(double);
       if (c == CLS_AA && lbytes <= ((size_t)1 << 30) && !getenv("EXB_AA_NO_LUT")) CUDA_TRY(cudaMalloc(&k.lut, lbytes));
+      // DNA GAMMA, few partitions (the constant-bank path): tip look-up table built together with the d-table
+      if (c == CLS_DNA && !e->cat && idx <= kMaxParamPartitions && !getenv("EXB_DNA_NO_LUT"))
+        CUDA_TRY(cudaMalloc(&k.lut, (size_t)(e->mxtips + 1) * idx * kDnaLutRow * sizeof(double)));
     }
     if (n == 0) continue;
     // host images of tips / weights on the class site axis (padding: gap code, weight 0)
@@ -786,12 +786,16 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   rc = flush_models(e);
   if (rc) return rc;
   if (e->timing) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
-  for (int c = 0; c < 2; c++) {
+  const double *dtab_use[2] = {nullptr, nullptr}, *lut_use[2] = {nullptr, nullptr};
+  for (int c = 0; c < 2; c++) {                    // tables first: d-table (makeP exponentials), AA tip look-up table
     ClassState &k = e->cls[c];
     if (k.tiles_h.empty()) continue;
-    const double *dtab_use = k.dtab;
-    if (e->host_dtab[c]) dtab_use = (const double *)(e->stage_use + e->o_dtab[c]);
-    else {
+    dtab_use[c] = k.dtab;
+    lut_use[c] = k.lut;
+    if (e->host_dtab[c]) {
+      dtab_use[c] = (const double *)(e->stage_use + e->o_dtab[c]);
+      if (c == CLS_DNA) lut_use[c] = nullptr;      // short descriptor: no table launch, tips go through the contraction
+    } else {
       DtabArgs d;
       d.dtab = k.dtab; d.models = k.models; d.cls_part_global = k.part_global;
       d.lzq = (const double *)(e->stage_use + e->o_lzq); d.lzr = (const double *)(e->stage_use + e->o_lzr);
@@ -799,20 +803,27 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
       d.model_doubles = k.model_doubles; d.row = k.dtab_row;
       d.cat_rates = e->cat ? k.cat_rates : nullptr; d.max_cats = e->max_cats;
       d.eign_cat_stride = c == CLS_AA ? 20 : 0; d.rates_off = c == CLS_AA ? kAaRates : k.S; d.lg4_off = c == CLS_AA ? kAaLg4 : -1;
-      launch_dtab(d, e->stream);
+      d.lut = k.lut; d.entries = (const DevEntry *)(e->stage_use + e->o_entries); d.first = first;
+      if (c == CLS_DNA && k.lut) launch_dna_tables(d, e->stream);
+      else                       launch_dtab(d, e->stream);
       e->launches++;
     }
-    if (k.lut) {
+    if (c == CLS_AA && k.lut) {
       LutArgs l;
-      l.lut = k.lut; l.models = k.models; l.dtab = dtab_use;
+      l.lut = k.lut; l.models = k.models; l.dtab = dtab_use[c];
       l.entries = (const DevEntry *)(e->stage_use + e->o_entries);
       l.count = count; l.first = first; l.nparts_cls = k.nparts;
       l.ncat = e->cat ? e->max_cats : 4; l.dtab_row = k.dtab_row; l.cat = e->cat ? 1 : 0;
       launch_aa_lut(l, e->stream);
       e->launches++;
     }
+  }
+  if (e->timing) CUDA_TRY(cudaEventRecord(e->ev_a, e->stream));
+  for (int c = 0; c < 2; c++) {
+    ClassState &k = e->cls[c];
+    if (k.tiles_h.empty()) continue;
     TraverseArgs a;
-    a.dtab = dtab_use; a.lut = k.lut; a.nparts_cls = k.nparts; a.tile_sites = e->tile_sites;
+    a.dtab = dtab_use[c]; a.lut = lut_use[c]; a.nparts_cls = k.nparts; a.tile_sites = e->tile_sites;
     a.rate_cat = e->cat ? k.rate_cat : nullptr; a.max_cats = e->max_cats; a.dtab_row = k.dtab_row;
     a.tiles = k.tiles; a.clv = k.clv; a.tips = k.tips; a.wgt = k.wgt; a.sum = k.sum; a.models = k.models;
     a.N = k.N; a.mxtips = e->mxtips; a.nparts = e->P; a.nbranches = e->nb;
@@ -846,6 +857,8 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
     }
     e->launches++;
   }
+  if (e->timing) CUDA_TRY(cudaEventRecord(e->ev_b, e->stream));
+  e->phases_valid = e->timing;
   FinishArgs f;
   f.gs = e->gs; f.scale_inc = e->scale_inc;
   f.entries = (const DevEntry *)(e->stage_use + e->o_entries);
@@ -862,17 +875,25 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   return EXB_OK;
 }
 
+static P2pArgs p2p_args(const exb_engine *e)
+{
+  P2pArgs x;
+  memset(&x, 0, sizeof x);
+  x.nranks = e->p2p ? e->nranks : 1; x.rank = e->rank;
+  for (int r = 0; r < e->nranks && e->p2p; r++) { x.peer_buf[r] = e->peer_buf[r]; x.peer_flags[r] = e->peer_flags[r]; }
+  return x;
+}
+
 // Single rank: the finish kernel writes results and a completion flag into pinned host memory; the host polls.
 static void set_finish_outputs(exb_engine *e, FinishArgs &f)
 {
   f.ticket = e->ticket;
-  f.nranks = 1; f.rank = 0; f.xseq = 0;
+  f.x.nranks = 1; f.x.rank = 0; f.xseq = 0;
   if (e->comm && !e->p2p) { f.out_host = nullptr; f.done_flag_host = nullptr; f.seq = 0; return; }   // NCCL after the kernel
   if (++e->seq == 0xFFFFFFFFu) e->seq = 1;          // 0xFFFFFFFF is the kernel's "peer lost" marker
   f.out_host = e->out_h; f.done_flag_host = e->done_flag; f.seq = e->seq;
   if (e->p2p) {
-    f.nranks = e->nranks; f.rank = e->rank;
-    for (int r = 0; r < e->nranks; r++) { f.peer_buf[r] = e->peer_buf[r]; f.peer_flags[r] = e->peer_flags[r]; }
+    f.x = p2p_args(e);
     if (f.mode == MODE_EVALUATE || f.mode == MODE_CORE) e->xseq += 1;
     f.xseq = e->xseq;
   }
@@ -883,8 +904,11 @@ static int wait_done(exb_engine *e)
   if (e->comm && !e->p2p) { CUDA_TRY(cudaStreamSynchronize(e->stream)); }
   else {
     unsigned long spins = 0;
-    while (*e->done_flag != e->seq) {
-      if (*e->done_flag == 0xFFFFFFFFu)
+    for (;;) {
+      // acquire: the results in out_h were written before the flag (the kernel orders them with __threadfence_system)
+      const unsigned int flag = __atomic_load_n((const unsigned int *)e->done_flag, __ATOMIC_ACQUIRE);
+      if (flag == e->seq) break;
+      if (flag == 0xFFFFFFFFu)
         return fail(EXB_ERR_NCCL, "a peer rank did not deliver its partial sums within 20 s (all-reduce inside finish_kernel)");
       if ((++spins & 0xFFFF) == 0) {                 // a faulting kernel must not hang the host
         const cudaError_t q = cudaStreamQuery(e->stream);
@@ -893,6 +917,8 @@ static int wait_done(exb_engine *e)
       }
 #if defined(__x86_64__)
       __builtin_ia32_pause();
+#elif defined(__aarch64__)
+      asm volatile("yield" ::: "memory");
 #endif
     }
   }
@@ -956,10 +982,11 @@ extern "C" int exb_core(exb_engine *e, const double *lz, const unsigned char *ex
   for (int m = 0; m < e->P; m++) mk[m] = executeModel ? (executeModel[m] != 0) : 1;
   // core-lz and mask are adjacent at the tail of the staging area: one small copy
   e->stage_use = e->stage_d;
-  CUDA_TRY(cudaMemcpyAsync(e->stage_d + e->off_corelz, e->stage_h + e->off_corelz, e->stage_bytes - e->off_corelz,
+  CUDA_TRY(cudaMemcpyAsync(e->stage_d + e->off_corelz, e->stage_h + e->off_corelz, e->off_mask + (size_t)e->P - e->off_corelz,
                            cudaMemcpyHostToDevice, e->stream));
   int rc = flush_models(e);
   if (rc) return rc;
+  e->phases_valid = false;
   if (e->timing) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
   for (int c = 0; c < 2; c++) {
     ClassState &k = e->cls[c];
@@ -1004,7 +1031,9 @@ extern "C" int exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const
                             double *result, int *curvatOK, int *iterations)
 {
   if (!e || !e->committed) return fail(EXB_ERR_STATE, "engine not committed");
-  if (e->comm) return fail(EXB_ERR_STATE, "exb_makenewz: device-resident Newton-Raphson is single-rank; use exb_makenewz_prepare + exb_core");
+  if (e->comm && !e->p2p)
+    return fail(EXB_ERR_STATE, "exb_makenewz: with several ranks the device-resident Newton-Raphson needs the in-kernel all-reduce "
+                "(all ranks on one node with peer access, exb_comm_is_p2p); use exb_makenewz_prepare + exb_core");
   if (count < 1 || !z0 || !result) return fail(EXB_ERR_ARG, "exb_makenewz: bad arguments");
   if (e->nb > kMaxBranchSlots) return fail(EXB_ERR_ARG, "exb_makenewz: more than %d branch slots", kMaxBranchSlots);
   // 1. newviews + sum table (the first-iteration work of topLevelMakenewz); the mask of that pass is the one the
@@ -1032,6 +1061,7 @@ extern "C" int exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const
   a.part_out = e->out_d;
   a.part_has_sites = e->part_has_sites; a.part_tile_begin = e->part_tile_begin; a.part_tile_count = e->part_tile_count;
   a.part_cls = e->part_cls; a.nparts = e->P; a.nbranches = e->nb; a.max_cats = e->max_cats;
+  a.x = p2p_args(e); a.xseq0 = e->xseq;
   const int blocks = std::max(1, std::min(total_tiles, e->nr_max_blocks));
   const int lr = launch_newton_raphson(a, blocks, e->stream);
   if (lr != 0) return fail(EXB_ERR_CUDA, "cooperative launch of the Newton-Raphson kernel failed: %s", cudaGetErrorString((cudaError_t)lr));
@@ -1040,6 +1070,10 @@ extern "C" int exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const
   CUDA_TRY(cudaMemcpyAsync(h, e->nr_state_d, sizeof *h, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   if (e->timing) cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
+  if (e->p2p) {
+    if (h->peer_lost) return fail(EXB_ERR_NCCL, "a peer rank did not deliver its derivative sums within 20 s (all-reduce inside newton_raphson_kernel)");
+    e->xseq = h->xseq;                              // every rank ran the same number of exchanges
+  }
   for (int b = 0; b < e->nb; b++) {
     result[b] = h->z[b];
     if (curvatOK) curvatOK[b] = h->curvatOK[b];
@@ -1176,6 +1210,7 @@ extern "C" int exb_evaluate_partial(exb_engine *e, const exb_entry *ti, int coun
     scratch_need = std::max(scratch_need, (size_t)blocks[c] * nslots * e->cls[c].S * kPartialThreads * sizeof(double));
   }
   CUDA_TRY(grow(&e->pp_scratch, &e->pp_scratch_cap, scratch_need));
+  e->phases_valid = false;
   if (e->timing) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
   for (int c = 0; c < 2; c++) {
     if (chunks[c].empty()) continue;
@@ -1219,9 +1254,9 @@ extern "C" int exb_comm_unique_id(void *id_out)
 static int setup_p2p(exb_engine *e)
 {
   const int n = e->nranks;
-  // opt-in for now (EXB_P2P=1): verified on 2 and 4 GPUs, not yet on 8; see DESIGN.md 6
+  // default on one node; EXB_P2P=0 keeps ncclAllReduce after the kernel
   const char *want = getenv("EXB_P2P");
-  if (n > kMaxP2pRanks || !want || atoi(want) == 0 || !g_nccl.AllGather) return EXB_OK;
+  if (n > kMaxP2pRanks || (want && atoi(want) == 0) || !g_nccl.AllGather) return EXB_OK;
   struct Card { cudaIpcMemHandle_t h; int ok; int device; char host[64]; };
   const size_t data_bytes = (size_t)2 * n * 2 * e->P * sizeof(double);
   const size_t flag_off = (data_bytes + 255) & ~(size_t)255;
@@ -1268,6 +1303,10 @@ static int setup_p2p(exb_engine *e)
     return EXB_OK;
   }
   e->p2p = true;
+  // one exchange now: maps the peers' pages (IPC mappings are established lazily) outside anybody's timed region
+  e->xseq = 1;
+  launch_p2p_warmup(p2p_args(e), e->xseq, 2 * e->P, e->stream);
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
   return EXB_OK;
 }
 
@@ -1331,6 +1370,17 @@ extern "C" int exb_last_kernel_ms(exb_engine *e, float *ms)
 {
   if (!e || !ms) return fail(EXB_ERR_ARG, "exb_last_kernel_ms: null argument");
   *ms = e->last_ms;
+  return EXB_OK;
+}
+
+extern "C" int exb_last_phase_ms(exb_engine *e, float *ms3)
+{
+  if (!e || !ms3) return fail(EXB_ERR_ARG, "exb_last_phase_ms: null argument");
+  if (!e->phases_valid) return fail(EXB_ERR_STATE, "exb_last_phase_ms: the last call was not a timed traversal call");
+  CUDA_TRY(cudaEventSynchronize(e->ev1));
+  cudaEventElapsedTime(&ms3[0], e->ev0, e->ev_a);
+  cudaEventElapsedTime(&ms3[1], e->ev_a, e->ev_b);
+  cudaEventElapsedTime(&ms3[2], e->ev_b, e->ev1);
   return EXB_OK;
 }
 

@@ -44,6 +44,9 @@ struct DevEntry { int tipCase, p, q, r; };
 // Row 0 (the branch entry of evaluate) carries the diagonal table of calcDiagptable in its q side.
 constexpr int kDnaDtabRow = 32;
 constexpr int kAaDtabRow  = 160;
+// DNA tip look-up table, built with the d-table when a class holds few partitions (dna_tables_kernel):
+//   row (512 doubles) per (entry, class-partition): [side q/r][16 codes][c][l] = sum_j P[l][j] tipVector[code][j]
+constexpr int kDnaLutRow  = 512;
 
 // CAT / PSR (one rate category per site, axml.h:349): the table has one [2 sides][S] block per category of the
 // partition, row = max_cats * 2 * S, and a site picks its block through rate_cat[site].
@@ -56,6 +59,8 @@ struct DtabArgs {
   int count, nparts_cls, nbranches, states, model_doubles, row, max_cats;
   int eign_cat_stride;       // doubles between the EIGN of consecutive categories (0: shared, DNA; 20: AA)
   int rates_off, lg4_off;    // offsets of gammaRates[4] / the LG4 flag inside a model block (lg4_off < 0: none)
+  // dna_tables_kernel only: the tip look-up table and what it needs to know about the entries
+  double *lut; const DevEntry *entries; int first;
 };
 
 // Everything a traversal kernel needs.  Passed by value (fits the 4 KB parameter space).
@@ -82,7 +87,8 @@ struct TraverseArgs {
   unsigned int *scale_inc;  // [maxEntries][P]  per-entry scaler increments (integer atomics: deterministic)
   double       *tile_out;   // [ntiles][2]      per-tile partial sums (evaluate: lnL; core: d1,d2)
   const double *dtab;       // [count][nparts_cls][row]
-  const double *lut;        // AA only, may be null: [count][nparts_cls][2 sides][23 codes][4 | max_cats][20] = P(t) * tipVector[code]
+  const double *lut;        // tip look-up table, may be null.  AA: [count][nparts_cls][2 sides][23 codes][4 | max_cats][20] = P(t) * tipVector[code];
+                            // DNA GAMMA: [count][nparts_cls][2 sides][16 codes][4][4]
   const int    *rate_cat;   // CAT: [N] rate category of every site; null under GAMMA
   int           max_cats;   // CAT: categories per partition in dtab / lut rows
   int           dtab_row;   // doubles per (entry, partition) in dtab
@@ -109,6 +115,12 @@ struct CoreArgs {
 };
 
 constexpr int kMaxP2pRanks = 16;
+// several GPUs on one node: the all-reduce is done by the kernels themselves over CUDA-IPC mapped peer buffers (p2p.cuh)
+struct P2pArgs {
+  int           nranks, rank;                    // nranks <= 1: no exchange
+  double       *peer_buf[kMaxP2pRanks];          // receive buffers: [2 slots][nranks][stride] doubles (entry `rank` is mine)
+  unsigned int *peer_flags[kMaxP2pRanks];        // [nranks] sequence flags in each receive buffer
+};
 struct FinishArgs {
   // scaler fix-up: gs[p] = gs[q] + gs[r] + inc  for every newview entry, in order
   unsigned int *gs;          // [P][2*mxtips]
@@ -132,13 +144,9 @@ struct FinishArgs {
   unsigned int *ticket;           // block arrival counter (self-resetting)
   unsigned int  seq;              // value to publish in *done_flag_host
   int           gs_in_smem;       // scaler chain staged in shared memory (set by launch_finish)
-  // several GPUs on one node: the all-reduce of evaluateGeneric / topLevelMakenewz (evaluateGenericSpecial.c:968-975,
-  // makenewzGenericSpecial.c:1241-1248) is part of this kernel.  Every rank stores its per-partition sums straight
-  // into every peer's receive buffer over NVLink (CUDA IPC mappings), raises a sequence flag there, waits for
-  // the peers' flags in its own memory and adds the nranks contributions in rank order -- the same bits on every rank.
-  int           nranks, rank;     // nranks <= 1: no exchange
-  double       *peer_buf[kMaxP2pRanks];          // receive buffers: [2 slots][nranks][2*P] doubles (entry `rank` is mine)
-  unsigned int *peer_flags[kMaxP2pRanks];        // [nranks] sequence flags in each receive buffer
+  // several GPUs on one node: the all-reduce of evaluateGeneric / topLevelMakenewz is part of this kernel (p2p.cuh);
+  // receive-buffer rows are 2*P doubles
+  P2pArgs       x;
   unsigned int  xseq;             // exchange number (slot = xseq & 1)
 };
 
@@ -160,6 +168,8 @@ struct NrState {
   int budget[kMaxBranchSlots];
   unsigned char done[kMaxBranchSlots], curvatOK[kMaxBranchSlots];
   int all_done, iterations;
+  unsigned int xseq;        // multi-rank: number of the last exchange used
+  int peer_lost;            // multi-rank: a peer did not deliver within the watchdog time
 };
 struct NrArgs {
   NrState *state;
@@ -172,6 +182,10 @@ struct NrArgs {
   double *part_out;               // [2][P]
   const int *part_has_sites, *part_tile_begin, *part_tile_count, *part_cls;
   int nparts, nbranches;
+  // several GPUs on one node: one exchange per iteration inside the kernel (p2p.cuh); the first one is number xseq0 + 1,
+  // the last one used is left in state->xseq
+  P2pArgs x;
+  unsigned int xseq0;
 };
 int launch_newton_raphson(const NrArgs &a, int blocks, cudaStream_t s);
 int newton_raphson_max_blocks(int device);
@@ -199,12 +213,29 @@ void launch_partial(const PartialArgs &a, int states, int blocks, cudaStream_t s
 int partial_max_blocks(int states, int device);
 
 void launch_dtab(const DtabArgs &a, cudaStream_t s);
+void launch_dna_tables(const DtabArgs &a, cudaStream_t s);
 void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
 void launch_traverse_dna_cat(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
 void launch_core_dna(const CoreArgs &a, int ntiles, cudaStream_t s);
 void launch_traverse_aa(const TraverseArgs &a, bool any_lg4, int ntiles, cudaStream_t s);
 void launch_core_aa(const CoreArgs &a, int ntiles, cudaStream_t s);
 void launch_finish(const FinishArgs &a, cudaStream_t s);
+void launch_p2p_warmup(const P2pArgs &x, unsigned int xseq, int stride, cudaStream_t s);
+
+// Dynamic shared memory above 48 KB is an opt-in per (kernel, device): remember what each device was given.
+constexpr int kMaxDevices = 64;
+template <class Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, size_t (&done)[kMaxDevices])
+{
+  int dev = 0;
+  cudaError_t r = cudaGetDevice(&dev);
+  if (r != cudaSuccess) return r;
+  size_t &have = done[dev >= 0 && dev < kMaxDevices ? dev : 0];
+  if (bytes <= have && dev < kMaxDevices) return cudaSuccess;
+  r = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (r == cudaSuccess) have = bytes;
+  return r;      // a failure also surfaces as a launch error, which the engine reports
+}
 
 // ---- device helpers shared by the kernels --------------------------------------------------------------
 #ifdef __CUDACC__

@@ -82,33 +82,25 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 enum ChildMode : int { CH_MEM = 0, CH_CARRY = 1, CH_LUT = 2 };
 
 // Which of the 20 contraction indices does lane tq feed into k-step s?  The sum over k is order-free, so A and B
-// fragments may use any common assignment.  PERM = false: the natural one, k = 4s + tq; a C-fragment (which holds
-// columns 8t + 2tq + {0,1}) then has to be re-distributed with two shuffles and a select per k-step.  PERM = true:
-// k-steps 0..3 take the columns the lane already holds (t = s/2, element s&1), and only k-step 4 moves data: lanes
-// 2,3 fetch columns 17 / 19 from lanes 0,1 -- one shuffle per contraction instead of ten.
-template <bool PERM>
+// fragments may use any common assignment.  The natural one (k = 4s + tq) would force a C-fragment -- which holds
+// columns 8t + 2tq + {0,1} -- to be re-distributed with two shuffles and a select per k-step (measured: SHFL + FSEL
+// took more issue slots than the DMMAs).  Instead k-steps 0..3 take the columns the lane already holds (t = s/2,
+// element s&1), and only k-step 4 moves data: lanes 2,3 fetch columns 17 / 19 from lanes 0,1 -- one shuffle per
+// contraction instead of ten (36.7 -> 32.0 ms per C4 traversal).
 __device__ __forceinline__ int kappa(int s, int tq)
 {
-  if (!PERM) return 4 * s + tq;
   return s < 4 ? 8 * (s >> 1) + 2 * tq + (s & 1) : (tq < 2 ? 16 + 2 * tq : 13 + 2 * tq);
 }
 
 // A operand of k-step s taken from a value in C-fragment layout (v[t][e] = column 8t + 2tq + e of my row)
-template <bool PERM>
 __device__ __forceinline__ double c_to_a(const double (&v)[3][2], int s, int lane, int tq)
 {
-  if (PERM) {
-    if (s < 4) return v[s >> 1][s & 1];
-    const double moved = __shfl_sync(0xffffffffu, v[2][1], (lane & ~3) | (tq & 1));
-    return tq < 2 ? v[2][0] : moved;
-  }
-  const int sl = (lane & ~3) | (((s & 1) << 1) | (tq >> 1));
-  const double e0 = __shfl_sync(0xffffffffu, v[s >> 1][0], sl);
-  const double e1 = __shfl_sync(0xffffffffu, v[s >> 1][1], sl);
-  return (tq & 1) ? e1 : e0;
+  if (s < 4) return v[s >> 1][s & 1];
+  const double moved = __shfl_sync(0xffffffffu, v[2][1], (lane & ~3) | (tq & 1));
+  return tq < 2 ? v[2][0] : moved;
 }
 
-template <int MODE, bool PERM>
+template <int MODE>
 __device__ __forceinline__ void child_y(double (&y)[3][2], const double (&carry)[4][3][2], const double (*fEI)[32],
                                         const double *x, const double *lutrow, const double *dside,
                                         int c, int lane, int tq)
@@ -126,8 +118,8 @@ __device__ __forceinline__ void child_y(double (&y)[3][2], const double (&carry)
   double av[5];
   #pragma unroll
   for (int s = 0; s < 5; s++) {
-    const int k = kappa<PERM>(s, tq);
-    if (MODE == CH_CARRY) av[s] = c_to_a<PERM>(carry[c], s, lane, tq);
+    const int k = kappa(s, tq);
+    if (MODE == CH_CARRY) av[s] = c_to_a(carry[c], s, lane, tq);
     else av[s] = x[k];
     av[s] *= __ldg(dside + k);
   }
@@ -162,7 +154,7 @@ struct AaSlotsGamma {              // GAMMA: one site, slot = category: a base a
 };
 
 // KC: true -> slot c uses the eigen-system of category c (GAMMA; LG4 makes them differ); false -> system 0 (CAT)
-template <int QM, int RM, bool KC, bool PERM, class Slots>
+template <int QM, int RM, bool KC, class Slots>
 __device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const AaConstsSmem &K,
                                          const Slots &sl, int lane, int tq)
 {
@@ -171,8 +163,8 @@ __device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const AaConst
     const double (*fEI)[32] = K.fragEI[KC ? c : 0];
     const double (*fEV)[32] = K.fragEV[KC ? c : 0];
     double y1[3][2], y2[3][2];
-    child_y<QM, PERM>(y1, carry, fEI, sl.xq(c), sl.lq(c), sl.dq(c), c, lane, tq);
-    child_y<RM, PERM>(y2, carry, fEI, sl.xr(c), sl.lr(c), sl.dq(c) + S, c, lane, tq);
+    child_y<QM>(y1, carry, fEI, sl.xq(c), sl.lq(c), sl.dq(c), c, lane, tq);
+    child_y<RM>(y2, carry, fEI, sl.xr(c), sl.lr(c), sl.dq(c) + S, c, lane, tq);
     // Z = Y1 (.) Y2 in C layout, then X3 = Z * EV
     #pragma unroll
     for (int t = 0; t < 3; t++) { y1[t][0] *= y2[t][0]; y1[t][1] *= y2[t][1]; }
@@ -181,7 +173,7 @@ __device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const AaConst
     for (int t = 0; t < 3; t++) x3[t][0] = x3[t][1] = 0.0;
     #pragma unroll
     for (int s = 0; s < 5; s++) {
-      const double az = c_to_a<PERM>(y1, s, lane, tq);    // Z[g][kappa(s, tq)]
+      const double az = c_to_a(y1, s, lane, tq);    // Z[g][kappa(s, tq)]
       #pragma unroll
       for (int t = 0; t < 3; t++) dmma(x3[t][0], x3[t][1], az, fEV[s * 3 + t][lane]);
     }
@@ -212,8 +204,7 @@ __device__ __forceinline__ void aa_entry(double (&carry)[4][3][2], const AaConst
 //              log are per site.
 // LG4 = true : every Gamma category has its own eigen-system (LG4M / LG4X partitions in the class): per-category B
 //              fragments and tip vectors.  false: one system -- fragment and tip addresses do not depend on the category.
-// PERM: contraction-index assignment of the fragments, see kappa() (true: opt-in until run on a GPU, EXB_AA_PERM=1)
-template <bool CAT, bool LG4, bool PERM>
+template <bool CAT, bool LG4>
 __global__ void __launch_bounds__(kAaThreads, 1)
 traverse_aa_kernel(const TraverseArgs a)
 {
@@ -240,7 +231,7 @@ traverse_aa_kernel(const TraverseArgs a)
     // B fragments per category: EI_c^T[k = 4s+tq][n = 8t+g] = EI_c[n][k];  EV_c[k][n];  zero padding for n >= 20
     for (int i = tid; i < NSYS * 15 * 32; i += kAaThreads) {
       const int kc = i / 480, f = (i % 480) >> 5, ln = i & 31, fs = f / 3, ft = f % 3;
-      const int k = kappa<PERM>(fs, ln & 3), n = 8 * ft + (ln >> 2);
+      const int k = kappa(fs, ln & 3), n = 8 * ft + (ln >> 2);
       K.fragEI[kc][f][ln] = n < S ? model[kAaEI + kc * 400 + n * S + k] : 0.0;
       K.fragEV[kc][f][ln] = n < S ? model[kAaEV + kc * 400 + k * S + n] : 0.0;
     }
@@ -272,7 +263,6 @@ traverse_aa_kernel(const TraverseArgs a)
     const size_t site0 = (size_t)tile.site0 + chunk0 + (CAT ? i0 : lsite[0]);   // CAT: slot c sits at site0 + 8c
     const size_t soff = site0 * XSPAN;
     double carry[4][3][2];                                // CLV of the entry just computed, C-fragment layout
-    long long carry_node = -1;
     #pragma unroll
     for (int c = 0; c < 4; c++)
       #pragma unroll
@@ -281,14 +271,14 @@ traverse_aa_kernel(const TraverseArgs a)
     int w0 = a.first;
     do {
     const int w1 = min(w0 + kWindow, a.count);
-    stage_window<TSITES>(dyn, &mbar, phase, a, N, XSPAN, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
-                         w0 == a.first && a.mode != MODE_NEWVIEW);
+    phase = stage_window<TSITES>(dyn, &mbar, phase, a.entries, a.tips, a.mxtips, N, XSPAN, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
+                         a.first, a.count, w0 == a.first && a.mode != MODE_NEWVIEW);
     for (int e = w0; e < w1; e++) {
       const SEntry en = ents[e - w0];
       const double *drow = drow0 + (size_t)e * dstride;
       const bool q_inner = en.tipCase == 2, r_inner = en.tipCase != 0;
-      const int qsrc = !q_inner ? SRC_TIP : (en.qoff == carry_node ? SRC_CARRY : SRC_LOAD);
-      const int rsrc = !r_inner ? SRC_TIP : (en.roff == carry_node ? SRC_CARRY : SRC_LOAD);
+      const int qsrc = !q_inner ? SRC_TIP : ((en.flags & kFlagCarryA) ? SRC_CARRY : SRC_LOAD);
+      const int rsrc = !r_inner ? SRC_TIP : ((en.flags & kFlagCarryB) ? SRC_CARRY : SRC_LOAD);
       const double *lutE = a.lut ? a.lut + ((size_t)e * a.nparts_cls + tile.part_cls) * 2 * lutside : nullptr;
       // memory sources: a global CLV or the tip vector in shared memory; tip tables when they exist
       typename std::conditional<CAT, AaSlotsCat, AaSlotsGamma>::type sl;
@@ -311,12 +301,12 @@ traverse_aa_kernel(const TraverseArgs a)
         sl.drow = drow;
       }
       const bool qlut = !q_inner && lutE, rlut = !r_inner && lutE;
-      if (qlut && rlut)                   aa_entry<CH_LUT, CH_LUT, LG4, PERM>(carry, K, sl, lane, tq);
-      else if (qlut && rsrc == SRC_CARRY) aa_entry<CH_LUT, CH_CARRY, LG4, PERM>(carry, K, sl, lane, tq);
-      else if (qlut)                      aa_entry<CH_LUT, CH_MEM, LG4, PERM>(carry, K, sl, lane, tq);
-      else if (rsrc == SRC_CARRY)         aa_entry<CH_MEM, CH_CARRY, LG4, PERM>(carry, K, sl, lane, tq);
-      else if (qsrc == SRC_CARRY)         aa_entry<CH_CARRY, CH_MEM, LG4, PERM>(carry, K, sl, lane, tq);
-      else                                aa_entry<CH_MEM, CH_MEM, LG4, PERM>(carry, K, sl, lane, tq);
+      if (qlut && rlut)                   aa_entry<CH_LUT, CH_LUT, LG4>(carry, K, sl, lane, tq);
+      else if (qlut && rsrc == SRC_CARRY) aa_entry<CH_LUT, CH_CARRY, LG4>(carry, K, sl, lane, tq);
+      else if (qlut)                      aa_entry<CH_LUT, CH_MEM, LG4>(carry, K, sl, lane, tq);
+      else if (rsrc == SRC_CARRY)         aa_entry<CH_MEM, CH_CARRY, LG4>(carry, K, sl, lane, tq);
+      else if (qsrc == SRC_CARRY)         aa_entry<CH_CARRY, CH_MEM, LG4>(carry, K, sl, lane, tq);
+      else                                aa_entry<CH_MEM, CH_MEM, LG4>(carry, K, sl, lane, tq);
 
       if (r_inner) {                            // TIP_TIP is never rescaled (avxLikelihood.c:1393-1440)
         unsigned int cnt = 0;
@@ -366,7 +356,6 @@ traverse_aa_kernel(const TraverseArgs a)
         }
       }
       __syncwarp();
-      carry_node = en.poff;
     }
     } while ((w0 += kWindow) < a.count);
 
@@ -374,8 +363,8 @@ traverse_aa_kernel(const TraverseArgs a)
 
     // ---------------- branch (entry 0): evaluate or sum table (C-fragment layout on both ends) ----------------
     const SEntry br = ents[kWindow];
-    const bool ptip = br.ptip_qtip & 1, qtip = br.ptip_qtip & 2;
-    const bool p_carry = !ptip && br.poff == carry_node, q_carry = !qtip && br.qoff == carry_node;
+    const bool ptip = br.flags & kFlagPTip, qtip = br.flags & kFlagQTip;
+    const bool p_carry = br.flags & kFlagCarryA, q_carry = br.flags & kFlagCarryB;
     const bool lg4 = LG4 && model[kAaLg4] != 0.0;       // an ordinary partition next to LG4 ones keeps log(0.25 |sum|)
     double term = 0.0;
     #pragma unroll
@@ -462,8 +451,8 @@ void launch_aa_lut(const LutArgs &a, cudaStream_t s)
   const int blocks = a.count * a.nparts_cls * 2;
   if (blocks <= 0) return;
   const size_t smem = (size_t)(1600 + 1840 + a.ncat * 20) * sizeof(double);
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(aa_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); configured = true; }
+  static size_t configured[kMaxDevices];
+  ensure_dynamic_smem(aa_lut_kernel, 64 * 1024, configured);
   aa_lut_kernel<<<blocks, 256, smem, s>>>(a);
 }
 
@@ -481,26 +470,13 @@ core_aa_kernel(const CoreArgs a)
   if (threadIdx.x == 0) { a.tile_out[2 * (size_t)blockIdx.x] = t1; a.tile_out[2 * (size_t)blockIdx.x + 1] = t2; }
 }
 
-template <bool CAT, bool LG4, bool PERM>
-static void launch_aa_perm(const TraverseArgs &a, int ntiles, cudaStream_t s)
-{
-  const size_t smem = ((window_smem_bytes<(CAT ? 384 : 96)>() + 127) & ~(size_t)127) + sizeof(AaConstsSmem);
-  static size_t configured = 0;
-  if (smem > configured) {
-    const size_t want = std::min<size_t>(227 * 1024 - 16384, std::max<size_t>(smem, 64 * 1024));
-    cudaFuncSetAttribute(traverse_aa_kernel<CAT, LG4, PERM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
-    configured = want;
-  }
-  traverse_aa_kernel<CAT, LG4, PERM><<<ntiles, kAaThreads, smem, s>>>(a);
-}
-
 template <bool CAT, bool LG4>
 static void launch_aa_variant(const TraverseArgs &a, int ntiles, cudaStream_t s)
 {
-  static int perm = -1;
-  if (perm < 0) { const char *v = getenv("EXB_AA_PERM"); perm = v ? atoi(v) : 0; }
-  if (perm) launch_aa_perm<CAT, LG4, true>(a, ntiles, s);
-  else      launch_aa_perm<CAT, LG4, false>(a, ntiles, s);
+  const size_t smem = ((window_smem_bytes<(CAT ? 384 : 96)>() + 127) & ~(size_t)127) + sizeof(AaConstsSmem);
+  static size_t configured[kMaxDevices];
+  ensure_dynamic_smem(traverse_aa_kernel<CAT, LG4>, std::min<size_t>(227 * 1024 - 16384, std::max<size_t>(smem, 64 * 1024)), configured);
+  traverse_aa_kernel<CAT, LG4><<<ntiles, kAaThreads, smem, s>>>(a);
 }
 
 void launch_traverse_aa(const TraverseArgs &a, bool any_lg4, int ntiles, cudaStream_t s)

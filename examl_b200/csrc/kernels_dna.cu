@@ -60,83 +60,55 @@ __device__ __forceinline__ void st256(double *p, const double v[4])
 
 }  // namespace
 
+// |v| < 2^-256 for all four values, decided on the integer pipe (the FP64 pipe is the busy one): the biased exponent
+// of 2^-256 is 767 = 0x2FF, so fabs(v) < minlikelihood  <=>  (high word & 0x7fffffff) < 0x2FF00000 (NaN: false, like <).
+__device__ __forceinline__ bool all_tiny(const double (&v)[4])
+{
+  const unsigned int h0 = (unsigned int)__double2hiint(v[0]) & 0x7fffffffu, h1 = (unsigned int)__double2hiint(v[1]) & 0x7fffffffu,
+                     h2 = (unsigned int)__double2hiint(v[2]) & 0x7fffffffu, h3 = (unsigned int)__double2hiint(v[3]) & 0x7fffffffu;
+  return max(max(h0, h1), max(h2, h3)) < 0x2FF00000u;
+}
+
 // One traversal entry for the NS sites of a thread, compiled once per combination of child sources so that the
 // NS loop carries no branch on tip case / carry / scaling.
-//   source: 0 = tip (staged tip row + shared tip vector), 1 = carry registers, 2 = CLV load
-template <int QS, int RS, int NS, bool PARAM>
+//   source: 0 = tip, 1 = carry registers, 2 = CLV load
+// Loop order: every EI / EV constant is fetched once per entry and used for all NS sites (constant-outer, site-inner;
+// the compiler keeps them in uniform registers), in stages that keep the live set inside the register budget:
+//   (A) gather the children;  d (.) x for inner children
+//   (B) row l of EI for all sites -> ab[s][l] = a_q[l] * a_r[l]
+//   (C) column m of EV for all sites -> v[s][m]
+// LUT: a tip child contributes a_q[l] = sum_j P[l][j] tipVector[code][j] straight from the per-call table built by
+// dna_tables_kernel (the reference's umpX1 / umpX2, avxLikelihood.c:93-118): one 32-byte load instead of 15 flops.
+template <int QS, int RS, int NS, bool PARAM, bool LUT>
 __device__ __forceinline__ unsigned int dna_entry(double (&carry)[NS][4], const TraverseArgs &a, const DnaConsts &kc, const DnaShared &sh,
-                                                  const uint8_t *stips, const SEntry &en, const double (&dq)[4], const double (&dr)[4],
+                                                  const uint8_t *stips, const SEntry &en, const double *drow_e, const double *lut_e,
                                                   const size_t (&eoff)[NS], const bool (&valid)[NS], const int (&lsite)[NS], int c, int lane)
 {
 #define EI_(i) (PARAM ? kc.EI[i] : sh.EI[i])
 #define EV_(i) (PARAM ? kc.EV[i] : sh.EV[i])
-  double x1[NS][4], x2[NS][4];
+  constexpr bool QL = LUT && QS == 0, RL = LUT && RS == 0;     // side comes from the table: no exponentials, no EI
+  double dq[4], dr[4];
+  if (!QL) ld256_ro(drow_e, dq);
+  if (!RL) ld256_ro(drow_e + 4, dr);
+  double qa[NS][4], ra[NS][4];         // table side: a[l]; computed side: x[0], d[1] x[1], d[2] x[2], d[3] x[3]
   #pragma unroll
-  for (int s = 0; s < NS; s++) {
-    if (QS == 1) { x1[s][0] = carry[s][0]; x1[s][1] = carry[s][1]; x1[s][2] = carry[s][2]; x1[s][3] = carry[s][3]; }
-    else if (QS == 2) ld256(a.clv + en.qoff + eoff[s], x1[s]);
-    else { const double *tv = &sh.tip[4 * stips[en.qoff + lsite[s]]]; x1[s][0] = tv[0]; x1[s][1] = tv[1]; x1[s][2] = tv[2]; x1[s][3] = tv[3]; }
-    if (RS == 1) { x2[s][0] = carry[s][0]; x2[s][1] = carry[s][1]; x2[s][2] = carry[s][2]; x2[s][3] = carry[s][3]; }
-    else if (RS == 2) ld256(a.clv + en.roff + eoff[s], x2[s]);
-    else { const double *tv = &sh.tip[4 * stips[en.roff + lsite[s]]]; x2[s][0] = tv[0]; x2[s][1] = tv[1]; x2[s][2] = tv[2]; x2[s][3] = tv[3]; }
-  }
-  unsigned int cnt = 0;
-  double *const dst = a.clv + en.poff;
-  #pragma unroll
-  for (int s = 0; s < NS; s++) {
-    const double tq1 = dq[1] * x1[s][1], tq2 = dq[2] * x1[s][2], tq3 = dq[3] * x1[s][3];
-    const double tr1 = dr[1] * x2[s][1], tr2 = dr[2] * x2[s][2], tr3 = dr[3] * x2[s][3];
-    double v[4] = {0.0, 0.0, 0.0, 0.0};
-    #pragma unroll
-    for (int l = 0; l < 4; l++) {
-      const double al = x1[s][0] + EI_(l * 4 + 1) * tq1 + EI_(l * 4 + 2) * tq2 + EI_(l * 4 + 3) * tq3;
-      const double ar = x2[s][0] + EI_(l * 4 + 1) * tr1 + EI_(l * 4 + 2) * tr2 + EI_(l * 4 + 3) * tr3;
-      const double ab = al * ar;
-      #pragma unroll
-      for (int m = 0; m < 4; m++) v[m] += ab * EV_(l * 4 + m);
+  for (int s = 0; s < NS; s++) {                      // (A)
+    if (QL) ld256_ro(lut_e + 16 * stips[en.qoff + lsite[s]], qa[s]);
+    else {
+      double x1[4];
+      if (QS == 1) { x1[0] = carry[s][0]; x1[1] = carry[s][1]; x1[2] = carry[s][2]; x1[3] = carry[s][3]; }
+      else if (QS == 2) ld256(a.clv + en.qoff + eoff[s], x1);
+      else { const double *tv = &sh.tip[4 * stips[en.qoff + lsite[s]]]; x1[0] = tv[0]; x1[1] = tv[1]; x1[2] = tv[2]; x1[3] = tv[3]; }
+      qa[s][0] = x1[0]; qa[s][1] = dq[1] * x1[1]; qa[s][2] = dq[2] * x1[2]; qa[s][3] = dq[3] * x1[3];
     }
-    if (RS != 0) {                           // TIP_TIP is never rescaled (avxLikelihood.c:87-160)
-      const bool small = fabs(v[0]) < kMinLikelihood && fabs(v[1]) < kMinLikelihood &&
-                         fabs(v[2]) < kMinLikelihood && fabs(v[3]) < kMinLikelihood;
-      const unsigned int b = __ballot_sync(0xffffffffu, small);
-      if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {            // all 16 values of the site are tiny
-        #pragma unroll
-        for (int m = 0; m < 4; m++) v[m] *= kTwoToThe256;
-        if (c == 0 && valid[s]) cnt += (unsigned int)a.wgt[eoff[s] >> 4];
-      }
+    if (RL) ld256_ro(lut_e + 256 + 16 * stips[en.roff + lsite[s]], ra[s]);
+    else {
+      double x2[4];
+      if (RS == 1) { x2[0] = carry[s][0]; x2[1] = carry[s][1]; x2[2] = carry[s][2]; x2[3] = carry[s][3]; }
+      else if (RS == 2) ld256(a.clv + en.roff + eoff[s], x2);
+      else { const double *tv = &sh.tip[4 * stips[en.roff + lsite[s]]]; x2[0] = tv[0]; x2[1] = tv[1]; x2[2] = tv[2]; x2[3] = tv[3]; }
+      ra[s][0] = x2[0]; ra[s][1] = dr[1] * x2[1]; ra[s][2] = dr[2] * x2[2]; ra[s][3] = dr[3] * x2[3];
     }
-    if (valid[s]) st256(dst + eoff[s], v);
-    carry[s][0] = v[0]; carry[s][1] = v[1]; carry[s][2] = v[2]; carry[s][3] = v[3];
-  }
-  return cnt;
-#undef EI_
-#undef EV_
-}
-
-// The same entry with the loops interchanged: every EI / EV constant is fetched once per entry and used for all NS
-// sites (constant-outer, site-inner) instead of once per site.  In the site-outer form above the compiler re-loads the
-// 28 constants for every site (LDC: 29 of the ~105 instructions per site).  Stages keep the live set inside the
-// register budget: (A) d (.) x for all sites, (B) row l of EI -> ab[s][l], (C) v[s][:] += ab[s][l] * EV[l][:].
-// Opt-in (EXB_DNA_SPEC=2) until it has been run against the parity tests on a GPU.
-template <int QS, int RS, int NS, bool PARAM>
-__device__ __forceinline__ unsigned int dna_entry_staged(double (&carry)[NS][4], const TraverseArgs &a, const DnaConsts &kc, const DnaShared &sh,
-                                                         const uint8_t *stips, const SEntry &en, const double (&dq)[4], const double (&dr)[4],
-                                                         const size_t (&eoff)[NS], const bool (&valid)[NS], const int (&lsite)[NS], int c, int lane)
-{
-#define EI_(i) (PARAM ? kc.EI[i] : sh.EI[i])
-#define EV_(i) (PARAM ? kc.EV[i] : sh.EV[i])
-  double q0[NS], q1[NS], q2[NS], q3[NS], r0[NS], r1[NS], r2[NS], r3[NS];
-  #pragma unroll
-  for (int s = 0; s < NS; s++) {                      // (A) gather + exponentials
-    double x1[4], x2[4];
-    if (QS == 1) { x1[0] = carry[s][0]; x1[1] = carry[s][1]; x1[2] = carry[s][2]; x1[3] = carry[s][3]; }
-    else if (QS == 2) ld256(a.clv + en.qoff + eoff[s], x1);
-    else { const double *tv = &sh.tip[4 * stips[en.qoff + lsite[s]]]; x1[0] = tv[0]; x1[1] = tv[1]; x1[2] = tv[2]; x1[3] = tv[3]; }
-    if (RS == 1) { x2[0] = carry[s][0]; x2[1] = carry[s][1]; x2[2] = carry[s][2]; x2[3] = carry[s][3]; }
-    else if (RS == 2) ld256(a.clv + en.roff + eoff[s], x2);
-    else { const double *tv = &sh.tip[4 * stips[en.roff + lsite[s]]]; x2[0] = tv[0]; x2[1] = tv[1]; x2[2] = tv[2]; x2[3] = tv[3]; }
-    q0[s] = x1[0]; q1[s] = dq[1] * x1[1]; q2[s] = dq[2] * x1[2]; q3[s] = dq[3] * x1[3];
-    r0[s] = x2[0]; r1[s] = dr[1] * x2[1]; r2[s] = dr[2] * x2[2]; r3[s] = dr[3] * x2[3];
   }
   double ab[NS][4];
   #pragma unroll
@@ -144,31 +116,26 @@ __device__ __forceinline__ unsigned int dna_entry_staged(double (&carry)[NS][4],
     const double e1 = EI_(l * 4 + 1), e2 = EI_(l * 4 + 2), e3 = EI_(l * 4 + 3);
     #pragma unroll
     for (int s = 0; s < NS; s++) {
-      const double al = q0[s] + e1 * q1[s] + e2 * q2[s] + e3 * q3[s];
-      const double ar = r0[s] + e1 * r1[s] + e2 * r2[s] + e3 * r3[s];
+      const double al = QL ? qa[s][l] : fma(e3, qa[s][3], fma(e2, qa[s][2], fma(e1, qa[s][1], qa[s][0])));
+      const double ar = RL ? ra[s][l] : fma(e3, ra[s][3], fma(e2, ra[s][2], fma(e1, ra[s][1], ra[s][0])));
       ab[s][l] = al * ar;
     }
   }
   double v[NS][4];
   #pragma unroll
-  for (int m = 0; m < 4; m++) {                       // (C) one column of EV for all sites; same summation order over l
+  for (int m = 0; m < 4; m++) {                       // (C) one column of EV for all sites
     const double f0 = EV_(0 * 4 + m), f1 = EV_(1 * 4 + m), f2 = EV_(2 * 4 + m), f3 = EV_(3 * 4 + m);
     #pragma unroll
-    for (int s = 0; s < NS; s++) {
-      double t = 0.0;
-      t += ab[s][0] * f0; t += ab[s][1] * f1; t += ab[s][2] * f2; t += ab[s][3] * f3;
-      v[s][m] = t;
-    }
+    for (int s = 0; s < NS; s++)
+      v[s][m] = fma(ab[s][3], f3, fma(ab[s][2], f2, fma(ab[s][1], f1, ab[s][0] * f0)));
   }
   unsigned int cnt = 0;
   double *const dst = a.clv + en.poff;
   #pragma unroll
   for (int s = 0; s < NS; s++) {
-    if (RS != 0) {
-      const bool small = fabs(v[s][0]) < kMinLikelihood && fabs(v[s][1]) < kMinLikelihood &&
-                         fabs(v[s][2]) < kMinLikelihood && fabs(v[s][3]) < kMinLikelihood;
-      const unsigned int b = __ballot_sync(0xffffffffu, small);
-      if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {
+    if (RS != 0) {                           // TIP_TIP is never rescaled (avxLikelihood.c:87-160)
+      const unsigned int b = __ballot_sync(0xffffffffu, all_tiny(v[s]));
+      if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {            // all 16 values of the site are tiny
         #pragma unroll
         for (int m = 0; m < 4; m++) v[s][m] *= kTwoToThe256;
         if (c == 0 && valid[s]) cnt += (unsigned int)a.wgt[eoff[s] >> 4];
@@ -216,6 +183,49 @@ void launch_dtab(const DtabArgs &a, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------------------------------
+// DNA GAMMA, few partitions: d-table row AND the tip look-up tables of one (entry, partition) per block.
+//   lut[e][pc][side][code][c][l] = sum_j P_c,side[l][j] * tipVector[code][j],   P[l][j] = EI[l][j] * d[c][side][j], P[l][0] = 1
+// -- what the reference tabulates per node as umpX1 / umpX2 (avxLikelihood.c:93-118, 168-187): a tip child then costs the
+// traverse kernel one 32-byte load instead of 15 flops.  Same operation order as the in-kernel contraction.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dna_tables_kernel(const DtabArgs a)
+{
+  __shared__ double d[32], EI[16], tip[64];
+  const int tid = threadIdx.x;
+  const int pc = blockIdx.x % a.nparts_cls, e = blockIdx.x / a.nparts_cls;
+  const double *model = a.models + (size_t)pc * kDnaModelDoubles;   // EIGN[4] rates[4] EI[16] EV[16] tip[64]
+  if (tid < 32) {
+    const int c = tid >> 3, side = (tid >> 2) & 1, k = tid & 3;
+    const int slot = a.nbranches > 1 ? a.cls_part_global[pc] : 0;
+    const double lz = side ? a.lzr[(size_t)e * a.nbranches + slot] : a.lzq[(size_t)e * a.nbranches + slot];
+    const double v = !k ? 1.0 : exp(model[4 + c] * (model[k] * lz));       // makeP newviewGenericSpecial.c:95-112
+    d[tid] = v;
+    a.dtab[((size_t)e * a.nparts_cls + pc) * kDnaDtabRow + tid] = v;
+  } else if (tid < 48) EI[tid - 32] = model[8 + tid - 32];
+  else if (tid >= 64 && tid < 128) tip[tid - 64] = model[40 + tid - 64];
+  if (e < a.first) return;                       // the branch entry has no children to tabulate (uniform per block)
+  const int tc = a.entries[e].tipCase;
+  if (tc == 2) return;
+  __syncthreads();
+  const int code = tid >> 4, c = (tid >> 2) & 3, l = tid & 3;
+  const double *tv = tip + 4 * code;
+  double *out = a.lut + ((size_t)e * a.nparts_cls + pc) * kDnaLutRow + tid;
+  #pragma unroll
+  for (int side = 0; side < 2; side++) {
+    if (side == 1 && tc != 0) break;
+    const double *dd = d + c * 8 + side * 4;
+    out[side * 256] = fma(EI[l * 4 + 3], dd[3] * tv[3], fma(EI[l * 4 + 2], dd[2] * tv[2], fma(EI[l * 4 + 1], dd[1] * tv[1], tv[0])));
+  }
+}
+
+void launch_dna_tables(const DtabArgs &a, cudaStream_t s)
+{
+  const int blocks = a.count * a.nparts_cls;
+  if (blocks > 0) dna_tables_kernel<<<blocks, 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Fused traversal: newviews [first, count) for this tile, then (optionally) evaluate or the sum table
 // at the branch described by entry 0.   NS = sites per thread (tile chunk = 64*NS sites).
 //
@@ -224,7 +234,7 @@ void launch_dtab(const DtabArgs &a, cudaStream_t s)
 // (TMA, 1-D) per row, all completing on a single mbarrier -- the only cold HBM reads of the kernel
 // are issued up front and in bulk instead of one dependent byte load per entry.
 // ------------------------------------------------------------------------------------------------------
-template <int NS, bool PARAM, int MINB, int SPEC>
+template <int NS, bool PARAM, int MINB, bool LUT>
 __global__ void __launch_bounds__(kThreads, MINB)
 traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
 {
@@ -249,11 +259,11 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
   }
-#define EI_(i) (PARAM ? kc.EI[i] : sh.EI[i])
-#define EV_(i) (PARAM ? kc.EV[i] : sh.EV[i])
 
   const double *drow = a.dtab + ((size_t)tile.part_cls * 4 + c) * 8;       // + e * nparts_cls * 32
   const size_t dstride = (size_t)a.nparts_cls * kDnaDtabRow;
+  const double *lrow = LUT ? a.lut + (size_t)tile.part_cls * kDnaLutRow + c * 4 : nullptr;   // + e * nparts_cls * 512 (+ 256: r side)
+  const size_t lstride = (size_t)a.nparts_cls * kDnaLutRow;
   double acc = 0.0;
   uint32_t phase = 0;
 
@@ -270,7 +280,6 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
       eoff[s] = ((size_t)tile.site0 + chunk0 + lsite[s]) * 16 + c * 4;
     }
     double carry[NS][4];
-    long long carry_node = -1;                 // poff of the entry whose CLV sits in carry[]
     #pragma unroll
     for (int s = 0; s < NS; s++) { carry[s][0] = carry[s][1] = carry[s][2] = carry[s][3] = 0.0; }
 
@@ -278,79 +287,26 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
     int w0 = a.first;
     do {
     const int w1 = min(w0 + kWindow, a.count);
-    stage_window<TS>(dyn, &mbar, phase, a, N, 16, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
-                     w0 == a.first && a.mode != MODE_NEWVIEW);
+    phase = stage_window<TS>(dyn, &mbar, phase, a.entries, a.tips, a.mxtips, N, 16, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
+                     a.first, a.count, w0 == a.first && a.mode != MODE_NEWVIEW);
     for (int e = w0; e < w1; e++) {
       const SEntry en = ents[e - w0];
-      double dq[4], dr[4];
-      ld256_ro(drow + (size_t)e * dstride, dq);
-      ld256_ro(drow + (size_t)e * dstride + 4, dr);
-
+      const double *drow_e = drow + (size_t)e * dstride;
+      const double *lut_e = LUT ? lrow + (size_t)e * lstride : nullptr;
       const bool q_inner = en.tipCase == 2, r_inner = en.tipCase != 0;
-      const bool q_carry = q_inner && en.qoff == carry_node, r_carry = r_inner && en.roff == carry_node;
-
-      if constexpr (SPEC != 0) {
-        const int qs = !q_inner ? 0 : (q_carry ? 1 : 2), rs = !r_inner ? 0 : (r_carry ? 1 : 2);
-        unsigned int cnt;
-#define DNA_ENTRY(QS, RS) (SPEC == 2 ? dna_entry_staged<QS, RS, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane) \
-                                     : dna_entry<QS, RS, NS, PARAM>(carry, a, kc, sh, stips, en, dq, dr, eoff, valid, lsite, c, lane))
-        switch (qs * 3 + rs) {                   // block-uniform
-        case 0:  cnt = DNA_ENTRY(0, 0); break;
-        case 1:  cnt = DNA_ENTRY(0, 1); break;
-        case 2:  cnt = DNA_ENTRY(0, 2); break;
-        case 5:  cnt = DNA_ENTRY(1, 2); break;
-        case 7:  cnt = DNA_ENTRY(2, 1); break;
-        default: cnt = DNA_ENTRY(2, 2); break;
-        }
+      const bool q_carry = en.flags & kFlagCarryA, r_carry = en.flags & kFlagCarryB;
+      const int qs = !q_inner ? 0 : (q_carry ? 1 : 2), rs = !r_inner ? 0 : (r_carry ? 1 : 2);
+      unsigned int cnt;
+#define DNA_ENTRY(QS, RS) dna_entry<QS, RS, NS, PARAM, LUT>(carry, a, kc, sh, stips, en, drow_e, lut_e, eoff, valid, lsite, c, lane)
+      switch (qs * 3 + rs) {                   // block-uniform
+      case 0:  cnt = DNA_ENTRY(0, 0); break;
+      case 1:  cnt = DNA_ENTRY(0, 1); break;
+      case 2:  cnt = DNA_ENTRY(0, 2); break;
+      case 5:  cnt = DNA_ENTRY(1, 2); break;
+      case 7:  cnt = DNA_ENTRY(2, 1); break;
+      default: cnt = DNA_ENTRY(2, 2); break;
+      }
 #undef DNA_ENTRY
-        carry_node = en.poff;
-        if (r_inner && __any_sync(0xffffffffu, cnt != 0)) {
-          const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
-          if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
-        }
-        continue;
-      }
-      // gather the children of all NS sites first (independent loads in flight together)
-      double x1[NS][4], x2[NS][4];
-      #pragma unroll
-      for (int s = 0; s < NS; s++) {
-        if (q_carry) { x1[s][0] = carry[s][0]; x1[s][1] = carry[s][1]; x1[s][2] = carry[s][2]; x1[s][3] = carry[s][3]; }
-        else if (q_inner) ld256(a.clv + en.qoff + eoff[s], x1[s]);
-        else { const double *tv = &sh.tip[4 * stips[en.qoff + lsite[s]]]; x1[s][0] = tv[0]; x1[s][1] = tv[1]; x1[s][2] = tv[2]; x1[s][3] = tv[3]; }
-        if (r_carry) { x2[s][0] = carry[s][0]; x2[s][1] = carry[s][1]; x2[s][2] = carry[s][2]; x2[s][3] = carry[s][3]; }
-        else if (r_inner) ld256(a.clv + en.roff + eoff[s], x2[s]);
-        else { const double *tv = &sh.tip[4 * stips[en.roff + lsite[s]]]; x2[s][0] = tv[0]; x2[s][1] = tv[1]; x2[s][2] = tv[2]; x2[s][3] = tv[3]; }
-      }
-
-      unsigned int cnt = 0;
-      #pragma unroll
-      for (int s = 0; s < NS; s++) {
-        // a[l] = sum_j P[l][j] x[j], P[l][j] = d[j] * EI[l][j], P[l][0] = 1  (newviewGenericSpecial.c:118-129)
-        const double tq1 = dq[1] * x1[s][1], tq2 = dq[2] * x1[s][2], tq3 = dq[3] * x1[s][3];
-        const double tr1 = dr[1] * x2[s][1], tr2 = dr[2] * x2[s][2], tr3 = dr[3] * x2[s][3];
-        double v[4] = {0.0, 0.0, 0.0, 0.0};
-        #pragma unroll
-        for (int l = 0; l < 4; l++) {
-          const double al = x1[s][0] + EI_(l * 4 + 1) * tq1 + EI_(l * 4 + 2) * tq2 + EI_(l * 4 + 3) * tq3;
-          const double ar = x2[s][0] + EI_(l * 4 + 1) * tr1 + EI_(l * 4 + 2) * tr2 + EI_(l * 4 + 3) * tr3;
-          const double ab = al * ar;
-          #pragma unroll
-          for (int m = 0; m < 4; m++) v[m] += ab * EV_(l * 4 + m);
-        }
-        if (r_inner) {                         // TIP_TIP is never rescaled (avxLikelihood.c:87-160)
-          const bool small = fabs(v[0]) < kMinLikelihood && fabs(v[1]) < kMinLikelihood &&
-                             fabs(v[2]) < kMinLikelihood && fabs(v[3]) < kMinLikelihood;
-          const unsigned int b = __ballot_sync(0xffffffffu, small);
-          if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {          // all 16 values of the site are tiny
-            #pragma unroll
-            for (int m = 0; m < 4; m++) v[m] *= kTwoToThe256;
-            if (c == 0 && valid[s]) cnt += (unsigned int)a.wgt[eoff[s] >> 4];
-          }
-        }
-        if (valid[s]) st256(a.clv + en.poff + eoff[s], v);
-        carry[s][0] = v[0]; carry[s][1] = v[1]; carry[s][2] = v[2]; carry[s][3] = v[3];
-      }
-      carry_node = en.poff;
       if (r_inner && __any_sync(0xffffffffu, cnt != 0)) {
         const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
@@ -362,8 +318,8 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
 
     // ---------------- branch (entry 0): evaluate or sum table ----------------
     const SEntry br = ents[kWindow];
-    const bool ptip = br.ptip_qtip & 1, qtip = br.ptip_qtip & 2;
-    const bool p_carry = !ptip && br.poff == carry_node, q_carry = !qtip && br.qoff == carry_node;
+    const bool ptip = br.flags & kFlagPTip, qtip = br.flags & kFlagQTip;
+    const bool p_carry = br.flags & kFlagCarryA, q_carry = br.flags & kFlagCarryB;
     double diag[4];
     ld256_ro(drow, diag);                      // row 0, q side: calcDiagptable (diag[0] = 1)
 
@@ -391,8 +347,6 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
       }
     }
   }
-#undef EI_
-#undef EV_
 
   if (a.mode == MODE_EVALUATE) {
     const double tot = block_sum(acc, sh.red);
@@ -444,13 +398,12 @@ traverse_dna_cat_kernel(const TraverseArgs a, const DnaConsts kc)
     const int cat = a.rate_cat[site];
     const double *drow = a.dtab + ((size_t)tile.part_cls * a.max_cats + cat) * 8;    // + e * dstride; q side +0, r side +4
     double carry[4] = {0.0, 0.0, 0.0, 0.0};
-    long long carry_node = -1;
 
     int w0 = a.first;
     do {
     const int w1 = min(w0 + kWindow, a.count);
-    stage_window<TS>(dyn, &mbar, phase, a, N, 4, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
-                     w0 == a.first && a.mode != MODE_NEWVIEW);
+    phase = stage_window<TS>(dyn, &mbar, phase, a.entries, a.tips, a.mxtips, N, 4, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
+                     a.first, a.count, w0 == a.first && a.mode != MODE_NEWVIEW);
     for (int e = w0; e < w1; e++) {
       const SEntry en = ents[e - w0];
       double dq[4], dr[4];
@@ -458,10 +411,10 @@ traverse_dna_cat_kernel(const TraverseArgs a, const DnaConsts kc)
       ld256_ro(drow + (size_t)e * dstride + 4, dr);
       const bool q_inner = en.tipCase == 2, r_inner = en.tipCase != 0;
       double x1[4], x2[4];
-      if (q_inner && en.qoff == carry_node) { x1[0] = carry[0]; x1[1] = carry[1]; x1[2] = carry[2]; x1[3] = carry[3]; }
+      if (en.flags & kFlagCarryA) { x1[0] = carry[0]; x1[1] = carry[1]; x1[2] = carry[2]; x1[3] = carry[3]; }
       else if (q_inner) ld256(a.clv + en.qoff + eoff, x1);
       else { const double *tv = &sh.tip[4 * stips[en.qoff + lsite]]; x1[0] = tv[0]; x1[1] = tv[1]; x1[2] = tv[2]; x1[3] = tv[3]; }
-      if (r_inner && en.roff == carry_node) { x2[0] = carry[0]; x2[1] = carry[1]; x2[2] = carry[2]; x2[3] = carry[3]; }
+      if (en.flags & kFlagCarryB) { x2[0] = carry[0]; x2[1] = carry[1]; x2[2] = carry[2]; x2[3] = carry[3]; }
       else if (r_inner) ld256(a.clv + en.roff + eoff, x2);
       else { const double *tv = &sh.tip[4 * stips[en.roff + lsite]]; x2[0] = tv[0]; x2[1] = tv[1]; x2[2] = tv[2]; x2[3] = tv[3]; }
 
@@ -492,18 +445,17 @@ traverse_dna_cat_kernel(const TraverseArgs a, const DnaConsts kc)
       }
       if (valid) st256(a.clv + en.poff + eoff, v);
       carry[0] = v[0]; carry[1] = v[1]; carry[2] = v[2]; carry[3] = v[3];
-      carry_node = en.poff;
     }
     } while ((w0 += kWindow) < a.count);
     if (a.mode == MODE_NEWVIEW) continue;
 
     const SEntry br = ents[kWindow];
-    const bool ptip = br.ptip_qtip & 1, qtip = br.ptip_qtip & 2;
+    const bool ptip = br.flags & kFlagPTip, qtip = br.flags & kFlagQTip;
     double xa[4], xb[4];
-    if (!ptip && br.poff == carry_node) { xa[0] = carry[0]; xa[1] = carry[1]; xa[2] = carry[2]; xa[3] = carry[3]; }
+    if (br.flags & kFlagCarryA) { xa[0] = carry[0]; xa[1] = carry[1]; xa[2] = carry[2]; xa[3] = carry[3]; }
     else if (!ptip) ld256(a.clv + br.poff + eoff, xa);
     else { const double *tv = &sh.tip[4 * stips[br.poff + lsite]]; xa[0] = tv[0]; xa[1] = tv[1]; xa[2] = tv[2]; xa[3] = tv[3]; }
-    if (!qtip && br.qoff == carry_node) { xb[0] = carry[0]; xb[1] = carry[1]; xb[2] = carry[2]; xb[3] = carry[3]; }
+    if (br.flags & kFlagCarryB) { xb[0] = carry[0]; xb[1] = carry[1]; xb[2] = carry[2]; xb[3] = carry[3]; }
     else if (!qtip) ld256(a.clv + br.qoff + eoff, xb);
     else { const double *tv = &sh.tip[4 * stips[br.qoff + lsite]]; xb[0] = tv[0]; xb[1] = tv[1]; xb[2] = tv[2]; xb[3] = tv[3]; }
     if (a.mode == MODE_SUM) {
@@ -550,73 +502,49 @@ size_t traverse_dna_smem(int ns)
   return (size_t)(kWindow + 1) * sizeof(SEntry) + (size_t)(2 * kWindow + 2) * 64 * ns;
 }
 
-template <int NS, bool PARAM, int MINB, int SPEC>
-static void launch_spec(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
+template <int NS, bool PARAM, int MINB, bool LUT>
+static void launch_variant(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
 {
   const size_t smem = traverse_dna_smem(NS);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(traverse_dna_kernel<NS, PARAM, MINB, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(227 * 1024 - 2048, std::max<size_t>(smem, 64 * 1024)));
-    configured = std::max<size_t>(smem, 64 * 1024);
-  }
-  traverse_dna_kernel<NS, PARAM, MINB, SPEC><<<ntiles, kThreads, smem, s>>>(a, kc);
+  static size_t configured[kMaxDevices];
+  ensure_dynamic_smem(traverse_dna_kernel<NS, PARAM, MINB, LUT>, std::min<size_t>(227 * 1024 - 2048, std::max<size_t>(smem, 64 * 1024)), configured);
+  traverse_dna_kernel<NS, PARAM, MINB, LUT><<<ntiles, kThreads, smem, s>>>(a, kc);
 }
 
-template <int NS, bool PARAM, int MINB>
-static void launch_minb(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
+// NS sites per thread: 4 for full tiles (128 registers, 2 CTAs per SM), fewer for small tiles (3 CTAs per SM)
+template <int NS, int MINB>
+static void launch_ns(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
 {
-  // default: the entry body compiled once per child-source combination (dna_entry<QS,RS>): ~460 instead of ~600
-  // instructions per warp and entry, 6.0 -> 5.5 ms per traversal on the bench workload.  EXB_DNA_SPEC=0 selects the
-  // single body with run-time source selection (kept for comparison).
-  static int spec = -1;
-  if (spec < 0) { const char *v = getenv("EXB_DNA_SPEC"); spec = v ? atoi(v) : 1; }
-  if (spec == 2)  launch_spec<NS, PARAM, MINB, 2>(a, kc, ntiles, s);     // staged body, opt-in (see dna_entry_staged)
-  else if (spec)  launch_spec<NS, PARAM, MINB, 1>(a, kc, ntiles, s);
-  else            launch_spec<NS, PARAM, MINB, 0>(a, kc, ntiles, s);
-}
-
-template <int NS, bool PARAM>
-static void launch_one(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
-{
-  static int minb = -1;                          // development knob: EXB_DNA_MINB = 2 | 3 (CTAs per SM the registers are budgeted for)
-  if (minb < 0) { const char *v = getenv("EXB_DNA_MINB"); minb = v ? atoi(v) : (NS >= 4 ? 2 : 3); }
-  if (minb <= 2) launch_minb<NS, PARAM, 2>(a, kc, ntiles, s);
-  else           launch_minb<NS, PARAM, 3>(a, kc, ntiles, s);
-}
-
-template <int NS>
-static void launch_ns(const TraverseArgs &a, const DnaConsts *kc, int ntiles, cudaStream_t s)
-{
-  if (kc) launch_one<NS, true>(a, *kc, ntiles, s);
-  else {
-    DnaConsts none;
-    memset(&none, 0, sizeof none);
-    launch_one<NS, false>(a, none, ntiles, s);
-  }
+  if (a.lut) launch_variant<NS, true, MINB, true>(a, kc, ntiles, s);
+  else       launch_variant<NS, true, MINB, false>(a, kc, ntiles, s);
 }
 
 void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *kc, int ntiles, cudaStream_t s)
 {
   if (ntiles <= 0) return;
+  if (!kc) {                                     // many partitions: EI / EV from shared memory (a row / column at a time)
+    DnaConsts none;
+    memset(&none, 0, sizeof none);
+    static int ns_many = -1;                     // development knob: EXB_DNA_NS_MANY = 1 | 2 | 4 sites per thread
+    if (ns_many < 0) { const char *v = getenv("EXB_DNA_NS_MANY"); ns_many = v ? atoi(v) : 4; }
+    if (a.tile_sites <= 64 || ns_many == 1)       launch_variant<1, false, 3, false>(a, none, ntiles, s);
+    else if (a.tile_sites <= 128 || ns_many == 2) launch_variant<2, false, 3, false>(a, none, ntiles, s);
+    else                                          launch_variant<4, false, 2, false>(a, none, ntiles, s);
+    return;
+  }
   // chunk = 64*NS sites
-  int ns = a.tile_sites <= 64 ? 1 : (a.tile_sites <= 128 ? 2 : 4);
-  if (!kc) ns = 1;                               // shared-memory constants: one site per thread keeps the registers in budget
-  if (ns == 1) launch_ns<1>(a, kc, ntiles, s);
-  else if (ns == 2) launch_ns<2>(a, kc, ntiles, s);
-  else launch_ns<4>(a, kc, ntiles, s);
+  if (a.tile_sites <= 64)       launch_ns<1, 3>(a, *kc, ntiles, s);
+  else if (a.tile_sites <= 128) launch_ns<2, 3>(a, *kc, ntiles, s);
+  else                          launch_ns<4, 2>(a, *kc, ntiles, s);
 }
 void launch_traverse_dna_cat(const TraverseArgs &a, const DnaConsts *kc, int ntiles, cudaStream_t s)
 {
   if (ntiles <= 0) return;
   const size_t smem = window_smem_bytes<256>();
-  static size_t configured[2] = {0, 0};
-  const int v = kc ? 1 : 0;
-  if (smem > configured[v]) {
-    const size_t want = std::min<size_t>(227 * 1024 - 2048, std::max<size_t>(smem, 64 * 1024));
-    if (kc) cudaFuncSetAttribute(traverse_dna_cat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
-    else    cudaFuncSetAttribute(traverse_dna_cat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
-    configured[v] = want;
-  }
+  static size_t configured[2][kMaxDevices];
+  const size_t want = std::min<size_t>(227 * 1024 - 2048, std::max<size_t>(smem, 64 * 1024));
+  if (kc) ensure_dynamic_smem(traverse_dna_cat_kernel<true>, want, configured[1]);
+  else    ensure_dynamic_smem(traverse_dna_cat_kernel<false>, want, configured[0]);
   if (kc) traverse_dna_cat_kernel<true><<<ntiles, kThreads, smem, s>>>(a, *kc);
   else {
     DnaConsts none;

@@ -7,9 +7,13 @@
 // barrier, block 0 reduces tile partials per partition in fixed order and advances the per-branch-slot state machine
 // (identical to the host code: curvature guard z = 0.37 z + 0.63, step z *= exp(-d1/d2) with the 0.25 zprev + 0.75
 // cap, |z - zprev| <= zstep, the -20 give-up), another barrier, until every slot has converged.
-// Single rank only (the multi-rank path keeps the host loop with one NCCL all-reduce per iteration).
+// Several ranks on one node: after the per-partition reduction block 0 stores this rank's 2P sums into every peer's
+// receive buffer (CUDA-IPC over NVLink, p2p.cuh), waits for the peers' rows and adds them in rank order -- every rank
+// then advances an identical state machine with identical inputs, so all ranks leave the loop in the same iteration.
+// No host round trip per iteration on any rank (the reference: one MPI_Allreduce per iteration, :1241-1248).
 #include "engine.cuh"
 #include "core_tile.cuh"
+#include "p2p.cuh"
 
 namespace exb {
 
@@ -108,9 +112,19 @@ newton_raphson_kernel(const NrArgs a)
     }
     grid_barrier(a.barrier, gen);
 
-    // ---- block 0: partitions -> slots, NR update ----
+    // ---- block 0: (all-reduce over the ranks,) partitions -> slots, NR update ----
     if (blockIdx.x == 0) {
-      if (tid == 0) {
+      bool peers_ok = true;
+      if (a.x.nranks > 1) {
+        const unsigned int xs = a.xseq0 + 1u + (unsigned int)st->iterations;
+        const size_t row = p2p_row(a.x, xs, a.x.rank, 2 * P);
+        for (int r = 0; r < a.x.nranks; r++)
+          for (int i = tid; i < 2 * P; i += kThreads) a.x.peer_buf[r][row + i] = a.part_out[i];
+        peers_ok = p2p_finish_exchange(a.x, xs, 2 * P, 2 * P, a.part_out, nullptr);
+        if (tid == 0) st->xseq = xs;
+      }
+      if (tid == 0 && !peers_ok) { st->peer_lost = 1; st->iterations += 1; st->all_done = 1; }
+      if (tid == 0 && peers_ok) {
         // partitions -> slots in partition order (makenewzGenericSpecial.c:921-946)
         for (int i = 0; i < nb; i++) { st->d1[i] = 0.0; st->d2[i] = 0.0; }
         for (int m = 0; m < P; m++) {

@@ -18,10 +18,14 @@ constexpr int kWindow = 96;                  // entries per window
 
 struct SEntry {            // a traversal entry as the threads consume it (32 B)
   int tipCase;             // -1 for the branch entry
-  int ptip_qtip;           // branch entry only: bit0 = p is a tip, bit1 = q is a tip
+  int flags;               // kFlag*: which operand is a tip (branch entry) / sits in the carry registers
   long long poff, qoff, roff;   // inner node: element offset of its CLV (node_index * N * span, unique per node);
                                 // tip: byte offset of its staged row inside the window's tip area
 };
+
+// branch entry: p / q is a tip.  Any entry: the operand is the CLV the previous entry of this call produced, i.e. it is
+// still in the thread's carry registers (newview entries: q / r; branch entry: p / q).
+constexpr int kFlagPTip = 1, kFlagQTip = 2, kFlagCarryA = 4, kFlagCarryB = 8;
 
 __device__ __forceinline__ uint32_t stage_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
@@ -57,13 +61,16 @@ __host__ __device__ constexpr size_t window_smem_bytes()
 }
 
 // Stage entries [w0, w1) (slots 0 .. w1-w0-1) and, when `with_branch`, the branch entry 0 (slot kWindow).
-// Must be called by every thread of the CTA; ends with all staged data visible to all threads.
+// Must be called by every thread of the CTA; ends with all staged data visible to all threads.  Returns the mbarrier
+// phase for the next call.  Takes plain values (not the kernel's argument struct) so that nothing of the caller has to
+// live in local memory for this non-inlined call.
 //   dyn      : dynamic shared memory base (window_smem_bytes<TSB>() bytes, 16-byte aligned)
 //   span_el  : doubles per site in a CLV (node stride = N * span_el)
+//   first, count : the call's newview entries are [first, count) -- carry flags look at the predecessor entry
 template <int TSB>
-__device__ __noinline__ void stage_window(unsigned char *dyn, uint64_t *mbar, uint32_t &phase, const TraverseArgs &a,
-                                             size_t N, int span_el, size_t chunk_site0, unsigned nchunk,
-                                             int w0, int w1, bool with_branch)
+__device__ __noinline__ uint32_t stage_window(unsigned char *dyn, uint64_t *mbar, uint32_t phase, const DevEntry *entries,
+                                              const uint8_t *tips, int mxtips, size_t N, int span_el, size_t chunk_site0,
+                                              unsigned nchunk, int w0, int w1, int first, int count, bool with_branch)
 {
   SEntry *ents = reinterpret_cast<SEntry *>(dyn);
   uint8_t *stips = dyn + (size_t)(kWindow + 1) * sizeof(SEntry);
@@ -71,27 +78,31 @@ __device__ __noinline__ void stage_window(unsigned char *dyn, uint64_t *mbar, ui
   __syncthreads();                             // the previous window's readers are done with ents / stips
   for (int j = tid; j < (w1 - w0) + (with_branch ? 1 : 0); j += blockDim.x) {
     const bool is_branch = j == (w1 - w0);
-    const DevEntry en = a.entries[is_branch ? 0 : w0 + j];
+    const DevEntry en = entries[is_branch ? 0 : w0 + j];
     const int slot = is_branch ? kWindow : j;
+    // the node whose CLV the threads still hold when this entry is processed: the previous newview entry's parent
+    const int prev = is_branch ? (count > first ? entries[count - 1].p : -1) : (w0 + j > first ? entries[w0 + j - 1].p : -1);
     SEntry se;
     se.tipCase = is_branch ? -1 : en.tipCase;
-    se.ptip_qtip = (en.p <= a.mxtips ? 1 : 0) | (en.q <= a.mxtips ? 2 : 0);
+    if (is_branch) se.flags = (en.p <= mxtips ? kFlagPTip : 0) | (en.q <= mxtips ? kFlagQTip : 0) |
+                              (en.p == prev ? kFlagCarryA : 0) | (en.q == prev ? kFlagCarryB : 0);
+    else           se.flags = (en.q == prev ? kFlagCarryA : 0) | (en.r == prev ? kFlagCarryB : 0);
     // tips: q uses row 2*slot, r (or a tip p of the branch entry) row 2*slot+1
-    se.poff = en.p > a.mxtips ? (long long)(en.p - a.mxtips - 1) * (long long)N * span_el : (long long)(2 * slot + 1) * TSB;
-    se.qoff = en.q > a.mxtips ? (long long)(en.q - a.mxtips - 1) * (long long)N * span_el : (long long)(2 * slot) * TSB;
-    se.roff = en.r > a.mxtips ? (long long)(en.r - a.mxtips - 1) * (long long)N * span_el : (long long)(2 * slot + 1) * TSB;
+    se.poff = en.p > mxtips ? (long long)(en.p - mxtips - 1) * (long long)N * span_el : (long long)(2 * slot + 1) * TSB;
+    se.qoff = en.q > mxtips ? (long long)(en.q - mxtips - 1) * (long long)N * span_el : (long long)(2 * slot) * TSB;
+    se.roff = en.r > mxtips ? (long long)(en.r - mxtips - 1) * (long long)N * span_el : (long long)(2 * slot + 1) * TSB;
     ents[slot] = se;
   }
   __syncthreads();
   if (tid < 32) {
     const uint32_t bytes = (nchunk + 15u) & ~15u;
-    const uint8_t *gsrc = a.tips + chunk_site0;
+    const uint8_t *gsrc = tips + chunk_site0;
     const int n = (w1 - w0) + (with_branch ? 1 : 0);
     int mine = 0;
     for (int j = lane; j < n; j += 32) {
       const bool is_branch = j == (w1 - w0);
-      const DevEntry en = a.entries[is_branch ? 0 : w0 + j];
-      if (is_branch) mine += (en.p <= a.mxtips) + (en.q <= a.mxtips);
+      const DevEntry en = entries[is_branch ? 0 : w0 + j];
+      if (is_branch) mine += (en.p <= mxtips) + (en.q <= mxtips);
       else           mine += (en.tipCase <= 1) + (en.tipCase == 0);
     }
     const int total = __reduce_add_sync(0xffffffffu, mine);
@@ -99,11 +110,11 @@ __device__ __noinline__ void stage_window(unsigned char *dyn, uint64_t *mbar, ui
     __syncwarp();
     for (int j = lane; j < n; j += 32) {
       const bool is_branch = j == (w1 - w0);
-      const DevEntry en = a.entries[is_branch ? 0 : w0 + j];
+      const DevEntry en = entries[is_branch ? 0 : w0 + j];
       const int slot = is_branch ? kWindow : j;
       if (is_branch) {
-        if (en.p <= a.mxtips) bulk_g2s(stips + (size_t)(2 * slot + 1) * TSB, gsrc + (size_t)(en.p - 1) * N, bytes, mbar);
-        if (en.q <= a.mxtips) bulk_g2s(stips + (size_t)(2 * slot) * TSB, gsrc + (size_t)(en.q - 1) * N, bytes, mbar);
+        if (en.p <= mxtips) bulk_g2s(stips + (size_t)(2 * slot + 1) * TSB, gsrc + (size_t)(en.p - 1) * N, bytes, mbar);
+        if (en.q <= mxtips) bulk_g2s(stips + (size_t)(2 * slot) * TSB, gsrc + (size_t)(en.q - 1) * N, bytes, mbar);
       } else {
         if (en.tipCase <= 1) bulk_g2s(stips + (size_t)(2 * slot) * TSB, gsrc + (size_t)(en.q - 1) * N, bytes, mbar);
         if (en.tipCase == 0) bulk_g2s(stips + (size_t)(2 * slot + 1) * TSB, gsrc + (size_t)(en.r - 1) * N, bytes, mbar);
@@ -111,7 +122,7 @@ __device__ __noinline__ void stage_window(unsigned char *dyn, uint64_t *mbar, ui
     }
   }
   mbar_wait(mbar, phase);
-  phase ^= 1;
+  return phase ^ 1u;
 }
 
 }  // namespace exb

@@ -157,8 +157,10 @@ int  exb_core(exb_engine *e, const double *lz, const unsigned char *executeModel
  * and the scalar update stay on the GPU (one cooperative kernel with grid barriers); a single copy brings back
  * result[numBranches] (the new z, in [zmin, zmax]), curvatOK[numBranches] (tr->curvatOK) and the number of
  * iterations (iterationsDone, may be NULL).  z0[numBranches] are the start values (= ti[0] branch values), maxiter as in makenewzGeneric,
- * executeModel[] the initial mask.  Single rank only: with a communicator (exb_comm_init, nranks > 1) it returns
- * EXB_ERR_STATE and the caller runs the loop itself with exb_makenewz_prepare + exb_core. */
+ * executeModel[] the initial mask.  With several ranks on one node (exb_comm_is_p2p) the all-reduce of every iteration
+ * (makenewzGenericSpecial.c:1241-1248) happens inside the same kernel over NVLink peer buffers and every rank returns the
+ * same bits; with a communicator but no peer access (several nodes) it returns EXB_ERR_STATE and the caller runs the
+ * loop itself with exb_makenewz_prepare + exb_core. */
 int  exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
                   const unsigned char *executeModel, const double *z0, int maxiter,
                   double *result, int *curvatOK, int *iterationsDone);
@@ -186,9 +188,8 @@ int  exb_comm_unique_id(void *id_out);
 int  exb_comm_init(exb_engine *e, int rank, int nranks, const void *id);
 /* 1 when the ranks found each other on one node and mapped each other's receive buffers (CUDA IPC over NVLink):
  * the all-reduce then happens inside the finish kernel -- partial sums stored straight into every peer's memory,
- * summed in rank order on every GPU -- and no NCCL call remains on the per-call path (selected with EXB_P2P=1 in
- * the environment of every rank).  0: NCCL all-reduce after the kernel (the default; also several nodes or no
- * peer access). */
+ * summed in rank order on every GPU -- and no NCCL call remains on the per-call path (the default on one node).
+ * 0: NCCL all-reduce after the kernel (several nodes, no peer access, or EXB_P2P=0 in the environment). */
 int  exb_comm_is_p2p(exb_engine *e);
 
 /* ---- introspection (tests, benchmarks) ----------------------------------------------------- */
@@ -203,6 +204,10 @@ int  exb_read_sumtable(exb_engine *e, int model, double *out);
 /* Device time in milliseconds of the kernels of the most recent hot-path call (CUDA events
  * on the engine's stream), and the number of kernel launches the engine has made so far. */
 int  exb_last_kernel_ms(exb_engine *e, float *ms);
+/* The same time split by phase for the most recent traversal call (exb_newview / exb_evaluate / exb_makenewz_prepare):
+ * ms3[0] = d-table and tip look-up kernels (makeP, newviewGenericSpecial.c:78), ms3[1] = the traverse kernels,
+ * ms3[2] = the finish kernel (scaler chain, per-partition reduction, in-kernel all-reduce).  Needs timing on. */
+int  exb_last_phase_ms(exb_engine *e, float *ms3);
 /* Switch the per-call CUDA events off (default on); saves two driver calls per hot-path call. */
 int  exb_set_timing(exb_engine *e, int on);
 long exb_launch_count(exb_engine *e);

@@ -37,6 +37,12 @@ def main():
     want = full.evaluateIterative(ti).copy()
     full.makenewzIterative(tree.partial_traversal(tree.start))
     want_d = full.execCore([np.log(0.7)])
+    # the whole Newton-Raphson loop on one GPU (device kernel) and through the host loop
+    inner = tree.start.back
+    ti_nr = tree.partial_traversal(inner)          # built once: building it re-orients the tree's x flags
+    z0 = list(inner.z)
+    want_z, want_ok, want_it = full.makenewz(ti_nr, z0, 10)
+    host_z = Likelihood(tree, full, len(parts)).makenewzGeneric(inner, inner.back, z0, 10)
     full.close()
 
     # sharded: rank r owns a contiguous slice of every partition (partition 1 is empty everywhere)
@@ -60,12 +66,28 @@ def main():
             d = eng.execCore([np.log(0.7)])
             stable = stable and d[0][0] == got_d[0][0] and d[1][0] == got_d[1][0]
     mode = "p2p-in-kernel" if eng.comm_is_p2p() else "nccl"
+    # device-resident Newton-Raphson across the ranks (one in-kernel exchange per iteration): same decisions as on one
+    # GPU, same bits on every rank, and the ordinary calls keep working afterwards (the exchange counter moved on)
+    nr_ok, got_z, got_it = True, np.zeros(1), -1
+    if eng.comm_is_p2p():
+        got_z, got_ok, got_it = eng.makenewz(ti_nr, z0, 10)
+        nr_ok = got_it == want_it and abs(got_z[0] - want_z[0]) <= 1e-9 * want_z[0] and abs(got_z[0] - host_z[0]) <= 1e-9 * host_z[0]
+        for _ in range(3):
+            z2, _, it2 = eng.makenewz(ti_nr, z0, 10)
+            nr_ok = nr_ok and z2[0] == got_z[0] and it2 == got_it
+        nr_ok = nr_ok and bool(np.array_equal(eng.evaluateIterative(ti), got))
+    else:
+        try:
+            eng.makenewz(ti_nr, z0, 10)
+            nr_ok = False                       # must refuse without peer access
+        except Exception:
+            pass
 
-    ok = stable and bool(np.all(np.abs(got - want) <= 1e-11 * np.maximum(np.abs(want), 1.0)))
+    ok = stable and nr_ok and bool(np.all(np.abs(got - want) <= 1e-11 * np.maximum(np.abs(want), 1.0)))
     ok = ok and abs(got_d[0][0] - want_d[0][0]) <= 1e-9 * max(1.0, abs(want_d[0][0]))
     ok = ok and abs(got_d[1][0] - want_d[1][0]) <= 1e-9 * max(1.0, abs(want_d[1][0]))
     # every rank holds bit-identical results (the all-reduce is part of the call)
-    t = torch.tensor(np.concatenate([got, got_d[0], got_d[1]]), device="cuda")
+    t = torch.tensor(np.concatenate([got, got_d[0], got_d[1], got_z]), device="cuda")
     gathered = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(gathered, t)
     ok = ok and all(torch.equal(gathered[0], g) for g in gathered)
@@ -73,7 +95,8 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if int(flag.item()) else "FAIL", "allreduce", mode, "world", world, "lnL", got.tolist(), "want", want.tolist(),
-              "d", [float(got_d[0][0]), float(got_d[1][0])], "want_d", [float(want_d[0][0]), float(want_d[1][0])])
+              "d", [float(got_d[0][0]), float(got_d[1][0])], "want_d", [float(want_d[0][0]), float(want_d[1][0])],
+              "device NR z", float(got_z[0]), "iterations", got_it, "1-GPU", float(want_z[0]), want_it, "host loop", float(host_z[0]))
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) else 1)
 

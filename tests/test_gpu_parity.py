@@ -376,3 +376,76 @@ def test_many_partitions_shared_memory_constants(cuda_factory, oracle_factory):
     _compare_engines(gpu, cpu, tree, parts)
     mask = np.array([i % 3 != 0 for i in range(len(widths))], dtype=np.uint8)
     _compare_engines(gpu, cpu, tree, parts, mask=mask)
+
+
+# ---- the shapes of BASELINE configs 4 and 5 -----------------------------------------------------------------
+def test_c4_shape_aa_500_taxa_vs_oracle(cuda_factory, oracle_factory):
+    """C4's shape: LG+GAMMA on the 500-taxon bench tree (6 entry windows, DMMA path, scaling fires for AA at this
+    depth), 51 200 sites on the GPU; the oracle checks a site sample -- sites are independent, so the lnL of the
+    first 1 536 sites of the big engine (read through a weight mask) must equal a 1 536-site oracle run."""
+    import bench
+    w = bench.make_workload("aa", 1, sites=51_200)
+    tips = bench.make_sites(w.tree, 0, w.sites, "aa")
+    mc = bench.lg_model(0.5)
+    n = 1536
+    wgt = np.zeros(w.sites, dtype=np.int32)
+    wgt[:n] = 1
+    gpu = cuda_factory(w.taxa, 2, 1)
+    gpu.set_partition(0, 20, np.ones(w.sites, dtype=np.int32), tips)      # all sites, weight 1
+    gpu.set_partition(1, 20, wgt[:4096].copy(), tips[:, :4096].copy())    # the sample again as its own partition (ragged tile)
+    gpu.commit()
+    gpu.set_model(0, mc); gpu.set_model(1, mc)
+    cpu = oracle_factory(w.taxa, 1, 1)
+    cpu.set_partition(0, 20, np.ones(n, dtype=np.int32), tips[:, :n].copy())
+    cpu.set_model(0, mc)
+    got = gpu.evaluateIterative(w.ti)
+    want = cpu.evaluateIterative(w.ti)[0]
+    assert abs(got[1] - want) <= 1e-10 * abs(want), (got[1], want)
+    # CLV of the root's inner node for the sample sites: big partition == small partition == oracle, scalers included
+    root = w.ti[0].qNumber
+    a, b = gpu.read_clv(0, root)[:n], gpu.read_clv(1, root)[:n]
+    c = cpu.read_clv(0, root)
+    assert np.array_equal(a, b)
+    scale = np.abs(c).max(axis=(1, 2), keepdims=True)
+    assert np.all(np.abs(a - c) <= 1e-10 * scale)
+    assert cpu.read_scaler(0, root) > 0, "the AA scaling path must fire at this depth"
+    assert gpu.read_scaler(1, root) == cpu.read_scaler(0, root)
+    # linearity over the site axis: lnL(all) = sum over 4 quarter engines
+    q = w.sites // 4
+    tot = 0.0
+    for k in range(4):
+        e = cuda_factory(w.taxa, 1, 1)
+        e.set_partition(0, 20, np.ones(q, dtype=np.int32), tips[:, k * q:(k + 1) * q].copy())
+        e.commit(); e.set_model(0, mc)
+        tot += e.evaluateIterative(w.ti)[0]
+        e.close()
+    assert abs(tot - got[0]) <= 1e-10 * abs(tot), (tot, got[0])
+
+
+def test_c5_shape_1250_partitions_vs_oracle(cuda_factory, oracle_factory):
+    """C5's per-GPU shape: 1 250 DNA partitions (here x 96 sites to stay small) with per-partition models on the
+    354-taxon tree, masks on; every partition's lnL against the oracle (8 distinct (data, model) combinations)."""
+    import bench
+    w = bench.make_workload("c5", 1)
+    W, P = 96, 1250
+    tips = bench.make_sites(w.tree, 0, 8 * W, "dna")
+    models = [bench.gtr_model(m) for m in range(8)]
+    gpu = cuda_factory(w.taxa, P, 1)
+    for m in range(P):
+        gpu.set_partition(m, 4, np.ones(W, dtype=np.int32), tips[:, (m % 8) * W:(m % 8 + 1) * W].copy())
+    gpu.commit()
+    for m in range(P):
+        gpu.set_model(m, models[(m // 8) % 8])            # data block m % 8, model (m / 8) % 8: 64 combinations
+    cpu = oracle_factory(w.taxa, 64, 1)
+    for j in range(64):
+        cpu.set_partition(j, 4, np.ones(W, dtype=np.int32), tips[:, (j % 8) * W:(j % 8 + 1) * W].copy())
+        cpu.set_model(j, models[j // 8])
+    want64 = cpu.evaluateIterative(w.ti)
+    want = np.array([want64[(m % 8) + 8 * ((m // 8) % 8)] for m in range(P)])
+    got = gpu.evaluateIterative(w.ti).copy()
+    assert np.all(np.abs(got - want) <= 1e-10 * np.abs(want)), np.max(np.abs(got - want) / np.abs(want))
+    # masked: executed partitions recomputed, masked ones untouched (eval:856-859)
+    mask = (np.arange(P) % 3 != 0).astype(np.uint8)
+    out = np.full(P, 7.0)
+    gpu.evaluateIterative(w.ti, mask, out=out)
+    assert np.array_equal(out[mask == 1], got[mask == 1]) and np.all(out[mask == 0] == 7.0)

@@ -21,7 +21,8 @@ import build as hostcheck_build  # noqa: E402
 EXE = hostcheck_build.build()
 pytestmark = pytest.mark.skipif(EXE is None or not os.path.exists(PARSER),
                                 reason="tests/hostcheck/_build/examl-hostcheck or oracle/_ref/parse-examl not built")
-ENV = {"EXAML_B200_HOST_NR": "1"}
+# every workflow runs with the constants guard on: a model change that is not followed by a full traversal would abort
+ENV = {"EXAML_B200_HOST_NR": "1", "EXAML_B200_CHECK_CONSTANTS": "1"}
 
 
 def _rel(a, b):
