@@ -513,9 +513,6 @@ extern "C" int exb_commit(exb_engine *e)
       // AA tip look-up table (optional: skipped when it would not fit comfortably, e.g. thousands of AA partitions)
       const size_t lbytes = (size_t)(e->mxtips + 1) * idx * 2 * 23 * 20 * (e->cat ? e->max_cats : 4) * sizeof(double);
       if (c == CLS_AA && lbytes <= ((size_t)1 << 30) && !getenv("EXB_AA_NO_LUT")) CUDA_TRY(cudaMalloc(&k.lut, lbytes));
-      // DNA GAMMA, few partitions (the constant-bank path): tip look-up table built together with the d-table
-      if (c == CLS_DNA && !e->cat && idx <= kMaxParamPartitions && !getenv("EXB_DNA_NO_LUT"))
-        CUDA_TRY(cudaMalloc(&k.lut, (size_t)(e->mxtips + 1) * idx * kDnaLutRow * sizeof(double)));
     }
     if (n == 0) continue;
     // host images of tips / weights on the class site axis (padding: gap code, weight 0)
@@ -786,16 +783,13 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   rc = flush_models(e);
   if (rc) return rc;
   if (e->timing) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
-  const double *dtab_use[2] = {nullptr, nullptr}, *lut_use[2] = {nullptr, nullptr};
+  const double *dtab_use[2] = {nullptr, nullptr};
   for (int c = 0; c < 2; c++) {                    // tables first: d-table (makeP exponentials), AA tip look-up table
     ClassState &k = e->cls[c];
     if (k.tiles_h.empty()) continue;
     dtab_use[c] = k.dtab;
-    lut_use[c] = k.lut;
-    if (e->host_dtab[c]) {
-      dtab_use[c] = (const double *)(e->stage_use + e->o_dtab[c]);
-      if (c == CLS_DNA) lut_use[c] = nullptr;      // short descriptor: no table launch, tips go through the contraction
-    } else {
+    if (e->host_dtab[c]) dtab_use[c] = (const double *)(e->stage_use + e->o_dtab[c]);
+    else {
       DtabArgs d;
       d.dtab = k.dtab; d.models = k.models; d.cls_part_global = k.part_global;
       d.lzq = (const double *)(e->stage_use + e->o_lzq); d.lzr = (const double *)(e->stage_use + e->o_lzr);
@@ -803,9 +797,7 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
       d.model_doubles = k.model_doubles; d.row = k.dtab_row;
       d.cat_rates = e->cat ? k.cat_rates : nullptr; d.max_cats = e->max_cats;
       d.eign_cat_stride = c == CLS_AA ? 20 : 0; d.rates_off = c == CLS_AA ? kAaRates : k.S; d.lg4_off = c == CLS_AA ? kAaLg4 : -1;
-      d.lut = k.lut; d.entries = (const DevEntry *)(e->stage_use + e->o_entries); d.first = first;
-      if (c == CLS_DNA && k.lut) launch_dna_tables(d, e->stream);
-      else                       launch_dtab(d, e->stream);
+      launch_dtab(d, e->stream);
       e->launches++;
     }
     if (c == CLS_AA && k.lut) {
@@ -823,7 +815,7 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
     ClassState &k = e->cls[c];
     if (k.tiles_h.empty()) continue;
     TraverseArgs a;
-    a.dtab = dtab_use[c]; a.lut = lut_use[c]; a.nparts_cls = k.nparts; a.tile_sites = e->tile_sites;
+    a.dtab = dtab_use[c]; a.lut = k.lut; a.nparts_cls = k.nparts; a.tile_sites = e->tile_sites;
     a.rate_cat = e->cat ? k.rate_cat : nullptr; a.max_cats = e->max_cats; a.dtab_row = k.dtab_row;
     a.tiles = k.tiles; a.clv = k.clv; a.tips = k.tips; a.wgt = k.wgt; a.sum = k.sum; a.models = k.models;
     a.N = k.N; a.mxtips = e->mxtips; a.nparts = e->P; a.nbranches = e->nb;

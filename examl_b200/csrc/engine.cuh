@@ -44,9 +44,6 @@ struct DevEntry { int tipCase, p, q, r; };
 // Row 0 (the branch entry of evaluate) carries the diagonal table of calcDiagptable in its q side.
 constexpr int kDnaDtabRow = 32;
 constexpr int kAaDtabRow  = 160;
-// DNA tip look-up table, built with the d-table when a class holds few partitions (dna_tables_kernel):
-//   row (512 doubles) per (entry, class-partition): [side q/r][16 codes][c][l] = sum_j P[l][j] tipVector[code][j]
-constexpr int kDnaLutRow  = 512;
 
 // CAT / PSR (one rate category per site, axml.h:349): the table has one [2 sides][S] block per category of the
 // partition, row = max_cats * 2 * S, and a site picks its block through rate_cat[site].
@@ -59,8 +56,6 @@ struct DtabArgs {
   int count, nparts_cls, nbranches, states, model_doubles, row, max_cats;
   int eign_cat_stride;       // doubles between the EIGN of consecutive categories (0: shared, DNA; 20: AA)
   int rates_off, lg4_off;    // offsets of gammaRates[4] / the LG4 flag inside a model block (lg4_off < 0: none)
-  // dna_tables_kernel only: the tip look-up table and what it needs to know about the entries
-  double *lut; const DevEntry *entries; int first;
 };
 
 // Everything a traversal kernel needs.  Passed by value (fits the 4 KB parameter space).
@@ -87,8 +82,7 @@ struct TraverseArgs {
   unsigned int *scale_inc;  // [maxEntries][P]  per-entry scaler increments (integer atomics: deterministic)
   double       *tile_out;   // [ntiles][2]      per-tile partial sums (evaluate: lnL; core: d1,d2)
   const double *dtab;       // [count][nparts_cls][row]
-  const double *lut;        // tip look-up table, may be null.  AA: [count][nparts_cls][2 sides][23 codes][4 | max_cats][20] = P(t) * tipVector[code];
-                            // DNA GAMMA: [count][nparts_cls][2 sides][16 codes][4][4]
+  const double *lut;        // AA only, may be null: [count][nparts_cls][2 sides][23 codes][4 | max_cats][20] = P(t) * tipVector[code]
   const int    *rate_cat;   // CAT: [N] rate category of every site; null under GAMMA
   int           max_cats;   // CAT: categories per partition in dtab / lut rows
   int           dtab_row;   // doubles per (entry, partition) in dtab
@@ -213,7 +207,6 @@ void launch_partial(const PartialArgs &a, int states, int blocks, cudaStream_t s
 int partial_max_blocks(int states, int device);
 
 void launch_dtab(const DtabArgs &a, cudaStream_t s);
-void launch_dna_tables(const DtabArgs &a, cudaStream_t s);
 void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
 void launch_traverse_dna_cat(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
 void launch_core_dna(const CoreArgs &a, int ntiles, cudaStream_t s);

@@ -69,46 +69,47 @@ __device__ __forceinline__ bool all_tiny(const double (&v)[4])
   return max(max(h0, h1), max(h2, h3)) < 0x2FF00000u;
 }
 
+// cp.async (LDGSTS): 32 bytes global -> this thread's slot of the prefetch ring, no registers, L2-only caching
+__device__ __forceinline__ void async_copy32(void *smem_dst, const void *gsrc)
+{
+  const uint32_t d = stage_smem_u32(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d + 16u), "l"(reinterpret_cast<const char *>(gsrc) + 16) : "memory");
+}
+__device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void async_wait_all_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 // One traversal entry for the NS sites of a thread, compiled once per combination of child sources so that the
 // NS loop carries no branch on tip case / carry / scaling.
-//   source: 0 = tip, 1 = carry registers, 2 = CLV load
+//   source: 0 = tip (staged code -> tip vector in shared memory), 1 = carry registers,
+//           2 = inner CLV that was brought into this thread's slot of the prefetch ring by cp.async,
+//           3 = inner CLV read straight from global memory (the second of two loaded children: rare)
 // Loop order: every EI / EV constant is fetched once per entry and used for all NS sites (constant-outer, site-inner;
 // the compiler keeps them in uniform registers), in stages that keep the live set inside the register budget:
-//   (A) gather the children;  d (.) x for inner children
-//   (B) row l of EI for all sites -> ab[s][l] = a_q[l] * a_r[l]
+//   (A) gather the children, d (.) x      (B) row l of EI for all sites -> ab[s][l] = a_q[l] * a_r[l]
 //   (C) column m of EV for all sites -> v[s][m]
-// LUT: a tip child contributes a_q[l] = sum_j P[l][j] tipVector[code][j] straight from the per-call table built by
-// dna_tables_kernel (the reference's umpX1 / umpX2, avxLikelihood.c:93-118): one 32-byte load instead of 15 flops.
-template <int QS, int RS, int NS, bool PARAM, bool LUT>
+template <int QS, int RS, int NS, bool PARAM>
 __device__ __forceinline__ unsigned int dna_entry(double (&carry)[NS][4], const TraverseArgs &a, const DnaConsts &kc, const DnaShared &sh,
-                                                  const uint8_t *stips, const SEntry &en, const double *drow_e, const double *lut_e,
+                                                  const uint8_t *stips, const SEntry &en, const double *sd, const double *ring,
                                                   const size_t (&eoff)[NS], const bool (&valid)[NS], const int (&lsite)[NS], int c, int lane)
 {
 #define EI_(i) (PARAM ? kc.EI[i] : sh.EI[i])
 #define EV_(i) (PARAM ? kc.EV[i] : sh.EV[i])
-  constexpr bool QL = LUT && QS == 0, RL = LUT && RS == 0;     // side comes from the table: no exponentials, no EI
-  double dq[4], dr[4];
-  if (!QL) ld256_ro(drow_e, dq);
-  if (!RL) ld256_ro(drow_e + 4, dr);
-  double qa[NS][4], ra[NS][4];         // table side: a[l]; computed side: x[0], d[1] x[1], d[2] x[2], d[3] x[3]
+  const double dq1 = sd[1], dq2 = sd[2], dq3 = sd[3], dr1 = sd[5], dr2 = sd[6], dr3 = sd[7];   // [side][k], d[0] = 1
+  double qa[NS][4], ra[NS][4];         // x[0], d[1] x[1], d[2] x[2], d[3] x[3]
   #pragma unroll
   for (int s = 0; s < NS; s++) {                      // (A)
-    if (QL) ld256_ro(lut_e + 16 * stips[en.qoff + lsite[s]], qa[s]);
-    else {
-      double x1[4];
-      if (QS == 1) { x1[0] = carry[s][0]; x1[1] = carry[s][1]; x1[2] = carry[s][2]; x1[3] = carry[s][3]; }
-      else if (QS == 2) ld256(a.clv + en.qoff + eoff[s], x1);
-      else { const double *tv = &sh.tip[4 * stips[en.qoff + lsite[s]]]; x1[0] = tv[0]; x1[1] = tv[1]; x1[2] = tv[2]; x1[3] = tv[3]; }
-      qa[s][0] = x1[0]; qa[s][1] = dq[1] * x1[1]; qa[s][2] = dq[2] * x1[2]; qa[s][3] = dq[3] * x1[3];
-    }
-    if (RL) ld256_ro(lut_e + 256 + 16 * stips[en.roff + lsite[s]], ra[s]);
-    else {
-      double x2[4];
-      if (RS == 1) { x2[0] = carry[s][0]; x2[1] = carry[s][1]; x2[2] = carry[s][2]; x2[3] = carry[s][3]; }
-      else if (RS == 2) ld256(a.clv + en.roff + eoff[s], x2);
-      else { const double *tv = &sh.tip[4 * stips[en.roff + lsite[s]]]; x2[0] = tv[0]; x2[1] = tv[1]; x2[2] = tv[2]; x2[3] = tv[3]; }
-      ra[s][0] = x2[0]; ra[s][1] = dr[1] * x2[1]; ra[s][2] = dr[2] * x2[2]; ra[s][3] = dr[3] * x2[3];
-    }
+    double x1[4], x2[4];
+    if (QS == 1) { x1[0] = carry[s][0]; x1[1] = carry[s][1]; x1[2] = carry[s][2]; x1[3] = carry[s][3]; }
+    else if (QS == 2) { const double *r = ring + (size_t)s * kThreads * 4; x1[0] = r[0]; x1[1] = r[1]; x1[2] = r[2]; x1[3] = r[3]; }
+    else if (QS == 3) ld256(a.clv + en.qoff + eoff[s], x1);
+    else { const double *tv = &sh.tip[4 * stips[en.qoff + lsite[s]]]; x1[0] = tv[0]; x1[1] = tv[1]; x1[2] = tv[2]; x1[3] = tv[3]; }
+    if (RS == 1) { x2[0] = carry[s][0]; x2[1] = carry[s][1]; x2[2] = carry[s][2]; x2[3] = carry[s][3]; }
+    else if (RS == 2) { const double *r = ring + (size_t)s * kThreads * 4; x2[0] = r[0]; x2[1] = r[1]; x2[2] = r[2]; x2[3] = r[3]; }
+    else if (RS == 3) ld256(a.clv + en.roff + eoff[s], x2);
+    else { const double *tv = &sh.tip[4 * stips[en.roff + lsite[s]]]; x2[0] = tv[0]; x2[1] = tv[1]; x2[2] = tv[2]; x2[3] = tv[3]; }
+    qa[s][0] = x1[0]; qa[s][1] = dq1 * x1[1]; qa[s][2] = dq2 * x1[2]; qa[s][3] = dq3 * x1[3];
+    ra[s][0] = x2[0]; ra[s][1] = dr1 * x2[1]; ra[s][2] = dr2 * x2[2]; ra[s][3] = dr3 * x2[3];
   }
   double ab[NS][4];
   #pragma unroll
@@ -116,8 +117,8 @@ __device__ __forceinline__ unsigned int dna_entry(double (&carry)[NS][4], const 
     const double e1 = EI_(l * 4 + 1), e2 = EI_(l * 4 + 2), e3 = EI_(l * 4 + 3);
     #pragma unroll
     for (int s = 0; s < NS; s++) {
-      const double al = QL ? qa[s][l] : fma(e3, qa[s][3], fma(e2, qa[s][2], fma(e1, qa[s][1], qa[s][0])));
-      const double ar = RL ? ra[s][l] : fma(e3, ra[s][3], fma(e2, ra[s][2], fma(e1, ra[s][1], ra[s][0])));
+      const double al = fma(e3, qa[s][3], fma(e2, qa[s][2], fma(e1, qa[s][1], qa[s][0])));
+      const double ar = fma(e3, ra[s][3], fma(e2, ra[s][2], fma(e1, ra[s][1], ra[s][0])));
       ab[s][l] = al * ar;
     }
   }
@@ -183,49 +184,6 @@ void launch_dtab(const DtabArgs &a, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------------------------------
-// DNA GAMMA, few partitions: d-table row AND the tip look-up tables of one (entry, partition) per block.
-//   lut[e][pc][side][code][c][l] = sum_j P_c,side[l][j] * tipVector[code][j],   P[l][j] = EI[l][j] * d[c][side][j], P[l][0] = 1
-// -- what the reference tabulates per node as umpX1 / umpX2 (avxLikelihood.c:93-118, 168-187): a tip child then costs the
-// traverse kernel one 32-byte load instead of 15 flops.  Same operation order as the in-kernel contraction.
-// ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-dna_tables_kernel(const DtabArgs a)
-{
-  __shared__ double d[32], EI[16], tip[64];
-  const int tid = threadIdx.x;
-  const int pc = blockIdx.x % a.nparts_cls, e = blockIdx.x / a.nparts_cls;
-  const double *model = a.models + (size_t)pc * kDnaModelDoubles;   // EIGN[4] rates[4] EI[16] EV[16] tip[64]
-  if (tid < 32) {
-    const int c = tid >> 3, side = (tid >> 2) & 1, k = tid & 3;
-    const int slot = a.nbranches > 1 ? a.cls_part_global[pc] : 0;
-    const double lz = side ? a.lzr[(size_t)e * a.nbranches + slot] : a.lzq[(size_t)e * a.nbranches + slot];
-    const double v = !k ? 1.0 : exp(model[4 + c] * (model[k] * lz));       // makeP newviewGenericSpecial.c:95-112
-    d[tid] = v;
-    a.dtab[((size_t)e * a.nparts_cls + pc) * kDnaDtabRow + tid] = v;
-  } else if (tid < 48) EI[tid - 32] = model[8 + tid - 32];
-  else if (tid >= 64 && tid < 128) tip[tid - 64] = model[40 + tid - 64];
-  if (e < a.first) return;                       // the branch entry has no children to tabulate (uniform per block)
-  const int tc = a.entries[e].tipCase;
-  if (tc == 2) return;
-  __syncthreads();
-  const int code = tid >> 4, c = (tid >> 2) & 3, l = tid & 3;
-  const double *tv = tip + 4 * code;
-  double *out = a.lut + ((size_t)e * a.nparts_cls + pc) * kDnaLutRow + tid;
-  #pragma unroll
-  for (int side = 0; side < 2; side++) {
-    if (side == 1 && tc != 0) break;
-    const double *dd = d + c * 8 + side * 4;
-    out[side * 256] = fma(EI[l * 4 + 3], dd[3] * tv[3], fma(EI[l * 4 + 2], dd[2] * tv[2], fma(EI[l * 4 + 1], dd[1] * tv[1], tv[0])));
-  }
-}
-
-void launch_dna_tables(const DtabArgs &a, cudaStream_t s)
-{
-  const int blocks = a.count * a.nparts_cls;
-  if (blocks > 0) dna_tables_kernel<<<blocks, 256, 0, s>>>(a);
-}
-
-// ------------------------------------------------------------------------------------------------------
 // Fused traversal: newviews [first, count) for this tile, then (optionally) evaluate or the sum table
 // at the branch described by entry 0.   NS = sites per thread (tile chunk = 64*NS sites).
 //
@@ -234,16 +192,30 @@ void launch_dna_tables(const DtabArgs &a, cudaStream_t s)
 // (TMA, 1-D) per row, all completing on a single mbarrier -- the only cold HBM reads of the kernel
 // are issued up front and in bulk instead of one dependent byte load per entry.
 // ------------------------------------------------------------------------------------------------------
-template <int NS, bool PARAM, int MINB, bool LUT>
+// Window of the DNA GAMMA kernel: 48 entries keep (entries + tip rows + d-table rows + the prefetch ring) of a
+// 256-site chunk at ~102 KB, i.e. two CTAs per SM.
+constexpr int kDnaWindow = 48;
+
+// Which child of an entry goes through the prefetch ring: 1 = q, 2 = r, 0 = none (tips and carry need no load)
+__device__ __forceinline__ int ring_child(const SEntry &en)
+{
+  const bool q_load = en.tipCase == 2 && !(en.flags & kFlagCarryA), r_load = en.tipCase != 0 && !(en.flags & kFlagCarryB);
+  return q_load ? 1 : (r_load ? 2 : 0);
+}
+
+template <int NS, bool PARAM, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
 {
   constexpr int TS = 64 * NS;                  // sites per chunk = bytes per staged tip row
+  constexpr int KW = kDnaWindow;
   __shared__ DnaShared sh;
   __shared__ __align__(8) uint64_t mbar;
   extern __shared__ __align__(16) unsigned char dyn[];
-  const SEntry *ents = reinterpret_cast<const SEntry *>(dyn);                  // window entries; slot kWindow = branch entry
-  const uint8_t *stips = dyn + (size_t)(kWindow + 1) * sizeof(SEntry);          // [2*kWindow + 2][TS] staged tip rows
+  const SEntry *ents = reinterpret_cast<const SEntry *>(dyn);                  // window entries; slot KW = branch entry
+  const uint8_t *stips = dyn + (size_t)(KW + 1) * sizeof(SEntry);               // [2 KW + 2][TS] staged tip rows
+  const double *sdtab = reinterpret_cast<const double *>(dyn + window_dtab_offset<TS, KW>());     // [KW + 1][32] d-table rows
+  double *ring = reinterpret_cast<double *>(dyn + window_smem_bytes<TS, KW>(kDnaDtabRow));          // [2][NS][256 threads][4]
 
   const Tile tile = a.tiles[blockIdx.x];
   if (!a.mask[tile.part]) return;
@@ -260,10 +232,9 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
     __syncthreads();
   }
 
-  const double *drow = a.dtab + ((size_t)tile.part_cls * 4 + c) * 8;       // + e * nparts_cls * 32
+  const double *drow0 = a.dtab + (size_t)tile.part_cls * kDnaDtabRow;       // row of entry e: + e * dstride
   const size_t dstride = (size_t)a.nparts_cls * kDnaDtabRow;
-  const double *lrow = LUT ? a.lut + (size_t)tile.part_cls * kDnaLutRow + c * 4 : nullptr;   // + e * nparts_cls * 512 (+ 256: r side)
-  const size_t lstride = (size_t)a.nparts_cls * kDnaLutRow;
+  double *const myring = ring + (size_t)tid * 4;                            // + (buffer * NS + s) * 256 * 4
   double acc = 0.0;
   uint32_t phase = 0;
 
@@ -279,32 +250,54 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
       lsite[s] = valid[s] ? (int)i : 0;
       eoff[s] = ((size_t)tile.site0 + chunk0 + lsite[s]) * 16 + c * 4;
     }
-    double carry[NS][4];
+    double carry[NS][4];                       // CLV of the entry just computed (kFlagCarry* say when it is an operand)
     #pragma unroll
     for (int s = 0; s < NS; s++) { carry[s][0] = carry[s][1] = carry[s][2] = carry[s][3] = 0.0; }
 
     // ---------------- newview entries, one window at a time ----------------
     int w0 = a.first;
     do {
-    const int w1 = min(w0 + kWindow, a.count);
-    phase = stage_window<TS>(dyn, &mbar, phase, a.entries, a.tips, a.mxtips, N, 16, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
-                     a.first, a.count, w0 == a.first && a.mode != MODE_NEWVIEW);
+    const int w1 = min(w0 + KW, a.count);
+    phase = stage_window<TS, KW>(dyn, &mbar, phase, a.entries, a.tips, a.mxtips, N, 16, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
+                                 a.first, a.count, w0 == a.first && a.mode != MODE_NEWVIEW, drow0, dstride, kDnaDtabRow);
     for (int e = w0; e < w1; e++) {
       const SEntry en = ents[e - w0];
-      const double *drow_e = drow + (size_t)e * dstride;
-      const double *lut_e = LUT ? lrow + (size_t)e * lstride : nullptr;
+      // The one inner child that is neither a tip nor in the carry registers comes through the prefetch ring: its
+      // cp.async was issued while the PREVIOUS entry was being computed (the window's first entry issues its own).
+      const int mine = ring_child(en);
+      if (e == w0 && mine) {
+        const double *src = a.clv + (mine == 1 ? en.qoff : en.roff);
+        #pragma unroll
+        for (int s = 0; s < NS; s++) async_copy32(myring + (size_t)((e & 1) * NS + s) * kThreads * 4, src + eoff[s]);
+      }
+      async_commit();
+      if (e + 1 < w1) {
+        const SEntry nx = ents[e + 1 - w0];
+        const int next = ring_child(nx);
+        if (next) {
+          const double *src = a.clv + (next == 1 ? nx.qoff : nx.roff);
+          #pragma unroll
+          for (int s = 0; s < NS; s++) async_copy32(myring + (size_t)(((e + 1) & 1) * NS + s) * kThreads * 4, src + eoff[s]);
+        }
+      }
+      async_commit();
+      async_wait_all_but_last();               // this entry's operand has landed; the next entry's stays in flight
+
+      const double *sd = sdtab + (size_t)(e - w0) * kDnaDtabRow + c * 8;
+      const double *rg = myring + (size_t)((e & 1) * NS) * kThreads * 4;
       const bool q_inner = en.tipCase == 2, r_inner = en.tipCase != 0;
-      const bool q_carry = en.flags & kFlagCarryA, r_carry = en.flags & kFlagCarryB;
-      const int qs = !q_inner ? 0 : (q_carry ? 1 : 2), rs = !r_inner ? 0 : (r_carry ? 1 : 2);
+      // sources: 0 tip, 1 carry, 2 ring, 3 direct load (r, only when q already uses the ring)
+      const int qs = !q_inner ? 0 : ((en.flags & kFlagCarryA) ? 1 : 2);
+      const int rs = !r_inner ? 0 : ((en.flags & kFlagCarryB) ? 1 : (mine == 2 ? 2 : 3));
       unsigned int cnt;
-#define DNA_ENTRY(QS, RS) dna_entry<QS, RS, NS, PARAM, LUT>(carry, a, kc, sh, stips, en, drow_e, lut_e, eoff, valid, lsite, c, lane)
-      switch (qs * 3 + rs) {                   // block-uniform
-      case 0:  cnt = DNA_ENTRY(0, 0); break;
-      case 1:  cnt = DNA_ENTRY(0, 1); break;
-      case 2:  cnt = DNA_ENTRY(0, 2); break;
-      case 5:  cnt = DNA_ENTRY(1, 2); break;
-      case 7:  cnt = DNA_ENTRY(2, 1); break;
-      default: cnt = DNA_ENTRY(2, 2); break;
+#define DNA_ENTRY(QS, RS) dna_entry<QS, RS, NS, PARAM>(carry, a, kc, sh, stips, en, sd, rg, eoff, valid, lsite, c, lane)
+      switch (qs * 4 + rs) {                   // block-uniform
+      case 0:  cnt = DNA_ENTRY(0, 0); break;   // TIP_TIP
+      case 1:  cnt = DNA_ENTRY(0, 1); break;   // TIP_INNER, inner child = previous entry
+      case 2:  cnt = DNA_ENTRY(0, 2); break;   // TIP_INNER, inner child loaded
+      case 6:  cnt = DNA_ENTRY(1, 2); break;   // INNER_INNER, q = previous entry
+      case 9:  cnt = DNA_ENTRY(2, 1); break;   // INNER_INNER, r = previous entry
+      default: cnt = DNA_ENTRY(2, 3); break;   // INNER_INNER, both loaded
       }
 #undef DNA_ENTRY
       if (r_inner && __any_sync(0xffffffffu, cnt != 0)) {
@@ -312,16 +305,15 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
         if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
       }
     }
-    } while ((w0 += kWindow) < a.count);
+    } while ((w0 += KW) < a.count);
 
     if (a.mode == MODE_NEWVIEW) continue;
 
     // ---------------- branch (entry 0): evaluate or sum table ----------------
-    const SEntry br = ents[kWindow];
+    const SEntry br = ents[KW];
     const bool ptip = br.flags & kFlagPTip, qtip = br.flags & kFlagQTip;
     const bool p_carry = br.flags & kFlagCarryA, q_carry = br.flags & kFlagCarryB;
-    double diag[4];
-    ld256_ro(drow, diag);                      // row 0, q side: calcDiagptable (diag[0] = 1)
+    const double *diag = sdtab + (size_t)KW * kDnaDtabRow + c * 8;     // row 0, q side: calcDiagptable (diag[0] = 1)
 
     #pragma unroll
     for (int s = 0; s < NS; s++) {
@@ -499,43 +491,40 @@ core_dna_kernel(const CoreArgs a)
 
 size_t traverse_dna_smem(int ns)
 {
-  return (size_t)(kWindow + 1) * sizeof(SEntry) + (size_t)(2 * kWindow + 2) * 64 * ns;
+  // entries + tip rows + d-table rows of a window, then the prefetch ring [2][ns][256 threads] x 32 B
+  return (size_t)(kDnaWindow + 1) * sizeof(SEntry) + (size_t)(2 * kDnaWindow + 2) * 64 * ns +
+         (size_t)(kDnaWindow + 1) * kDnaDtabRow * sizeof(double) + (size_t)2 * ns * kThreads * 32;
 }
 
-template <int NS, bool PARAM, int MINB, bool LUT>
+template <int NS, bool PARAM, int MINB>
 static void launch_variant(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
 {
   const size_t smem = traverse_dna_smem(NS);
   static size_t configured[kMaxDevices];
-  ensure_dynamic_smem(traverse_dna_kernel<NS, PARAM, MINB, LUT>, std::min<size_t>(227 * 1024 - 2048, std::max<size_t>(smem, 64 * 1024)), configured);
-  traverse_dna_kernel<NS, PARAM, MINB, LUT><<<ntiles, kThreads, smem, s>>>(a, kc);
+  ensure_dynamic_smem(traverse_dna_kernel<NS, PARAM, MINB>, std::min<size_t>(227 * 1024 - 2048, std::max<size_t>(smem, 64 * 1024)), configured);
+  traverse_dna_kernel<NS, PARAM, MINB><<<ntiles, kThreads, smem, s>>>(a, kc);
 }
 
-// NS sites per thread: 4 for full tiles (128 registers, 2 CTAs per SM), fewer for small tiles (3 CTAs per SM)
-template <int NS, int MINB>
-static void launch_ns(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
-{
-  if (a.lut) launch_variant<NS, true, MINB, true>(a, kc, ntiles, s);
-  else       launch_variant<NS, true, MINB, false>(a, kc, ntiles, s);
-}
-
+// NS sites per thread: 4 for full tiles (128 registers, 2 CTAs per SM), fewer for small tiles (3 CTAs per SM).
+// kc: EI / EV of the launch's single partition as kernel parameters (constant bank -> uniform registers);
+// null: many partitions in one launch, every CTA reads its partition's EI / EV from shared memory.
 void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *kc, int ntiles, cudaStream_t s)
 {
   if (ntiles <= 0) return;
-  if (!kc) {                                     // many partitions: EI / EV from shared memory (a row / column at a time)
+  static int ns_max = -1;                        // development knob: EXB_DNA_NS = 1 | 2 | 4 sites per thread at most
+  if (ns_max < 0) { const char *v = getenv("EXB_DNA_NS"); ns_max = v ? atoi(v) : 4; }
+  const int ns = (a.tile_sites <= 64 || ns_max == 1) ? 1 : ((a.tile_sites <= 128 || ns_max == 2) ? 2 : 4);
+  if (!kc) {
     DnaConsts none;
     memset(&none, 0, sizeof none);
-    static int ns_many = -1;                     // development knob: EXB_DNA_NS_MANY = 1 | 2 | 4 sites per thread
-    if (ns_many < 0) { const char *v = getenv("EXB_DNA_NS_MANY"); ns_many = v ? atoi(v) : 4; }
-    if (a.tile_sites <= 64 || ns_many == 1)       launch_variant<1, false, 3, false>(a, none, ntiles, s);
-    else if (a.tile_sites <= 128 || ns_many == 2) launch_variant<2, false, 3, false>(a, none, ntiles, s);
-    else                                          launch_variant<4, false, 2, false>(a, none, ntiles, s);
+    if (ns == 1)      launch_variant<1, false, 3>(a, none, ntiles, s);
+    else if (ns == 2) launch_variant<2, false, 3>(a, none, ntiles, s);
+    else              launch_variant<4, false, 2>(a, none, ntiles, s);
     return;
   }
-  // chunk = 64*NS sites
-  if (a.tile_sites <= 64)       launch_ns<1, 3>(a, *kc, ntiles, s);
-  else if (a.tile_sites <= 128) launch_ns<2, 3>(a, *kc, ntiles, s);
-  else                          launch_ns<4, 2>(a, *kc, ntiles, s);
+  if (ns == 1)      launch_variant<1, true, 3>(a, *kc, ntiles, s);
+  else if (ns == 2) launch_variant<2, true, 3>(a, *kc, ntiles, s);
+  else              launch_variant<4, true, 2>(a, *kc, ntiles, s);
 }
 void launch_traverse_dna_cat(const TraverseArgs &a, const DnaConsts *kc, int ntiles, cudaStream_t s)
 {

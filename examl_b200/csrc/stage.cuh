@@ -54,32 +54,44 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                :: "r"(stage_smem_u32(dst)), "l"(src), "r"(bytes), "r"(stage_smem_u32(bar)) : "memory");
 }
 
-template <int TSB>          // bytes per staged tip row = sites per chunk
-__host__ __device__ constexpr size_t window_smem_bytes()
+// Shared-memory layout of a window of KW entries with TSB-byte tip rows:
+//   [KW + 1] SEntry | [2 KW + 2][TSB] tip rows | (optional) [KW + 1][DROW] doubles: the entries' d-table rows
+template <int TSB, int KW = kWindow>          // TSB: bytes per staged tip row = sites per chunk
+__host__ __device__ constexpr size_t window_smem_bytes(int drow_doubles = 0)
 {
-  return (size_t)(kWindow + 1) * sizeof(SEntry) + (size_t)(2 * kWindow + 2) * TSB;
+  return (size_t)(KW + 1) * sizeof(SEntry) + (size_t)(2 * KW + 2) * TSB + (size_t)(KW + 1) * drow_doubles * sizeof(double);
+}
+template <int TSB, int KW = kWindow>
+__host__ __device__ constexpr size_t window_dtab_offset()
+{
+  return (size_t)(KW + 1) * sizeof(SEntry) + (size_t)(2 * KW + 2) * TSB;
 }
 
-// Stage entries [w0, w1) (slots 0 .. w1-w0-1) and, when `with_branch`, the branch entry 0 (slot kWindow).
+// Stage entries [w0, w1) (slots 0 .. w1-w0-1) and, when `with_branch`, the branch entry 0 (slot KW).
 // Must be called by every thread of the CTA; ends with all staged data visible to all threads.  Returns the mbarrier
 // phase for the next call.  Takes plain values (not the kernel's argument struct) so that nothing of the caller has to
 // live in local memory for this non-inlined call.
-//   dyn      : dynamic shared memory base (window_smem_bytes<TSB>() bytes, 16-byte aligned)
+//   dyn      : dynamic shared memory base (16-byte aligned)
 //   span_el  : doubles per site in a CLV (node stride = N * span_el)
 //   first, count : the call's newview entries are [first, count) -- carry flags look at the predecessor entry
-template <int TSB>
+//   drow     : null, or this partition's row of entry 0 in the d-table; rows of `drow_doubles` doubles, `dstride` doubles
+//              apart, are staged behind the tips (row of entry e in slot e - w0, the branch entry's row 0 in slot KW): the
+//              exponentials of an entry then cost the threads a shared-memory read instead of an L2 round trip
+template <int TSB, int KW = kWindow>
 __device__ __noinline__ uint32_t stage_window(unsigned char *dyn, uint64_t *mbar, uint32_t phase, const DevEntry *entries,
                                               const uint8_t *tips, int mxtips, size_t N, int span_el, size_t chunk_site0,
-                                              unsigned nchunk, int w0, int w1, int first, int count, bool with_branch)
+                                              unsigned nchunk, int w0, int w1, int first, int count, bool with_branch,
+                                              const double *drow = nullptr, size_t dstride = 0, int drow_doubles = 0)
 {
   SEntry *ents = reinterpret_cast<SEntry *>(dyn);
-  uint8_t *stips = dyn + (size_t)(kWindow + 1) * sizeof(SEntry);
+  uint8_t *stips = dyn + (size_t)(KW + 1) * sizeof(SEntry);
+  double *sdtab = reinterpret_cast<double *>(dyn + window_dtab_offset<TSB, KW>());
   const int tid = threadIdx.x, lane = tid & 31;
   __syncthreads();                             // the previous window's readers are done with ents / stips
   for (int j = tid; j < (w1 - w0) + (with_branch ? 1 : 0); j += blockDim.x) {
     const bool is_branch = j == (w1 - w0);
     const DevEntry en = entries[is_branch ? 0 : w0 + j];
-    const int slot = is_branch ? kWindow : j;
+    const int slot = is_branch ? KW : j;
     // the node whose CLV the threads still hold when this entry is processed: the previous newview entry's parent
     const int prev = is_branch ? (count > first ? entries[count - 1].p : -1) : (w0 + j > first ? entries[w0 + j - 1].p : -1);
     SEntry se;
@@ -96,6 +108,7 @@ __device__ __noinline__ uint32_t stage_window(unsigned char *dyn, uint64_t *mbar
   __syncthreads();
   if (tid < 32) {
     const uint32_t bytes = (nchunk + 15u) & ~15u;
+    const uint32_t dbytes = (uint32_t)drow_doubles * (uint32_t)sizeof(double);
     const uint8_t *gsrc = tips + chunk_site0;
     const int n = (w1 - w0) + (with_branch ? 1 : 0);
     int mine = 0;
@@ -106,12 +119,12 @@ __device__ __noinline__ uint32_t stage_window(unsigned char *dyn, uint64_t *mbar
       else           mine += (en.tipCase <= 1) + (en.tipCase == 0);
     }
     const int total = __reduce_add_sync(0xffffffffu, mine);
-    if (lane == 0) mbar_expect_tx(mbar, (uint32_t)total * bytes);
+    if (lane == 0) mbar_expect_tx(mbar, (uint32_t)total * bytes + (drow ? (uint32_t)n * dbytes : 0u));
     __syncwarp();
     for (int j = lane; j < n; j += 32) {
       const bool is_branch = j == (w1 - w0);
       const DevEntry en = entries[is_branch ? 0 : w0 + j];
-      const int slot = is_branch ? kWindow : j;
+      const int slot = is_branch ? KW : j;
       if (is_branch) {
         if (en.p <= mxtips) bulk_g2s(stips + (size_t)(2 * slot + 1) * TSB, gsrc + (size_t)(en.p - 1) * N, bytes, mbar);
         if (en.q <= mxtips) bulk_g2s(stips + (size_t)(2 * slot) * TSB, gsrc + (size_t)(en.q - 1) * N, bytes, mbar);
@@ -119,6 +132,7 @@ __device__ __noinline__ uint32_t stage_window(unsigned char *dyn, uint64_t *mbar
         if (en.tipCase <= 1) bulk_g2s(stips + (size_t)(2 * slot) * TSB, gsrc + (size_t)(en.q - 1) * N, bytes, mbar);
         if (en.tipCase == 0) bulk_g2s(stips + (size_t)(2 * slot + 1) * TSB, gsrc + (size_t)(en.r - 1) * N, bytes, mbar);
       }
+      if (drow) bulk_g2s(sdtab + (size_t)slot * drow_doubles, drow + (size_t)(is_branch ? 0 : w0 + j) * dstride, dbytes, mbar);
     }
   }
   mbar_wait(mbar, phase);
