@@ -442,7 +442,11 @@ def run_b200(w: SimpleNamespace, args, rank: int, world: int, local_rank: int, s
     is_p2p = eng.comm_is_p2p() if world > 1 else False
 
     times = torch.tensor([wall, wall_e2e, dev_ms / 1e3] + list(phases / 1e3), dtype=torch.float64, device="cuda")
+    per_rank = None
     if world > 1:
+        gathered = [torch.empty_like(times) for _ in range(world)]
+        dist.all_gather(gathered, times)
+        per_rank = [[round(1e3 * float(v) / steps, 4) for v in g.tolist()] for g in gathered]   # ms per step, every rank
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     wall, wall_e2e, dev_s, ph_tab, ph_trav, ph_fin = [float(x) for x in times.tolist()]
 
@@ -519,6 +523,8 @@ def run_b200(w: SimpleNamespace, args, rank: int, world: int, local_rank: int, s
             "roofline": roofline,
             "setup": {"generate_s": t_gen, "engine_s": t_setup},
         }
+        if per_rank:
+            res["per_rank_ms_per_step"] = {"columns": ["wall", "wall_e2e", "kernels", "tables", "traverse", "finish"], "ranks": per_rank}
     # free the arena before anything else allocates (parity engine, next workload)
     eng.close()
     if rank == 0:
@@ -539,7 +545,7 @@ def run_b200(w: SimpleNamespace, args, rank: int, world: int, local_rank: int, s
 def secondary_summary(r: dict) -> dict:
     """What the headline line carries about another workload."""
     keep = ("value", "unit", "ms_per_step", "steps", "kernel_ms_per_step", "kernel_phases_ms", "kernel_value", "scaling",
-            "roofline", "parity", "cpu_baseline", "gpu_launches")
+            "roofline", "parity", "cpu_baseline", "gpu_launches", "per_rank_ms_per_step")
     s = {k: r[k] for k in keep if k in r}
     s["config"] = r["config"]
     s["e2e"] = {k: r["e2e"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")}

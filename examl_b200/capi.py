@@ -24,7 +24,7 @@ EXPORTS = [
     "exb_comm_unique_id", "exb_comm_init", "exb_read_clv", "exb_read_scaler",
     "exb_read_sumtable", "exb_last_kernel_ms", "exb_launch_count", "exb_set_tile_sites", "exb_set_timing",
     "exb_set_rate_model", "exb_set_categories", "exb_set_model_lg4", "exb_evaluate_partial", "exb_comm_is_p2p",
-    "exb_last_phase_ms",
+    "exb_last_phase_ms", "exb_set_aa_precision",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -144,6 +144,10 @@ class Engine:
         """rateHetModel: 0 = CAT / PSR (one rate category per site), 1 = GAMMA (axml.h:349-350).  Before set_partition."""
         self.cat = rate_het_model == 0
         self._check(self._f("set_rate_model")(self._h, C.c_int(rate_het_model), C.c_int(max_categories)))
+
+    def set_aa_precision(self, mode: int) -> None:
+        """0 = FP64 (default), 1 = 3xTF32 on tcgen05 (mixed precision; include/examl_b200.h).  Before set_partition / commit."""
+        self._check(self._f("set_aa_precision")(self._h, C.c_int(mode)))
 
     def set_categories(self, model: int, per_site_rates, rate_category) -> None:
         """CAT / PSR: pInfo.perSiteRates[numberOfCategories], pInfo.rateCategory[width]."""

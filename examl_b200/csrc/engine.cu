@@ -262,10 +262,12 @@ struct ClassState {
 struct exb_engine {
   int device = 0, mxtips = 0, P = 0, nb = 1;
   int tile_sites = 256;
+  bool tile_sites_set = false;         // exb_set_tile_sites was called: no automatic balancing
   bool committed = false;
   std::vector<HostPart> parts;
   ClassState cls[2];
   bool cat = false;                    // CAT / PSR: one rate category per site (span = S)
+  bool aa_tc = false;                  // AA GAMMA newview on tcgen05 in 3xTF32 (mixed precision, exb_set_aa_precision)
   int max_cats = 4;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_a = nullptr, ev_b = nullptr;   // call start / end, traverse start / end
@@ -338,6 +340,7 @@ extern "C" int exb_create(exb_engine **out, int device, int mxtips, int numParti
   e->cls[CLS_DNA].S = 4;  e->cls[CLS_DNA].span = 16; e->cls[CLS_DNA].codes = 16; e->cls[CLS_DNA].model_doubles = kDnaModelDoubles;
   e->cls[CLS_AA].S = 20;  e->cls[CLS_AA].span = 80;  e->cls[CLS_AA].codes = 23;  e->cls[CLS_AA].model_doubles = kAaModelDoubles;
   e->cls[CLS_DNA].dtab_row = kDnaDtabRow; e->cls[CLS_AA].dtab_row = kAaDtabRow;
+  { const char *v = getenv("EXB_AA_PRECISION"); e->aa_tc = v && strcmp(v, "tf32x3") == 0; }
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&e->ev0));
   CUDA_TRY(cudaEventCreate(&e->ev1));
@@ -395,6 +398,14 @@ extern "C" int exb_set_rate_model(exb_engine *e, int rateHetModel, int maxCatego
   return EXB_OK;
 }
 
+extern "C" int exb_set_aa_precision(exb_engine *e, int mode)
+{
+  if (!e || e->committed) return fail(EXB_ERR_STATE, "exb_set_aa_precision: must be called before exb_commit");
+  if (mode != EXB_AA_FP64 && mode != EXB_AA_TF32X3) return fail(EXB_ERR_ARG, "exb_set_aa_precision: unknown mode %d", mode);
+  e->aa_tc = mode == EXB_AA_TF32X3;
+  return EXB_OK;
+}
+
 extern "C" int exb_set_categories(exb_engine *e, int model, int numberOfCategories, const double *perSiteRates, const int *rateCategory)
 {
   if (!e || !e->committed) return fail(EXB_ERR_STATE, "exb_set_categories: call exb_commit first");
@@ -432,6 +443,7 @@ extern "C" int exb_set_tile_sites(exb_engine *e, int sites)
   if (!e || e->committed) return fail(EXB_ERR_STATE, "exb_set_tile_sites: must be called before exb_commit");
   if (sites < 32 || sites % 32) return fail(EXB_ERR_ARG, "exb_set_tile_sites: %d is not a positive multiple of 32", sites);
   e->tile_sites = sites;
+  e->tile_sites_set = true;
   return EXB_OK;
 }
 
@@ -478,8 +490,20 @@ extern "C" int exb_commit(exb_engine *e)
       tbegin[m] = (int)k.tiles_h.size();
       // AA tiles are whole 96-site chunks (12 warps x 8 sites)
       // (CAT: 384-site chunks, 12 warps x 32 sites)
-      const size_t aachunk = e->cat ? 384 : 96;
-      const size_t tsz = c == CLS_AA ? (size_t)((e->tile_sites + aachunk - 1) / aachunk) * aachunk : (size_t)e->tile_sites;
+      const size_t aachunk = e->cat ? 384 : (e->aa_tc ? 32 : 96);      // (tcgen05 path: 32 sites x 4 categories = the MMA's M)
+      size_t tsz = c == CLS_AA ? (size_t)((e->tile_sites + aachunk - 1) / aachunk) * aachunk : (size_t)e->tile_sites;
+      // One big DNA partition on a few waves of CTAs (strong scaling: 125 k sites per GPU are 1.65 waves of 256-site
+      // tiles): cut it into k full waves of equal tiles instead, so that the last wave is not a third empty.
+      if (c == CLS_DNA && !e->cat && !e->tile_sites_set && e->P == 1) {
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+        const size_t slots = (size_t)2 * (sms > 0 ? sms : 148);           // 2 CTAs per SM at 4 sites per thread
+        const size_t waves = (p.width + slots * tsz - 1) / (slots * tsz);
+        if (waves >= 1 && waves <= 6) {
+          const size_t want = (p.width + waves * slots - 1) / (waves * slots);
+          tsz = std::min<size_t>(tsz, std::max<size_t>(144, (want + 15) / 16 * 16));     // > 128 keeps 4 sites per thread
+        }
+      }
       for (size_t s = 0; s < p.width; s += tsz) {
         Tile t;
         t.site0 = (uint32_t)(n + s);
@@ -845,7 +869,17 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
     } else {
       bool any_lg4 = false;                        // per-category eigen-systems anywhere in the class?
       for (int pc = 0; pc < k.nparts; pc++) any_lg4 = any_lg4 || k.models_h[(size_t)pc * k.model_doubles + kAaLg4] != 0.0;
-      launch_traverse_aa(a, any_lg4, (int)k.tiles_h.size(), e->stream);
+      if (e->aa_tc && !e->cat && !any_lg4 && k.lut) {
+        // mixed-precision mode: the newview entries on tcgen05 (3xTF32), the branch tail (evaluate / sum table) by the
+        // FP64 kernel on the CLVs just written
+        if (count > first) { launch_traverse_aa_tc(a, (int)k.tiles_h.size(), e->stream); e->launches++; }
+        if (mode != MODE_NEWVIEW) {
+          TraverseArgs tail = a;
+          tail.first = count;
+          launch_traverse_aa(tail, any_lg4, (int)k.tiles_h.size(), e->stream);
+        } else e->launches--;
+      } else
+        launch_traverse_aa(a, any_lg4, (int)k.tiles_h.size(), e->stream);
     }
     e->launches++;
   }

@@ -211,6 +211,7 @@ void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *single_partitio
 void launch_traverse_dna_cat(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
 void launch_core_dna(const CoreArgs &a, int ntiles, cudaStream_t s);
 void launch_traverse_aa(const TraverseArgs &a, bool any_lg4, int ntiles, cudaStream_t s);
+void launch_traverse_aa_tc(const TraverseArgs &a, int ntiles, cudaStream_t s);
 void launch_core_aa(const CoreArgs &a, int ntiles, cudaStream_t s);
 void launch_finish(const FinishArgs &a, cudaStream_t s);
 void launch_p2p_warmup(const P2pArgs &x, unsigned int xseq, int stride, cudaStream_t s);

@@ -63,6 +63,10 @@ __device__ __forceinline__ void st256(double *p, const double *v)
 }
 enum Src : int { SRC_TIP = 0, SRC_CARRY = 1, SRC_LOAD = 2 };
 
+// fabs(v) < 2^-256 on the integer pipe (the FP64 pipe belongs to the DMMAs): the biased exponent of 2^-256 is 0x2FF
+__device__ __forceinline__ unsigned int abs_hi(double v) { return (unsigned int)__double2hiint(v) & 0x7fffffffu; }
+constexpr unsigned int kMinLikelihoodHi = 0x2FF00000u;
+
 // D(8x8) += A(8x4) * B(4x8), FP64 tensor pipe (SASS: DMMA.8x8x4).
 //   A: thread holds A[lane/4][lane%4]; B: thread holds B[lane%4][lane/4]; C/D: C[lane/4][2*(lane%4) + {0,1}].
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
@@ -311,13 +315,13 @@ traverse_aa_kernel(const TraverseArgs a)
       if (r_inner) {                            // TIP_TIP is never rescaled (avxLikelihood.c:1393-1440)
         unsigned int cnt = 0;
         if (!CAT) {
-          bool small = true;
+          unsigned int hi = 0;
           #pragma unroll
           for (int c = 0; c < 4; c++)
             #pragma unroll
             for (int t = 0; t < 3; t++)            // padding columns hold exact zeros and pass the test
-              small = small && (fabs(carry[c][t][0]) < kMinLikelihood) && (fabs(carry[c][t][1]) < kMinLikelihood);
-          const unsigned int b = __ballot_sync(0xffffffffu, small);
+              hi = max(hi, max(abs_hi(carry[c][t][0]), abs_hi(carry[c][t][1])));
+          const unsigned int b = __ballot_sync(0xffffffffu, hi < kMinLikelihoodHi);
           if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {            // all 80 values of the site are tiny
             #pragma unroll
             for (int c = 0; c < 4; c++)
@@ -328,11 +332,10 @@ traverse_aa_kernel(const TraverseArgs a)
         } else {
           #pragma unroll
           for (int c = 0; c < 4; c++) {            // one site per slot: all 20 values of that site tiny
-            bool small = true;
+            unsigned int hi = 0;
             #pragma unroll
-            for (int t = 0; t < 3; t++)
-              small = small && (fabs(carry[c][t][0]) < kMinLikelihood) && (fabs(carry[c][t][1]) < kMinLikelihood);
-            const unsigned int b = __ballot_sync(0xffffffffu, small);
+            for (int t = 0; t < 3; t++) hi = max(hi, max(abs_hi(carry[c][t][0]), abs_hi(carry[c][t][1])));
+            const unsigned int b = __ballot_sync(0xffffffffu, hi < kMinLikelihoodHi);
             if (((b >> (lane & ~3)) & 0xFu) == 0xFu) {
               #pragma unroll
               for (int t = 0; t < 3; t++) { carry[c][t][0] *= kTwoToThe256; carry[c][t][1] *= kTwoToThe256; }

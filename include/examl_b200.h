@@ -122,6 +122,17 @@ int  exb_set_model(exb_engine *e, int model, const double *EIGN, const double *E
 int  exb_set_model_lg4(exb_engine *e, int model, const double *EIGN, const double *EV, const double *EI,
                        const double *tipVector, const double *gammaRates, const double *weights);
 
+/* Arithmetic of the protein (20-state) GAMMA newview.  EXB_AA_FP64 (default): FP64 throughout, on the FP64 tensor pipe
+ * (DMMA) -- the reference's precision (newviewGTRGAMMAPROT_AVX avxLikelihood.c:1312).  EXB_AA_TF32X3: the contractions
+ * run on the tcgen05 tensor cores as 3xTF32 products with FP32 accumulators in tensor memory, site vectors renormalised
+ * by an exact power of two per node; CLVs are still stored as FP64.  Measured (tools/mixed_precision_study.py,
+ * tests/test_gpu_parity.py): lnL within 1e-7 relative of the FP64 path -- inside north_star's 1e-6 -- but per-site
+ * log-likelihoods differ by up to ~2e-3, so it is opt-in (also: EXB_AA_PRECISION=tf32x3 in the environment).  Applies
+ * to GAMMA partitions with a single eigen-system (not LG4M / LG4X, not PSR).  Before exb_commit. */
+#define EXB_AA_FP64    0
+#define EXB_AA_TF32X3  1
+int  exb_set_aa_precision(exb_engine *e, int mode);
+
 /* EXB_CAT only: pInfo.numberOfCategories, pInfo.perSiteRates[numberOfCategories], pInfo.rateCategory[width]
  * (rewritten by optimizeRateCategories, optimizeModel.c:2403).  Cheap when unchanged (host-side compare). */
 int  exb_set_categories(exb_engine *e, int model, int numberOfCategories, const double *perSiteRates,

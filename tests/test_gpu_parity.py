@@ -449,3 +449,59 @@ def test_c5_shape_1250_partitions_vs_oracle(cuda_factory, oracle_factory):
     out = np.full(P, 7.0)
     gpu.evaluateIterative(w.ti, mask, out=out)
     assert np.array_equal(out[mask == 1], got[mask == 1]) and np.all(out[mask == 0] == 7.0)
+
+
+# ---- mixed precision: the AA newview on tcgen05 (3xTF32, FP32 accumulators in tensor memory) -----------------------
+def _tc_factory(cuda_factory):
+    def make(mxtips, nparts, nbranches=1, **kw):
+        e = cuda_factory(mxtips, nparts, nbranches, **kw)
+        e.set_aa_precision(1)
+        return e
+    return make
+
+
+def test_tf32x3_reference_goldens_within_north_star_bar(cuda_factory):
+    """exb_set_aa_precision(EXB_AA_TF32X3): the reference's own testData/140 state and the aa60 synthetic state.  Bar =
+    north_star's 1e-6 relative on lnL (measured ~1e-8, tools/mixed_precision_study.py); the FP64 path is held to 5e-12."""
+    from golden_util import load_engine, load_json, traversal_of
+    for tag in ("aa140", "aa60"):
+        st = load_json(f"{tag}.first.json")
+        eng = load_engine(_tc_factory(cuda_factory), st)
+        lh = eng.evaluateIterative(traversal_of(st))
+        assert abs(lh.sum() - st["likelihood"]) <= 1e-6 * abs(st["likelihood"]), (tag, lh.sum(), st["likelihood"])
+        ref = load_engine(cuda_factory, st)
+        lr = ref.evaluateIterative(traversal_of(st))
+        print(tag, "tf32x3 lnL", lh.sum(), "fp64 lnL", lr.sum(), "rel", abs(lh.sum() - lr.sum()) / abs(lr.sum()))
+        assert abs(lh.sum() - lr.sum()) <= 1e-6 * abs(lr.sum())
+
+
+@pytest.mark.parametrize("mxtips,widths,mode", [(24, [300], "signal"), (150, [517, 40], "iid"), (400, [1000], "signal")])
+def test_tf32x3_vs_oracle(cuda_factory, oracle_factory, mxtips, widths, mode):
+    """CLVs (relative to the site's largest entry), scaler counts up to borderline sites, lnL, repeatability, ragged
+    tiles, several partitions, and the makenewz path on top of tcgen05-written CLVs."""
+    tree, parts, models = random_case(mxtips, widths, [20] * len(widths), seed=31, mode=mode)
+    gpu = build_engine(_tc_factory(cuda_factory), tree, parts, models)
+    cpu = build_engine(oracle_factory, tree, parts, models)
+    ti = tree.full_traversal()
+    lg, lc = gpu.evaluateIterative(ti).copy(), cpu.evaluateIterative(ti)
+    assert np.all(np.abs(lg - lc) <= 1e-6 * np.abs(lc)), (lg, lc)
+    assert np.array_equal(gpu.evaluateIterative(ti), lg)                   # bitwise repeatable
+    worst = 0.0
+    for m, (s, tips, wgt) in enumerate(parts):
+        tot_g = tot_c = 0
+        for e in ti[1:]:
+            a, b = gpu.read_clv(m, e.pNumber), cpu.read_clv(m, e.pNumber)
+            sg, sc = gpu.read_scaler(m, e.pNumber), cpu.read_scaler(m, e.pNumber)
+            tot_g, tot_c = sg, sc
+            if sg == sc:                          # same scaling decisions: the vectors are directly comparable
+                scale = np.abs(b).max(axis=(1, 2), keepdims=True)
+                worst = max(worst, float((np.abs(a - b) / scale).max()))
+        assert abs(tot_g - tot_c) <= 0.02 * max(tot_c, 50), (tot_g, tot_c)
+    assert worst <= 5e-2, worst
+    # partial traversal + Newton-Raphson on the mixed-precision CLVs agrees with the oracle's branch length to 1e-4
+    from examl_b200.likelihood import Likelihood
+    lk, lk2 = Likelihood(tree, gpu, len(parts)), Likelihood(tree, cpu, len(parts))
+    p = tree.start.back
+    z1 = lk.makenewzGeneric(p, p.back, p.z, 10)
+    z2 = lk2.makenewzGeneric(p, p.back, p.z, 10)
+    assert abs(z1[0] - z2[0]) <= 1e-4 * z2[0], (z1, z2)
