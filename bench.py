@@ -333,6 +333,8 @@ def parity_check(w: SimpleNamespace, local_rank: int, lnl_parts: np.ndarray):
     tips = make_sites(w.tree, 0, n, w.kind)
     mc = model_for(w.kind)
     e2 = Engine(w.taxa, 1, 1, device=local_rank)
+    if getattr(w, "aa_precision", 0):
+        e2.set_aa_precision(w.aa_precision)
     o2 = OracleEngine(w.taxa, 1, 1)
     for e in (e2, o2):
         e.set_partition(0, w.states, np.ones(n, dtype=np.int32), tips)
@@ -366,6 +368,8 @@ def run_b200(w: SimpleNamespace, args, rank: int, world: int, local_rank: int, s
 
     t_setup = time.perf_counter()
     eng = Engine(w.taxa, w.nparts, 1, device=local_rank, tile_sites=args.tile)
+    if getattr(w, "aa_precision", 0):
+        eng.set_aa_precision(w.aa_precision)
     if w.model == "psr":
         eng.set_rate_model(0, 25)
     owned = {m for m, _, _ in mine}
@@ -468,7 +472,7 @@ def run_b200(w: SimpleNamespace, args, rank: int, world: int, local_rank: int, s
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{w.name}:{w.sites}x{w.taxa}")
-            if tj and world == 1 and w.model == "gamma":
+            if tj and world == 1 and w.model == "gamma" and not getattr(w, "aa_precision", 0):
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
@@ -490,7 +494,8 @@ def run_b200(w: SimpleNamespace, args, rank: int, world: int, local_rank: int, s
             tf = aflops / trav_s / 1e12
             roofline = {"bound": "tensor", "achieved": tf, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / DMMA_PEAK_TFLOPS,
                         "traffic": traffic, "dram_frac": dram_frac,
-                        "kernel": "traverse_aa_kernel", "kernel_ms": 1e3 * trav_s,
+                        "kernel": "traverse_aa_tc_kernel (tcgen05 kind::tf32; frac is against the FP64 DMMA peak for comparison)"
+                                  if getattr(w, "aa_precision", 0) else "traverse_aa_kernel", "kernel_ms": 1e3 * trav_s,
                         "peak_source": "FP64 tensor pipe (DMMA.8x8x4) measured on this pool with tools/microbench/fp64_rates.cu; "
                                        "MEASURED_PEAKS.json has no FP64 figure",
                         "algorithmic_flops_per_launch": aflops, "hbm_gbs_algorithmic": achieved,
@@ -626,9 +631,13 @@ def main():
 
     if args.workload == "dna" and args.model == "gamma" and not args.no_secondary and args.sites is None and args.taxa is None:
         sec = {}
-        for name, key in (("aa", "aa_c4"), ("c5", "c5")):
+        for name, key in (("aa", "aa_c4"), ("c5", "c5"), ("aa", "aa_c4_tcgen05_tf32x3")):
             try:
                 w2 = make_workload(name, world)
+                if key.endswith("tf32x3"):
+                    # the same C4 workload with the newview on the tcgen05 tensor cores (mixed precision, opt-in)
+                    w2.aa_precision = 1
+                    w2.desc += " -- newview on tcgen05 in 3xTF32 (exb_set_aa_precision), CLVs stored as FP64"
                 r2 = run_b200(w2, args, rank, world, local_rank, min(args.steps, 10), args.warmup, None,
                               cpu_baseline=not args.no_cpu_baseline and world == 1)
                 if rank == 0:

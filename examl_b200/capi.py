@@ -24,7 +24,7 @@ EXPORTS = [
     "exb_comm_unique_id", "exb_comm_init", "exb_read_clv", "exb_read_scaler",
     "exb_read_sumtable", "exb_last_kernel_ms", "exb_launch_count", "exb_set_tile_sites", "exb_set_timing",
     "exb_set_rate_model", "exb_set_categories", "exb_set_model_lg4", "exb_evaluate_partial", "exb_comm_is_p2p",
-    "exb_last_phase_ms", "exb_set_aa_precision",
+    "exb_last_phase_ms", "exb_set_aa_precision", "exb_set_sev", "exb_sev_stats",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -144,6 +144,16 @@ class Engine:
         """rateHetModel: 0 = CAT / PSR (one rate category per site), 1 = GAMMA (axml.h:349-350).  Before set_partition."""
         self.cat = rate_het_model == 0
         self._check(self._f("set_rate_model")(self._h, C.c_int(rate_het_model), C.c_int(max_categories)))
+
+    def set_sev(self, on: bool = True) -> None:
+        """-S: no CLV storage for (node, tile) pairs that are all-gap below the node.  Before set_partition / commit."""
+        self._check(self._f("set_sev")(self._h, C.c_int(1 if on else 0)))
+
+    def sev_stats(self):
+        """(blocks in use, blocks a dense arena would hold, bytes of slabs allocated)."""
+        a, b, c = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        self._check(self._f("sev_stats")(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return int(a.value), int(b.value), int(c.value)
 
     def set_aa_precision(self, mode: int) -> None:
         """0 = FP64 (default), 1 = 3xTF32 on tcgen05 (mixed precision; include/examl_b200.h).  Before set_partition / commit."""

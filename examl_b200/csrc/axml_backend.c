@@ -105,12 +105,11 @@ static void backend_init(tree *tr)
   int m;
   size_t nb = (size_t)tr->numBranches, slots = (size_t)tr->mxtips + 1;
 
-  /* -S (SEV memory saving, *_GAPPED_SAVE kernels): the reference's -S runs produce bit-identical likelihoods to
-     its dense runs (all-gap subtrees share one column instead of storing it per site; checked on testData/49).
-     The engine keeps dense CLVs in HBM, so the option is accepted and changes nothing but the host-side gap
-     bookkeeping the reference sets up for itself (axml.c:2085-2168); exb_commit reports the HBM it needs. */
-  if (tr->saveMemory && processID == 0)
-    printf("\nB200 back-end: -S accepted; CLVs stay dense in HBM (results are identical, the memory saving is not applied)\n");
+  /* -S (SEV memory saving, *_GAPPED_SAVE kernels): handed to the engine, which keeps no CLV block for (node, tile)
+     pairs that are all-gap below the node (exb_set_sev).  The host-side gap vectors the reference sets up for itself
+     (axml.c:2085-2168) stay unused.  Under PSR the engine's arena stays dense. */
+  if (tr->saveMemory && tr->rateHetModel == CAT && processID == 0)
+    printf("\nB200 back-end: -S under PSR: CLVs stay dense in HBM (results are identical, the memory saving is not applied)\n");
   for (m = 0; m < tr->NumberOfModels; m++) {
     const pInfo *p = &tr->partitionData[m];
     if (p->states != 4 && p->states != 20) refuse("binary or multi-state data");
@@ -119,6 +118,7 @@ static void backend_init(tree *tr)
   }
   if (exb_create(&g_engine, local_device(), tr->mxtips, tr->NumberOfModels, tr->numBranches) != EXB_OK)
     backend_fail("exb_create");
+  if (tr->saveMemory && exb_set_sev(g_engine, 1) != EXB_OK) backend_fail("exb_set_sev");
   if (tr->rateHetModel == CAT) {                 /* -m PSR: one rate category per site */
     if (exb_set_rate_model(g_engine, EXB_CAT, tr->maxCategories) != EXB_OK) backend_fail("exb_set_rate_model");
   }

@@ -242,7 +242,24 @@ struct HostPart {
   bool cats_set = false;
 };
 
+// -S (SEV at tile granularity): CLV blocks exist only for (node, tile) pairs that are not all-gap
+struct SevClass {
+  bool on = false;
+  size_t block_doubles = 0;                 // capacity of one block: tile capacity x span
+  int ntiles = 0;
+  std::vector<uint8_t> tipgap, nodegap;      // [mxtips][ntiles], [mxtips-2][ntiles]: all sites of the tile are gaps (below the node)
+  std::vector<double *> table_h;             // [mxtips-2][ntiles] block of the pair, null = none
+  double **table_d = nullptr;
+  double *gapcol = nullptr;                  // [mxtips-2][nparts][span]
+  int *gapw_d = nullptr;                     // [max_entries][nparts] weights of the all-gap tiles per (entry, partition)
+  std::vector<int> gapw_h, tile_wgt;
+  std::vector<double *> free_blocks;
+  std::vector<void *> slabs;
+  size_t blocks_in_use = 0;
+};
+
 struct ClassState {
+  SevClass sev;
   int S = 0, span = 0, codes = 0, model_doubles = 0;
   size_t N = 0;                        // padded number of sites
   int nparts = 0;
@@ -267,6 +284,7 @@ struct exb_engine {
   std::vector<HostPart> parts;
   ClassState cls[2];
   bool cat = false;                    // CAT / PSR: one rate category per site (span = S)
+  bool sev = false;                    // -S: no CLV storage for all-gap (node, tile) pairs (exb_set_sev)
   bool aa_tc = false;                  // AA GAMMA newview on tcgen05 in 3xTF32 (mixed precision, exb_set_aa_precision)
   int max_cats = 4;
   cudaStream_t stream = nullptr;
@@ -314,6 +332,8 @@ struct exb_engine {
 };
 
 constexpr int kMaxParamPartitions = 16;
+// -S: CLV blocks are carved from slabs of ~256 MB that are allocated on demand
+static size_t kSevSlabBlocks(size_t block_doubles) { return std::max<size_t>(1, ((size_t)256 << 20) / (block_doubles * sizeof(double))); }
 constexpr size_t kHostDtabBytes = 16 * 1024;     // per class
 constexpr int kHostDtabMaxExps = 256;            // ~25 ns each on the host: cheaper than a kernel launch below this
 
@@ -362,6 +382,11 @@ extern "C" void exb_destroy(exb_engine *e)
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (int c = 0; c < 2; c++) {
     ClassState &k = e->cls[c];
+    if (k.sev.on) {
+      for (void *sl : k.sev.slabs) cudaFree(sl);
+      k.clv = nullptr;
+      cudaFree(k.sev.table_d); cudaFree(k.sev.gapcol); cudaFree(k.sev.gapw_d);
+    }
     cudaFree(k.tiles); cudaFree(k.clv); cudaFree(k.sum); cudaFree(k.models); cudaFree(k.tile_out);
     cudaFree(k.tips); cudaFree(k.wgt); cudaFree(k.dtab); cudaFree(k.part_global); cudaFree(k.lut);
     cudaFree(k.rate_cat); cudaFree(k.cat_rates);
@@ -395,6 +420,30 @@ extern "C" int exb_set_rate_model(exb_engine *e, int rateHetModel, int maxCatego
     k.span = (e->cat ? 1 : 4) * k.S;
     k.dtab_row = (e->cat ? e->max_cats : 4) * 2 * k.S;
   }
+  return EXB_OK;
+}
+
+extern "C" int exb_set_sev(exb_engine *e, int on)
+{
+  if (!e || e->committed) return fail(EXB_ERR_STATE, "exb_set_sev: must be called before exb_commit");
+  e->sev = on != 0;
+  return EXB_OK;
+}
+
+extern "C" int exb_sev_stats(exb_engine *e, size_t *blocks_in_use, size_t *blocks_dense, size_t *bytes_allocated)
+{
+  if (!e || !e->committed) return fail(EXB_ERR_STATE, "exb_sev_stats: engine not committed");
+  size_t used = 0, dense = 0, bytes = 0;
+  for (int c = 0; c < 2; c++) {
+    const ClassState &k = e->cls[c];
+    if (!k.sev.on) continue;
+    used += k.sev.blocks_in_use;
+    dense += (size_t)(e->mxtips - 2) * k.sev.ntiles;
+    bytes += k.sev.slabs.size() * (size_t)kSevSlabBlocks(k.sev.block_doubles) * k.sev.block_doubles * sizeof(double);
+  }
+  if (blocks_in_use) *blocks_in_use = used;
+  if (blocks_dense) *blocks_dense = dense;
+  if (bytes_allocated) *bytes_allocated = bytes;
   return EXB_OK;
 }
 
@@ -492,6 +541,8 @@ extern "C" int exb_commit(exb_engine *e)
       // (CAT: 384-site chunks, 12 warps x 32 sites)
       const size_t aachunk = e->cat ? 384 : (e->aa_tc ? 32 : 96);      // (tcgen05 path: 32 sites x 4 categories = the MMA's M)
       size_t tsz = c == CLS_AA ? (size_t)((e->tile_sites + aachunk - 1) / aachunk) * aachunk : (size_t)e->tile_sites;
+      // tcgen05 path: one 32-site chunk per CTA unless told otherwise -- four co-resident CTAs per SM want many small tiles
+      if (c == CLS_AA && e->aa_tc && !e->cat && !e->tile_sites_set) tsz = 32;
       // One big DNA partition on a few waves of CTAs (strong scaling: 125 k sites per GPU are 1.65 waves of 256-site
       // tiles): cut it into k full waves of equal tiles instead, so that the last wave is not a third empty.
       if (c == CLS_DNA && !e->cat && !e->tile_sites_set && e->P == 1) {
@@ -558,6 +609,44 @@ extern "C" int exb_commit(exb_engine *e)
       CUDA_TRY(cudaMalloc(&k.rate_cat, n * sizeof(int)));
       CUDA_TRY(cudaMemset(k.rate_cat, 0, n * sizeof(int)));
     }
+    if (e->sev && !e->cat && !(c == CLS_AA && e->aa_tc)) {
+      // -S: no dense arena.  Which (taxon, tile) pairs are all-gap is fixed by the alignment; blocks are handed out per call.
+      SevClass &v = k.sev;
+      v.on = true;
+      v.ntiles = (int)k.tiles_h.size();
+      size_t cap = 0;
+      for (const Tile &t : k.tiles_h) cap = std::max<size_t>(cap, t.nsites);
+      v.block_doubles = cap * k.span;
+      v.tipgap.assign((size_t)e->mxtips * v.ntiles, 1);
+      v.nodegap.assign((size_t)(e->mxtips - 2) * v.ntiles, 0);
+      v.table_h.assign((size_t)(e->mxtips - 2) * v.ntiles, nullptr);
+      v.tile_wgt.assign(v.ntiles, 0);
+      const uint8_t gapcode = (uint8_t)(k.codes - 1);
+      for (int t = 0; t < v.ntiles; t++) {
+        const Tile &tl = k.tiles_h[t];
+        for (uint32_t i = 0; i < tl.nsites; i++) v.tile_wgt[t] += wgt[tl.site0 + i];
+        for (int tip = 0; tip < e->mxtips; tip++) {
+          const uint8_t *row = &tips[(size_t)tip * n + tl.site0];
+          for (uint32_t i = 0; i < tl.nsites; i++) if (row[i] != gapcode) { v.tipgap[(size_t)tip * v.ntiles + t] = 0; break; }
+        }
+      }
+      CUDA_TRY(cudaMalloc(&v.table_d, v.table_h.size() * sizeof(double *)));
+      CUDA_TRY(cudaMemset(v.table_d, 0, v.table_h.size() * sizeof(double *)));
+      CUDA_TRY(cudaMalloc(&v.gapcol, (size_t)(e->mxtips - 2) * k.nparts * k.span * sizeof(double)));
+      CUDA_TRY(cudaMemset(v.gapcol, 0, (size_t)(e->mxtips - 2) * k.nparts * k.span * sizeof(double)));
+      v.gapw_h.assign((size_t)(e->mxtips + 1) * k.nparts, 0);
+      CUDA_TRY(cudaMalloc(&v.gapw_d, v.gapw_h.size() * sizeof(int)));
+      CUDA_TRY(cudaMemset(v.gapw_d, 0, v.gapw_h.size() * sizeof(int)));
+      void *slab = nullptr;                        // the first slab doubles as the base all block offsets are relative to
+      const size_t nblk = kSevSlabBlocks(v.block_doubles);
+      if (cudaMalloc(&slab, nblk * v.block_doubles * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(EXB_ERR_CUDA, "exb_commit: cannot allocate the first CLV slab (-S)");
+      }
+      v.slabs.push_back(slab);
+      for (size_t b = nblk; b-- > 0;) v.free_blocks.push_back((double *)slab + b * v.block_doubles);
+      k.clv = (double *)slab;
+    } else {
     const size_t clv_bytes = (size_t)(e->mxtips - 2) * n * k.span * sizeof(double);
     if (cudaMalloc(&k.clv, clv_bytes) != cudaSuccess) {
       cudaGetLastError();
@@ -565,6 +654,7 @@ extern "C" int exb_commit(exb_engine *e)
                   clv_bytes / 1e9, n, k.S, e->mxtips - 2);
     }
     CUDA_TRY(cudaMemset(k.clv, 0, clv_bytes));
+    }
     CUDA_TRY(cudaMalloc(&k.sum, n * k.span * sizeof(double)));
     CUDA_TRY(cudaMemset(k.sum, 0, n * k.span * sizeof(double)));
     CUDA_TRY(cudaMalloc(&k.tiles, k.tiles_h.size() * sizeof(Tile)));
@@ -793,6 +883,55 @@ static int stage_traversal(exb_engine *e, const exb_entry *ti, int count, int fi
   return EXB_OK;
 }
 
+// -S: walk the descriptor on the host and bring the block table up to date: node p is all-gap in a tile iff both children
+// are (x3_gap = x1_gap & x2_gap, newviewGenericSpecial.c:1182); all-gap pairs give their block back, the others get one.
+// Also sums, per (entry, partition), the pattern weights of the all-gap tiles (scaling events of all-gap sites).
+static int sev_update(exb_engine *e, const exb_entry *ti, int count, int first, const unsigned char *mask)
+{
+  for (int c = 0; c < 2; c++) {
+    ClassState &k = e->cls[c];
+    SevClass &v = k.sev;
+    if (!v.on) continue;
+    const int nt = v.ntiles;
+    std::fill(v.gapw_h.begin(), v.gapw_h.begin() + (size_t)count * k.nparts, 0);
+    for (int i = first; i < count; i++) {
+      const int p = ti[i].pNumber, q = ti[i].qNumber, r = ti[i].rNumber;
+      const size_t row = (size_t)(p - e->mxtips - 1) * nt;
+      const uint8_t *gq = q <= e->mxtips ? &v.tipgap[(size_t)(q - 1) * nt] : &v.nodegap[(size_t)(q - e->mxtips - 1) * nt];
+      const uint8_t *gr = r <= e->mxtips ? &v.tipgap[(size_t)(r - 1) * nt] : &v.nodegap[(size_t)(r - e->mxtips - 1) * nt];
+      bool dirty = false;
+      for (int t = 0; t < nt; t++) {
+        const Tile &tl = k.tiles_h[t];
+        if (mask && !mask[tl.part]) continue;        // a masked partition is not recomputed: its CLVs and gap state stay
+        const uint8_t g = gq[t] & gr[t];
+        v.nodegap[row + t] = g;
+        double *&blk = v.table_h[row + t];
+        if (g) {
+          v.gapw_h[(size_t)i * k.nparts + tl.part_cls] += v.tile_wgt[t];
+          if (blk) { v.free_blocks.push_back(blk); blk = nullptr; v.blocks_in_use--; dirty = true; }
+        } else if (!blk) {
+          if (v.free_blocks.empty()) {
+            void *slab = nullptr;
+            const size_t nblk = kSevSlabBlocks(v.block_doubles);
+            if (cudaMalloc(&slab, nblk * v.block_doubles * sizeof(double)) != cudaSuccess) {
+              cudaGetLastError();
+              return fail(EXB_ERR_CUDA, "-S: out of HBM after %zu CLV blocks of %.1f KB (%zu slabs)", v.blocks_in_use,
+                          v.block_doubles * sizeof(double) / 1024.0, v.slabs.size());
+            }
+            v.slabs.push_back(slab);
+            for (size_t b = nblk; b-- > 0;) v.free_blocks.push_back((double *)slab + b * v.block_doubles);
+          }
+          blk = v.free_blocks.back(); v.free_blocks.pop_back(); v.blocks_in_use++; dirty = true;
+        }
+      }
+      if (dirty) CUDA_TRY(cudaMemcpyAsync(v.table_d + row, &v.table_h[row], (size_t)nt * sizeof(double *), cudaMemcpyHostToDevice, e->stream));
+    }
+    if (count > first)
+      CUDA_TRY(cudaMemcpyAsync(v.gapw_d, v.gapw_h.data(), (size_t)count * k.nparts * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  }
+  return EXB_OK;
+}
+
 static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int first, const double *qz, const double *rz,
                          const unsigned char *mask, int mode)
 {
@@ -806,6 +945,7 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   if (rc) return rc;
   rc = flush_models(e);
   if (rc) return rc;
+  if (e->sev) { rc = sev_update(e, ti, count, first, mask); if (rc) return rc; }
   if (e->timing) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
   const double *dtab_use[2] = {nullptr, nullptr};
   for (int c = 0; c < 2; c++) {                    // tables first: d-table (makeP exponentials), AA tip look-up table
@@ -823,6 +963,17 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
       d.eign_cat_stride = c == CLS_AA ? 20 : 0; d.rates_off = c == CLS_AA ? kAaRates : k.S; d.lg4_off = c == CLS_AA ? kAaLg4 : -1;
       launch_dtab(d, e->stream);
       e->launches++;
+    }
+    if (k.sev.on) {                                 // -S: gap columns of the descriptor's nodes (needs the d-table)
+      GapcolArgs g;
+      g.gapcol = k.sev.gapcol; g.entries = (const DevEntry *)(e->stage_use + e->o_entries);
+      g.first = first; g.count = count; g.mxtips = e->mxtips;
+      g.dtab = dtab_use[c]; g.dtab_row = k.dtab_row; g.nparts_cls = k.nparts;
+      g.models = k.models; g.model_doubles = k.model_doubles; g.states = k.S;
+      g.gapw = k.sev.gapw_d; g.cls_part_global = k.part_global; g.mask = e->stage_use + e->o_mask;
+      g.scale_inc = e->scale_inc; g.nparts = e->P;
+      launch_gapcol(g, e->stream);
+      if (count > first) e->launches++;
     }
     if (c == CLS_AA && k.lut) {
       LutArgs l;
@@ -849,6 +1000,8 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
     a.mask = e->stage_use + e->o_mask;
     a.count = count; a.first = first; a.mode = mode;
     a.scale_inc = e->scale_inc; a.tile_out = k.tile_out;
+    a.sev_table = k.sev.on ? k.sev.table_d : nullptr; a.sev_tipgap = nullptr; a.sev_gapcol = k.sev.gapcol;
+    a.sev_ntiles = k.sev.ntiles; a.sev_tile0 = 0;
     if (c == CLS_DNA && k.nparts <= kMaxParamPartitions) {
       // few partitions: one launch per partition, its EI/EV travel as kernel parameters (constant bank)
       for (int pc = 0; pc < k.nparts; pc++) {
@@ -858,6 +1011,7 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
         memcpy(kc.EV, &k.models_h[(size_t)pc * k.model_doubles + 24], sizeof kc.EV);
         TraverseArgs ap = a;
         ap.tiles = k.tiles + k.cp_tile_begin[pc];
+        ap.sev_tile0 = k.cp_tile_begin[pc];
         ap.tile_out = k.tile_out + 2 * (size_t)k.cp_tile_begin[pc];
         if (e->cat) launch_traverse_dna_cat(ap, &kc, k.cp_tile_count[pc], e->stream);
         else        launch_traverse_dna(ap, &kc, k.cp_tile_count[pc], e->stream);
@@ -1365,6 +1519,19 @@ extern "C" int exb_read_clv(exb_engine *e, int model, int nodeNumber, double *ou
   ClassState &k = e->cls[p.cls];
   if (p.width == 0) return EXB_OK;
   CUDA_TRY(cudaSetDevice(e->device));
+  if (k.sev.on) {                                  // -S: tile by tile -- a block, or the node's gap column for every site
+    const size_t row = (size_t)(nodeNumber - e->mxtips - 1);
+    std::vector<double> gap((size_t)k.span);
+    CUDA_TRY(cudaMemcpy(gap.data(), k.sev.gapcol + (row * k.nparts + p.part_cls) * k.span, k.span * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int t = k.cp_tile_begin[p.part_cls]; t < k.cp_tile_begin[p.part_cls] + k.cp_tile_count[p.part_cls]; t++) {
+      const Tile &tl = k.tiles_h[t];
+      double *dst = out + (size_t)(tl.site0 - p.site0) * k.span;
+      const double *blk = k.sev.table_h[row * k.sev.ntiles + t];
+      if (blk) CUDA_TRY(cudaMemcpy(dst, blk, (size_t)tl.nsites * k.span * sizeof(double), cudaMemcpyDeviceToHost));
+      else for (uint32_t i = 0; i < tl.nsites; i++) memcpy(dst + (size_t)i * k.span, gap.data(), k.span * sizeof(double));
+    }
+    return EXB_OK;
+  }
   const double *src = k.clv + ((size_t)(nodeNumber - e->mxtips - 1) * k.N + p.site0) * k.span;
   CUDA_TRY(cudaMemcpy(out, src, p.width * k.span * sizeof(double), cudaMemcpyDeviceToHost));
   return EXB_OK;

@@ -88,6 +88,13 @@ struct TraverseArgs {
   int           dtab_row;   // doubles per (entry, partition) in dtab
   int           nparts_cls;
   int           tile_sites; // sites per tile (multiple of 32)
+  // -S (SEV, subtree equality vectors at tile granularity; null / 0 when off): a (node, tile) pair whose sites are all
+  // gaps in the whole subtree below the node owns no CLV block -- every such site equals the node's "gap column"
+  const double *const *sev_table;   // [mxtips-2][sev_ntiles] block of the (node, tile) pair; null = all-gap
+  const uint8_t *sev_tipgap;        // [mxtips][sev_ntiles]   1 = all sites of the tile are gaps in this taxon (unused by the kernels: tips always go through their codes)
+  const double *sev_gapcol;         // [mxtips-2][nparts_cls][span] CLV of an all-gap site at every inner node
+  int           sev_ntiles;         // tiles of the class
+  int           sev_tile0;          // class-wide index of this launch's tile 0
 };
 
 // DNA constants of a class that holds a single partition: passed by value so that every EI/EV
@@ -215,6 +222,19 @@ void launch_traverse_aa_tc(const TraverseArgs &a, int ntiles, cudaStream_t s);
 void launch_core_aa(const CoreArgs &a, int ntiles, cudaStream_t s);
 void launch_finish(const FinishArgs &a, cudaStream_t s);
 void launch_p2p_warmup(const P2pArgs &x, unsigned int xseq, int stride, cudaStream_t s);
+
+// -S: gap columns of the inner nodes of a descriptor, in entry order (kernels_sev.cu)
+struct GapcolArgs {
+  double *gapcol;              // [mxtips-2][nparts_cls][span]
+  const DevEntry *entries; int first, count, mxtips;
+  const double *dtab; int dtab_row, nparts_cls;
+  const double *models; int model_doubles, states;
+  const int *gapw;             // [count][nparts_cls] summed pattern weights of the partition's all-gap tiles at entry's node
+  const int *cls_part_global;  // [nparts_cls] -> global partition
+  const unsigned char *mask;   // [P]
+  unsigned int *scale_inc; int nparts;
+};
+void launch_gapcol(const GapcolArgs &a, cudaStream_t s);
 
 // Dynamic shared memory above 48 KB is an opt-in per (kernel, device): remember what each device was given.
 constexpr int kMaxDevices = 64;

@@ -276,9 +276,12 @@ traverse_aa_kernel(const TraverseArgs a)
     do {
     const int w1 = min(w0 + kWindow, a.count);
     phase = stage_window<TSITES>(dyn, &mbar, phase, a.entries, a.tips, a.mxtips, N, XSPAN, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
-                         a.first, a.count, w0 == a.first && a.mode != MODE_NEWVIEW);
+                         a.first, a.count, w0 == a.first && a.mode != MODE_NEWVIEW, nullptr, 0, 0,
+                         SevView{CAT ? nullptr : a.sev_table, a.sev_gapcol, a.clv, a.sev_ntiles, a.sev_tile0 + (int)blockIdx.x, tile.part_cls,
+                                 a.nparts_cls, XSPAN, tile.site0});
     for (int e = w0; e < w1; e++) {
       const SEntry en = ents[e - w0];
+      if (en.flags & kFlagGapP) continue;       // -S: all sites of the tile are gaps below this node: nothing to compute or store
       const double *drow = drow0 + (size_t)e * dstride;
       const bool q_inner = en.tipCase == 2, r_inner = en.tipCase != 0;
       const int qsrc = !q_inner ? SRC_TIP : ((en.flags & kFlagCarryA) ? SRC_CARRY : SRC_LOAD);
@@ -298,8 +301,8 @@ traverse_aa_kernel(const TraverseArgs a)
         }
       } else {
         const int code1 = q_inner ? 0 : stips[en.qoff + lsite[0]], code2 = r_inner ? 0 : stips[en.roff + lsite[0]];
-        sl.x1 = q_inner ? a.clv + en.qoff + soff : &K.tip[0][S * code1];
-        sl.x2 = r_inner ? a.clv + en.roff + soff : &K.tip[0][S * code2];
+        sl.x1 = q_inner ? a.clv + en.qoff + ((en.flags & kFlagGapA) ? 0 : soff) : &K.tip[0][S * code1];    // -S: gap column of the node
+        sl.x2 = r_inner ? a.clv + en.roff + ((en.flags & kFlagGapB) ? 0 : soff) : &K.tip[0][S * code2];
         sl.st1 = q_inner ? S : (LG4 ? 460 : 0); sl.st2 = r_inner ? S : (LG4 ? 460 : 0);
         sl.lut1 = lutE + (size_t)code1 * SPAN; sl.lut2 = lutE + lutside + (size_t)code2 * SPAN;
         sl.drow = drow;
@@ -382,10 +385,10 @@ traverse_aa_kernel(const TraverseArgs a)
         double2 xa = make_double2(0.0, 0.0), xb = make_double2(0.0, 0.0);
         if (p_carry) xa = make_double2(carry[c][t][0], carry[c][t][1]);
         else if (live) xa = ptip ? *reinterpret_cast<const double2 *>(tpa + col)
-                                 : ld128(a.clv + br.poff + soff + c * XSLOT + col);
+                                 : ld128(a.clv + br.poff + ((br.flags & kFlagGapA) ? 0 : soff) + c * XSLOT + col);
         if (q_carry) xb = make_double2(carry[c][t][0], carry[c][t][1]);
         else if (live) xb = qtip ? *reinterpret_cast<const double2 *>(tpb + col)
-                                 : ld128(a.clv + br.qoff + soff + c * XSLOT + col);
+                                 : ld128(a.clv + br.qoff + ((br.flags & kFlagGapB) ? 0 : soff) + c * XSLOT + col);
         if (a.mode == MODE_SUM) {
           if (valid[c] && live) *reinterpret_cast<double2 *>(a.sum + soff + c * XSLOT + col) = make_double2(xa.x * xb.x, xa.y * xb.y);
         } else if (live) {

@@ -102,11 +102,11 @@ __device__ __forceinline__ unsigned int dna_entry(double (&carry)[NS][4], const 
     double x1[4], x2[4];
     if (QS == 1) { x1[0] = carry[s][0]; x1[1] = carry[s][1]; x1[2] = carry[s][2]; x1[3] = carry[s][3]; }
     else if (QS == 2) { const double *r = ring + (size_t)s * kThreads * 4; x1[0] = r[0]; x1[1] = r[1]; x1[2] = r[2]; x1[3] = r[3]; }
-    else if (QS == 3) ld256(a.clv + en.qoff + eoff[s], x1);
+    else if (QS == 3) ld256(a.clv + en.qoff + ((en.flags & kFlagGapA) ? (size_t)(c * 4) : eoff[s]), x1);
     else { const double *tv = &sh.tip[4 * stips[en.qoff + lsite[s]]]; x1[0] = tv[0]; x1[1] = tv[1]; x1[2] = tv[2]; x1[3] = tv[3]; }
     if (RS == 1) { x2[0] = carry[s][0]; x2[1] = carry[s][1]; x2[2] = carry[s][2]; x2[3] = carry[s][3]; }
     else if (RS == 2) { const double *r = ring + (size_t)s * kThreads * 4; x2[0] = r[0]; x2[1] = r[1]; x2[2] = r[2]; x2[3] = r[3]; }
-    else if (RS == 3) ld256(a.clv + en.roff + eoff[s], x2);
+    else if (RS == 3) ld256(a.clv + en.roff + ((en.flags & kFlagGapB) ? (size_t)(c * 4) : eoff[s]), x2);
     else { const double *tv = &sh.tip[4 * stips[en.roff + lsite[s]]]; x2[0] = tv[0]; x2[1] = tv[1]; x2[2] = tv[2]; x2[3] = tv[3]; }
     qa[s][0] = x1[0]; qa[s][1] = dq1 * x1[1]; qa[s][2] = dq2 * x1[2]; qa[s][3] = dq3 * x1[3];
     ra[s][0] = x2[0]; ra[s][1] = dr1 * x2[1]; ra[s][2] = dr2 * x2[2]; ra[s][3] = dr3 * x2[3];
@@ -259,29 +259,35 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
     do {
     const int w1 = min(w0 + KW, a.count);
     phase = stage_window<TS, KW>(dyn, &mbar, phase, a.entries, a.tips, a.mxtips, N, 16, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
-                                 a.first, a.count, w0 == a.first && a.mode != MODE_NEWVIEW, drow0, dstride, kDnaDtabRow);
+                                 a.first, a.count, w0 == a.first && a.mode != MODE_NEWVIEW, drow0, dstride, kDnaDtabRow,
+                                 SevView{a.sev_table, a.sev_gapcol, a.clv, a.sev_ntiles, a.sev_tile0 + (int)blockIdx.x, tile.part_cls,
+                                         a.nparts_cls, 16, tile.site0});
     for (int e = w0; e < w1; e++) {
       const SEntry en = ents[e - w0];
       // The one inner child that is neither a tip nor in the carry registers comes through the prefetch ring: its
       // cp.async was issued while the PREVIOUS entry was being computed (the window's first entry issues its own).
-      const int mine = ring_child(en);
+      // (-S: an all-gap child is the node's gap column -- the same 32 bytes for every site of the thread.)
+      const int mine = (en.flags & kFlagGapP) ? 0 : ring_child(en);
       if (e == w0 && mine) {
         const double *src = a.clv + (mine == 1 ? en.qoff : en.roff);
+        const bool gap = en.flags & (mine == 1 ? kFlagGapA : kFlagGapB);
         #pragma unroll
-        for (int s = 0; s < NS; s++) async_copy32(myring + (size_t)((e & 1) * NS + s) * kThreads * 4, src + eoff[s]);
+        for (int s = 0; s < NS; s++) async_copy32(myring + (size_t)((e & 1) * NS + s) * kThreads * 4, src + (gap ? (size_t)(c * 4) : eoff[s]));
       }
       async_commit();
       if (e + 1 < w1) {
         const SEntry nx = ents[e + 1 - w0];
-        const int next = ring_child(nx);
+        const int next = (nx.flags & kFlagGapP) ? 0 : ring_child(nx);
         if (next) {
           const double *src = a.clv + (next == 1 ? nx.qoff : nx.roff);
+          const bool gap = nx.flags & (next == 1 ? kFlagGapA : kFlagGapB);
           #pragma unroll
-          for (int s = 0; s < NS; s++) async_copy32(myring + (size_t)(((e + 1) & 1) * NS + s) * kThreads * 4, src + eoff[s]);
+          for (int s = 0; s < NS; s++) async_copy32(myring + (size_t)(((e + 1) & 1) * NS + s) * kThreads * 4, src + (gap ? (size_t)(c * 4) : eoff[s]));
         }
       }
       async_commit();
       async_wait_all_but_last();               // this entry's operand has landed; the next entry's stays in flight
+      if (en.flags & kFlagGapP) continue;      // -S: all sites of the tile are gaps below this node: nothing to compute or store
 
       const double *sd = sdtab + (size_t)(e - w0) * kDnaDtabRow + c * 8;
       const double *rg = myring + (size_t)((e & 1) * NS) * kThreads * 4;
@@ -319,10 +325,10 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
     for (int s = 0; s < NS; s++) {
       double xa[4], xb[4];
       if (p_carry) { xa[0] = carry[s][0]; xa[1] = carry[s][1]; xa[2] = carry[s][2]; xa[3] = carry[s][3]; }
-      else if (!ptip) ld256(a.clv + br.poff + eoff[s], xa);
+      else if (!ptip) ld256(a.clv + br.poff + ((br.flags & kFlagGapA) ? (size_t)(c * 4) : eoff[s]), xa);
       else { const double *tv = &sh.tip[4 * stips[br.poff + lsite[s]]]; xa[0] = tv[0]; xa[1] = tv[1]; xa[2] = tv[2]; xa[3] = tv[3]; }
       if (q_carry) { xb[0] = carry[s][0]; xb[1] = carry[s][1]; xb[2] = carry[s][2]; xb[3] = carry[s][3]; }
-      else if (!qtip) ld256(a.clv + br.qoff + eoff[s], xb);
+      else if (!qtip) ld256(a.clv + br.qoff + ((br.flags & kFlagGapB) ? (size_t)(c * 4) : eoff[s]), xb);
       else { const double *tv = &sh.tip[4 * stips[br.qoff + lsite[s]]]; xb[0] = tv[0]; xb[1] = tv[1]; xb[2] = tv[2]; xb[3] = tv[3]; }
       if (a.mode == MODE_SUM) {
         double sm[4];

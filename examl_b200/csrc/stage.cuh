@@ -16,6 +16,11 @@ namespace exb {
 
 constexpr int kWindow = 96;                  // entries per window
 
+struct SevView {           // what stage_window needs to resolve (node, tile) pairs under -S; table == null: dense arena
+  const double *const *table; const double *gapcol; const double *clv;
+  int ntiles, tile, part_cls, nparts_cls, span; unsigned tile_site0;
+};
+
 struct SEntry {            // a traversal entry as the threads consume it (32 B)
   int tipCase;             // -1 for the branch entry
   int flags;               // kFlag*: which operand is a tip (branch entry) / sits in the carry registers
@@ -26,6 +31,9 @@ struct SEntry {            // a traversal entry as the threads consume it (32 B)
 // branch entry: p / q is a tip.  Any entry: the operand is the CLV the previous entry of this call produced, i.e. it is
 // still in the thread's carry registers (newview entries: q / r; branch entry: p / q).
 constexpr int kFlagPTip = 1, kFlagQTip = 2, kFlagCarryA = 4, kFlagCarryB = 8;
+// -S: the operand (newview: q / r, branch: p / q) resp. the newview entry's parent is an all-gap (node, tile): the operand
+// is read from the node's gap column (its offset then lacks the per-site term), the parent is neither computed nor stored
+constexpr int kFlagGapA = 16, kFlagGapB = 32, kFlagGapP = 64;
 
 __device__ __forceinline__ uint32_t stage_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
@@ -77,11 +85,15 @@ __host__ __device__ constexpr size_t window_dtab_offset()
 //   drow     : null, or this partition's row of entry 0 in the d-table; rows of `drow_doubles` doubles, `dstride` doubles
 //              apart, are staged behind the tips (row of entry e in slot e - w0, the branch entry's row 0 in slot KW): the
 //              exponentials of an entry then cost the threads a shared-memory read instead of an L2 round trip
+//   sev      : -S view of this tile (table == null: dense arena).  Inner-node offsets then come from the block table
+//              (relative to `clv`, minus the tile's first site so that the kernels' site term still applies), all-gap
+//              operands point at the node's gap column and are flagged
 template <int TSB, int KW = kWindow>
 __device__ __noinline__ uint32_t stage_window(unsigned char *dyn, uint64_t *mbar, uint32_t phase, const DevEntry *entries,
                                               const uint8_t *tips, int mxtips, size_t N, int span_el, size_t chunk_site0,
                                               unsigned nchunk, int w0, int w1, int first, int count, bool with_branch,
-                                              const double *drow = nullptr, size_t dstride = 0, int drow_doubles = 0)
+                                              const double *drow = nullptr, size_t dstride = 0, int drow_doubles = 0,
+                                              SevView sev = SevView{nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0u})
 {
   SEntry *ents = reinterpret_cast<SEntry *>(dyn);
   uint8_t *stips = dyn + (size_t)(KW + 1) * sizeof(SEntry);
@@ -103,6 +115,20 @@ __device__ __noinline__ uint32_t stage_window(unsigned char *dyn, uint64_t *mbar
     se.poff = en.p > mxtips ? (long long)(en.p - mxtips - 1) * (long long)N * span_el : (long long)(2 * slot + 1) * TSB;
     se.qoff = en.q > mxtips ? (long long)(en.q - mxtips - 1) * (long long)N * span_el : (long long)(2 * slot) * TSB;
     se.roff = en.r > mxtips ? (long long)(en.r - mxtips - 1) * (long long)N * span_el : (long long)(2 * slot + 1) * TSB;
+    if (sev.table) {
+      // inner nodes: block of (node, tile), or the node's gap column when the pair is all-gap
+      auto resolve = [&](int node, long long &off, int gapflag, int carryflag) {
+        if (node <= mxtips || node == 0) return;
+        const double *blk = sev.table[(size_t)(node - mxtips - 1) * sev.ntiles + sev.tile];
+        if (blk) off = (long long)(blk - sev.clv) - (long long)sev.tile_site0 * sev.span;
+        else {
+          off = (long long)(sev.gapcol + ((size_t)(node - mxtips - 1) * sev.nparts_cls + sev.part_cls) * sev.span - sev.clv);
+          se.flags = (se.flags | gapflag) & ~carryflag;
+        }
+      };
+      if (is_branch) { resolve(en.p, se.poff, kFlagGapA, kFlagCarryA); resolve(en.q, se.qoff, kFlagGapB, kFlagCarryB); }
+      else { resolve(en.p, se.poff, kFlagGapP, 0); resolve(en.q, se.qoff, kFlagGapA, kFlagCarryA); resolve(en.r, se.roff, kFlagGapB, kFlagCarryB); }
+    }
     ents[slot] = se;
   }
   __syncthreads();

@@ -122,6 +122,17 @@ int  exb_set_model(exb_engine *e, int model, const double *EIGN, const double *E
 int  exb_set_model_lg4(exb_engine *e, int model, const double *EIGN, const double *EV, const double *EI,
                        const double *tipVector, const double *gammaRates, const double *weights);
 
+/* -S, the memory saving option for gappy alignments (tr->saveMemory; SEV, newviewGenericSpecial.c:1160-1216,
+ * newviewGTRGAMMA_AVX_GAPPED_SAVE avxLikelihood.c:1806, ...PROT... :3125).  The reference keeps, per inner node, only the
+ * sites that are not all-gap in the subtree below it plus one shared "gap column".  The engine applies the idea per
+ * (node, tile of <= tile_sites sites): a pair whose sites are all gaps below the node owns no CLV block, is neither
+ * computed nor written, and reads as the node's gap column; blocks come from slabs allocated on demand, so the HBM
+ * footprint follows the data instead of (taxa - 2) x sites.  Results are those of the dense run.  GAMMA only (under
+ * EXB_CAT the arena stays dense).  Before exb_commit.  exb_sev_stats: blocks in use / blocks a dense arena would hold /
+ * bytes of slabs allocated (any pointer may be NULL). */
+int  exb_set_sev(exb_engine *e, int on);
+int  exb_sev_stats(exb_engine *e, size_t *blocks_in_use, size_t *blocks_dense, size_t *bytes_allocated);
+
 /* Arithmetic of the protein (20-state) GAMMA newview.  EXB_AA_FP64 (default): FP64 throughout, on the FP64 tensor pipe
  * (DMMA) -- the reference's precision (newviewGTRGAMMAPROT_AVX avxLikelihood.c:1312).  EXB_AA_TF32X3: the contractions
  * run on the tcgen05 tensor cores as 3xTF32 products with FP32 accumulators in tensor memory, site vectors renormalised

@@ -62,6 +62,7 @@ int exb_set_categories(exb_engine *e, int model, int n, const double *rates, con
 int exb_comm_unique_id(void *id_out) { memset(id_out, 0, EXB_UNIQUE_ID_BYTES); return EXB_OK; }
 int exb_comm_init(exb_engine *e, int rank, int nranks, const void *id) { (void)rank; (void)id; e->nranks = nranks; return EXB_OK; }
 int exb_comm_is_p2p(exb_engine *e) { (void)e; return 0; }
+int exb_set_sev(exb_engine *e, int on) { (void)e; (void)on; return EXB_OK; }     /* the CPU checker keeps dense CLVs */
 
 int exb_newview(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz, const unsigned char *mask)
 { e->calls++; return orc_newview(e->o, ti, count, qz, rz, mask); }

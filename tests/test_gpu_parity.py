@@ -505,3 +505,75 @@ def test_tf32x3_vs_oracle(cuda_factory, oracle_factory, mxtips, widths, mode):
     z1 = lk.makenewzGeneric(p, p.back, p.z, 10)
     z2 = lk2.makenewzGeneric(p, p.back, p.z, 10)
     assert abs(z1[0] - z2[0]) <= 1e-4 * z2[0], (z1, z2)
+
+
+# ---- -S: no CLV blocks for (node, tile) pairs that are all-gap below the node -------------------------------------------
+def _gappy_case(mxtips, widths, kinds, seed, mode="signal", missing=0.5):
+    """Phylogenomic missing data: in every partition a random subset of the taxa is entirely absent (gap code)."""
+    tree, parts, models = random_case(mxtips, widths, kinds, seed=seed, mode=mode)
+    rng = np.random.default_rng(seed + 5)
+    out = []
+    for s, tips, wgt in parts:
+        tips = tips.copy()
+        absent = rng.random(mxtips) < missing
+        absent[rng.integers(0, mxtips)] = False           # somebody is always there
+        tips[absent, :] = 15 if s == 4 else 22
+        out.append((s, tips, wgt))
+    return tree, out, models
+
+
+@pytest.mark.parametrize("mxtips,widths,kinds,tile,mode", [
+    (30, [600, 500, 300, 200], [4, 4, 4, 20], 256, "signal"),
+    (64, [130, 257, 96, 400], [4, 20, 4, 20], 64, "iid"),          # small tiles, scaling fires
+    (120, [40 + 9 * (i % 7) for i in range(20)], [4] * 20, 256, "signal"),   # > 16 DNA partitions: constants from shared memory
+])
+def test_sev_matches_dense_oracle_and_saves_blocks(cuda_factory, oracle_factory, mxtips, widths, kinds, tile, mode):
+    tree, parts, models = _gappy_case(mxtips, widths, kinds, seed=77, mode=mode)
+
+    def sev_factory(mx, npart, nb=1, **kw):
+        e = cuda_factory(mx, npart, nb, tile_sites=tile, **kw)
+        e.set_sev(True)
+        return e
+    gpu = build_engine(sev_factory, tree, parts, models)
+    cpu = build_engine(oracle_factory, tree, parts, models)
+    _compare_engines(gpu, cpu, tree, parts)                       # lnL, every CLV (gap tiles expand to the gap column), scalers
+    used, dense, nbytes = gpu.sev_stats()
+    assert 0 < used < 0.8 * dense, (used, dense)
+    # masks, then a different root (partial traversals re-orient nodes: blocks are handed back and taken)
+    mask = np.array([i % 2 == 0 for i in range(len(widths))], dtype=np.uint8)
+    _compare_engines(gpu, cpu, tree, parts, mask=mask)
+    from examl_b200.likelihood import Likelihood
+    tree2 = _gappy_case(mxtips, widths, kinds, seed=77, mode=mode)[0]          # same tree, own orientation flags
+    tree.full_traversal(); tree2.full_traversal()
+    lk, lk2 = Likelihood(tree, gpu, len(parts)), Likelihood(tree2, cpu, len(parts))
+    for num in (2, mxtips // 2, mxtips, mxtips + 3, 2 * mxtips - 3):
+        node, node2 = tree.nodep[num], tree2.nodep[num]
+        a, b = lk.evaluateGeneric(node, False), lk2.evaluateGeneric(node2, False)
+        assert abs(a - b) <= 1e-10 * abs(b), (num, a, b)
+        z1 = lk.makenewzGeneric(node, node.back, node.z, 10)
+        z2 = lk2.makenewzGeneric(node2, node2.back, node2.z, 10)
+        assert abs(z1[0] - z2[0]) <= 1e-8 * z2[0]
+    a, b = lk.evaluateGeneric(tree.start, True), lk2.evaluateGeneric(tree2.start, True)
+    assert abs(a - b) <= 1e-10 * abs(b)
+    used2, _, _ = gpu.sev_stats()
+    assert used2 == used, (used, used2)                            # back at the original orientation: same blocks in use
+    # the dense engine computes the same numbers
+    dense_eng = build_engine(lambda mx, npart, nb=1, **kw: cuda_factory(mx, npart, nb, tile_sites=tile, **kw), tree, parts, models)
+    assert np.allclose(dense_eng.evaluateIterative(tree.full_traversal()), gpu.evaluateIterative(tree.full_traversal()), rtol=1e-12, atol=0)
+
+
+def test_sev_footprint_follows_the_data(cuda_factory):
+    """A supermatrix that is 3/4 missing data: the slabs the engine allocated hold far less than the dense arena."""
+    tree, parts, models = _gappy_case(200, [20000] * 6, [4] * 6, seed=3, missing=0.75)
+    e = cuda_factory(200, 6, 1)
+    e.set_sev(True)
+    for m, (s, tips, wgt) in enumerate(parts):
+        e.set_partition(m, s, wgt, tips)
+    e.commit()
+    for m, mc in enumerate(models):
+        e.set_model(m, mc)
+    e.evaluateIterative(tree.full_traversal())
+    used, dense, nbytes = e.sev_stats()
+    dense_bytes = 198 * 120000 * 128
+    print("SEV blocks", used, "of", dense, "slab bytes", nbytes, "dense arena", dense_bytes)
+    assert used < 0.5 * dense and nbytes < 0.6 * dense_bytes
