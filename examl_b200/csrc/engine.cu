@@ -35,7 +35,7 @@ finish_kernel(const FinishArgs a)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int part = blockIdx.x; part < a.nparts; part += gridDim.x) {
     const bool exec = a.mask[part] && a.part_has_sites[part];
-    unsigned int *gs = a.gs + (size_t)part * 2 * a.mxtips;
+    unsigned int *gs = a.gs + (size_t)part * a.gs_stride;
     // ---- (1) scaler chain, sequential in the entries: warp 0, in shared memory when the row fits ----
     if (exec && a.count > a.first && warp == 0) {
       if (a.gs_in_smem) {
@@ -278,6 +278,7 @@ struct ClassState {
 
 struct exb_engine {
   int device = 0, mxtips = 0, P = 0, nb = 1;
+  int gs_stride = 0;                   // entries per partition row of gs
   int tile_sites = 256;
   bool tile_sites_set = false;         // exb_set_tile_sites was called: no automatic balancing
   bool committed = false;
@@ -674,8 +675,9 @@ extern "C" int exb_commit(exb_engine *e)
   CUDA_TRY(upload_ints(&e->part_cls, pcls));
 
   e->max_entries = e->mxtips + 1;                 // td[0].ti holds mxtips entries (axml.c:595)
-  CUDA_TRY(cudaMalloc(&e->gs, (size_t)e->P * 2 * e->mxtips * sizeof(unsigned int)));
-  CUDA_TRY(cudaMemset(e->gs, 0, (size_t)e->P * 2 * e->mxtips * sizeof(unsigned int)));
+  e->gs_stride = 2 * e->mxtips + kScratchNodes;   // globalScaler has 2*mxtips entries (axml.c:1966-1971); + the scratch nodes of exb_score_insertions
+  CUDA_TRY(cudaMalloc(&e->gs, (size_t)e->P * e->gs_stride * sizeof(unsigned int)));
+  CUDA_TRY(cudaMemset(e->gs, 0, (size_t)e->P * e->gs_stride * sizeof(unsigned int)));
   CUDA_TRY(cudaMalloc(&e->scale_inc, (size_t)e->max_entries * e->P * sizeof(unsigned int)));
   CUDA_TRY(cudaMemset(e->scale_inc, 0, (size_t)e->max_entries * e->P * sizeof(unsigned int)));
   CUDA_TRY(cudaMalloc(&e->out_d, (size_t)2 * e->P * sizeof(double)));
@@ -1040,7 +1042,7 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   if (e->timing) CUDA_TRY(cudaEventRecord(e->ev_b, e->stream));
   e->phases_valid = e->timing;
   FinishArgs f;
-  f.gs = e->gs; f.scale_inc = e->scale_inc;
+  f.gs = e->gs; f.gs_stride = e->gs_stride; f.scale_inc = e->scale_inc;
   f.entries = (const DevEntry *)(e->stage_use + e->o_entries);
   f.count = count; f.first = first; f.mxtips = e->mxtips; f.nparts = e->P;
   f.mask = e->stage_use + e->o_mask; f.part_has_sites = e->part_has_sites;
@@ -1182,7 +1184,7 @@ extern "C" int exb_core(exb_engine *e, const double *lz, const unsigned char *ex
   }
   FinishArgs f;
   memset(&f, 0, sizeof f);
-  f.gs = e->gs; f.scale_inc = e->scale_inc; f.entries = (const DevEntry *)(e->stage_use + e->off_entries);
+  f.gs = e->gs; f.gs_stride = e->gs_stride; f.scale_inc = e->scale_inc; f.entries = (const DevEntry *)(e->stage_use + e->off_entries);
   f.count = 0; f.first = 0; f.mxtips = e->mxtips; f.nparts = e->P;
   f.mask = e->stage_use + e->off_mask; f.part_has_sites = e->part_has_sites;
   f.tile_out[0] = e->cls[0].tile_out; f.tile_out[1] = e->cls[1].tile_out;
@@ -1543,7 +1545,7 @@ extern "C" int exb_read_scaler(exb_engine *e, int model, int nodeNumber, unsigne
   if (model < 0 || model >= e->P || nodeNumber < 1 || nodeNumber > 2 * e->mxtips - 2)
     return fail(EXB_ERR_ARG, "exb_read_scaler: bad partition/node");
   CUDA_TRY(cudaSetDevice(e->device));
-  CUDA_TRY(cudaMemcpy(out, e->gs + (size_t)model * 2 * e->mxtips + nodeNumber, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(out, e->gs + (size_t)model * e->gs_stride + nodeNumber, sizeof(unsigned int), cudaMemcpyDeviceToHost));
   return EXB_OK;
 }
 

@@ -11,7 +11,7 @@ constexpr double kTwoToThe256 =                      // axml.h:113-116
     115792089237316195423570985008687907853269984665640564039457584007913129639936.0;
 constexpr double kMinLikelihood = 1.0 / kTwoToThe256;  // axml.h:118
 
-enum Mode : int { MODE_NEWVIEW = 0, MODE_EVALUATE = 1, MODE_SUM = 2, MODE_CORE = 3 };
+enum Mode : int { MODE_NEWVIEW = 0, MODE_EVALUATE = 1, MODE_SUM = 2, MODE_CORE = 3, MODE_SCORE = 4 };
 
 // Data-type class: all partitions with the same number of states share one site axis.
 constexpr int CLS_DNA = 0;   // 4 states, 16 tip codes, span 16 doubles  (128 B per site and node)
@@ -36,7 +36,10 @@ struct Tile {
 };
 
 // traversalInfo without branch arrays (mirrors exb_entry)
+//   tipCase: -1 branch entry | 0..2 newview | (0..2) + kScoreBit: scoring entry of exb_score_insertions (p = -(candidate + 1))
 struct DevEntry { int tipCase, p, q, r; };
+constexpr int kScoreBit = 4;
+constexpr int kScratchNodes = 64;                    // EXB_SCRATCH_NODES: node numbers 2*mxtips-1 .. 2*mxtips-2+kScratchNodes
 
 // P(t) eigen-factor table, built once per call by dtab_kernel:
 //   DNA row (32 doubles) per (entry, class-partition): [c][side q/r][k] = exp(EIGN[k] * rate[c] * lz_side)
@@ -94,7 +97,11 @@ struct TraverseArgs {
   const uint8_t *sev_tipgap;        // [mxtips][sev_ntiles]   1 = all sites of the tile are gaps in this taxon (unused by the kernels: tips always go through their codes)
   const double *sev_gapcol;         // [mxtips-2][nparts_cls][span] CLV of an all-gap site at every inner node
   int           sev_ntiles;         // tiles of the class
-  int           sev_tile0;          // class-wide index of this launch's tile 0
+  int           sev_tile0;          // class-wide index of this launch's tile 0 (also indexes score_out)
+  // exb_score_insertions (MODE_SCORE; null / 0 otherwise)
+  long long     scratch_off;        // element offset of scratch node 0 relative to clv (node n: + (n - (2*mxtips-1)) * N * span)
+  double2      *score_out;          // [ncand][score_stride] per (candidate, tile, warp): {sum of wgt*log, summed weights of scaled sites}
+  int           score_stride;       // tiles of the class x warps per CTA
 };
 
 // DNA constants of a class that holds a single partition: passed by value so that every EI/EV
@@ -124,7 +131,8 @@ struct P2pArgs {
 };
 struct FinishArgs {
   // scaler fix-up: gs[p] = gs[q] + gs[r] + inc  for every newview entry, in order
-  unsigned int *gs;          // [P][2*mxtips]
+  unsigned int *gs;          // [P][gs_stride], gs_stride = 2*mxtips + kScratchNodes
+  int           gs_stride;
   unsigned int *scale_inc;   // [maxEntries][P] (re-zeroed here)
   const DevEntry *entries;
   int           count, first;
@@ -221,6 +229,22 @@ void launch_traverse_aa(const TraverseArgs &a, bool any_lg4, int ntiles, cudaStr
 void launch_traverse_aa_tc(const TraverseArgs &a, int ntiles, cudaStream_t s);
 void launch_core_aa(const CoreArgs &a, int ntiles, cudaStream_t s);
 void launch_finish(const FinishArgs &a, cudaStream_t s);
+
+// exb_score_insertions: scaler chain of the mixed descriptor (one block per partition), then the fixed-order reduction of
+// the per-(candidate, tile, warp) partials into lnl[candidate][partition]
+constexpr int kDnaWarps = 8, kAaWarps = 12;      // warps per CTA of the GAMMA traverse kernels (slots per tile in score_out)
+struct ScoreFinishArgs {
+  unsigned int *gs; int gs_stride;
+  unsigned int *scale_inc;
+  const DevEntry *entries; int count, mxtips, nparts, ncand;
+  const unsigned char *mask; const int *part_has_sites;
+  unsigned int *sc;                  // [P][ncand] gs[q] + gs[r] + gs[s] at the time of the scoring entry
+  const double2 *score_out[2]; int score_stride[2], warps[2];
+  const int *part_tile_begin, *part_tile_count, *part_cls;
+  double log_minlikelihood;
+  double *out;                       // [ncand][P]
+};
+void launch_score_finish(const ScoreFinishArgs &a, cudaStream_t s);
 void launch_p2p_warmup(const P2pArgs &x, unsigned int xseq, int stride, cudaStream_t s);
 
 // -S: gap columns of the inner nodes of a descriptor, in entry order (kernels_sev.cu)

@@ -30,6 +30,7 @@ namespace {
 constexpr int S = 20;
 constexpr int SPAN = 80;
 constexpr int kAaThreads = 384;  // 12 warps, one CTA per SM (the register budget of the DMMA pipeline)
+static_assert(kAaThreads == 32 * kAaWarps, "score_out slots per tile");
 
 struct AaShared { double red[32]; };
 
@@ -278,7 +279,7 @@ traverse_aa_kernel(const TraverseArgs a)
     phase = stage_window<TSITES>(dyn, &mbar, phase, a.entries, a.tips, a.mxtips, N, XSPAN, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
                          a.first, a.count, w0 == a.first && a.mode != MODE_NEWVIEW, nullptr, 0, 0,
                          SevView{CAT ? nullptr : a.sev_table, a.sev_gapcol, a.clv, a.sev_ntiles, a.sev_tile0 + (int)blockIdx.x, tile.part_cls,
-                                 a.nparts_cls, XSPAN, tile.site0});
+                                 a.nparts_cls, XSPAN, tile.site0}, a.scratch_off);
     for (int e = w0; e < w1; e++) {
       const SEntry en = ents[e - w0];
       if (en.flags & kFlagGapP) continue;       // -S: all sites of the tile are gaps below this node: nothing to compute or store
@@ -315,8 +316,8 @@ traverse_aa_kernel(const TraverseArgs a)
       else if (qsrc == SRC_CARRY)         aa_entry<CH_CARRY, CH_MEM, LG4>(carry, K, sl, lane, tq);
       else                                aa_entry<CH_MEM, CH_MEM, LG4>(carry, K, sl, lane, tq);
 
+      unsigned int cnt = 0;
       if (r_inner) {                            // TIP_TIP is never rescaled (avxLikelihood.c:1393-1440)
-        unsigned int cnt = 0;
         if (!CAT) {
           unsigned int hi = 0;
           #pragma unroll
@@ -346,10 +347,48 @@ traverse_aa_kernel(const TraverseArgs a)
             }
           }
         }
-        if (__any_sync(0xffffffffu, cnt != 0)) {
-          const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
-          if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
+      }
+      if (!CAT && (en.flags & kFlagScore)) {
+        // exb_score_insertions: the CLV just formed (carry, C-fragment layout) is the candidate's new node; contract it with
+        // the pruned subtree's CLV under the diagonal table of the branch p--s (evaluateGTRGAMMAPROT
+        // evaluateGenericSpecial.c:1393) and leave this warp's share in its own slot of score_out
+        const SEntry br = ents[kWindow];
+        const bool stip = br.flags & kFlagPTip;
+        const bool lg4 = LG4 && model[kAaLg4] != 0.0;
+        double term = 0.0;
+        #pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const double *tps = stip ? &K.tip[LG4 ? c : 0][S * stips[br.poff + lsite[0]]] : K.tip[0];
+          double tc = 0.0;
+          #pragma unroll
+          for (int t = 0; t < 3; t++) {
+            const int col = 8 * t + 2 * tq;
+            if (col >= S) continue;               // t == 2 && tq >= 2: padding
+            const double2 xs = stip ? *reinterpret_cast<const double2 *>(tps + col) : ld128(a.clv + br.poff + soff + c * XSLOT + col);
+            const double d0 = __ldg(drow0 + c * 40 + col), d1 = __ldg(drow0 + c * 40 + col + 1);   // row 0, q side
+            tc += carry[c][t][0] * xs.x * d0;
+            tc += carry[c][t][1] * xs.y * d1;
+          }
+          term += lg4 ? model[kAaWeights + c] * tc : tc;
         }
+        term += __shfl_xor_sync(0xffffffffu, term, 1);
+        term += __shfl_xor_sync(0xffffffffu, term, 2);
+        double part = (tq == 0 && valid[0]) ? (double)a.wgt[site0] * (lg4 ? log(fabs(term)) : log(0.25 * fabs(term))) : 0.0;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+        const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) {
+          double2 *slot = a.score_out + (size_t)en.poff * a.score_stride + (size_t)(a.sev_tile0 + (int)blockIdx.x) * (kAaThreads / 32) + warp;
+          double2 v = make_double2(part, (double)tot);
+          if (chunk0) { const double2 old = *slot; v.x += old.x; v.y += old.y; }
+          *slot = v;
+        }
+        __syncwarp();
+        continue;
+      }
+      if (__any_sync(0xffffffffu, cnt != 0)) {
+        const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
       }
       if (CAT || valid[0]) {
         double *dst = a.clv + en.poff + soff + 2 * tq;
@@ -365,7 +404,7 @@ traverse_aa_kernel(const TraverseArgs a)
     }
     } while ((w0 += kWindow) < a.count);
 
-    if (a.mode == MODE_NEWVIEW) continue;
+    if (a.mode == MODE_NEWVIEW || a.mode == MODE_SCORE) continue;
 
     // ---------------- branch (entry 0): evaluate or sum table (C-fragment layout on both ends) ----------------
     const SEntry br = ents[kWindow];
@@ -431,7 +470,7 @@ aa_lut_kernel(const LutArgs a)
   const int side = blockIdx.x & 1;
   const int ep = blockIdx.x >> 1, pc = ep % a.nparts_cls, e = ep / a.nparts_cls;
   if (e < a.first) return;
-  const int tc = a.entries[e].tipCase;
+  const int tc = a.entries[e].tipCase & 3;        // (scoring entries of exb_score_insertions carry kScoreBit)
   if (!(side == 0 ? tc <= 1 : tc == 0)) return;
   const int ncat = a.ncat, row = 23 * ncat * 20;
   const double *model = a.models + (size_t)pc * kAaModelDoubles;

@@ -32,6 +32,8 @@
 
 namespace exb {
 
+static_assert(kThreads == 32 * kDnaWarps, "score_out slots per tile");
+
 namespace {
 
 struct DnaShared {
@@ -91,7 +93,8 @@ __device__ __forceinline__ void async_wait_all_but_last() { asm volatile("cp.asy
 template <int QS, int RS, int NS, bool PARAM>
 __device__ __forceinline__ unsigned int dna_entry(double (&carry)[NS][4], const TraverseArgs &a, const DnaConsts &kc, const DnaShared &sh,
                                                   const uint8_t *stips, const SEntry &en, const double *sd, const double *ring,
-                                                  const size_t (&eoff)[NS], const bool (&valid)[NS], const int (&lsite)[NS], int c, int lane)
+                                                  const size_t (&eoff)[NS], const bool (&valid)[NS], const int (&lsite)[NS], int c, int lane,
+                                                  bool store)
 {
 #define EI_(i) (PARAM ? kc.EI[i] : sh.EI[i])
 #define EV_(i) (PARAM ? kc.EV[i] : sh.EV[i])
@@ -131,7 +134,7 @@ __device__ __forceinline__ unsigned int dna_entry(double (&carry)[NS][4], const 
       v[s][m] = fma(ab[s][3], f3, fma(ab[s][2], f2, fma(ab[s][1], f1, ab[s][0] * f0)));
   }
   unsigned int cnt = 0;
-  double *const dst = a.clv + en.poff;
+  double *const dst = a.clv + (store ? en.poff : 0);     // (a scoring entry's poff is its candidate index)
   #pragma unroll
   for (int s = 0; s < NS; s++) {
     if (RS != 0) {                           // TIP_TIP is never rescaled (avxLikelihood.c:87-160)
@@ -142,7 +145,7 @@ __device__ __forceinline__ unsigned int dna_entry(double (&carry)[NS][4], const 
         if (c == 0 && valid[s]) cnt += (unsigned int)a.wgt[eoff[s] >> 4];
       }
     }
-    if (valid[s]) st256(dst + eoff[s], v[s]);
+    if (valid[s] && store) st256(dst + eoff[s], v[s]);
     carry[s][0] = v[s][0]; carry[s][1] = v[s][1]; carry[s][2] = v[s][2]; carry[s][3] = v[s][3];
   }
   return cnt;
@@ -261,7 +264,7 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
     phase = stage_window<TS, KW>(dyn, &mbar, phase, a.entries, a.tips, a.mxtips, N, 16, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
                                  a.first, a.count, w0 == a.first && a.mode != MODE_NEWVIEW, drow0, dstride, kDnaDtabRow,
                                  SevView{a.sev_table, a.sev_gapcol, a.clv, a.sev_ntiles, a.sev_tile0 + (int)blockIdx.x, tile.part_cls,
-                                         a.nparts_cls, 16, tile.site0});
+                                         a.nparts_cls, 16, tile.site0}, a.scratch_off);
     for (int e = w0; e < w1; e++) {
       const SEntry en = ents[e - w0];
       // The one inner child that is neither a tip nor in the carry registers comes through the prefetch ring: its
@@ -296,7 +299,8 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
       const int qs = !q_inner ? 0 : ((en.flags & kFlagCarryA) ? 1 : 2);
       const int rs = !r_inner ? 0 : ((en.flags & kFlagCarryB) ? 1 : (mine == 2 ? 2 : 3));
       unsigned int cnt;
-#define DNA_ENTRY(QS, RS) dna_entry<QS, RS, NS, PARAM>(carry, a, kc, sh, stips, en, sd, rg, eoff, valid, lsite, c, lane)
+      const bool score = en.flags & kFlagScore;
+#define DNA_ENTRY(QS, RS) dna_entry<QS, RS, NS, PARAM>(carry, a, kc, sh, stips, en, sd, rg, eoff, valid, lsite, c, lane, !score)
       switch (qs * 4 + rs) {                   // block-uniform
       case 0:  cnt = DNA_ENTRY(0, 0); break;   // TIP_TIP
       case 1:  cnt = DNA_ENTRY(0, 1); break;   // TIP_INNER, inner child = previous entry
@@ -306,6 +310,37 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
       default: cnt = DNA_ENTRY(2, 3); break;   // INNER_INNER, both loaded
       }
 #undef DNA_ENTRY
+      if (score) {
+        // exb_score_insertions: the CLV just formed (carry) is the candidate's new node; contract it with the pruned
+        // subtree's CLV under the diagonal table of the branch p--s (evaluateGTRGAMMA evaluateGenericSpecial.c:1879) and
+        // leave this warp's share in its own slot of score_out -- summed over chunks here, over warps and tiles by
+        // score_finish_kernel in a fixed order
+        const SEntry br = ents[KW];
+        const double *diag = sdtab + (size_t)KW * kDnaDtabRow + c * 8;
+        double part = 0.0;
+        #pragma unroll
+        for (int s = 0; s < NS; s++) {
+          double xs[4];
+          if (br.flags & kFlagPTip) { const double *tv = &sh.tip[4 * stips[br.poff + lsite[s]]]; xs[0] = tv[0]; xs[1] = tv[1]; xs[2] = tv[2]; xs[3] = tv[3]; }
+          else ld256(a.clv + br.poff + eoff[s], xs);
+          double term = carry[s][0] * xs[0];
+          #pragma unroll
+          for (int k = 1; k < 4; k++) term += carry[s][k] * xs[k] * diag[k];
+          term += __shfl_xor_sync(0xffffffffu, term, 1);
+          term += __shfl_xor_sync(0xffffffffu, term, 2);
+          if (c == 0 && valid[s]) part += (double)a.wgt[eoff[s] >> 4] * log(0.25 * fabs(term));
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+        const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) {
+          double2 *slot = a.score_out + (size_t)en.poff * a.score_stride + (size_t)(a.sev_tile0 + (int)blockIdx.x) * (kThreads / 32) + (tid >> 5);
+          double2 v = make_double2(part, (double)tot);
+          if (chunk0) { const double2 old = *slot; v.x += old.x; v.y += old.y; }
+          *slot = v;
+        }
+        continue;
+      }
       if (r_inner && __any_sync(0xffffffffu, cnt != 0)) {
         const unsigned int tot = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0) atomicAdd(&a.scale_inc[(size_t)e * a.nparts + tile.part], tot);
@@ -313,7 +348,7 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
     }
     } while ((w0 += KW) < a.count);
 
-    if (a.mode == MODE_NEWVIEW) continue;
+    if (a.mode == MODE_NEWVIEW || a.mode == MODE_SCORE) continue;
 
     // ---------------- branch (entry 0): evaluate or sum table ----------------
     const SEntry br = ents[KW];

@@ -34,6 +34,9 @@ constexpr int kFlagPTip = 1, kFlagQTip = 2, kFlagCarryA = 4, kFlagCarryB = 8;
 // -S: the operand (newview: q / r, branch: p / q) resp. the newview entry's parent is an all-gap (node, tile): the operand
 // is read from the node's gap column (its offset then lacks the per-site term), the parent is neither computed nor stored
 constexpr int kFlagGapA = 16, kFlagGapB = 32, kFlagGapP = 64;
+// exb_score_insertions: the entry forms the CLV of a candidate's new node in registers and scores it against the pruned
+// subtree (the branch entry's p) instead of storing it; poff then holds the candidate index
+constexpr int kFlagScore = 128;
 
 __device__ __forceinline__ uint32_t stage_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
@@ -85,6 +88,8 @@ __host__ __device__ constexpr size_t window_dtab_offset()
 //   drow     : null, or this partition's row of entry 0 in the d-table; rows of `drow_doubles` doubles, `dstride` doubles
 //              apart, are staged behind the tips (row of entry e in slot e - w0, the branch entry's row 0 in slot KW): the
 //              exponentials of an entry then cost the threads a shared-memory read instead of an L2 round trip
+//   scratch_off : element offset (relative to the CLV arena) of scratch node 2*mxtips-1, the first of the nodes that only
+//              exb_score_insertions uses
 //   sev      : -S view of this tile (table == null: dense arena).  Inner-node offsets then come from the block table
 //              (relative to `clv`, minus the tile's first site so that the kernels' site term still applies), all-gap
 //              operands point at the node's gap column and are flagged
@@ -93,7 +98,8 @@ __device__ __noinline__ uint32_t stage_window(unsigned char *dyn, uint64_t *mbar
                                               const uint8_t *tips, int mxtips, size_t N, int span_el, size_t chunk_site0,
                                               unsigned nchunk, int w0, int w1, int first, int count, bool with_branch,
                                               const double *drow = nullptr, size_t dstride = 0, int drow_doubles = 0,
-                                              SevView sev = SevView{nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0u})
+                                              SevView sev = SevView{nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0u},
+                                              long long scratch_off = 0)
 {
   SEntry *ents = reinterpret_cast<SEntry *>(dyn);
   uint8_t *stips = dyn + (size_t)(KW + 1) * sizeof(SEntry);
@@ -105,16 +111,24 @@ __device__ __noinline__ uint32_t stage_window(unsigned char *dyn, uint64_t *mbar
     const DevEntry en = entries[is_branch ? 0 : w0 + j];
     const int slot = is_branch ? KW : j;
     // the node whose CLV the threads still hold when this entry is processed: the previous newview entry's parent
+    // (a scoring entry leaves a CLV that belongs to no node: its p is negative and matches nothing)
     const int prev = is_branch ? (count > first ? entries[count - 1].p : -1) : (w0 + j > first ? entries[w0 + j - 1].p : -1);
+    const bool score = !is_branch && (en.tipCase & kScoreBit);
     SEntry se;
-    se.tipCase = is_branch ? -1 : en.tipCase;
+    se.tipCase = is_branch ? -1 : (en.tipCase & 3);
     if (is_branch) se.flags = (en.p <= mxtips ? kFlagPTip : 0) | (en.q <= mxtips ? kFlagQTip : 0) |
                               (en.p == prev ? kFlagCarryA : 0) | (en.q == prev ? kFlagCarryB : 0);
-    else           se.flags = (en.q == prev ? kFlagCarryA : 0) | (en.r == prev ? kFlagCarryB : 0);
-    // tips: q uses row 2*slot, r (or a tip p of the branch entry) row 2*slot+1
-    se.poff = en.p > mxtips ? (long long)(en.p - mxtips - 1) * (long long)N * span_el : (long long)(2 * slot + 1) * TSB;
-    se.qoff = en.q > mxtips ? (long long)(en.q - mxtips - 1) * (long long)N * span_el : (long long)(2 * slot) * TSB;
-    se.roff = en.r > mxtips ? (long long)(en.r - mxtips - 1) * (long long)N * span_el : (long long)(2 * slot + 1) * TSB;
+    else           se.flags = (en.q == prev ? kFlagCarryA : 0) | (en.r == prev ? kFlagCarryB : 0) | (score ? kFlagScore : 0);
+    // inner nodes: CLV offset in the arena (scratch nodes: in their own allocation); tips: q uses row 2*slot, r (or a
+    // tip p of the branch entry) row 2*slot+1
+    auto node_off = [&](int node, int tiprow) -> long long {
+      if (node <= mxtips) return (long long)tiprow * TSB;
+      if (node > 2 * mxtips - 2) return scratch_off + (long long)(node - (2 * mxtips - 1)) * (long long)N * span_el;
+      return (long long)(node - mxtips - 1) * (long long)N * span_el;
+    };
+    se.poff = score ? (long long)(-en.p - 1) : node_off(en.p, 2 * slot + 1);
+    se.qoff = node_off(en.q, 2 * slot);
+    se.roff = node_off(en.r, 2 * slot + 1);
     if (sev.table) {
       // inner nodes: block of (node, tile), or the node's gap column when the pair is all-gap
       auto resolve = [&](int node, long long &off, int gapflag, int carryflag) {
@@ -142,7 +156,7 @@ __device__ __noinline__ uint32_t stage_window(unsigned char *dyn, uint64_t *mbar
       const bool is_branch = j == (w1 - w0);
       const DevEntry en = entries[is_branch ? 0 : w0 + j];
       if (is_branch) mine += (en.p <= mxtips) + (en.q <= mxtips);
-      else           mine += (en.tipCase <= 1) + (en.tipCase == 0);
+      else           mine += ((en.tipCase & 3) <= 1) + ((en.tipCase & 3) == 0);
     }
     const int total = __reduce_add_sync(0xffffffffu, mine);
     if (lane == 0) mbar_expect_tx(mbar, (uint32_t)total * bytes + (drow ? (uint32_t)n * dbytes : 0u));
@@ -155,8 +169,8 @@ __device__ __noinline__ uint32_t stage_window(unsigned char *dyn, uint64_t *mbar
         if (en.p <= mxtips) bulk_g2s(stips + (size_t)(2 * slot + 1) * TSB, gsrc + (size_t)(en.p - 1) * N, bytes, mbar);
         if (en.q <= mxtips) bulk_g2s(stips + (size_t)(2 * slot) * TSB, gsrc + (size_t)(en.q - 1) * N, bytes, mbar);
       } else {
-        if (en.tipCase <= 1) bulk_g2s(stips + (size_t)(2 * slot) * TSB, gsrc + (size_t)(en.q - 1) * N, bytes, mbar);
-        if (en.tipCase == 0) bulk_g2s(stips + (size_t)(2 * slot + 1) * TSB, gsrc + (size_t)(en.r - 1) * N, bytes, mbar);
+        if ((en.tipCase & 3) <= 1) bulk_g2s(stips + (size_t)(2 * slot) * TSB, gsrc + (size_t)(en.q - 1) * N, bytes, mbar);
+        if ((en.tipCase & 3) == 0) bulk_g2s(stips + (size_t)(2 * slot + 1) * TSB, gsrc + (size_t)(en.r - 1) * N, bytes, mbar);
       }
       if (drow) bulk_g2s(sdtab + (size_t)slot * drow_doubles, drow + (size_t)(is_branch ? 0 : w0 + j) * dstride, dbytes, mbar);
     }

@@ -199,6 +199,34 @@ int  exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const double *q
 int  exb_evaluate_partial(exb_engine *e, const exb_entry *entries, int count, const double *qz, const double *rz,
                           size_t n, const int *models, const int *sites, const double *rates, double *out);
 
+/* Batched scoring of lazy SPR insertions.  The reference scores ONE candidate at a time:
+ * testInsertBIG (searchAlgo.c:682) -> insertBIG, non-thorough branch (searchAlgo.c:519-535: both new branches get
+ * sqrt(z_qr)) -> newviewGeneric(p) -> evaluateGeneric(p->next->next), i.e. two calls and ~3 node updates per candidate
+ * branch, and the CLVs on the path from the pruning point are re-oriented node by node as addTraverseBIG
+ * (searchAlgo.c:785) walks outwards.  This entry point executes ONE mixed descriptor for a whole pruned subtree:
+ *   ti[0]          the subtree: pNumber = node s = p->back whose CLV (or tip) looks away from the insertion point,
+ *                  qz[0..numBranches) = z of the branch p--s (evaluate's diagonal table, calcDiagptable);
+ *   ti[1..count)   in order, either an ordinary newview entry (tipCase 0..2) -- used for the CLVs that have to look
+ *                  TOWARDS a candidate branch; they may write to, and read from, scratch nodes numbered
+ *                  2*mxtips-1 .. 2*mxtips-2+EXB_SCRATCH_NODES that exist only for this purpose, so the tree's own CLVs
+ *                  and orientation stay untouched -- or a scoring entry (tipCase | EXB_SCORE): the CLV of a new node
+ *                  joining qNumber and rNumber with branch values qz / rz is formed in registers (scaled like any
+ *                  newview, avxLikelihood.c:253-311), never stored, and contracted with the subtree's CLV:
+ *                      lnl[pNumber][m] = sum_i wgt[i] log(0.25 |sum_c sum_k x_new[i][c][k] x_s[i][c][k] diag[c][k]|)
+ *                                        + (scalings) * log(minlikelihood)
+ *                  -- by the pulley principle the value evaluateGeneric returns at (p->next->next, r) after that insertion.
+ *                  pNumber of a scoring entry = index k of the candidate (0 <= k < ncand).
+ * lnl[ncand * numPartitions] (candidate-major) is globally reduced like exb_evaluate's output; masked partitions
+ * read 0.  Scratch CLVs and their scaler counts persist between calls, so a long scan may be cut into several calls
+ * anywhere.  GAMMA, dense arena (not under EXB_CAT, -S or EXB_AA_TF32X3: EXB_ERR_STATE, the caller then scores the
+ * candidates one by one as before). */
+#define EXB_SCORE          4
+#define EXB_SCRATCH_NODES 64
+int  exb_score_insertions(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
+                          const unsigned char *executeModel, int ncand, double *lnl);
+/* 1 when exb_score_insertions is available in the engine's configuration */
+int  exb_can_score_insertions(exb_engine *e);
+
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------------ */
 
 /* NCCL bootstrap: rank 0 obtains an opaque id (EXB_UNIQUE_ID_BYTES bytes), the launcher

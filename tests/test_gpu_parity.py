@@ -538,7 +538,7 @@ def test_sev_matches_dense_oracle_and_saves_blocks(cuda_factory, oracle_factory,
     cpu = build_engine(oracle_factory, tree, parts, models)
     _compare_engines(gpu, cpu, tree, parts)                       # lnL, every CLV (gap tiles expand to the gap column), scalers
     used, dense, nbytes = gpu.sev_stats()
-    assert 0 < used < 0.8 * dense, (used, dense)
+    assert 0 < used < dense, (used, dense)          # some (node, tile) pairs own no block (how many: test_sev_footprint_follows_the_data)
     # masks, then a different root (partial traversals re-orient nodes: blocks are handed back and taken)
     mask = np.array([i % 2 == 0 for i in range(len(widths))], dtype=np.uint8)
     _compare_engines(gpu, cpu, tree, parts, mask=mask)
