@@ -25,7 +25,10 @@ EXPORTS = [
     "exb_read_sumtable", "exb_last_kernel_ms", "exb_launch_count", "exb_set_tile_sites", "exb_set_timing",
     "exb_set_rate_model", "exb_set_categories", "exb_set_model_lg4", "exb_evaluate_partial", "exb_comm_is_p2p",
     "exb_last_phase_ms", "exb_set_aa_precision", "exb_set_sev", "exb_sev_stats",
+    "exb_score_insertions", "exb_can_score_insertions", "exb_max_entries",
 ]
+SCORE = 4                 # EXB_SCORE: tipCase bit of a scoring entry
+SCRATCH_NODES = 64        # EXB_SCRATCH_NODES
 UNIQUE_ID_BYTES = 128
 
 
@@ -242,6 +245,24 @@ class Engine:
         self._check(self._f("evaluate_partial")(self._h, t.arr, C.c_int(t.count), _dptr(t.qz), _dptr(t.rz),
                                                 C.c_size_t(ra.shape[0]), _dptr(mo), _dptr(si), _dptr(ra), _dptr(out)))
         return out
+
+    def scoreInsertions(self, ti, ncand: int, execute_model=None) -> np.ndarray:
+        """Batched lazy-SPR scoring (exb_score_insertions): ti[0] = the pruned subtree (pNumber, qz = its branch), then
+        newview entries (scratch nodes 2*mxtips-1.. allowed) and scoring entries (tipCase | SCORE, pNumber = candidate).
+        Returns lnl[ncand, partitions]."""
+        t = self.pack(ti)
+        m = self._mask(execute_model, self.nparts)
+        out = np.zeros((ncand, self.nparts))
+        self._check(self._f("score_insertions")(self._h, t.arr, C.c_int(t.count), _dptr(t.qz), _dptr(t.rz), _dptr(m),
+                                                C.c_int(ncand), _dptr(out)))
+        return out
+
+    def max_entries(self) -> int:
+        """Entries one descriptor may hold."""
+        return 1 << 30 if self.prefix != "exb_" else int(self._f("max_entries")(self._h))
+
+    def can_score_insertions(self) -> bool:
+        return self.prefix != "exb_" or bool(self._f("can_score_insertions")(self._h))
 
     # ---- multi-GPU -------------------------------------------------------------------------
     def comm_unique_id(self) -> bytes:

@@ -368,12 +368,19 @@ static void set_all_models(tree *tr, boolean value)
   for (m = 0; m < tr->NumberOfModels; m++) tr->executeModel[m] = value;
 }
 
+static boolean scan_serve_newview(tree *tr, nodeptr p);
+static boolean scan_serve_evaluate(tree *tr, nodeptr p);
+static void scan_flush(tree *tr);
+
 void evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal)
 {
   nodeptr q = p->back;
   traversalInfo *ti = tr->td[0].ti;
   double sum = 0.0;
   int b, m;
+
+  if (!fullTraversal && scan_serve_evaluate(tr, p)) return;     /* a lazy insertion whose score is already in the table */
+  scan_flush(tr);
 
   ti[0].pNumber = p->number;
   ti[0].qNumber = q->number;
@@ -402,6 +409,8 @@ void newviewGeneric(tree *tr, nodeptr p, boolean masked)
 {
   int m;
   if (isTip(p->number, tr->mxtips)) return;
+  if (!masked && scan_serve_newview(tr, p)) return;             /* the new node of a lazy insertion the scan has scored */
+  scan_flush(tr);
 
   tr->td[0].count = 0;
   computeTraversalInfo(p, tr->td[0].ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
@@ -512,6 +521,8 @@ void makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxiter, do
   traversalInfo *ti = tr->td[0].ti;
   int i;
 
+  scan_flush(tr);
+
   ti[0].pNumber = p->number;
   ti[0].qNumber = q->number;
   for (i = 0; i < tr->numBranches; i++) {
@@ -540,6 +551,259 @@ void makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxiter, do
     newton_raphson(tr, z0, maxiter, result);
 
   for (i = 0; i < tr->numBranches; i++) tr->executeModel[i] = TRUE;
+}
+
+
+/* ---------------------------------------------------------------------------------------------- */
+/* batched scoring of lazy SPR insertions                                           */
+/* ---------------------------------------------------------------------------------------------- */
+/* rearrangeBIG (searchAlgo.c:800) prunes the subtree at p and lets addTraverseBIG (searchAlgo.c:785) try it in every
+ * branch within the rearrangement radius, one testInsertBIG (searchAlgo.c:682) at a time: hook p in with both halves at
+ * sqrt(z) (insertBIG, non-thorough branch, searchAlgo.c:519-535), newviewGeneric(p), evaluateGeneric(p->next->next),
+ * unhook.  On a GPU that is two small calls per candidate.  The walk is predictable, though: it depends on the topology
+ * only (the lhCutoff test merely prunes it), and the score of a candidate does not depend on the candidates before it.
+ * A maintainer therefore brackets the four addTraverseBIG calls of each side of rearrangeBIG with
+ *
+ *     batchedInsertionScanBegin(tr, p, p1, p2, mintrav, maxtrav);   ...addTraverseBIG...   batchedInsertionScanEnd(tr);
+ *
+ * (INTEGRATION.md shows the patch; without it nothing below is ever active).  Begin walks the same branches in the same
+ * order, builds ONE mixed descriptor -- the CLVs looking from the pruning point towards each candidate go into the
+ * engine's scratch nodes level by level, subtrees that do not look at the walk get their ordinary computeTraversalInfo
+ * entries, one scoring entry per candidate -- and obtains all log likelihoods with exb_score_insertions.  The unchanged
+ * testInsertBIG then runs as always: its newviewGeneric(p) and evaluateGeneric(p->next->next) are answered from the
+ * table (all bookkeeping -- bestOfNode, endLH, lhAVG / lhDEC, the cutoff -- stays the reference's code, it just reads
+ * tr->likelihood).  The tree's own CLVs and x flags are not re-oriented by the scan, so after End the state is the one
+ * right after removeNodeBIG.  Anything that does not match the table (a thorough insertion, a different node) takes the
+ * ordinary path; a newview that was answered from the table but is then needed for real is computed first (scan_flush). */
+extern int Thorough;                               /* globalVariables.h; set by computeBIGRAPID, searchAlgo.c:1984 */
+
+typedef struct {
+  int active;
+  nodeptr p;                    /* the node whose subtree p->back is being re-inserted */
+  int ncand, cursor;
+  nodeptr *cand;                /* [ncand] the record q of candidate branch (q, q->back), in addTraverseBIG order */
+  double *lnl;                  /* [ncand][NumberOfModels] */
+  int pending;                  /* candidate whose newviewGeneric(p) was answered from the table; -1: none */
+  /* descriptor under construction */
+  exb_entry *ent; double *qz, *rz; int n, cap, ccap;
+  int failed;
+} scan_state;
+static scan_state g_spr = {0, NULL, 0, 0, NULL, NULL, -1, NULL, NULL, NULL, 0, 0, 0, 0};
+/* EXAML_B200_SPR_STATS=1: one line at exit (tests assert that the insertions really came from the table) */
+static long g_spr_scans = 0, g_spr_scored = 0, g_spr_served = 0, g_spr_flushed = 0, g_spr_calls = 0;
+static void spr_report(void)
+{
+  if (processID == 0)
+    printf("B200 back-end, batched insertion scoring: %ld scans, %ld engine calls, %ld candidates scored, %ld served from the table, "
+           "%ld answered newviews computed after all\n", g_spr_scans, g_spr_calls, g_spr_scored, g_spr_served, g_spr_flushed);
+}
+
+static void spr_reserve(tree *tr, int more)
+{
+  const size_t nb = (size_t)tr->numBranches;
+  if (g_spr.n + more <= g_spr.cap) return;
+  g_spr.cap = 2 * (g_spr.n + more) + 64;
+  g_spr.ent = (exb_entry *)realloc(g_spr.ent, (size_t)g_spr.cap * sizeof(exb_entry));
+  g_spr.qz = (double *)realloc(g_spr.qz, (size_t)g_spr.cap * nb * sizeof(double));
+  g_spr.rz = (double *)realloc(g_spr.rz, (size_t)g_spr.cap * nb * sizeof(double));
+  if (!g_spr.ent || !g_spr.qz || !g_spr.rz) { fprintf(stderr, "out of memory\n"); MPI_Abort(MPI_COMM_WORLD, -1); exit(-1); }
+}
+
+/* append an entry with children (a, az) and (b, bz); a tip child goes into q (newviewGenericSpecial.c:742-750) */
+static void spr_emit(tree *tr, int scoreBit, int pNumber, int a, const double *az, int b, const double *bz)
+{
+  const int nb = tr->numBranches;
+  const boolean at = isTip(a, tr->mxtips), bt = isTip(b, tr->mxtips);
+  exb_entry *t;
+  int i;
+  if (bt && !at) { int x = a; const double *xz = az; a = b; az = bz; b = x; bz = xz; }
+  spr_reserve(tr, 1);
+  t = &g_spr.ent[g_spr.n];
+  t->tipCase = ((at && bt) ? TIP_TIP : ((at || bt) ? TIP_INNER : INNER_INNER)) | scoreBit;
+  t->pNumber = pNumber; t->qNumber = a; t->rNumber = b;
+  for (i = 0; i < nb; i++) { g_spr.qz[(size_t)g_spr.n * nb + i] = az[i]; g_spr.rz[(size_t)g_spr.n * nb + i] = bz[i]; }
+  g_spr.n++;
+}
+
+/* make the CLV of rec's node look along rec, the way evaluateGeneric does on demand */
+static void spr_orient(tree *tr, nodeptr rec)
+{
+  int cnt = 0, i, b;
+  const int nb = tr->numBranches;
+  if (isTip(rec->number, tr->mxtips) || rec->x) return;
+  computeTraversalInfo(rec, tr->td[0].ti, &cnt, tr->mxtips, tr->numBranches, TRUE);   /* td[0] is free between calls */
+  spr_reserve(tr, cnt);
+  for (i = 0; i < cnt; i++) {
+    const traversalInfo *t = &tr->td[0].ti[i];
+    exb_entry *e = &g_spr.ent[g_spr.n];
+    e->tipCase = t->tipCase; e->pNumber = t->pNumber; e->qNumber = t->qNumber; e->rNumber = t->rNumber;
+    for (b = 0; b < nb; b++) { g_spr.qz[(size_t)g_spr.n * nb + b] = t->qz[b]; g_spr.rz[(size_t)g_spr.n * nb + b] = t->rz[b]; }
+    g_spr.n++;
+  }
+}
+
+/* addTraverseBIG's walk (searchAlgo.c:785-799).  up: the record of r's ring that looks back at the pruning point,
+   upNumber: the node (real at the top level, scratch below) whose CLV comes from there */
+static void spr_walk(tree *tr, nodeptr q, int mintrav, int maxtrav, int depth, nodeptr up, int upNumber)
+{
+  const int nb = tr->numBranches;
+  nodeptr r = q->back, sibRec, sib;
+  int uNumber, i;
+  if (g_spr.failed) return;
+  if (depth >= EXB_SCRATCH_NODES) { g_spr.failed = 1; return; }
+  sibRec = (r->next == up) ? r->next->next : r->next;     /* the third record of r's ring */
+  sib = sibRec->back;
+  spr_orient(tr, sib);
+  uNumber = 2 * tr->mxtips - 1 + depth;
+  spr_emit(tr, 0, uNumber, upNumber, up->z, sib->number, sibRec->z);
+  if (--mintrav <= 0) {
+    double zz[NUM_BRANCHES];
+    spr_orient(tr, q);
+    for (i = 0; i < nb; i++) {                     /* insertBIG searchAlgo.c:522-531 */
+      zz[i] = sqrt(q->z[i]);
+      if (zz[i] < zmin) zz[i] = zmin;
+      if (zz[i] > zmax) zz[i] = zmax;
+    }
+    if (g_spr.ncand == g_spr.ccap) {
+      g_spr.ccap = 2 * g_spr.ccap + 64;
+      g_spr.cand = (nodeptr *)realloc(g_spr.cand, (size_t)g_spr.ccap * sizeof(nodeptr));
+    }
+    spr_emit(tr, EXB_SCORE, g_spr.ncand, q->number, zz, uNumber, zz);
+    g_spr.cand[g_spr.ncand++] = q;
+  }
+  if (!isTip(q->number, tr->mxtips) && --maxtrav > 0) {
+    spr_walk(tr, q->next->back, mintrav, maxtrav, depth + 1, q, uNumber);
+    spr_walk(tr, q->next->next->back, mintrav, maxtrav, depth + 1, q, uNumber);
+  }
+}
+
+void batchedInsertionScanBegin(tree *tr, nodeptr p, nodeptr p1, nodeptr p2, int mintrav, int maxtrav)
+{
+  static int enabled = -1;
+  const int nb = tr->numBranches, P = tr->NumberOfModels;
+  nodeptr s = p->back, side[2][2];
+  int k, m, at, i, cap;
+  g_spr.active = 0;
+  g_spr.pending = -1;
+  if (enabled < 0) {
+    enabled = getenv("EXAML_B200_NO_BATCHED_SPR") ? 0 : 1;
+    if (getenv("EXAML_B200_SPR_STATS")) atexit(spr_report);
+  }
+  if (!enabled || Thorough) return;
+  backend_sync(tr);
+  if (!exb_can_score_insertions(g_engine)) return;
+  g_spr.n = 0; g_spr.ncand = 0; g_spr.failed = 0;
+  /* entry 0: the pruned subtree and the branch p--s (the diagonal table of the evaluation) */
+  spr_reserve(tr, 1);
+  g_spr.ent[0].tipCase = -1; g_spr.ent[0].pNumber = s->number; g_spr.ent[0].qNumber = s->number; g_spr.ent[0].rNumber = 0;
+  for (i = 0; i < nb; i++) { g_spr.qz[i] = p->z[i]; g_spr.rz[i] = 1.0; }
+  g_spr.n = 1;
+  spr_orient(tr, s);
+  side[0][0] = p1; side[0][1] = p2; side[1][0] = p2; side[1][1] = p1;
+  for (k = 0; k < 2; k++) {
+    nodeptr a = side[k][0], b = side[k][1];
+    if (isTip(a->number, tr->mxtips)) continue;
+    spr_orient(tr, b);                             /* b's CLV must look at a */
+    spr_walk(tr, a->next->back, mintrav, maxtrav, 0, a, b->number);
+    spr_walk(tr, a->next->next->back, mintrav, maxtrav, 0, a, b->number);
+  }
+  if (g_spr.failed || g_spr.ncand == 0) return;
+  g_spr.lnl = (double *)realloc(g_spr.lnl, (size_t)g_spr.ncand * P * sizeof(double));
+  for (m = 0; m < P; m++) g_mask[m] = tr->executeModel[m] ? 1 : 0;
+  /* a descriptor holds exb_max_entries entries: cut the list anywhere (scratch CLVs persist), candidates renumbered per call */
+  cap = exb_max_entries(g_engine) - 1;
+  for (at = 1; at < g_spr.n; ) {
+    const int n = (g_spr.n - at < cap) ? g_spr.n - at : cap;
+    int first = -1, cnt = 0;
+    exb_entry e0 = g_spr.ent[at - 1];
+    double *q0 = (double *)malloc(2 * (size_t)nb * sizeof(double)), *r0 = q0 + nb;
+    /* slot at-1 temporarily becomes entry 0 of this call */
+    memcpy(q0, g_spr.qz + (size_t)(at - 1) * nb, (size_t)nb * sizeof(double));
+    memcpy(r0, g_spr.rz + (size_t)(at - 1) * nb, (size_t)nb * sizeof(double));
+    g_spr.ent[at - 1] = g_spr.ent[0];
+    memcpy(g_spr.qz + (size_t)(at - 1) * nb, g_spr.qz, (size_t)nb * sizeof(double));
+    for (i = at; i < at + n; i++)
+      if (g_spr.ent[i].tipCase & EXB_SCORE) { if (first < 0) first = g_spr.ent[i].pNumber; g_spr.ent[i].pNumber -= first; cnt++; }
+    m = exb_score_insertions(g_engine, g_spr.ent + at - 1, n + 1, g_spr.qz + (size_t)(at - 1) * nb, g_spr.rz + (size_t)(at - 1) * nb,
+                             g_mask, cnt, cnt ? g_spr.lnl + (size_t)first * P : NULL);
+    g_spr_calls++;
+    g_spr.ent[at - 1] = e0;
+    memcpy(g_spr.qz + (size_t)(at - 1) * nb, q0, (size_t)nb * sizeof(double));
+    memcpy(g_spr.rz + (size_t)(at - 1) * nb, r0, (size_t)nb * sizeof(double));
+    free(q0);
+    if (m != EXB_OK) {
+      static int told = 0;
+      if (!told && processID == 0) printf("\nB200 back-end: batched insertion scoring not used (%s)\n", exb_last_error());
+      told = 1;
+      return;                                      /* candidates are scored one by one as before */
+    }
+    at += n;
+  }
+  g_spr.p = p; g_spr.cursor = 0; g_spr.active = 1;
+  g_spr_scans++; g_spr_scored += g_spr.ncand;
+}
+
+void batchedInsertionScanEnd(tree *tr)
+{
+  scan_flush(tr);
+  g_spr.active = 0;
+}
+
+static int scan_lookup(nodeptr q)
+{
+  int i;
+  for (i = 0; i < g_spr.ncand; i++) {
+    const int k = (g_spr.cursor + i) % g_spr.ncand;
+    if (g_spr.cand[k] == q) { g_spr.cursor = k; return k; }
+  }
+  return -1;
+}
+
+/* newviewGeneric(tr, p, FALSE) of insertBIG: p hooked between a candidate's ends with the lazy branch values? */
+static boolean scan_serve_newview(tree *tr, nodeptr p)
+{
+  int k, i;
+  nodeptr q, r;
+  if (!g_spr.active || p != g_spr.p || Thorough) return FALSE;
+  scan_flush(tr);
+  q = p->next->back; r = p->next->next->back;
+  if (!q || !r) return FALSE;
+  k = scan_lookup(q);
+  if (k < 0) return FALSE;
+  for (i = 0; i < tr->numBranches; i++)            /* both halves equal: the lazy insertion, not the restored original */
+    if (p->next->z[i] != p->next->next->z[i]) return FALSE;
+  g_spr.pending = k;
+  return TRUE;
+}
+
+static boolean scan_serve_evaluate(tree *tr, nodeptr pnn)
+{
+  int m, k = g_spr.pending;
+  double sum = 0.0;
+  if (!g_spr.active || k < 0) return FALSE;
+  if (pnn != g_spr.p->next->next || g_spr.p->next->back != g_spr.cand[k]) return FALSE;
+  for (m = 0; m < tr->NumberOfModels; m++) {
+    tr->perPartitionLH[m] = g_spr.lnl[(size_t)k * tr->NumberOfModels + m];
+    sum += tr->perPartitionLH[m];
+  }
+  tr->likelihood = sum;
+  g_spr_served++;
+  g_spr.pending = -1;           /* the caller unhooks p next: its CLV never has to exist */
+  return TRUE;
+}
+
+/* A newview answered from the table is needed after all: compute it now. */
+static void scan_flush(tree *tr)
+{
+  if (g_spr.pending >= 0) {
+    nodeptr p = g_spr.p;
+    const int was = g_spr.active;
+    g_spr.pending = -1;
+    g_spr.active = 0;
+    g_spr_flushed++;
+    if (p->next->back && p->next->next->back) newviewGeneric(tr, p, FALSE);
+    g_spr.active = was;
+  }
 }
 
 /* ---------------------------------------------------------------------------------------------- */

@@ -147,6 +147,102 @@ void launch_p2p_warmup(const P2pArgs &x, unsigned int xseq, int stride, cudaStre
   p2p_warmup_kernel<<<1, 32, 0, s>>>(x, xseq, stride);
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// exb_score_insertions, after the traverse kernels.
+// (1) score_chain_kernel, one warp per partition: the scaler bookkeeping of the mixed descriptor in entry order --
+//     newview entries gs[p] = gs[q] + gs[r] + inc as in finish_kernel (scratch nodes have slots behind the tree's own),
+//     scoring entries record sc[candidate] = gs[q] + gs[r] + gs[s] as it stands at that point of the walk.
+// (2) score_reduce_kernel, one block per (candidate, partition): the per-(tile, warp) partials in fixed order, then
+//     lnl = sum + (scaled-site weights + sc) * log(minlikelihood)   (evaluateGenericSpecial.c:830).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+score_chain_kernel(const ScoreFinishArgs a)
+{
+  extern __shared__ unsigned int gsm[];            // one scaler row (gs_stride) when it fits, else the row is used in place
+  const int lane = threadIdx.x;
+  const int s_node = a.entries[0].p;
+  for (int part = blockIdx.x; part < a.nparts; part += gridDim.x) {
+    unsigned int *sc = a.sc + (size_t)part * a.ncand;
+    if (!(a.mask[part] && a.part_has_sites[part])) {
+      for (int k = lane; k < a.ncand; k += 32) sc[k] = 0;
+      continue;
+    }
+    unsigned int *row = a.gs + (size_t)part * a.gs_stride;
+    const bool staged = a.gs_in_smem;
+    unsigned int *gs = staged ? gsm : row;
+    if (staged) { for (int i = lane; i < a.gs_stride; i += 32) gs[i] = row[i]; }
+    __syncwarp();
+    for (int e0 = 1; e0 < a.count; e0 += 32) {
+      const int e = e0 + lane;
+      unsigned int inc = 0; DevEntry en = {0, 0, 0, 0};
+      if (e < a.count) {
+        en = a.entries[e];
+        if (!(en.tipCase & kScoreBit)) {
+          inc = a.scale_inc[(size_t)e * a.nparts + part];
+          if (inc) a.scale_inc[(size_t)e * a.nparts + part] = 0;
+        }
+      }
+      const int n = min(32, a.count - e0);
+      for (int j = 0; j < n; j++) {                 // lane j's entry, in order
+        const int tj = __shfl_sync(0xffffffffu, en.tipCase, j), pj = __shfl_sync(0xffffffffu, en.p, j),
+                  qj = __shfl_sync(0xffffffffu, en.q, j), rj = __shfl_sync(0xffffffffu, en.r, j);
+        const unsigned int ij = __shfl_sync(0xffffffffu, inc, j);
+        if (lane == 0) {
+          if (tj & kScoreBit) sc[-pj - 1] = gs[qj] + gs[rj] + gs[s_node];
+          else gs[pj] = gs[qj] + gs[rj] + ij;
+        }
+        __syncwarp();
+      }
+    }
+    if (staged) { for (int i = lane; i < a.gs_stride; i += 32) row[i] = gs[i]; }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(128)
+score_reduce_kernel(const ScoreFinishArgs a)
+{
+  __shared__ double red0[4], red1[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = blockIdx.x;
+  for (int part = blockIdx.y; part < a.nparts; part += gridDim.y) {
+    const bool exec = a.mask[part] && a.part_has_sites[part];
+    double s0 = 0.0, s1 = 0.0;
+    if (exec) {
+      const int c = a.part_cls[part];
+      const double2 *v = a.score_out[c] + (size_t)k * a.score_stride[c] + (size_t)a.part_tile_begin[part] * a.warps[c];
+      const int n = a.part_tile_count[part] * a.warps[c];
+      for (int t = tid; t < n; t += 128) { const double2 x = v[t]; s0 += x.x; s1 += x.y; }
+      #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_down_sync(0xffffffffu, s0, o);
+        s1 += __shfl_down_sync(0xffffffffu, s1, o);
+      }
+    }
+    if (lane == 0) { red0[warp] = s0; red1[warp] = s1; }
+    __syncthreads();
+    if (tid == 0) {
+      s0 = ((red0[0] + red0[1]) + (red0[2] + red0[3]));
+      s1 = ((red1[0] + red1[1]) + (red1[2] + red1[3]));
+      a.out[(size_t)k * a.nparts + part] = exec ? s0 + (s1 + (double)a.sc[(size_t)part * a.ncand + k]) * a.log_minlikelihood : 0.0;
+    }
+    __syncthreads();
+  }
+}
+
+void launch_score_finish(const ScoreFinishArgs &a0, cudaStream_t s)
+{
+  ScoreFinishArgs a = a0;
+  if (a.ncand <= 0) return;
+  const size_t smem = (size_t)a.gs_stride * sizeof(unsigned int);
+  const int blocks = a.nparts < 592 ? a.nparts : 592;
+  a.gs_in_smem = smem <= 40 * 1024;               // else the scaler row is walked in place
+  score_chain_kernel<<<blocks, 32, a.gs_in_smem ? smem : 0, s>>>(a);
+  dim3 grid((unsigned)a.ncand, (unsigned)(a.nparts < 4096 ? a.nparts : 4096));
+  score_reduce_kernel<<<grid, 128, 0, s>>>(a);
+}
+
 void launch_finish(const FinishArgs &a0, cudaStream_t s)
 {
   FinishArgs a = a0;
@@ -274,6 +370,9 @@ struct ClassState {
   std::vector<double> models_h;
   std::vector<int> cp_tile_begin, cp_tile_count, cp_global;   // per class-partition: its run of tiles, global index
   int dirty_lo = 1 << 30, dirty_hi = -1;   // range of class-partitions whose constants must be re-uploaded
+  // exb_score_insertions: CLVs of the scratch nodes [scratch_nodes][N][span] and the per-(candidate, tile, warp) partials
+  double *scratch = nullptr; int scratch_nodes = 0;
+  double2 *score_out = nullptr; size_t score_out_cap = 0;
 };
 
 struct exb_engine {
@@ -325,6 +424,10 @@ struct exb_engine {
   unsigned int *nr_barrier = nullptr;
   unsigned char *nr_mask = nullptr;
   int nr_max_blocks = 0;
+  // exb_score_insertions: scaler sums per (partition, candidate), results [ncand][P] on the device and in pinned memory
+  unsigned int *score_sc = nullptr; size_t score_sc_cap = 0;
+  double *score_d = nullptr; size_t score_d_cap = 0;
+  double *score_h = nullptr; size_t score_h_cap = 0;
   // exb_evaluate_partial: growable device buffers (descriptor + pairs | results | slot stacks)
   unsigned char *pp_in = nullptr; size_t pp_in_cap = 0;
   double *pp_out = nullptr; size_t pp_out_cap = 0;
@@ -391,7 +494,9 @@ extern "C" void exb_destroy(exb_engine *e)
     cudaFree(k.tiles); cudaFree(k.clv); cudaFree(k.sum); cudaFree(k.models); cudaFree(k.tile_out);
     cudaFree(k.tips); cudaFree(k.wgt); cudaFree(k.dtab); cudaFree(k.part_global); cudaFree(k.lut);
     cudaFree(k.rate_cat); cudaFree(k.cat_rates);
+    cudaFree(k.scratch); cudaFree(k.score_out);
   }
+  cudaFree(e->score_sc); cudaFree(e->score_d); cudaFreeHost(e->score_h);
   cudaFree(e->stage_d); cudaFreeHost(e->stage_h);
   cudaFree(e->part_has_sites); cudaFree(e->part_tile_begin); cudaFree(e->part_tile_count); cudaFree(e->part_cls);
   cudaFree(e->gs); cudaFree(e->scale_inc); cudaFree(e->out_d); cudaFreeHost(e->out_h);
@@ -525,6 +630,15 @@ extern "C" int exb_commit(exb_engine *e)
   for (int m = 0; m < e->P; m++)
     if (!e->parts[m].defined) return fail(EXB_ERR_STATE, "exb_commit: partition %d was never described", m);
 
+  // Descriptor capacity: td[0].ti holds mxtips entries (axml.c:595) + the branch entry; the mixed descriptors of
+  // exb_score_insertions (a scratch CLV and a scoring entry per candidate) are longer -- three times that, unless the
+  // per-entry tables (d-table rows, branch slots) of a many-partition run would then take more than ~1 GB
+  {
+    size_t per_entry = sizeof(DevEntry) + (size_t)2 * e->nb * sizeof(double);
+    for (const HostPart &p : e->parts) per_entry += (size_t)(p.cls == CLS_AA ? 2 * 23 * 80 + 160 : 32) * (e->cat ? (e->max_cats + 3) / 4 : 1) * sizeof(double) + sizeof(unsigned int);
+    e->max_entries = e->mxtips + 1;
+    if (per_entry * (size_t)(3 * e->mxtips + 1) <= ((size_t)1 << 30)) e->max_entries = 3 * e->mxtips + 1;
+  }
   std::vector<int> has_sites(e->P), tbegin(e->P, 0), tcount(e->P, 0), pcls(e->P, 0);
   for (int c = 0; c < 2; c++) {
     ClassState &k = e->cls[c];
@@ -580,14 +694,14 @@ extern "C" int exb_commit(exb_engine *e)
       for (int m = 0; m < e->P; m++) if (e->parts[m].cls == c) pg.push_back(m);
       CUDA_TRY(cudaMalloc(&k.part_global, pg.size() * sizeof(int)));
       CUDA_TRY(cudaMemcpy(k.part_global, pg.data(), pg.size() * sizeof(int), cudaMemcpyHostToDevice));
-      const size_t dbytes = (size_t)(e->mxtips + 1) * idx * k.dtab_row * sizeof(double);
+      const size_t dbytes = (size_t)e->max_entries * idx * k.dtab_row * sizeof(double);
       CUDA_TRY(cudaMalloc(&k.dtab, dbytes));
       if (e->cat) {
         CUDA_TRY(cudaMalloc(&k.cat_rates, (size_t)idx * e->max_cats * sizeof(double)));
         CUDA_TRY(cudaMemset(k.cat_rates, 0, (size_t)idx * e->max_cats * sizeof(double)));
       }
       // AA tip look-up table (optional: skipped when it would not fit comfortably, e.g. thousands of AA partitions)
-      const size_t lbytes = (size_t)(e->mxtips + 1) * idx * 2 * 23 * 20 * (e->cat ? e->max_cats : 4) * sizeof(double);
+      const size_t lbytes = (size_t)e->max_entries * idx * 2 * 23 * 20 * (e->cat ? e->max_cats : 4) * sizeof(double);
       if (c == CLS_AA && lbytes <= ((size_t)1 << 30) && !getenv("EXB_AA_NO_LUT")) CUDA_TRY(cudaMalloc(&k.lut, lbytes));
     }
     if (n == 0) continue;
@@ -635,7 +749,7 @@ extern "C" int exb_commit(exb_engine *e)
       CUDA_TRY(cudaMemset(v.table_d, 0, v.table_h.size() * sizeof(double *)));
       CUDA_TRY(cudaMalloc(&v.gapcol, (size_t)(e->mxtips - 2) * k.nparts * k.span * sizeof(double)));
       CUDA_TRY(cudaMemset(v.gapcol, 0, (size_t)(e->mxtips - 2) * k.nparts * k.span * sizeof(double)));
-      v.gapw_h.assign((size_t)(e->mxtips + 1) * k.nparts, 0);
+      v.gapw_h.assign((size_t)e->max_entries * k.nparts, 0);
       CUDA_TRY(cudaMalloc(&v.gapw_d, v.gapw_h.size() * sizeof(int)));
       CUDA_TRY(cudaMemset(v.gapw_d, 0, v.gapw_h.size() * sizeof(int)));
       void *slab = nullptr;                        // the first slab doubles as the base all block offsets are relative to
@@ -674,7 +788,6 @@ extern "C" int exb_commit(exb_engine *e)
   CUDA_TRY(upload_ints(&e->part_tile_count, tcount));
   CUDA_TRY(upload_ints(&e->part_cls, pcls));
 
-  e->max_entries = e->mxtips + 1;                 // td[0].ti holds mxtips entries (axml.c:595)
   e->gs_stride = 2 * e->mxtips + kScratchNodes;   // globalScaler has 2*mxtips entries (axml.c:1966-1971); + the scratch nodes of exb_score_insertions
   CUDA_TRY(cudaMalloc(&e->gs, (size_t)e->P * e->gs_stride * sizeof(unsigned int)));
   CUDA_TRY(cudaMemset(e->gs, 0, (size_t)e->P * e->gs_stride * sizeof(unsigned int)));
@@ -802,11 +915,13 @@ static void set_finish_outputs(exb_engine *e, FinishArgs &f);
 
 // Validate and stage a traversal descriptor; one H2D copy of exactly the bytes in use.
 static int stage_traversal(exb_engine *e, const exb_entry *ti, int count, int first, const double *qz, const double *rz,
-                           const unsigned char *mask)
+                           const unsigned char *mask, int ncand = -1, int *max_scratch = nullptr)
 {
   if (count < first || count > e->max_entries)
     return fail(EXB_ERR_ARG, "traversal of %d entries (max %d)", count, e->max_entries);
-  const int lo = e->mxtips + 1, hi = 2 * e->mxtips - 2;
+  // exb_score_insertions (ncand >= 0): scoring entries, and newviews may use the scratch nodes behind the tree's own
+  const int lo = e->mxtips + 1, hi_tree = 2 * e->mxtips - 2, hi = ncand >= 0 ? hi_tree + kScratchNodes : hi_tree;
+  int scratch_top = -1;
   auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
   size_t off = 0;
   e->o_entries = off; off = align16(off + (size_t)count * sizeof(DevEntry));
@@ -819,12 +934,13 @@ static int stage_traversal(exb_engine *e, const exb_entry *ti, int count, int fi
   for (int i = 0; i < count; i++) {
     const exb_entry &t = ti[i];
     if (i < first) {
-      if (t.pNumber < 1 || t.pNumber > hi || t.qNumber < 1 || t.qNumber > hi)
-        return fail(EXB_ERR_ARG, "branch entry has node numbers %d,%d outside 1..%d", t.pNumber, t.qNumber, hi);
+      if (t.pNumber < 1 || t.pNumber > hi_tree || t.qNumber < 1 || t.qNumber > hi_tree)
+        return fail(EXB_ERR_ARG, "branch entry has node numbers %d,%d outside 1..%d", t.pNumber, t.qNumber, hi_tree);
       de[i] = DevEntry{-1, t.pNumber, t.qNumber, 0};
     } else {
-      bool ok = t.pNumber >= lo && t.pNumber <= hi;
-      switch (t.tipCase) {
+      const bool score = ncand >= 0 && t.tipCase >= 0 && (t.tipCase & EXB_SCORE);
+      bool ok = score ? (t.pNumber >= 0 && t.pNumber < ncand) : (t.pNumber >= lo && t.pNumber <= hi);
+      switch (score ? (t.tipCase & ~EXB_SCORE) : t.tipCase) {
       case EXB_TIP_TIP:     ok = ok && t.qNumber >= 1 && t.qNumber < lo && t.rNumber >= 1 && t.rNumber < lo; break;
       case EXB_TIP_INNER:   ok = ok && t.qNumber >= 1 && t.qNumber < lo && t.rNumber >= lo && t.rNumber <= hi; break;
       case EXB_INNER_INNER: ok = ok && t.qNumber >= lo && t.qNumber <= hi && t.rNumber >= lo && t.rNumber <= hi; break;
@@ -832,7 +948,10 @@ static int stage_traversal(exb_engine *e, const exb_entry *ti, int count, int fi
       }
       if (!ok) return fail(EXB_ERR_ARG, "traversal entry %d is inconsistent (tipCase=%d p=%d q=%d r=%d, mxtips=%d)",
                            i, t.tipCase, t.pNumber, t.qNumber, t.rNumber, e->mxtips);
-      de[i] = DevEntry{t.tipCase, t.pNumber, t.qNumber, t.rNumber};
+      de[i] = score ? DevEntry{(t.tipCase & 3) | kScoreBit, -t.pNumber - 1, t.qNumber, t.rNumber}
+                    : DevEntry{t.tipCase, t.pNumber, t.qNumber, t.rNumber};
+      if (!score) scratch_top = std::max(scratch_top, t.pNumber - hi_tree - 1);
+      scratch_top = std::max(scratch_top, std::max(t.qNumber, t.rNumber) - hi_tree - 1);
     }
     for (int b = 0; b < e->nb; b++) {
       const double zq = qz[(size_t)i * e->nb + b];
@@ -843,6 +962,7 @@ static int stage_traversal(exb_engine *e, const exb_entry *ti, int count, int fi
   }
   unsigned char *mk = e->stage_h + e->o_mask;
   for (int m = 0; m < e->P; m++) mk[m] = mask ? (mask[m] != 0) : 1;
+  if (max_scratch) *max_scratch = scratch_top;
 
   // Short descriptors (the partial traversals of a tree search): the few exponentials of the d-table are computed
   // here and travel with the descriptor -- one kernel launch less on the critical path of the call.
@@ -934,8 +1054,10 @@ static int sev_update(exb_engine *e, const exb_entry *ti, int count, int first, 
   return EXB_OK;
 }
 
+static int score_prepare(exb_engine *e, int ncand, int max_scratch);
+
 static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int first, const double *qz, const double *rz,
-                         const unsigned char *mask, int mode)
+                         const unsigned char *mask, int mode, int ncand = -1)
 {
   if (!e || !e->committed) return fail(EXB_ERR_STATE, "engine not committed");
   if (!ti || !qz || (count > first && !rz)) return fail(EXB_ERR_ARG, "null traversal arguments");
@@ -943,8 +1065,10 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   int rc = check_models(e, mask);
   if (rc) return rc;
   // the previous call has been synchronised, so the pinned staging area is free
-  rc = stage_traversal(e, ti, count, first, qz, rz, mask);
+  int max_scratch = -1;
+  rc = stage_traversal(e, ti, count, first, qz, rz, mask, ncand, &max_scratch);
   if (rc) return rc;
+  if (mode == MODE_SCORE) { rc = score_prepare(e, ncand, max_scratch); if (rc) return rc; }
   rc = flush_models(e);
   if (rc) return rc;
   if (e->sev) { rc = sev_update(e, ti, count, first, mask); if (rc) return rc; }
@@ -1004,6 +1128,9 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
     a.scale_inc = e->scale_inc; a.tile_out = k.tile_out;
     a.sev_table = k.sev.on ? k.sev.table_d : nullptr; a.sev_tipgap = nullptr; a.sev_gapcol = k.sev.gapcol;
     a.sev_ntiles = k.sev.ntiles; a.sev_tile0 = 0;
+    a.scratch_off = mode == MODE_SCORE && k.scratch ? (long long)(k.scratch - k.clv) : 0;
+    a.score_out = mode == MODE_SCORE ? k.score_out : nullptr;
+    a.score_stride = (int)k.tiles_h.size() * (c == CLS_DNA ? kDnaWarps : kAaWarps);
     if (c == CLS_DNA && k.nparts <= kMaxParamPartitions) {
       // few partitions: one launch per partition, its EI/EV travel as kernel parameters (constant bank)
       for (int pc = 0; pc < k.nparts; pc++) {
@@ -1041,6 +1168,26 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   }
   if (e->timing) CUDA_TRY(cudaEventRecord(e->ev_b, e->stream));
   e->phases_valid = e->timing;
+  if (mode == MODE_SCORE) {
+    ScoreFinishArgs f;
+    f.gs = e->gs; f.gs_stride = e->gs_stride; f.scale_inc = e->scale_inc;
+    f.entries = (const DevEntry *)(e->stage_use + e->o_entries);
+    f.count = count; f.mxtips = e->mxtips; f.nparts = e->P; f.ncand = ncand;
+    f.mask = e->stage_use + e->o_mask; f.part_has_sites = e->part_has_sites;
+    f.sc = e->score_sc;
+    for (int c = 0; c < 2; c++) {
+      f.score_out[c] = e->cls[c].score_out;
+      f.warps[c] = c == CLS_DNA ? kDnaWarps : kAaWarps;
+      f.score_stride[c] = (int)e->cls[c].tiles_h.size() * f.warps[c];
+    }
+    f.part_tile_begin = e->part_tile_begin; f.part_tile_count = e->part_tile_count; f.part_cls = e->part_cls;
+    f.log_minlikelihood = log(kMinLikelihood); f.out = e->score_d;
+    launch_score_finish(f, e->stream);
+    e->launches += 2;
+    if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+    CUDA_TRY(cudaGetLastError());
+    return EXB_OK;
+  }
   FinishArgs f;
   f.gs = e->gs; f.gs_stride = e->gs_stride; f.scale_inc = e->scale_inc;
   f.entries = (const DevEntry *)(e->stage_use + e->o_entries);
@@ -1261,6 +1408,86 @@ extern "C" int exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const
     if (curvatOK) curvatOK[b] = h->curvatOK[b];
   }
   if (iterations) *iterations = h->iterations;
+  return EXB_OK;
+}
+
+
+// ---- batched scoring of lazy SPR insertions (testInsertBIG searchAlgo.c:682) ----
+extern "C" int exb_max_entries(exb_engine *e) { return e && e->committed ? e->max_entries : 0; }
+
+extern "C" int exb_can_score_insertions(exb_engine *e)
+{
+  if (!e || !e->committed || e->cat || e->sev) return 0;
+  if (e->aa_tc && !e->cls[CLS_AA].tiles_h.empty()) return 0;
+  return 1;
+}
+
+// Buffers of a scoring call: scratch CLVs up to node index max_scratch (grown with their contents: a scan may be cut into
+// several calls and deeper levels can appear later), per-(candidate, tile, warp) partials, scaler sums, results.
+static int score_prepare(exb_engine *e, int ncand, int max_scratch)
+{
+  for (int c = 0; c < 2; c++) {
+    ClassState &k = e->cls[c];
+    if (k.tiles_h.empty()) continue;
+    if (max_scratch >= k.scratch_nodes) {
+      const int want = std::min(kScratchNodes, std::max(max_scratch + 1, k.scratch_nodes + 4));
+      const size_t node_bytes = k.N * k.span * sizeof(double);
+      double *grown = nullptr;
+      if (cudaMalloc(&grown, (size_t)want * node_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(EXB_ERR_CUDA, "exb_score_insertions: cannot allocate %d scratch CLVs of %.2f GB", want, node_bytes / 1e9);
+      }
+      if (k.scratch) {
+        CUDA_TRY(cudaMemcpyAsync(grown, k.scratch, (size_t)k.scratch_nodes * node_bytes, cudaMemcpyDeviceToDevice, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        cudaFree(k.scratch);
+      }
+      k.scratch = grown; k.scratch_nodes = want;
+    }
+    const size_t need = (size_t)ncand * k.tiles_h.size() * (c == CLS_DNA ? kDnaWarps : kAaWarps) * sizeof(double2);
+    if (need > k.score_out_cap) {
+      cudaFree(k.score_out); k.score_out = nullptr; k.score_out_cap = 0;
+      if (cudaMalloc(&k.score_out, need + need / 4) != cudaSuccess) { cudaGetLastError(); return fail(EXB_ERR_CUDA, "exb_score_insertions: out of HBM for the partial sums"); }
+      k.score_out_cap = need + need / 4;
+    }
+  }
+  const size_t nres = (size_t)ncand * e->P;
+  if (nres * sizeof(unsigned int) > e->score_sc_cap) {
+    cudaFree(e->score_sc); e->score_sc = nullptr; e->score_sc_cap = 0;
+    CUDA_TRY(cudaMalloc(&e->score_sc, 2 * nres * sizeof(unsigned int)));
+    e->score_sc_cap = 2 * nres * sizeof(unsigned int);
+  }
+  if (nres * sizeof(double) > e->score_d_cap) {
+    cudaFree(e->score_d); e->score_d = nullptr; e->score_d_cap = 0;
+    CUDA_TRY(cudaMalloc(&e->score_d, 2 * nres * sizeof(double)));
+    e->score_d_cap = 2 * nres * sizeof(double);
+  }
+  if (nres * sizeof(double) > e->score_h_cap) {
+    cudaFreeHost(e->score_h); e->score_h = nullptr; e->score_h_cap = 0;
+    CUDA_TRY(cudaMallocHost(&e->score_h, 2 * nres * sizeof(double)));
+    e->score_h_cap = 2 * nres * sizeof(double);
+  }
+  return EXB_OK;
+}
+
+extern "C" int exb_score_insertions(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
+                                    const unsigned char *executeModel, int ncand, double *lnl)
+{
+  if (!e || !e->committed) return fail(EXB_ERR_STATE, "engine not committed");
+  if (!exb_can_score_insertions(e))
+    return fail(EXB_ERR_STATE, "exb_score_insertions: not available under PSR, -S or the tf32x3 protein mode (score the candidates one by one)");
+  if (count < 1 || ncand < 0 || (ncand > 0 && !lnl)) return fail(EXB_ERR_ARG, "exb_score_insertions: bad arguments");
+  int rc = run_traversal(e, ti, count, 1, qz, rz, executeModel, MODE_SCORE, ncand);
+  if (rc) return rc;
+  const size_t n = (size_t)ncand * e->P;
+  if (n && e->comm) {
+    const int r = g_nccl.AllReduce(e->score_d, e->score_d, n, kNcclFloat64, kNcclSum, e->comm, e->stream);
+    if (r != 0) return fail(EXB_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  }
+  if (n) CUDA_TRY(cudaMemcpyAsync(e->score_h, e->score_d, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if (e->timing) cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
+  if (n) memcpy(lnl, e->score_h, n * sizeof(double));
   return EXB_OK;
 }
 

@@ -234,7 +234,7 @@ void launch_finish(const FinishArgs &a, cudaStream_t s);
 // the per-(candidate, tile, warp) partials into lnl[candidate][partition]
 constexpr int kDnaWarps = 8, kAaWarps = 12;      // warps per CTA of the GAMMA traverse kernels (slots per tile in score_out)
 struct ScoreFinishArgs {
-  unsigned int *gs; int gs_stride;
+  unsigned int *gs; int gs_stride, gs_in_smem;
   unsigned int *scale_inc;
   const DevEntry *entries; int count, mxtips, nparts, ncand;
   const unsigned char *mask; const int *part_has_sites;

@@ -226,6 +226,9 @@ int  exb_score_insertions(exb_engine *e, const exb_entry *ti, int count, const d
                           const unsigned char *executeModel, int ncand, double *lnl);
 /* 1 when exb_score_insertions is available in the engine's configuration */
 int  exb_can_score_insertions(exb_engine *e);
+/* Entries one descriptor may hold (any traversal call): at least mxtips + 1 like td[0].ti (axml.c:595), normally
+ * 3 * mxtips + 1 so that a whole insertion scan fits one call. */
+int  exb_max_entries(exb_engine *e);
 
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------------ */
 

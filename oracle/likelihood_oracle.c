@@ -16,6 +16,9 @@
  *   CAT / PSR           newviewCAT_FLEX newviewGenericSpecial.c:217-427, evaluateCAT_FLEX
  *                       evaluateGenericSpecial.c:232-330, sumCAT_FLEX makenewzGenericSpecial.c:170-249,
  *                       coreCAT_FLEX makenewzGenericSpecial.c:394-519 (one rate category per site)
+ *   orc_score_insertions testInsertBIG searchAlgo.c:682 in its non-thorough form (insertBIG searchAlgo.c:519-535 +
+ *                       newviewGeneric + evaluateGeneric), executed candidate by candidate with the functions above:
+ *                       the checker of the batched exb_score_insertions
  *   orc_evaluate_partial evaluatePartialGenericSpecial.c:259 (evaluatePartialGeneric) ->
  *                       :190-255 (evaluatePartialCAT_FLEX) + :92-187 (computeVectorCAT_FLEX): one site,
  *                       one explicit rate, the whole traversal recomputed from the tips
@@ -44,6 +47,7 @@
 typedef struct { int tipCase, pNumber, qNumber, rNumber; } orc_entry;
 
 #define ORC_MAX_CATS 64
+#define ORC_SCRATCH_NODES 64    /* EXB_SCRATCH_NODES; one more slot holds the candidate's new node */
 
 typedef struct {
   int states, codes;
@@ -54,6 +58,7 @@ typedef struct {
   int *wgt;
   unsigned char *tips;          /* [mxtips][width] */
   double *clv;                  /* [(mxtips-2)][width][4][S] */
+  double *scratch;              /* [ORC_SCRATCH_NODES + 1][width][4][S]: nodes that exist only for orc_score_insertions (lazy) */
   double *sum;                  /* [width][4][S] */
   unsigned int *scaler;         /* [2*mxtips] (axml.c:1966-1971) */
   double EIGN[20], EV[400], EI[400], tipVector[23 * 20], gammaRates[4];
@@ -88,7 +93,7 @@ void orc_destroy(orc_engine *e)
   if (!e) return;
   for (m = 0; m < e->nparts; m++) {
     free(e->parts[m].wgt); free(e->parts[m].tips); free(e->parts[m].clv);
-    free(e->parts[m].sum); free(e->parts[m].scaler); free(e->parts[m].rateCategory);
+    free(e->parts[m].sum); free(e->parts[m].scaler); free(e->parts[m].rateCategory); free(e->parts[m].scratch);
   }
   free(e->parts); free(e);
 }
@@ -106,7 +111,7 @@ int orc_set_partition(orc_engine *e, int model, int states, size_t width, const 
   memcpy(p->tips, y, (size_t)e->mxtips * width);
   p->clv = (double *)calloc((size_t)(e->mxtips - 2) * width * span + 1, sizeof(double));
   p->sum = (double *)calloc(width * span + 1, sizeof(double));
-  p->scaler = (unsigned int *)calloc(2 * (size_t)e->mxtips, sizeof(unsigned int));
+  p->scaler = (unsigned int *)calloc(2 * (size_t)e->mxtips + ORC_SCRATCH_NODES + 1, sizeof(unsigned int));
   return 0;
 }
 
@@ -156,6 +161,8 @@ static void orc_make_p(const orc_engine *e, double z, const orc_part *p, double 
 
 static double *clv_of(const orc_engine *e, const orc_part *p, int number)
 {
+  if (number > 2 * e->mxtips - 2)
+    return p->scratch + (size_t)(number - (2 * e->mxtips - 1)) * p->width * (size_t)orc_R(e) * (size_t)p->states;
   return p->clv + (size_t)(number - e->mxtips - 1) * p->width * (size_t)orc_R(e) * (size_t)p->states;
 }
 static const unsigned char *tip_of(const orc_engine *e, const orc_part *p, int number)
@@ -259,44 +266,83 @@ static void branch_ends(const orc_engine *e, const orc_part *p, const orc_entry 
   else { *xa = clv_of(e, p, P); *xb = clv_of(e, p, Q); }
 }
 
-/* GAMMA: evaluateGAMMA_FLEX eval:154-228 (log(0.25 |term|)); CAT: evaluateCAT_FLEX eval:232-330 (log |term|). */
+/* GAMMA: evaluateGAMMA_FLEX eval:154-228 (log(0.25 |term|)); CAT: evaluateCAT_FLEX eval:232-330 (log |term|).
+   Log likelihood of partition m at the branch (P, Q) with branch value z, scalers of both ends undone (eval:830). */
+static double orc_branch_value(const orc_engine *e, int m, int P, int Q, double z)
+{
+  const orc_part *p = &e->parts[m];
+  int c, k, n, R = orc_R(e);
+  int S = p->states, span = R * S, np = orc_np(e, p);
+  const double *rates = orc_rates(e, p);
+  double diag[ORC_MAX_CATS * 20], lz, sum = 0.0;
+  const unsigned char *tipA, *tipB; const double *xa, *xb;
+  orc_entry t0;
+  size_t i;
+  t0.tipCase = -1; t0.pNumber = P; t0.qNumber = Q; t0.rNumber = 0;
+  lz = (z < ORC_ZMIN) ? log(ORC_ZMIN) : log(z);
+  for (n = 0; n < np; n++) {
+    diag[n * S] = 1.0;
+    for (k = 1; k < S; k++) diag[n * S + k] = p->lg4 ? exp(rates[n] * orc_EIGN(p, n)[k] * lz)   /* eval:122-145 */
+                                                     : exp(rates[n] * (p->EIGN[k] * lz));
+  }
+  branch_ends(e, p, &t0, &tipA, &tipB, &xa, &xb);
+  for (i = 0; i < p->width; i++) {
+    double term = 0.0;
+    for (c = 0; c < R; c++) {
+      const double *dg = diag + (size_t)orc_pidx(e, p, i, c) * S;
+      double t = 0.0;
+      for (k = 0; k < S; k++) {
+        double l = tipA ? orc_tipv(p, c)[(size_t)S * tipA[i] + k] : xa[i * span + c * S + k];
+        double r = tipB ? orc_tipv(p, c)[(size_t)S * tipB[i] + k] : xb[i * span + c * S + k];
+        t += l * r * dg[k];
+      }
+      term += p->lg4 ? p->weights[c] * t : t;          /* evaluateGTRGAMMAPROT_LG4 eval:1164-1287 */
+    }
+    sum += p->wgt[i] * ((e->cat || p->lg4) ? log(fabs(term)) : log(0.25 * fabs(term)));
+  }
+  sum += (double)(p->scaler[P] + p->scaler[Q]) * log(ORC_MINLIKELIHOOD);
+  return sum;
+}
+
 int orc_evaluate(orc_engine *e, const orc_entry *ti, int count, const double *qz, const double *rz,
                  const unsigned char *mask, double *perPartitionLH)
 {
-  int m, c, k, n, nb = e->nbranches, R = orc_R(e);
+  int m, nb = e->nbranches;
   orc_run_newviews(e, ti, 1, count, qz, rz, mask);
   for (m = 0; m < e->nparts; m++) {
+    if (!executes(e, mask, m)) { if (e->parts[m].width == 0) perPartitionLH[m] = 0.0; continue; }
+    perPartitionLH[m] = orc_branch_value(e, m, ti[0].pNumber, ti[0].qNumber, qz[nb > 1 ? m : 0]);
+  }
+  return 0;
+}
+
+/* The mixed descriptor of exb_score_insertions, executed the way the reference scores a lazy insertion: entries without the
+   scoring bit are ordinary newviews (scratch nodes allowed); a scoring entry (tipCase | 4, pNumber = candidate) inserts a new
+   node between qNumber and rNumber with branch values qz / rz -- insertBIG's non-thorough hook-ups, searchAlgo.c:519-535 --,
+   computes its CLV (newviewGeneric(tr, p)) and evaluates the tree across the branch to the pruned subtree ti[0].pNumber with
+   branch value ti[0].qz (evaluateGeneric; the reference evaluates at (p->next->next, r), which is the same likelihood by the
+   pulley principle).  lnl[ncand][nparts]; masked partitions read 0. */
+int orc_score_insertions(orc_engine *e, const orc_entry *ti, int count, const double *qz, const double *rz,
+                         const unsigned char *mask, int ncand, double *lnl)
+{
+  const int nb = e->nbranches, newnode = 2 * e->mxtips - 1 + ORC_SCRATCH_NODES;
+  int i, m;
+  for (m = 0; m < e->nparts; m++) {
     orc_part *p = &e->parts[m];
-    int S = p->states, span = R * S, np = orc_np(e, p);
-    const double *rates = orc_rates(e, p);
-    double diag[ORC_MAX_CATS * 20], z, lz, sum = 0.0;
-    const unsigned char *tipA, *tipB; const double *xa, *xb;
-    size_t i;
-    if (!executes(e, mask, m)) { if (p->width == 0) perPartitionLH[m] = 0.0; continue; }
-    z = qz[nb > 1 ? m : 0];
-    lz = (z < ORC_ZMIN) ? log(ORC_ZMIN) : log(z);
-    for (n = 0; n < np; n++) {
-      diag[n * S] = 1.0;
-      for (k = 1; k < S; k++) diag[n * S + k] = p->lg4 ? exp(rates[n] * orc_EIGN(p, n)[k] * lz)   /* eval:122-145 */
-                                                       : exp(rates[n] * (p->EIGN[k] * lz));
+    if (!p->scratch)
+      p->scratch = (double *)calloc((size_t)(ORC_SCRATCH_NODES + 1) * p->width * (size_t)orc_R(e) * (size_t)p->states + 1, sizeof(double));
+  }
+  for (i = 0; i < ncand * e->nparts; i++) lnl[i] = 0.0;
+  for (i = 1; i < count; i++) {
+    if (!(ti[i].tipCase & 4)) { orc_run_newviews(e, ti, i, i + 1, qz, rz, mask); continue; }
+    for (m = 0; m < e->nparts; m++) {
+      orc_entry t = ti[i];
+      int slot = nb > 1 ? m : 0;
+      if (!executes(e, mask, m)) continue;
+      t.tipCase &= 3; t.pNumber = newnode;
+      orc_newview_entry(e, &e->parts[m], &t, qz[(size_t)i * nb + slot], rz[(size_t)i * nb + slot]);
+      lnl[(size_t)ti[i].pNumber * e->nparts + m] = orc_branch_value(e, m, newnode, ti[0].pNumber, qz[slot]);
     }
-    branch_ends(e, p, &ti[0], &tipA, &tipB, &xa, &xb);
-    for (i = 0; i < p->width; i++) {
-      double term = 0.0;
-      for (c = 0; c < R; c++) {
-        const double *dg = diag + (size_t)orc_pidx(e, p, i, c) * S;
-        double t = 0.0;
-        for (k = 0; k < S; k++) {
-          double l = tipA ? orc_tipv(p, c)[(size_t)S * tipA[i] + k] : xa[i * span + c * S + k];
-          double r = tipB ? orc_tipv(p, c)[(size_t)S * tipB[i] + k] : xb[i * span + c * S + k];
-          t += l * r * dg[k];
-        }
-        term += p->lg4 ? p->weights[c] * t : t;          /* evaluateGTRGAMMAPROT_LG4 eval:1164-1287 */
-      }
-      sum += p->wgt[i] * ((e->cat || p->lg4) ? log(fabs(term)) : log(0.25 * fabs(term)));
-    }
-    sum += (double)(p->scaler[ti[0].pNumber] + p->scaler[ti[0].qNumber]) * log(ORC_MINLIKELIHOOD);
-    perPartitionLH[m] = sum;
   }
   return 0;
 }

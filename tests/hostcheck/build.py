@@ -16,6 +16,7 @@ from examl_b200.build_dropin import CFLAGS, KEEP, OBJ, REF   # noqa: E402  (the 
 
 OUT = os.path.join(HERE, "_build")
 EXE = os.path.join(OUT, "examl-hostcheck")
+EXE_SPR = os.path.join(OUT, "examl-hostcheck-spr")     # searchAlgo.c with the batched-insertion hooks
 
 
 def build(force: bool = False) -> str | None:
@@ -23,7 +24,8 @@ def build(force: bool = False) -> str | None:
         return EXE if os.path.exists(EXE) else None
     srcs = [os.path.join(ROOT, "examl_b200", "csrc", "axml_backend.c"), os.path.join(HERE, "exb_on_oracle.c"),
             os.path.join(ROOT, "oracle", "likelihood_oracle.c"), os.path.join(ROOT, "oracle", "ref_probe.c"), __file__]
-    if not force and os.path.exists(EXE) and all(os.path.getmtime(EXE) >= os.path.getmtime(s) for s in srcs):
+    srcs.append(os.path.join(ROOT, "examl_b200", "build_dropin.py"))
+    if not force and os.path.exists(EXE) and os.path.exists(EXE_SPR) and all(os.path.getmtime(EXE_SPR) >= os.path.getmtime(s) for s in srcs):
         return EXE
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref", "-j8"])
     os.makedirs(OUT, exist_ok=True)
@@ -35,8 +37,12 @@ def build(force: bool = False) -> str | None:
         subprocess.check_call(["gcc"] + flags + inc + ["-c", "-o", o, src])
         objs.append(o)
     objs += [os.path.join(OBJ, "avx", k + ".o") for k in KEEP] + [os.path.join(OBJ, "mpi_tcp.o"), os.path.join(OBJ, "avx", "ref_probe.o")]
-    subprocess.check_call(["gcc", "-o", EXE] + objs + ["-Wl,--wrap=evaluateGeneric", "-Wl,--wrap=makenewzGeneric",
-                                                       "-Wl,--wrap=evaluatePartialGeneric", "-lm"])
+    wrap = ["-Wl,--wrap=evaluateGeneric", "-Wl,--wrap=makenewzGeneric", "-Wl,--wrap=evaluatePartialGeneric", "-lm"]
+    subprocess.check_call(["gcc", "-o", EXE] + objs + wrap)
+    # the same harness with the batched-insertion hooks in rearrangeBIG (examl_b200/build_dropin.py: the maintainer patch)
+    from examl_b200.build_dropin import patched_search_object
+    spr_o = patched_search_object()
+    subprocess.check_call(["gcc", "-o", EXE_SPR] + [spr_o if o.endswith(os.sep + "searchAlgo.o") else o for o in objs] + wrap)
     return EXE
 
 

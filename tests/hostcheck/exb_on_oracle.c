@@ -31,8 +31,10 @@ int orc_makenewz_prepare(orc_engine *e, const exb_entry *ti, int count, const do
 int orc_core(orc_engine *e, const double *lz, const unsigned char *mask, double *d1, double *d2);
 int orc_evaluate_partial(orc_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz, size_t n,
                          const int *models, const int *sites, const double *rates, double *out);
+int orc_score_insertions(orc_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
+                         const unsigned char *mask, int ncand, double *lnl);
 
-struct exb_engine { orc_engine *o; int P, nb, nranks; long calls; };
+struct exb_engine { orc_engine *o; int P, nb, nranks, cat; long calls; };
 static char g_err[256] = "";
 
 const char *exb_last_error(void) { return g_err; }
@@ -47,7 +49,7 @@ int exb_create(exb_engine **out, int device, int mxtips, int numPartitions, int 
   return EXB_OK;
 }
 void exb_destroy(exb_engine *e) { if (e) { orc_destroy(e->o); free(e); } }
-int exb_set_rate_model(exb_engine *e, int rateHetModel, int maxCategories) { return orc_set_rate_model(e->o, rateHetModel, maxCategories); }
+int exb_set_rate_model(exb_engine *e, int rateHetModel, int maxCategories) { e->cat = rateHetModel == EXB_CAT; return orc_set_rate_model(e->o, rateHetModel, maxCategories); }
 int exb_set_partition(exb_engine *e, int model, int states, size_t width, const int *wgt, const unsigned char *y)
 { return orc_set_partition(e->o, model, states, width, wgt, y); }
 int exb_commit(exb_engine *e) { (void)e; return EXB_OK; }
@@ -113,5 +115,18 @@ int exb_evaluate_partial(exb_engine *e, const exb_entry *ti, int count, const do
     snprintf(g_err, sizeof g_err, "orc_evaluate_partial refused the call");
     return EXB_ERR_ARG;
   }
+  return EXB_OK;
+}
+
+/* batched lazy-SPR scoring: the oracle executes the mixed descriptor candidate by candidate; sum over ranks like exb_evaluate */
+int exb_can_score_insertions(exb_engine *e) { return !e->cat; }
+int exb_max_entries(exb_engine *e) { (void)e; return 1 << 20; }
+int exb_score_insertions(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
+                         const unsigned char *mask, int ncand, double *lnl)
+{
+  e->calls++;
+  if (e->cat) { snprintf(g_err, sizeof g_err, "hostcheck harness: no batched scoring under PSR (like the CUDA engine)"); return EXB_ERR_STATE; }
+  orc_score_insertions(e->o, ti, count, qz, rz, mask, ncand, lnl);
+  if (ncand > 0) allreduce(e, lnl, ncand * e->P);
   return EXB_OK;
 }

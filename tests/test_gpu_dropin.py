@@ -150,3 +150,42 @@ def test_search_and_quartet_workflows(args):
         else:
             assert best0 is not None and best1 is not None
             assert _rel(best1, best0) < NORTH_STAR_RTOL, (best1, best0)
+
+
+@pytest.mark.skipif(not have_binaries(), reason="bin/examl-b200-spr / oracle/_ref/parse-examl not built")
+@pytest.mark.parametrize("case", ["dna49", "small", "small-M", "aa"])
+def test_batched_insertion_scoring_behind_the_search(case):
+    """SURVEY 8 f-4 on the GPU: bin/examl-b200-spr = the drop-in with the maintainer patch in rearrangeBIG.
+    Every pruned subtree's lazy insertions are scored by one exb_score_insertions call; testInsertBIG is answered from the
+    table.  The search ends where the reference's does (testData/49: -16221.368990)."""
+    import os, re, time
+    from dropin_util import ROOT
+    exe = os.path.join(ROOT, "bin", "examl-b200-spr")
+    if not os.path.exists(exe):
+        pytest.skip("bin/examl-b200-spr not built")
+    env = {"EXAML_B200_SPR_STATS": "1"}
+    with tempfile.TemporaryDirectory() as tmp:
+        if case == "dna49":
+            binary, tree, _ = write_inputs("dna49", tmp)
+            args, best0 = ["-m", "GAMMA", "-f", "d"], -16221.368990
+        elif case == "aa":
+            from dropin_util import small_aa_case
+            binary, tree = small_aa_case(tmp, ["LG, p0 = 1-120"], taxa=12)
+            args = ["-m", "GAMMA", "-f", "d"]
+            r0, best0, _ = run_mode(REFERENCE, binary, tree, tmp, "REF", args)
+            assert r0.returncode == 0
+        else:
+            binary, tree = small_dna_case(tmp, taxa=20, sites=600, seed=13)
+            args = ["-m", "GAMMA", "-f", "d"] + (["-M"] if case == "small-M" else [])
+            r0, best0, _ = run_mode(REFERENCE, binary, tree, tmp, "REF", args)
+            assert r0.returncode == 0
+        t0 = time.time()
+        r1, best1, _ = run_mode(exe, binary, tree, tmp, "SPR", args, env=env)
+        dt = time.time() - t0
+        assert r1.returncode == 0, r1.stdout[-3000:]
+        assert best1 >= best0 * (1 + NORTH_STAR_RTOL), (best1, best0)
+        m = re.search(r"batched insertion scoring: (\d+) scans, (\d+) engine calls, (\d+) candidates scored, (\d+) served from the table, (\d+) answered", r1.stdout)
+        assert m, r1.stdout[-800:]
+        scans, calls, scored, served, flushed = map(int, m.groups())
+        assert scans > 10 and served > scans and flushed == 0, m.group(0)
+        print(case, "search with batched insertion scoring: %.1f s, final lnL" % dt, best1, "reference", best0, "|", m.group(0))

@@ -577,3 +577,72 @@ def test_sev_footprint_follows_the_data(cuda_factory):
     dense_bytes = 198 * 120000 * 128
     print("SEV blocks", used, "of", dense, "slab bytes", nbytes, "dense arena", dense_bytes)
     assert used < 0.5 * dense and nbytes < 0.6 * dense_bytes
+
+
+# ---- batched scoring of lazy SPR insertions (exb_score_insertions) ----------------------------------------
+@pytest.mark.parametrize("mxtips,widths,kinds,nb,tile,mode,maxtrav", [
+    (16, [700], [4], 1, None, "signal", 5),                    # one DNA partition: constants as kernel parameters
+    (40, [300, 200], [4, 20], 1, 1024, "iid", 8),              # several chunks per tile, scaling fires, windows of 48 / 96 entries
+    (24, [150, 90, 60], [4, 20, 4], 3, 64, "signal", 6),       # -M: one branch slot per partition; small tiles
+    (30, [40 + 7 * (i % 5) for i in range(20)], [4] * 20, 1, None, "signal", 4),   # > 16 DNA partitions: constants from shared memory
+    (150, [96], [20], 1, None, "iid", 12),                     # AA, hundreds of candidates: the scan is cut into several calls
+])
+def test_score_insertions_vs_oracle(cuda_factory, oracle_factory, mxtips, widths, kinds, nb, tile, mode, maxtrav):
+    """The reference scores one insertion per newviewGeneric + evaluateGeneric pair (testInsertBIG searchAlgo.c:682); the
+    engine takes the whole walk of addTraverseBIG as one mixed descriptor.  Same descriptor on the CUDA engine and on the
+    oracle (whose orc_score_insertions is pinned to the candidate-by-candidate procedure by tests/test_spr_batch.py)."""
+    from examl_b200.likelihood import Likelihood
+    from examl_b200.spr import build_scan, remove_node, score_scan
+    from spr_util import prunable_nodes
+    tree, parts, models = random_case(mxtips, widths, kinds, seed=31, mode=mode, num_branches=nb)
+    tree2 = random_case(mxtips, widths, kinds, seed=31, mode=mode, num_branches=nb)[0]
+    kw = {} if tile is None else {"tile_sites": tile}
+    gpu = build_engine(lambda mx, npart, nbr=1: cuda_factory(mx, npart, nbr, **kw), tree, parts, models)
+    cpu = build_engine(oracle_factory, tree2, parts, models)
+    assert gpu.can_score_insertions()
+    lk, lk2 = Likelihood(tree, gpu, len(parts)), Likelihood(tree2, cpu, len(parts))
+    lk.evaluateGeneric(tree.start, True); lk2.evaluateGeneric(tree2.start, True)
+    rng = np.random.default_rng(8)
+    nodes, nodes2 = prunable_nodes(tree), prunable_nodes(tree2)
+    mask = np.array([1] * len(parts), dtype=np.uint8)
+    for rnd, pick in enumerate(rng.choice(len(nodes), size=3, replace=False)):
+        p, p_2 = nodes[pick], nodes2[pick]
+        zqr = [a * b for a, b in zip(p.next.z, p.next.next.z)]
+        saved = [(p.next.back, list(p.next.z), p.next.next.back, list(p.next.next.z)) for p in (p, p_2)]
+        p1, p2 = remove_node(tree, p, zqr)
+        q1, q2 = remove_node(tree2, p_2, zqr)
+        for l, a, b in ((lk, p1, p2), (lk2, q1, q2)):
+            l.newviewGeneric(a); l.newviewGeneric(b)
+        ti, cands = build_scan(tree, p, p1, p2, 1, maxtrav)
+        ti2, cands2 = build_scan(tree2, p_2, q1, q2, 1, maxtrav)
+        assert [c.number for c in cands] == [c.number for c in cands2] and len(cands) > 0
+        if rnd == 2 and len(parts) > 1:
+            mask[1] = 0                                            # a masked partition reads 0
+        got = score_scan(gpu, ti, len(cands), max_entries=mxtips + 1, execute_model=mask)
+        want = score_scan(cpu, ti2, len(cands2), max_entries=mxtips + 1, execute_model=mask)
+        assert np.all(np.abs(got - want) <= 5e-12 * np.abs(want)), np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300))
+        assert np.all(got[:, mask == 0] == 0.0)
+        mask[:] = 1
+        # the same call again gives the same bits
+        assert np.array_equal(got, score_scan(gpu, ti, len(cands), max_entries=mxtips + 1)) or rnd == 2
+        from examl_b200.phylo import hookup
+        for pp, sv in ((p, saved[0]), (p_2, saved[1])):
+            hookup(pp.next, sv[0], sv[1]); hookup(pp.next.next, sv[2], sv[3])
+        lk.newviewGeneric(p); lk2.newviewGeneric(p_2)
+        a, b = lk.evaluateGeneric(p, False), lk2.evaluateGeneric(p_2, False)
+        assert abs(a - b) <= 5e-12 * abs(b)
+    # the tree's own CLVs and scalers are what the ordinary path leaves behind
+    a, b = lk.evaluateGeneric(tree.start, True), lk2.evaluateGeneric(tree2.start, True)
+    assert abs(a - b) <= 5e-12 * abs(b)
+
+
+def test_score_insertions_refused_where_not_built(cuda_factory):
+    """PSR and -S engines say so (the drop-in then scores candidate by candidate)."""
+    tree, parts, models = random_case(8, [64], [4], seed=1)
+    e = cuda_factory(8, 1, 1)
+    e.set_sev(True)
+    e.set_partition(0, 4, parts[0][2], parts[0][1]); e.commit(); e.set_model(0, models[0])
+    assert not e.can_score_insertions()
+    from examl_b200.capi import EngineError
+    with pytest.raises(EngineError):
+        e.scoreInsertions(tree.full_traversal()[:1], 0)

@@ -94,6 +94,29 @@ def test_search_and_quartet_workflows(args):
             assert _rel(best1, best0) < 1e-6, (best1, best0)
 
 
+@pytest.mark.parametrize("args,taxa", [(["-m", "GAMMA", "-f", "d"], 24), (["-m", "GAMMA", "-f", "d", "-M"], 12), (["-m", "PSR", "-f", "d"], 12)])
+def test_batched_insertion_scan_behind_the_search(args, taxa):
+    """rearrangeBIG with the maintainer patch (batchedInsertionScanBegin / End around its addTraverseBIG
+    calls, examl_b200/build_dropin.py SPR_PATCH).  The lazy insertions of every pruned subtree are scored by ONE
+    exb_score_insertions call and testInsertBIG's newviewGeneric / evaluateGeneric pairs are answered from that table; the
+    search must end where the reference's does.  Under PSR the engine has no batched scoring and the same binary takes
+    the ordinary path."""
+    import re
+    with tempfile.TemporaryDirectory() as tmp:
+        binary, tree = small_dna_case(tmp, taxa=taxa, sites=400, seed=21)
+        r0, best0, _ = run_mode(REFERENCE, binary, tree, tmp, "REF", args)
+        r1, best1, _ = run_mode(hostcheck_build.EXE_SPR, binary, tree, tmp, "SPR", args, env=dict(ENV, EXAML_B200_SPR_STATS="1"))
+        assert r0.returncode == 0 and r1.returncode == 0, (r0.stdout[-1500:], r1.stdout[-1500:])
+        assert _rel(best1, best0) < 1e-6, (best1, best0)
+        m = re.search(r"batched insertion scoring: (\d+) scans, (\d+) engine calls, (\d+) candidates scored, (\d+) served from the table, (\d+) answered", r1.stdout)
+        assert m, r1.stdout[-800:]
+        scans, calls, scored, served, flushed = map(int, m.groups())
+        if "PSR" in args:
+            assert scans == 0 and served == 0
+        else:
+            assert scans > 10 and calls == scans and served > scans and served <= scored and flushed == 0, m.group(0)
+
+
 def test_restart_from_checkpoint():
     """-R: the search state comes back from ExaML_binaryCheckpoint (searchAlgo.c:1726); CLVs are not part of it, so the
     back-end must rebuild everything from the first full traversal after the restart."""
