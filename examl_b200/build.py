@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libexaml_b200.so")
 SOURCES = ["engine.cu", "kernels_dna.cu", "kernels_aa.cu", "kernels_aa_tc.cu", "kernels_sev.cu", "kernels_nr.cu", "kernels_partial.cu"]
-HEADERS = ["engine.cuh", "core_tile.cuh", "stage.cuh", "p2p.cuh", os.path.join("..", "..", "include", "examl_b200.h")]
+HEADERS = ["engine.cuh", "core_tile.cuh", "stage.cuh", "p2p.cuh", "finish.cuh", os.path.join("..", "..", "include", "examl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

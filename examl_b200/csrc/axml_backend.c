@@ -100,6 +100,10 @@ static void backend_comm_init(void)
   (void)i;
 }
 
+/* EXAML_B200_SPR_STATS=1: call statistics at exit */
+static long g_calls_eval_full = 0, g_calls_eval = 0, g_calls_newview = 0, g_calls_makenewz = 0, g_entries_total = 0;
+static void spr_report(void);
+
 static void backend_init(tree *tr)
 {
   int m;
@@ -129,6 +133,7 @@ static void backend_init(tree *tr)
   }
   if (exb_commit(g_engine) != EXB_OK) backend_fail("exb_commit");
   exb_set_timing(g_engine, 0);
+  if (getenv("EXAML_B200_SPR_STATS")) atexit(spr_report);
   backend_comm_init();
   g_entries = (exb_entry *)malloc(slots * sizeof(exb_entry));
   g_qz = (double *)malloc(slots * nb * sizeof(double));
@@ -398,6 +403,8 @@ void evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal)
   storeExecuteMaskInTraversalDescriptor(tr);
   tr->td[0].traversalHasChanged = TRUE;
 
+  if (fullTraversal) g_calls_eval_full++; else g_calls_eval++;
+  g_entries_total += tr->td[0].count - 1;
   evaluateIterative(tr);            /* newviews + lnL at the branch + all-reduce, on the GPU */
 
   for (m = 0; m < tr->NumberOfModels; m++) sum += tr->perPartitionLH[m];
@@ -419,6 +426,8 @@ void newviewGeneric(tree *tr, nodeptr p, boolean masked)
   if (masked)
     for (m = 0; m < tr->NumberOfModels; m++) tr->executeModel[m] = tr->partitionConverged[m] ? FALSE : TRUE;
 
+  g_calls_newview++;
+  g_entries_total += tr->td[0].count;
   if (tr->td[0].count > 0) {
     storeExecuteMaskInTraversalDescriptor(tr);
     newviewIterative(tr, 0);
@@ -535,6 +544,8 @@ void makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxiter, do
   tr->td[0].count = 1;
   if (!p->x) computeTraversalInfo(p, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
   if (!q->x) computeTraversalInfo(q, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
+  g_calls_makenewz++;
+  g_entries_total += tr->td[0].count - 1;
 
   /* the whole Newton-Raphson loop on the device: single rank, or all ranks on one node (in-kernel all-reduce) */
   if ((g_ranks == 1 || exb_comm_is_p2p(g_engine)) && !getenv("EXAML_B200_HOST_NR")) {
@@ -593,6 +604,9 @@ static scan_state g_spr = {0, NULL, 0, 0, NULL, NULL, -1, NULL, NULL, NULL, 0, 0
 static long g_spr_scans = 0, g_spr_scored = 0, g_spr_served = 0, g_spr_flushed = 0, g_spr_calls = 0;
 static void spr_report(void)
 {
+  if (processID == 0)
+    printf("B200 back-end, likelihood calls: %ld evaluateGeneric (full) + %ld (partial), %ld newviewGeneric, %ld makenewzGeneric; "
+           "%ld descriptor entries\n", g_calls_eval_full, g_calls_eval, g_calls_newview, g_calls_makenewz, g_entries_total);
   if (processID == 0)
     printf("B200 back-end, batched insertion scoring: %ld scans, %ld engine calls, %ld candidates scored, %ld served from the table, "
            "%ld answered newviews computed after all\n", g_spr_scans, g_spr_calls, g_spr_scored, g_spr_served, g_spr_flushed);
@@ -685,10 +699,7 @@ void batchedInsertionScanBegin(tree *tr, nodeptr p, nodeptr p1, nodeptr p2, int 
   int k, m, at, i, cap;
   g_spr.active = 0;
   g_spr.pending = -1;
-  if (enabled < 0) {
-    enabled = getenv("EXAML_B200_NO_BATCHED_SPR") ? 0 : 1;
-    if (getenv("EXAML_B200_SPR_STATS")) atexit(spr_report);
-  }
+  if (enabled < 0) enabled = getenv("EXAML_B200_NO_BATCHED_SPR") ? 0 : 1;
   if (!enabled || Thorough) return;
   backend_sync(tr);
   if (!exb_can_score_insertions(g_engine)) return;

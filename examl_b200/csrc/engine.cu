@@ -7,6 +7,7 @@
 #include "../../include/examl_b200.h"
 #include "engine.cuh"
 #include "p2p.cuh"
+#include "finish.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -22,117 +23,24 @@
 namespace exb {
 
 // ------------------------------------------------------------------------------------------------------
-// finish kernel: (1) scaler bookkeeping globalScaler[p] = globalScaler[q] + globalScaler[r] + increment
-// (newviewGenericSpecial.c:1503-1506) for every newview entry in order; (2) deterministic reduction of
-// the per-tile partial sums of each partition; (3) evaluate only: undo the scaling,
-// + (gs[p] + gs[q]) * log(minlikelihood) (evaluateGenericSpecial.c:830).  One block per partition.
+// finish kernel (finish.cuh): scaler bookkeeping, per-partition reduction, scaling undo, results to the host.
+// One block per partition.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 finish_kernel(const FinishArgs a)
 {
   extern __shared__ unsigned int gsm[];            // one scaler row (2*mxtips) when it fits
   __shared__ double red0[4], red1[4];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int part = blockIdx.x; part < a.nparts; part += gridDim.x) {
-    const bool exec = a.mask[part] && a.part_has_sites[part];
-    unsigned int *gs = a.gs + (size_t)part * a.gs_stride;
-    // ---- (1) scaler chain, sequential in the entries: warp 0, in shared memory when the row fits ----
-    if (exec && a.count > a.first && warp == 0) {
-      if (a.gs_in_smem) {
-        for (int i = lane; i < 2 * a.mxtips; i += 32) gsm[i] = gs[i];
-        __syncwarp();
-        for (int e0 = a.first; e0 < a.count; e0 += 32) {
-          const int e = e0 + lane;
-          unsigned int inc = 0; DevEntry en = {0, 0, 0, 0};
-          if (e < a.count) {
-            en = a.entries[e];
-            inc = a.scale_inc[(size_t)e * a.nparts + part];
-            if (inc) a.scale_inc[(size_t)e * a.nparts + part] = 0;
-          }
-          const int n = min(32, a.count - e0);
-          for (int j = 0; j < n; j++) {               // lane j's entry, in order
-            const int pj = __shfl_sync(0xffffffffu, en.p, j), qj = __shfl_sync(0xffffffffu, en.q, j),
-                      rj = __shfl_sync(0xffffffffu, en.r, j);
-            const unsigned int ij = __shfl_sync(0xffffffffu, inc, j);
-            if (lane == 0) gsm[pj] = gsm[qj] + gsm[rj] + ij;
-            __syncwarp();
-          }
-        }
-        for (int i = lane; i < 2 * a.mxtips; i += 32) gs[i] = gsm[i];
-      } else if (lane == 0) {
-        for (int e = a.first; e < a.count; e++) {
-          const DevEntry en = a.entries[e];
-          unsigned int *inc = &a.scale_inc[(size_t)e * a.nparts + part];
-          gs[en.p] = gs[en.q] + gs[en.r] + *inc;
-          *inc = 0;
-        }
-      }
-    }
-    __syncthreads();                                 // gs[] of this partition is final; red[] is free
-    if (a.mode == MODE_NEWVIEW || a.mode == MODE_SUM) continue;
-    // ---- (2) tile partials -> partition, fixed order: thread-strided sums (loads in flight), warp tree, 4 warps ----
-    double s0 = 0.0, s1 = 0.0;
-    if (exec) {
-      const double2 *to = reinterpret_cast<const double2 *>((a.part_cls[part] ? a.tile_out[1] : a.tile_out[0]) +
-                                                             2 * (size_t)a.part_tile_begin[part]);
-      const int n = a.part_tile_count[part];
-      int t = tid;
-      for (; t + 3 * 128 < n; t += 4 * 128) {
-        const double2 v0 = to[t], v1 = to[t + 128], v2 = to[t + 256], v3 = to[t + 384];
-        s0 += v0.x; s1 += v0.y; s0 += v1.x; s1 += v1.y; s0 += v2.x; s1 += v2.y; s0 += v3.x; s1 += v3.y;
-      }
-      for (; t < n; t += 128) { const double2 v = to[t]; s0 += v.x; s1 += v.y; }
-      #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s0 += __shfl_down_sync(0xffffffffu, s0, o);
-        s1 += __shfl_down_sync(0xffffffffu, s1, o);
-      }
-    }
-    if (lane == 0) { red0[warp] = s0; red1[warp] = s1; }
-    __syncthreads();
-    if (tid == 0) {
-      s0 = ((red0[0] + red0[1]) + (red0[2] + red0[3]));
-      s1 = ((red1[0] + red1[1]) + (red1[2] + red1[3]));
-      if (a.mode == MODE_EVALUATE && exec) {
-        const DevEntry br = a.entries[0];
-        s0 += (double)(gs[br.p] + gs[br.q]) * a.log_minlikelihood;   // evaluateGenericSpecial.c:830
-      }
-      if (a.x.nranks > 1) {        // my contribution goes straight into every rank's receive buffer
-        const size_t at = p2p_row(a.x, a.xseq, a.x.rank, 2 * a.nparts) + part;
-        for (int r = 0; r < a.x.nranks; r++) {
-          a.x.peer_buf[r][at] = s0;
-          if (a.mode == MODE_CORE) a.x.peer_buf[r][at + a.nparts] = s1;
-        }
-      } else {
-        a.out[part] = s0;
-        if (a.out_host) a.out_host[part] = s0;
-        if (a.mode == MODE_CORE) {
-          a.out[a.nparts + part] = s1;
-          if (a.out_host) a.out_host[a.nparts + part] = s1;
-        }
-      }
-    }
-    __syncthreads();
-  }
+  finish_body(a, a.entries, a.mask, gsm, red0, red1, (int)blockIdx.x, (int)gridDim.x);
   if (a.done_flag_host) {
     // the last block to arrive publishes the completion flag after everybody's results are visible to the host
     __shared__ int last, peer_lost;
     __threadfence_system();
     __syncthreads();
-    if (tid == 0) { last = atomicAdd(a.ticket, 1u) == gridDim.x - 1; peer_lost = 0; }
+    if (threadIdx.x == 0) last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!last) return;
-    if (a.x.nranks > 1 && a.mode != MODE_NEWVIEW && a.mode != MODE_SUM) {
-      const bool ok = p2p_finish_exchange(a.x, a.xseq, (a.mode == MODE_CORE ? 2 : 1) * a.nparts, 2 * a.nparts, a.out, a.out_host);
-      if (tid == 0 && !ok) peer_lost = 1;
-      __threadfence_system();
-      __syncthreads();
-    }
-    if (tid == 0) {
-      *a.ticket = 0;
-      __threadfence_system();
-      *a.done_flag_host = peer_lost ? 0xFFFFFFFFu : a.seq;       // 0xFFFFFFFF: the host reports the lost peer
-    }
+    finish_publish(a, &peer_lost);
   }
 }
 
@@ -390,7 +298,7 @@ struct exb_engine {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_a = nullptr, ev_b = nullptr;   // call start / end, traverse start / end
   // per-call staging (pinned host + device mirror): entries | lzq | lzr | mask | lz(core)
-  size_t stage_bytes = 0;
+  size_t stage_bytes = 0, stage_used_bytes = 0;
   unsigned char *stage_h = nullptr, *stage_d = nullptr;
   size_t off_entries = 0, off_lzq = 0, off_lzr = 0, off_mask = 0, off_corelz = 0;   // capacity layout (exb_core uses the tail)
   // per traversal call: the descriptor is packed compactly and only the bytes in use are copied
@@ -436,6 +344,7 @@ struct exb_engine {
 };
 
 constexpr int kMaxParamPartitions = 16;
+constexpr int kNrSingleCtaTiles = 4;             // device Newton-Raphson: up to this many tiles one CTA does the whole loop
 // -S: CLV blocks are carved from slabs of ~256 MB that are allocated on demand
 static size_t kSevSlabBlocks(size_t block_doubles) { return std::max<size_t>(1, ((size_t)256 << 20) / (block_doubles * sizeof(double))); }
 constexpr size_t kHostDtabBytes = 16 * 1024;     // per class
@@ -915,7 +824,7 @@ static void set_finish_outputs(exb_engine *e, FinishArgs &f);
 
 // Validate and stage a traversal descriptor; one H2D copy of exactly the bytes in use.
 static int stage_traversal(exb_engine *e, const exb_entry *ti, int count, int first, const double *qz, const double *rz,
-                           const unsigned char *mask, int ncand = -1, int *max_scratch = nullptr)
+                           const unsigned char *mask, int ncand = -1, int *max_scratch = nullptr, bool copy = true)
 {
   if (count < first || count > e->max_entries)
     return fail(EXB_ERR_ARG, "traversal of %d entries (max %d)", count, e->max_entries);
@@ -1001,7 +910,8 @@ static int stage_traversal(exb_engine *e, const exb_entry *ti, int count, int fi
       }
   }
   e->stage_use = e->stage_d;
-  CUDA_TRY(cudaMemcpyAsync(e->stage_d, e->stage_h, off, cudaMemcpyHostToDevice, e->stream));
+  e->stage_used_bytes = off;
+  if (copy) CUDA_TRY(cudaMemcpyAsync(e->stage_d, e->stage_h, off, cudaMemcpyHostToDevice, e->stream));
   return EXB_OK;
 }
 
@@ -1066,8 +976,18 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   if (rc) return rc;
   // the previous call has been synchronised, so the pinned staging area is free
   int max_scratch = -1;
-  rc = stage_traversal(e, ti, count, first, qz, rz, mask, ncand, &max_scratch);
+  rc = stage_traversal(e, ti, count, first, qz, rz, mask, ncand, &max_scratch, false);
   if (rc) return rc;
+  // Short descriptor on a small DNA alignment: everything travels in the kernel parameters and the traverse kernel
+  // finishes the call itself (SmallCall, engine.cuh) -- no copy, one launch
+  static const bool small_ok = !getenv("EXB_NO_SMALL_CALLS");
+  const ClassState &kd = e->cls[CLS_DNA];
+  const bool small = small_ok && mode != MODE_SCORE && !e->cat && !e->sev && e->cls[CLS_AA].tiles_h.empty() && !kd.tiles_h.empty() &&
+                     kd.nparts <= kMaxParamPartitions && e->P <= kSmallParts && count <= kSmallEntries && e->host_dtab[CLS_DNA] &&
+                     (size_t)count * kd.nparts * kDnaDtabRow <= (size_t)kSmallDtabDoubles && e->total_tiles <= kSmallMaxTiles &&
+                     !(e->comm && !e->p2p) && 2 * (size_t)e->mxtips * sizeof(unsigned int) <= 40 * 1024;
+  if (small) e->stage_use = e->stage_h;              // (only a finish kernel that has to run on its own reads it, zero-copy)
+  else CUDA_TRY(cudaMemcpyAsync(e->stage_d, e->stage_h, e->stage_used_bytes, cudaMemcpyHostToDevice, e->stream));
   if (mode == MODE_SCORE) { rc = score_prepare(e, ncand, max_scratch); if (rc) return rc; }
   rc = flush_models(e);
   if (rc) return rc;
@@ -1112,6 +1032,33 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
     }
   }
   if (e->timing) CUDA_TRY(cudaEventRecord(e->ev_a, e->stream));
+  FinishArgs f;
+  memset(&f, 0, sizeof f);
+  bool folded = false;
+  if (mode != MODE_SCORE) {
+  f.gs = e->gs; f.gs_stride = e->gs_stride; f.scale_inc = e->scale_inc;
+  f.entries = (const DevEntry *)(e->stage_use + e->o_entries);
+  f.count = count; f.first = first; f.mxtips = e->mxtips; f.nparts = e->P;
+  f.mask = e->stage_use + e->o_mask; f.part_has_sites = e->part_has_sites;
+  f.tile_out[0] = e->cls[0].tile_out; f.tile_out[1] = e->cls[1].tile_out;
+  f.part_tile_begin = e->part_tile_begin; f.part_tile_count = e->part_tile_count; f.part_cls = e->part_cls;
+  f.mode = mode; f.log_minlikelihood = log(kMinLikelihood); f.out = e->out_d;
+    set_finish_outputs(e, f);
+  }
+  SmallCall sc;
+  int last_launched = -1;
+  if (small) {
+    const unsigned char *mk = e->stage_h + e->o_mask;
+    for (int pc = 0; pc < kd.nparts; pc++)
+      if (kd.cp_tile_count[pc] != 0 && mk[kd.cp_global[pc]]) last_launched = pc;
+    sc.count = count; sc.fold = 0;
+    memcpy(sc.entries, e->stage_h + e->o_entries, (size_t)count * sizeof(DevEntry));
+    memset(sc.mask, 0, sizeof sc.mask);
+    memcpy(sc.mask, mk, (size_t)e->P);
+    memcpy(sc.dtab, e->stage_h + e->o_dtab[CLS_DNA], (size_t)count * kd.nparts * kDnaDtabRow * sizeof(double));
+    sc.fin = f;
+    sc.fin.gs_in_smem = 1;
+  }
   for (int c = 0; c < 2; c++) {
     ClassState &k = e->cls[c];
     if (k.tiles_h.empty()) continue;
@@ -1142,8 +1089,12 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
         ap.tiles = k.tiles + k.cp_tile_begin[pc];
         ap.sev_tile0 = k.cp_tile_begin[pc];
         ap.tile_out = k.tile_out + 2 * (size_t)k.cp_tile_begin[pc];
+        if (small) {                                // the last launch of the call also finishes it
+          sc.fold = pc == last_launched;
+          folded = folded || sc.fold;
+        }
         if (e->cat) launch_traverse_dna_cat(ap, &kc, k.cp_tile_count[pc], e->stream);
-        else        launch_traverse_dna(ap, &kc, k.cp_tile_count[pc], e->stream);
+        else        launch_traverse_dna(ap, &kc, k.cp_tile_count[pc], e->stream, small ? &sc : nullptr);
         if (pc) e->launches++;
       }
     } else if (c == CLS_DNA) {
@@ -1169,36 +1120,29 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   if (e->timing) CUDA_TRY(cudaEventRecord(e->ev_b, e->stream));
   e->phases_valid = e->timing;
   if (mode == MODE_SCORE) {
-    ScoreFinishArgs f;
-    f.gs = e->gs; f.gs_stride = e->gs_stride; f.scale_inc = e->scale_inc;
-    f.entries = (const DevEntry *)(e->stage_use + e->o_entries);
-    f.count = count; f.mxtips = e->mxtips; f.nparts = e->P; f.ncand = ncand;
-    f.mask = e->stage_use + e->o_mask; f.part_has_sites = e->part_has_sites;
-    f.sc = e->score_sc;
+    ScoreFinishArgs sf;
+    sf.gs = e->gs; sf.gs_stride = e->gs_stride; sf.scale_inc = e->scale_inc;
+    sf.entries = (const DevEntry *)(e->stage_use + e->o_entries);
+    sf.count = count; sf.mxtips = e->mxtips; sf.nparts = e->P; sf.ncand = ncand;
+    sf.mask = e->stage_use + e->o_mask; sf.part_has_sites = e->part_has_sites;
+    sf.sc = e->score_sc;
     for (int c = 0; c < 2; c++) {
-      f.score_out[c] = e->cls[c].score_out;
-      f.warps[c] = c == CLS_DNA ? kDnaWarps : kAaWarps;
-      f.score_stride[c] = (int)e->cls[c].tiles_h.size() * f.warps[c];
+      sf.score_out[c] = e->cls[c].score_out;
+      sf.warps[c] = c == CLS_DNA ? kDnaWarps : kAaWarps;
+      sf.score_stride[c] = (int)e->cls[c].tiles_h.size() * sf.warps[c];
     }
-    f.part_tile_begin = e->part_tile_begin; f.part_tile_count = e->part_tile_count; f.part_cls = e->part_cls;
-    f.log_minlikelihood = log(kMinLikelihood); f.out = e->score_d;
-    launch_score_finish(f, e->stream);
+    sf.part_tile_begin = e->part_tile_begin; sf.part_tile_count = e->part_tile_count; sf.part_cls = e->part_cls;
+    sf.log_minlikelihood = log(kMinLikelihood); sf.out = e->score_d;
+    launch_score_finish(sf, e->stream);
     e->launches += 2;
     if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
     CUDA_TRY(cudaGetLastError());
     return EXB_OK;
   }
-  FinishArgs f;
-  f.gs = e->gs; f.gs_stride = e->gs_stride; f.scale_inc = e->scale_inc;
-  f.entries = (const DevEntry *)(e->stage_use + e->o_entries);
-  f.count = count; f.first = first; f.mxtips = e->mxtips; f.nparts = e->P;
-  f.mask = e->stage_use + e->o_mask; f.part_has_sites = e->part_has_sites;
-  f.tile_out[0] = e->cls[0].tile_out; f.tile_out[1] = e->cls[1].tile_out;
-  f.part_tile_begin = e->part_tile_begin; f.part_tile_count = e->part_tile_count; f.part_cls = e->part_cls;
-  f.mode = mode; f.log_minlikelihood = log(kMinLikelihood); f.out = e->out_d;
-  set_finish_outputs(e, f);
-  launch_finish(f, e->stream);
-  e->launches++;
+  if (!folded) {
+    launch_finish(f, e->stream);
+    e->launches++;
+  }
   if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
   CUDA_TRY(cudaGetLastError());
   return EXB_OK;
@@ -1369,15 +1313,21 @@ extern "C" int exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const
   //    state machine derives in its first round: executeModel && !curvatOK, with curvatOK == FALSE for every slot
   int rc = run_traversal(e, ti, count, 1, qz, rz, executeModel, MODE_SUM);
   if (rc) return rc;
-  // 2. initial state
+  // 2. initial state: as kernel parameters when it is small (no upload at all), else a NrState + mask upload
   NrState *h = e->nr_state_h;
-  memset(h, 0, sizeof *h);
-  for (int b = 0; b < e->nb; b++) { h->z[b] = z0[b]; h->z0[b] = z0[b]; h->budget[b] = maxiter; h->done[b] = 0; h->curvatOK[b] = 1; }
-  CUDA_TRY(cudaMemcpyAsync(e->nr_state_d, h, sizeof *h, cudaMemcpyHostToDevice, e->stream));
-  CUDA_TRY(cudaMemcpyAsync(e->nr_mask, e->stage_h + e->o_mask, (size_t)e->P, cudaMemcpyHostToDevice, e->stream));
-  CUDA_TRY(cudaMemsetAsync(e->nr_barrier, 0, sizeof(unsigned int), e->stream));
   NrArgs a;
   memset(&a, 0, sizeof a);
+  const bool from_args = e->nb <= kNrInitSlots && e->P <= kNrInitSlots;
+  if (from_args) {
+    a.init_from_args = 1; a.maxiter = maxiter;
+    for (int b = 0; b < e->nb; b++) a.z0[b] = z0[b];
+    for (int m = 0; m < e->P; m++) a.mask0[m] = (e->stage_h + e->o_mask)[m];
+  } else {
+    memset(h, 0, sizeof *h);
+    for (int b = 0; b < e->nb; b++) { h->z[b] = z0[b]; h->z0[b] = z0[b]; h->budget[b] = maxiter; h->done[b] = 0; h->curvatOK[b] = 1; }
+    CUDA_TRY(cudaMemcpyAsync(e->nr_state_d, h, sizeof *h, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->nr_mask, e->stage_h + e->o_mask, (size_t)e->P, cudaMemcpyHostToDevice, e->stream));
+  }
   a.state = e->nr_state_d; a.mask = e->nr_mask; a.barrier = e->nr_barrier;
   int total_tiles = 0;
   for (int c = 0; c < 2; c++) {
@@ -1391,14 +1341,37 @@ extern "C" int exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const
   a.part_has_sites = e->part_has_sites; a.part_tile_begin = e->part_tile_begin; a.part_tile_count = e->part_tile_count;
   a.part_cls = e->part_cls; a.nparts = e->P; a.nbranches = e->nb; a.max_cats = e->max_cats;
   a.x = p2p_args(e); a.xseq0 = e->xseq;
-  const int blocks = std::max(1, std::min(total_tiles, e->nr_max_blocks));
-  const int lr = launch_newton_raphson(a, blocks, e->stream);
-  if (lr != 0) return fail(EXB_ERR_CUDA, "cooperative launch of the Newton-Raphson kernel failed: %s", cudaGetErrorString((cudaError_t)lr));
+  // a handful of tiles: ONE CTA walks them (no grid barrier, no cooperative launch) -- on such alignments the latency of
+  // the call is everything; otherwise persistent CTAs with grid barriers
+  // ... and when (GAMMA) the sum table of those tiles fits in shared memory it is staged there once for all iterations
+  size_t staged = 0;
+  for (int c = 0; c < 2 && !e->cat; c++)
+    for (const Tile &t : e->cls[c].tiles_h) staged += (size_t)t.nsites * e->cls[c].span * sizeof(double) + (((size_t)t.nsites * sizeof(int) + 15) & ~(size_t)15);
+  if (e->cat || staged > kNrStagedBytes || total_tiles > 16 || e->P > kNrInitSlots) staged = 0;
+  const int blocks = (staged || total_tiles <= kNrSingleCtaTiles) ? 1 : std::max(1, std::min(total_tiles, e->nr_max_blocks));
+  if (blocks > 1) CUDA_TRY(cudaMemsetAsync(e->nr_barrier, 0, sizeof(unsigned int), e->stream));
+  // results: into pinned memory + the completion flag the host polls (the same flag the finish kernels raise)
+  if (++e->seq == 0xFFFFFFFFu) e->seq = 1;
+  a.result_host = h; a.done_flag_host = e->done_flag; a.seq = e->seq;
+  const int lr = launch_newton_raphson(a, blocks, staged, e->stream);
+  if (lr != 0) return fail(EXB_ERR_CUDA, "launch of the Newton-Raphson kernel failed: %s", cudaGetErrorString((cudaError_t)lr));
   e->launches++;
   if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
-  CUDA_TRY(cudaMemcpyAsync(h, e->nr_state_d, sizeof *h, cudaMemcpyDeviceToHost, e->stream));
-  CUDA_TRY(cudaStreamSynchronize(e->stream));
-  if (e->timing) cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1);
+  {
+    unsigned long spins = 0;
+    while (__atomic_load_n((const unsigned int *)e->done_flag, __ATOMIC_ACQUIRE) != e->seq) {
+      if ((++spins & 0xFFFF) == 0) {                 // a faulting kernel must not hang the host
+        const cudaError_t q = cudaStreamQuery(e->stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) return fail(EXB_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(q));
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#elif defined(__aarch64__)
+      asm volatile("yield" ::: "memory");
+#endif
+    }
+  }
+  if (e->timing) { CUDA_TRY(cudaEventSynchronize(e->ev1)); cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1); }
   if (e->p2p) {
     if (h->peer_lost) return fail(EXB_ERR_NCCL, "a peer rank did not deliver its derivative sums within 20 s (all-reduce inside newton_raphson_kernel)");
     e->xseq = h->xseq;                              // every rank ran the same number of exchanges
@@ -1410,7 +1383,6 @@ extern "C" int exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const
   if (iterations) *iterations = h->iterations;
   return EXB_OK;
 }
-
 
 // ---- batched scoring of lazy SPR insertions (testInsertBIG searchAlgo.c:682) ----
 extern "C" int exb_max_entries(exb_engine *e) { return e && e->committed ? e->max_entries : 0; }

@@ -159,6 +159,19 @@ struct FinishArgs {
   unsigned int  xseq;             // exchange number (slot = xseq & 1)
 };
 
+// Short descriptors on a small alignment (the thousands of partial traversals of a tree search): the whole call travels
+// in the kernel parameters -- descriptor, execute mask, the host-built d-table rows -- so no copy precedes the launch, and
+// the last CTA of the (last) traverse launch does the finish work itself (finish.cuh): one launch per call.
+constexpr int kSmallEntries = 8, kSmallParts = 8, kSmallDtabDoubles = 512, kSmallMaxTiles = 64;
+struct SmallCall {
+  int count, fold;                             // entries incl. the branch entry | this launch ends the call
+  DevEntry entries[kSmallEntries];
+  unsigned char mask[kSmallParts];
+  double dtab[kSmallDtabDoubles];              // [count][nparts_cls][32] as stage_traversal lays it out
+  FinishArgs fin;                              // entries / mask inside are ignored (the kernel's own copies are used)
+};
+struct NoSmallCall {};
+
 // AA tip look-up table: what precomputeTips / umpX do in the reference (avxLikelihood.c:1353-1389, mic_native_aa.c:97)
 constexpr int kAaLutRow = 23 * 80;
 struct LutArgs {
@@ -180,10 +193,11 @@ struct NrState {
   unsigned int xseq;        // multi-rank: number of the last exchange used
   int peer_lost;            // multi-rank: a peer did not deliver within the watchdog time
 };
+constexpr int kNrInitSlots = 8;     // start values travel as kernel parameters up to this many branch slots / partitions
 struct NrArgs {
   NrState *state;
   unsigned char *mask;            // [P] executeModel, updated by the state machine
-  unsigned int *barrier;          // monotonic arrival counter (zeroed before the launch)
+  unsigned int *barrier;          // monotonic arrival counter (zeroed before a launch of more than one CTA)
   const Tile *tiles[2]; int ntiles[2];
   const double *sum[2]; const int *wgt[2]; const double *models[2];
   const int *rate_cat[2]; const double *cat_rates[2]; int max_cats;     // CAT (null / 0 under GAMMA)
@@ -195,8 +209,16 @@ struct NrArgs {
   // the last one used is left in state->xseq
   P2pArgs x;
   unsigned int xseq0;
+  // start-up without copies (nbranches, nparts <= kNrInitSlots): z0 / maxiter / executeModel as parameters instead of a
+  // NrState and a mask uploaded beforehand
+  int init_from_args, maxiter;
+  double z0[kNrInitSlots];
+  unsigned char mask0[kNrInitSlots];
+  // results straight into pinned host memory + completion flag (the host polls; no device-to-host copy, no stream sync)
+  NrState *result_host; volatile unsigned int *done_flag_host; unsigned int seq;
 };
-int launch_newton_raphson(const NrArgs &a, int blocks, cudaStream_t s);
+constexpr size_t kNrStagedBytes = 192 * 1024;    // one-CTA Newton-Raphson: the sum table (+ weights) of all tiles in shared memory up to this size
+int launch_newton_raphson(const NrArgs &a, int blocks, size_t staged_bytes, cudaStream_t s);
 int newton_raphson_max_blocks(int device);
 
 // ---- per-site likelihood at an explicit rate (kernels_partial.cu; evaluatePartialGeneric) ----
@@ -222,7 +244,8 @@ void launch_partial(const PartialArgs &a, int states, int blocks, cudaStream_t s
 int partial_max_blocks(int states, int device);
 
 void launch_dtab(const DtabArgs &a, cudaStream_t s);
-void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
+void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s,
+                         const SmallCall *small = nullptr);
 void launch_traverse_dna_cat(const TraverseArgs &a, const DnaConsts *single_partition_consts, int ntiles, cudaStream_t s);
 void launch_core_dna(const CoreArgs &a, int ntiles, cudaStream_t s);
 void launch_traverse_aa(const TraverseArgs &a, bool any_lg4, int ntiles, cudaStream_t s);

@@ -26,7 +26,9 @@
 #include "engine.cuh"
 #include "core_tile.cuh"
 #include "stage.cuh"
+#include "finish.cuh"
 #include <algorithm>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -206,9 +208,11 @@ __device__ __forceinline__ int ring_child(const SEntry &en)
   return q_load ? 1 : (r_load ? 2 : 0);
 }
 
-template <int NS, bool PARAM, int MINB>
+// SMALL: the call (descriptor, mask, d-table rows, finish arguments) arrives in the kernel parameters and the last CTA
+// of a `fold` launch finishes the call (engine.cuh SmallCall) -- the per-call path of a tree search on a small alignment.
+template <int NS, bool PARAM, int MINB, bool SMALL = false>
 __global__ void __launch_bounds__(kThreads, MINB)
-traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
+traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc, const typename std::conditional<SMALL, SmallCall, NoSmallCall>::type sc)
 {
   constexpr int TS = 64 * NS;                  // sites per chunk = bytes per staged tip row
   constexpr int KW = kDnaWindow;
@@ -220,12 +224,21 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
   const double *sdtab = reinterpret_cast<const double *>(dyn + window_dtab_offset<TS, KW>());     // [KW + 1][32] d-table rows
   double *ring = reinterpret_cast<double *>(dyn + window_smem_bytes<TS, KW>(kDnaDtabRow));          // [2][NS][256 threads][4]
 
+  __shared__ DevEntry s_ent[SMALL ? kSmallEntries : 1];
+  __shared__ unsigned char s_mask[SMALL ? kSmallParts : 1];
+
   const Tile tile = a.tiles[blockIdx.x];
-  if (!a.mask[tile.part]) return;
+  if constexpr (!SMALL) { if (!a.mask[tile.part]) return; }      // (SMALL: masked partitions are not launched at all)
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int c = tid & 3;                       // Gamma category owned by this thread
   const size_t N = a.N;
+  const DevEntry *entries = a.entries;
+  if constexpr (SMALL) {
+    if (tid < sc.count) s_ent[tid] = sc.entries[tid];
+    if (tid < kSmallParts) s_mask[tid] = sc.mask[tid];
+    entries = s_ent;
+  }
   {
     const double *model = a.models + (size_t)tile.part_cls * kDnaModelDoubles;   // EIGN[4] rates[4] EI[16] EV[16] tip[64]
     if (tid < 64) sh.tip[tid] = model[40 + tid];
@@ -261,10 +274,22 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
     int w0 = a.first;
     do {
     const int w1 = min(w0 + KW, a.count);
-    phase = stage_window<TS, KW>(dyn, &mbar, phase, a.entries, a.tips, a.mxtips, N, 16, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
-                                 a.first, a.count, w0 == a.first && a.mode != MODE_NEWVIEW, drow0, dstride, kDnaDtabRow,
+    phase = stage_window<TS, KW>(dyn, &mbar, phase, entries, a.tips, a.mxtips, N, 16, (size_t)tile.site0 + chunk0, nchunk, w0, w1,
+                                 a.first, a.count, w0 == a.first && a.mode != MODE_NEWVIEW, SMALL ? nullptr : drow0, dstride, kDnaDtabRow,
                                  SevView{a.sev_table, a.sev_gapcol, a.clv, a.sev_ntiles, a.sev_tile0 + (int)blockIdx.x, tile.part_cls,
                                          a.nparts_cls, 16, tile.site0}, a.scratch_off);
+    if constexpr (SMALL) {
+      // the d-table rows came with the launch: this partition's row of every window entry (slot e - w0) and of the branch
+      // entry (slot KW) from the parameters into the window's table
+      double *sd = const_cast<double *>(sdtab);
+      const int nrows = (w1 - w0) + ((w0 == a.first && a.mode != MODE_NEWVIEW) ? 1 : 0);
+      for (int i = tid; i < nrows * kDnaDtabRow; i += kThreads) {
+        const int j = i / kDnaDtabRow, w = i % kDnaDtabRow;
+        const bool is_branch = j == (w1 - w0);
+        sd[(size_t)(is_branch ? KW : j) * kDnaDtabRow + w] = sc.dtab[((size_t)(is_branch ? 0 : w0 + j) * a.nparts_cls + tile.part_cls) * kDnaDtabRow + w];
+      }
+      __syncthreads();
+    }
     for (int e = w0; e < w1; e++) {
       const SEntry en = ents[e - w0];
       // The one inner child that is neither a tip nor in the carry registers comes through the prefetch ring: its
@@ -384,6 +409,22 @@ traverse_dna_kernel(const TraverseArgs a, const DnaConsts kc)
   if (a.mode == MODE_EVALUATE) {
     const double tot = block_sum(acc, sh.red);
     if (tid == 0) { a.tile_out[2 * (size_t)blockIdx.x] = tot; a.tile_out[2 * (size_t)blockIdx.x + 1] = 0.0; }
+  }
+  if constexpr (SMALL) {
+    if (sc.fold) {
+      // the last CTA of the call's last launch does what finish_kernel would do in a launch of its own
+      __shared__ int last, peer_lost;
+      __shared__ double red0[4], red1[4];
+      __threadfence();                             // CLVs, sum table, tile partials, scaler increments: visible device-wide
+      __syncthreads();
+      if (tid == 0) last = atomicAdd(sc.fin.ticket, 1u) == gridDim.x - 1;
+      __syncthreads();
+      if (last) {
+        finish_body(sc.fin, s_ent, s_mask, reinterpret_cast<unsigned int *>(dyn), red0, red1, 0, 1);
+        __threadfence_system();
+        finish_publish(sc.fin, &peer_lost);
+      }
+    }
   }
 }
 
@@ -538,18 +579,26 @@ size_t traverse_dna_smem(int ns)
 }
 
 template <int NS, bool PARAM, int MINB>
-static void launch_variant(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s)
+static void launch_variant(const TraverseArgs &a, const DnaConsts &kc, int ntiles, cudaStream_t s, const SmallCall *small = nullptr)
 {
   const size_t smem = traverse_dna_smem(NS);
+  if (small) {
+    if constexpr (PARAM) {
+      static size_t configured[kMaxDevices];
+      ensure_dynamic_smem(traverse_dna_kernel<NS, true, MINB, true>, std::min<size_t>(227 * 1024 - 2048, std::max<size_t>(smem, 64 * 1024)), configured);
+      traverse_dna_kernel<NS, true, MINB, true><<<ntiles, kThreads, smem, s>>>(a, kc, *small);
+    }
+    return;
+  }
   static size_t configured[kMaxDevices];
   ensure_dynamic_smem(traverse_dna_kernel<NS, PARAM, MINB>, std::min<size_t>(227 * 1024 - 2048, std::max<size_t>(smem, 64 * 1024)), configured);
-  traverse_dna_kernel<NS, PARAM, MINB><<<ntiles, kThreads, smem, s>>>(a, kc);
+  traverse_dna_kernel<NS, PARAM, MINB><<<ntiles, kThreads, smem, s>>>(a, kc, NoSmallCall{});
 }
 
 // NS sites per thread: 4 for full tiles (128 registers, 2 CTAs per SM), fewer for small tiles (3 CTAs per SM).
 // kc: EI / EV of the launch's single partition as kernel parameters (constant bank -> uniform registers);
 // null: many partitions in one launch, every CTA reads its partition's EI / EV from shared memory.
-void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *kc, int ntiles, cudaStream_t s)
+void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *kc, int ntiles, cudaStream_t s, const SmallCall *small)
 {
   if (ntiles <= 0) return;
   static int ns_max = -1;                        // development knob: EXB_DNA_NS = 1 | 2 | 4 sites per thread at most
@@ -563,9 +612,9 @@ void launch_traverse_dna(const TraverseArgs &a, const DnaConsts *kc, int ntiles,
     else              launch_variant<4, false, 2>(a, none, ntiles, s);
     return;
   }
-  if (ns == 1)      launch_variant<1, true, 3>(a, *kc, ntiles, s);
-  else if (ns == 2) launch_variant<2, true, 3>(a, *kc, ntiles, s);
-  else              launch_variant<4, true, 2>(a, *kc, ntiles, s);
+  if (ns == 1)      launch_variant<1, true, 3>(a, *kc, ntiles, s, small);
+  else if (ns == 2) launch_variant<2, true, 3>(a, *kc, ntiles, s, small);
+  else              launch_variant<4, true, 2>(a, *kc, ntiles, s, small);
 }
 void launch_traverse_dna_cat(const TraverseArgs &a, const DnaConsts *kc, int ntiles, cudaStream_t s)
 {

@@ -22,3 +22,10 @@ bench("evaluate, 0 newviews", lambda: eng.evaluateIterative(ti[:1]))
 bench("newview, 3 entries", lambda: eng.newviewIterative(ti[-3:]))
 bench("makenewz prepare (sum), 1 newview", lambda: eng.makenewzIterative(ti[:1] + ti[-1:]))
 bench("core (one NR iteration)", lambda: eng.execCore([np.log(0.8)]))
+br = ti[:1] + ti[-1:]
+z, ok, it = eng.makenewz(br, [0.9], 10)
+bench("makenewz on the device (%d NR iterations), 1 newview" % it, lambda: eng.makenewz(br, [0.9], 10))
+eng.set_timing(False)
+bench("  ... without CUDA events: makenewz", lambda: eng.makenewz(br, [0.9], 10))
+bench("  ... without CUDA events: evaluate, 3 newviews", lambda: eng.evaluateIterative(ti[:1] + ti[-3:]))
+bench("  ... without CUDA events: newview, 3 entries", lambda: eng.newviewIterative(ti[-3:]))
