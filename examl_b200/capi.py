@@ -44,7 +44,9 @@ _lib_cache = {}
 
 
 def load_library(path: str = LIB_PATH) -> C.CDLL:
-    """Open the CUDA engine.  There is no fallback: a missing library is an error."""
+    """Open the CUDA engine.  There is no fallback: a missing library is an error.  (EXB_LIBRARY: an alternative build of
+    the same CUDA library, e.g. one compiled with other tuning macros -- experiments only.)"""
+    path = os.environ.get("EXB_LIBRARY", path)
     if path in _lib_cache:
         return _lib_cache[path]
     if not os.path.exists(path):

@@ -71,16 +71,21 @@ static void refuse(const char *why)
   exit(-1);
 }
 
-/* Which GPU does this rank drive?  One rank per GPU; launchers export LOCAL_RANK (torchrun),
-   OMPI_COMM_WORLD_LOCAL_RANK or SLURM_LOCALID; otherwise the rank number is used. */
+/* Which GPU does this rank drive?  One rank per GPU; launchers export LOCAL_RANK (torchrun), OMPI_COMM_WORLD_LOCAL_RANK,
+   SLURM_LOCALID, MPI_LOCALRANKID / PMI_LOCAL_RANK (Hydra), MV2_COMM_WORLD_LOCAL_RANK; otherwise the rank number, modulo
+   EXAML_B200_GPUS_PER_NODE when that is given. */
 static int local_device(void)
 {
-  const char *names[] = {"EXAML_B200_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID", NULL};
+  const char *names[] = {"EXAML_B200_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID",
+                         "MPI_LOCALRANKID", "PMI_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", NULL};
+  const char *per_node = getenv("EXAML_B200_GPUS_PER_NODE");
   int i;
   for (i = 0; names[i]; i++) {
     const char *v = getenv(names[i]);
     if (v && *v) return atoi(v);
   }
+  /* no launcher variable: ranks are usually placed node by node, so the rank modulo the GPUs of a node */
+  if (per_node && atoi(per_node) > 0) return processID % atoi(per_node);
   return processID;
 }
 

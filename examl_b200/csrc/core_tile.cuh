@@ -21,10 +21,7 @@ __device__ __forceinline__ void core_ld256(const double *p, double *v)
 }
 
 // All threads of a 256-thread CTA; result valid in thread 0.
-// STAGED: `sum` / `wgt` point at a copy of THIS tile's rows in shared memory (row 0 = the tile's first site) -- the
-// single-CTA Newton-Raphson path keeps the sum table on chip across its iterations; otherwise they are the class-wide
-// arrays in global memory, indexed by site.
-template <int S, bool STAGED = false>
+template <int S>
 __device__ __forceinline__ void core_tile(const Tile &tile, const double *sum, const int *wgt, const double *model,
                                           double lz, CoreSmem &sh, double &out1, double &out2)
 {
@@ -45,17 +42,14 @@ __device__ __forceinline__ void core_tile(const Tile &tile, const double *sum, c
   for (int u = 0; u < npass; u++) {
     const int i = (u << 6) + (tid >> 2);
     const bool valid = i < (int)tile.nsites;
-    const size_t site = (STAGED ? (size_t)0 : (size_t)tile.site0) + (valid ? i : 0);
+    const size_t site = (size_t)tile.site0 + (valid ? i : 0);
     const double *p = sum + site * SPAN + c * S;
     const double w = (double)wgt[site];            // early: its latency hides under the contraction
     double L = 0.0, L1 = 0.0, L2 = 0.0;
     #pragma unroll
     for (int j = 0; j < S; j += 4) {
       double s[4];
-      if (STAGED) {
-        const double2 lo = *reinterpret_cast<const double2 *>(p + j), hi = *reinterpret_cast<const double2 *>(p + j + 2);
-        s[0] = lo.x; s[1] = lo.y; s[2] = hi.x; s[3] = hi.y;
-      } else core_ld256(p + j, s);
+      core_ld256(p + j, s);
       #pragma unroll
       for (int k = 0; k < 4; k++) {
         const double t = sh.d0[c * S + j + k] * s[k];

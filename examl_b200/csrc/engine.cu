@@ -563,7 +563,7 @@ extern "C" int exb_commit(exb_engine *e)
       tbegin[m] = (int)k.tiles_h.size();
       // AA tiles are whole 96-site chunks (12 warps x 8 sites)
       // (CAT: 384-site chunks, 12 warps x 32 sites)
-      const size_t aachunk = e->cat ? 384 : (e->aa_tc ? 32 : 96);      // (tcgen05 path: 32 sites x 4 categories = the MMA's M)
+      const size_t aachunk = e->cat ? kAaCatChunkSites : (e->aa_tc ? 32 : kAaChunkSites);      // (tcgen05 path: 32 sites x 4 categories = the MMA's M)
       size_t tsz = c == CLS_AA ? (size_t)((e->tile_sites + aachunk - 1) / aachunk) * aachunk : (size_t)e->tile_sites;
       // tcgen05 path: one 32-site chunk per CTA unless told otherwise -- four co-resident CTAs per SM want many small tiles
       if (c == CLS_AA && e->aa_tc && !e->cat && !e->tile_sites_set) tsz = 32;
@@ -1345,9 +1345,16 @@ extern "C" int exb_makenewz(exb_engine *e, const exb_entry *ti, int count, const
   // the call is everything; otherwise persistent CTAs with grid barriers
   // ... and when (GAMMA) the sum table of those tiles fits in shared memory it is staged there once for all iterations
   size_t staged = 0;
-  for (int c = 0; c < 2 && !e->cat; c++)
-    for (const Tile &t : e->cls[c].tiles_h) staged += (size_t)t.nsites * e->cls[c].span * sizeof(double) + (((size_t)t.nsites * sizeof(int) + 15) & ~(size_t)15);
-  if (e->cat || staged > kNrStagedBytes || total_tiles > 16 || e->P > kNrInitSlots) staged = 0;
+  if (!e->cat && from_args && total_tiles <= 16) {
+    for (int m = 0; m < e->P; m++) {
+      const HostPart &p = e->parts[m];
+      a.small_site0[m] = (unsigned int)p.site0; a.small_width[m] = (unsigned int)p.width;
+      a.small_cls[m] = p.cls; a.small_pc[m] = p.part_cls;
+      staged += ((p.width * (e->cls[p.cls].span + 1) * sizeof(double) + 15) & ~(size_t)15) + ((p.width * sizeof(int) + 15) & ~(size_t)15);
+    }
+    if (staged > kNrStagedBytes) staged = 0;
+    else if (staged == 0) staged = 16;              // (no local sites at all: still the one-CTA kernel)
+  }
   const int blocks = (staged || total_tiles <= kNrSingleCtaTiles) ? 1 : std::max(1, std::min(total_tiles, e->nr_max_blocks));
   if (blocks > 1) CUDA_TRY(cudaMemsetAsync(e->nr_barrier, 0, sizeof(unsigned int), e->stream));
   // results: into pinned memory + the completion flag the host polls (the same flag the finish kernels raise)

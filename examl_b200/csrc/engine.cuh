@@ -216,9 +216,12 @@ struct NrArgs {
   unsigned char mask0[kNrInitSlots];
   // results straight into pinned host memory + completion flag (the host polls; no device-to-host copy, no stream sync)
   NrState *result_host; volatile unsigned int *done_flag_host; unsigned int seq;
+  // newton_raphson_small_kernel (one CTA, everything on chip): where each partition's rows sit on its class's site axis
+  unsigned int small_site0[kNrInitSlots], small_width[kNrInitSlots];
+  int small_cls[kNrInitSlots], small_pc[kNrInitSlots];        // class and class-partition index of every partition
 };
 constexpr size_t kNrStagedBytes = 192 * 1024;    // one-CTA Newton-Raphson: the sum table (+ weights) of all tiles in shared memory up to this size
-int launch_newton_raphson(const NrArgs &a, int blocks, size_t staged_bytes, cudaStream_t s);
+int launch_newton_raphson(const NrArgs &a, int blocks, size_t staged_bytes, cudaStream_t s);   // staged_bytes > 0: the one-CTA kernel
 int newton_raphson_max_blocks(int device);
 
 // ---- per-site likelihood at an explicit rate (kernels_partial.cu; evaluatePartialGeneric) ----
@@ -255,7 +258,11 @@ void launch_finish(const FinishArgs &a, cudaStream_t s);
 
 // exb_score_insertions: scaler chain of the mixed descriptor (one block per partition), then the fixed-order reduction of
 // the per-(candidate, tile, warp) partials into lnl[candidate][partition]
-constexpr int kDnaWarps = 8, kAaWarps = 12;      // warps per CTA of the GAMMA traverse kernels (slots per tile in score_out)
+#ifndef EXB_AA_WARPS
+#define EXB_AA_WARPS 12
+#endif
+constexpr int kDnaWarps = 8, kAaWarps = EXB_AA_WARPS;   // warps per CTA of the GAMMA traverse kernels (slots per tile in score_out)
+constexpr int kAaChunkSites = 8 * kAaWarps, kAaCatChunkSites = 32 * kAaWarps;   // sites per chunk of the AA kernel (GAMMA: 8 per warp; PSR: 32)
 struct ScoreFinishArgs {
   unsigned int *gs; int gs_stride, gs_in_smem;
   unsigned int *scale_inc;

@@ -29,7 +29,7 @@ namespace {
 
 constexpr int S = 20;
 constexpr int SPAN = 80;
-constexpr int kAaThreads = 384;  // 12 warps, one CTA per SM (the register budget of the DMMA pipeline)
+constexpr int kAaThreads = 32 * kAaWarps;  // 12 warps, one CTA per SM (the register budget of the DMMA pipeline)
 static_assert(kAaThreads == 32 * kAaWarps, "score_out slots per tile");
 
 struct AaShared { double red[32]; };
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kAaThreads, 1)
 traverse_aa_kernel(const TraverseArgs a)
 {
   constexpr int NSYS = LG4 ? 4 : 1;            // eigen-systems kept in shared memory
-  constexpr int TSITES = CAT ? 384 : 96;       // sites per chunk = bytes per staged tip row
+  constexpr int TSITES = CAT ? kAaCatChunkSites : kAaChunkSites;   // sites per chunk = bytes per staged tip row
   constexpr int XSPAN = CAT ? 20 : 80;         // doubles per site in a CLV
   constexpr int XSLOT = CAT ? 8 * 20 : 20;     // distance between consecutive slots of my row in a CLV
   __shared__ AaShared sh;
@@ -518,7 +518,7 @@ core_aa_kernel(const CoreArgs a)
 template <bool CAT, bool LG4>
 static void launch_aa_variant(const TraverseArgs &a, int ntiles, cudaStream_t s)
 {
-  const size_t smem = ((window_smem_bytes<(CAT ? 384 : 96)>() + 127) & ~(size_t)127) + sizeof(AaConstsSmem);
+  const size_t smem = ((window_smem_bytes<(CAT ? kAaCatChunkSites : kAaChunkSites)>() + 127) & ~(size_t)127) + sizeof(AaConstsSmem);
   static size_t configured[kMaxDevices];
   ensure_dynamic_smem(traverse_aa_kernel<CAT, LG4>, std::min<size_t>(227 * 1024 - 16384, std::max<size_t>(smem, 64 * 1024)), configured);
   traverse_aa_kernel<CAT, LG4><<<ntiles, kAaThreads, smem, s>>>(a);

@@ -60,16 +60,11 @@ struct NrLocal {
 //     block 0      (exchange with the peer ranks,) partitions -> slots, Newton-Raphson update, the prelude of the next
 //                  iteration (topLevelMakenewz's loop top), publish
 // A launch of ONE CTA (a few tiles: the alignments on which the per-call latency is everything) has no grid barrier at all.
-// STAGED (one CTA, GAMMA, the sum table of all tiles fits in shared memory): the rows are brought on chip once and every
-// iteration reads them there -- the loop then costs microseconds per iteration instead of an L2 round trip per pass.
-template <bool STAGED>
-__global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2)
+__global__ void __launch_bounds__(kThreads, 2)
 newton_raphson_kernel(const NrArgs a)
 {
   __shared__ union { CoreSmem g; CoreCatSmem c; double red[32]; } shu;
   __shared__ NrLocal L;
-  extern __shared__ __align__(16) unsigned char nr_dyn[];     // STAGED: per tile [nsites][span] doubles, then [nsites] ints
-  __shared__ double smodel[STAGED ? kNrInitSlots : 1][88];    // STAGED (<= kNrInitSlots partitions): head of every model block
   CoreSmem &sh = shu.g;
   NrState *st = a.state;
   unsigned int gen = 0;
@@ -101,30 +96,6 @@ newton_raphson_kernel(const NrArgs a)
     if (tid == 0) st->all_done = L.all_done;
   };
 
-  if (STAGED) {
-    size_t off = 0;
-    for (int c = 0; c < 2; c++)
-      for (int t = 0; t < a.ntiles[c]; t++) {
-        const Tile tile = a.tiles[c][t];
-        const int span = c == CLS_DNA ? 16 : 80;
-        const double2 *src = reinterpret_cast<const double2 *>(a.sum[c] + (size_t)tile.site0 * span);
-        double2 *dst = reinterpret_cast<double2 *>(nr_dyn + off);
-        const int n2 = (int)tile.nsites * span / 2;
-        for (int i = tid; i < n2; i += kThreads) dst[i] = src[i];
-        off += (size_t)tile.nsites * span * sizeof(double);
-        int *wd = reinterpret_cast<int *>(nr_dyn + off);
-        for (int i = tid; i < (int)tile.nsites; i += kThreads) wd[i] = a.wgt[c][tile.site0 + i];
-        off += (((size_t)tile.nsites * sizeof(int)) + 15) & ~(size_t)15;
-      }
-    // the few model constants core_tile reads (EIGN, rates, LG4X weights: the head of a model block), per partition
-    for (int c = 0; c < 2; c++)
-      for (int t = 0; t < a.ntiles[c]; t++) {
-        const Tile tile = a.tiles[c][t];
-        const double *m = a.models[c] + (size_t)tile.part_cls * (c == CLS_DNA ? kDnaModelDoubles : kAaModelDoubles);
-        for (int i = tid; i < (c == CLS_DNA ? 8 : 88); i += kThreads) smodel[tile.part][i] = m[i];
-      }
-    // (the first grid_barrier below orders these writes before the first sweep)
-  }
   if (lead) {
     for (int i = tid; i < nb; i += kThreads) {
       if (a.init_from_args) {
@@ -146,22 +117,14 @@ newton_raphson_kernel(const NrArgs a)
     if (*(volatile int *)&st->all_done) break;
 
     // ---- derivatives: every CTA sweeps its share of the tiles of both classes ----
-    size_t soff = 0;
     for (int c = 0; c < 2; c++) {
       const int nt = a.ntiles[c];
       for (int t = blockIdx.x; t < nt; t += gridDim.x) {
         const Tile tile = a.tiles[c][t];
-        const size_t rows = soff, wrow = soff + (size_t)tile.nsites * (c == CLS_DNA ? 16 : 80) * sizeof(double);
-        if (STAGED) soff = wrow + ((((size_t)tile.nsites * sizeof(int)) + 15) & ~(size_t)15);
         if (!a.mask[tile.part]) continue;
         double t1, t2;
-        const double lz = STAGED ? L.lz[nb > 1 ? tile.part : 0] : st->lz[nb > 1 ? tile.part : 0];
-        if (STAGED) {
-          const double *srows = reinterpret_cast<const double *>(nr_dyn + rows);
-          const int *swgt = reinterpret_cast<const int *>(nr_dyn + wrow);
-          if (c == CLS_DNA) core_tile<4, true>(tile, srows, swgt, smodel[tile.part], lz, sh, t1, t2);
-          else              core_tile<20, true>(tile, srows, swgt, smodel[tile.part], lz, sh, t1, t2);
-        } else if (a.rate_cat[c]) {
+        const double lz = st->lz[nb > 1 ? tile.part : 0];
+        if (a.rate_cat[c]) {
           const double *rates = a.cat_rates[c] + (size_t)tile.part_cls * a.max_cats;
           if (c == CLS_DNA) core_tile_cat<4>(tile, a.sum[c], a.wgt[c], a.models[c] + (size_t)tile.part_cls * kDnaModelDoubles, a.rate_cat[c], rates, a.max_cats, lz, shu.c, t1, t2);
           else              core_tile_cat<20>(tile, a.sum[c], a.wgt[c], a.models[c] + (size_t)tile.part_cls * kAaModelDoubles, a.rate_cat[c], rates, a.max_cats, lz, shu.c, t1, t2);
@@ -268,27 +231,252 @@ newton_raphson_kernel(const NrArgs a)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// The same loop for a handful of tiles (alignments on which the latency of a call is everything): ONE CTA, an ordinary
+// launch, and nothing but shared memory inside the loop.  Prologue: the sum-table rows and weights of every partition
+// (contiguous on the class's site axis), the heads of the model blocks (EIGN, rates, LG4X weights), the partition tables
+// and the start values (kernel parameters) are brought on chip in one wave of independent loads.  Per iteration: the
+// exponential tables of all partitions, one sweep per partition over its rows (same per-site arithmetic as core_tile),
+// one block reduction per partition, the state machine -- a few microseconds, no global round trip.  GAMMA, at most
+// kNrInitSlots partitions / branch slots.  Several ranks: the per-iteration exchange goes through part_out as above.
+// ------------------------------------------------------------------------------------------------------
+namespace {
+struct SmallTables { double d0[kNrInitSlots][80], d1[kNrInitSlots][80], d2[kNrInitSlots][80], wc[kNrInitSlots][4]; };
+
+// first and second derivative sums of one partition over its staged rows; result valid in thread 0.
+// Thread = site (no shuffles, one division per site and pass); rows are staged with a stride of SPAN + 1 doubles so that
+// the threads of a warp read different banks.
+template <int S>
+__device__ __forceinline__ void small_sweep(const double *rows, const int *wgt, unsigned int nsites, const double *d0,
+                                            const double *d1, const double *d2, const double *wcat, double *red,
+                                            double &out1, double &out2)
+{
+  constexpr int SPAN = 4 * S, STRIDE = SPAN + 1;
+  double acc1 = 0.0, acc2 = 0.0;
+  for (unsigned int i = threadIdx.x; i < nsites; i += kThreads) {
+    const double *p = rows + (size_t)i * STRIDE;
+    double L = 0.0, L1 = 0.0, L2 = 0.0;
+    #pragma unroll 1
+    for (int c = 0; c < 4; c++) {
+      double l = 0.0, l1 = 0.0, l2 = 0.0;
+      #pragma unroll 4
+      for (int k = 0; k < S; k++) {
+        const double t = d0[c * S + k] * p[c * S + k];
+        l += t; l1 += t * d1[c * S + k]; l2 += t * d2[c * S + k];
+      }
+      if (S == 20) { const double wc = wcat[c]; l *= wc; l1 *= wc; l2 *= wc; }     // LG4X category weights (1.0 otherwise)
+      L += l; L1 += l1; L2 += l2;
+    }
+    const double inv = 1.0 / fabs(L);
+    const double g = L1 * inv, h = L2 * inv, w = (double)wgt[i];
+    acc1 += w * g;
+    acc2 += w * (h - g * g);
+  }
+  out1 = block_sum(acc1, red);
+  out2 = block_sum(acc2, red);
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+newton_raphson_small_kernel(const NrArgs a)
+{
+  extern __shared__ __align__(16) unsigned char nr_dyn[];     // per partition: [width][span + 1] doubles, then [width] ints (16-byte padded)
+  __shared__ SmallTables T;
+  __shared__ double red[32];
+  __shared__ double smodel[kNrInitSlots][88];
+  __shared__ double s_part[2 * kNrInitSlots];
+  __shared__ size_t s_rows[kNrInitSlots], s_wgt[kNrInitSlots];
+  __shared__ int s_cls[kNrInitSlots], s_has[kNrInitSlots];
+  __shared__ unsigned char s_mask[kNrInitSlots];
+  __shared__ struct {
+    double z[kNrInitSlots], z0[kNrInitSlots], zprev[kNrInitSlots], zstep[kNrInitSlots], lz[kNrInitSlots];
+    int budget[kNrInitSlots];
+    unsigned char done[kNrInitSlots], curvatOK[kNrInitSlots];
+    int all_done, iterations, peer_lost;
+    unsigned int xseq;
+  } L;
+  const int tid = threadIdx.x;
+  const int nb = a.nbranches, P = a.nparts;
+
+  // ---- prologue ----
+  if (tid == 0) {
+    size_t off = 0;
+    for (int m = 0; m < P; m++) {
+      const int c = a.small_cls[m];
+      s_cls[m] = c; s_has[m] = a.small_width[m] != 0;
+      s_rows[m] = off; off += (((size_t)a.small_width[m] * (c == CLS_DNA ? 17 : 81) * sizeof(double)) + 15) & ~(size_t)15;
+      s_wgt[m] = off;  off += ((size_t)a.small_width[m] * sizeof(int) + 15) & ~(size_t)15;
+    }
+    L.all_done = 0; L.iterations = 0; L.peer_lost = 0; L.xseq = a.xseq0;
+  }
+  if (tid < nb) {
+    L.z[tid] = a.z0[tid]; L.z0[tid] = a.z0[tid]; L.budget[tid] = a.maxiter; L.done[tid] = 0; L.curvatOK[tid] = 1;
+    L.zprev[tid] = 0.0; L.zstep[tid] = 0.0; L.lz[tid] = 0.0;
+  }
+  if (tid < P) s_mask[tid] = a.mask0[tid];
+  __syncthreads();
+  for (int m = 0; m < P; m++) {
+    // (all addresses come from the kernel parameters: one wave of independent loads)
+    const int c = a.small_cls[m], span = c == CLS_DNA ? 16 : 80;
+    const double2 *src = reinterpret_cast<const double2 *>(a.sum[c] + (size_t)a.small_site0[m] * span);
+    double *dst = reinterpret_cast<double *>(nr_dyn + s_rows[m]);
+    const int n2 = (int)a.small_width[m] * span / 2;
+    #pragma unroll 8
+    for (int i = tid; i < n2; i += kThreads) {
+      const double2 v = src[i];
+      const int e = 2 * i, site = e / span, k = e % span;            // row stride span + 1: bank-conflict-free thread-per-site reads
+      dst[(size_t)site * (span + 1) + k] = v.x;
+      dst[(size_t)site * (span + 1) + k + 1] = v.y;
+    }
+    int *wd = reinterpret_cast<int *>(nr_dyn + s_wgt[m]);
+    for (int i = tid; i < (int)a.small_width[m]; i += kThreads) wd[i] = a.wgt[c][a.small_site0[m] + i];
+    const double *mb = a.models[c] + (size_t)a.small_pc[m] * (c == CLS_DNA ? kDnaModelDoubles : kAaModelDoubles);
+    for (int i = tid; i < (c == CLS_DNA ? 8 : 88); i += kThreads) smodel[m][i] = mb[i];
+  }
+  __syncthreads();
+  // d1 = EIGN * rate, d2 = d1^2 (coreGTRGAMMA makenewzGenericSpecial.c:2330-2345) and the category weights: once
+  for (int i = tid; i < P * 80; i += kThreads) {
+    const int m = i / 80, w = i % 80, S = s_cls[m] == CLS_DNA ? 4 : 20;
+    if (w >= 4 * S) continue;
+    const int cc = w / S, k = w % S;
+    const double ki = S == 20 ? m_rate<20>(smodel[m], cc) : m_rate<4>(smodel[m], cc);
+    const double ek = S == 20 ? m_eign<20>(smodel[m], cc, k) : m_eign<4>(smodel[m], cc, k);
+    T.d1[m][w] = k ? ek * ki : 0.0;
+    T.d2[m][w] = k ? ek * ek * (ki * ki) : 0.0;
+    if (w < 4) T.wc[m][w] = S == 20 ? m_weight<20>(smodel[m], w) : 1.0;
+  }
+
+  // top of the do-loop in topLevelMakenewz (makenewzGenericSpecial.c:1161-1230)
+  auto prelude = [&]() {
+    if (tid < nb) {
+      const int i = tid;
+      if (!L.done[i] && L.curvatOK[i]) {
+        L.curvatOK[i] = 0;
+        L.zprev[i] = L.z[i];
+        L.zstep[i] = (1.0 - kZmaxD) * L.z[i] + kZmin;
+      }
+      if (!L.done[i] && !L.curvatOK[i]) {
+        double z = L.z[i];
+        if (z < kZmin) z = kZmin; else if (z > kZmaxD) z = kZmaxD;
+        L.z[i] = z;
+        L.lz[i] = log(z);
+      }
+    }
+    __syncthreads();
+    if (tid < P) {
+      if (nb > 1) { if (s_mask[tid]) s_mask[tid] = !L.curvatOK[tid]; }
+      else s_mask[tid] = !L.curvatOK[0];
+    }
+    __syncthreads();
+  };
+  __syncthreads();
+  prelude();
+
+  while (!L.all_done) {
+    // exponentials of every executed partition at its slot's trial lz: d0 = exp(EIGN * rate * lz), same association as core_tile
+    for (int i = tid; i < P * 80; i += kThreads) {
+      const int m = i / 80, w = i % 80, S = s_cls[m] == CLS_DNA ? 4 : 20;
+      if (w >= 4 * S || !s_mask[m]) continue;
+      const int cc = w / S, k = w % S;
+      const double ki = S == 20 ? m_rate<20>(smodel[m], cc) : m_rate<4>(smodel[m], cc);
+      const double ek = S == 20 ? m_eign<20>(smodel[m], cc, k) : m_eign<4>(smodel[m], cc, k);
+      T.d0[m][w] = k ? exp(ek * ki * L.lz[nb > 1 ? m : 0]) : 1.0;
+    }
+    __syncthreads();
+    for (int m = 0; m < P; m++) {
+      double s0 = 0.0, s1 = 0.0;
+      if (s_mask[m] && s_has[m]) {                   // block-uniform
+        const double *rows = reinterpret_cast<const double *>(nr_dyn + s_rows[m]);
+        const int *wg = reinterpret_cast<const int *>(nr_dyn + s_wgt[m]);
+        if (s_cls[m] == CLS_DNA) small_sweep<4>(rows, wg, a.small_width[m], T.d0[m], T.d1[m], T.d2[m], T.wc[m], red, s0, s1);
+        else                     small_sweep<20>(rows, wg, a.small_width[m], T.d0[m], T.d1[m], T.d2[m], T.wc[m], red, s0, s1);
+      }
+      if (tid == 0) { s_part[m] = s0; s_part[P + m] = s1; }
+    }
+    __syncthreads();
+    bool peers_ok = true;
+    if (a.x.nranks > 1) {
+      const unsigned int xs = a.xseq0 + 1u + (unsigned int)L.iterations;
+      const size_t row = p2p_row(a.x, xs, a.x.rank, 2 * P);
+      for (int r = 0; r < a.x.nranks; r++)
+        for (int i = tid; i < 2 * P; i += kThreads) a.x.peer_buf[r][row + i] = s_part[i];
+      peers_ok = p2p_finish_exchange(a.x, xs, 2 * P, 2 * P, a.part_out, nullptr);
+      for (int i = tid; i < 2 * P; i += kThreads) s_part[i] = a.part_out[i];
+      if (tid == 0) L.xseq = xs;
+      __syncthreads();
+    }
+    if (tid == 0 && !peers_ok) { L.peer_lost = 1; L.iterations += 1; L.all_done = 1; }
+    if (tid == 0 && peers_ok) {
+      int all = 1;
+      for (int i = 0; i < nb; i++) {                 // partitions -> slots in partition order (makenewzGenericSpecial.c:921-946)
+        double d1 = 0.0, d2 = 0.0;
+        if (nb > 1) { if (s_mask[i]) { d1 += s_part[i]; d2 += s_part[P + i]; } }
+        else for (int m = 0; m < P; m++) { if (!s_mask[m]) continue; d1 += s_part[m]; d2 += s_part[P + m]; }
+        if (!L.done[i] && !L.curvatOK[i]) {
+          if (d2 >= 0.0 && L.z[i] < kZmaxD)
+            L.zprev[i] = L.z[i] = 0.37 * L.z[i] + 0.63;
+          else
+            L.curvatOK[i] = 1;
+        }
+        if (L.curvatOK[i] && !L.done[i]) {
+          double z = L.z[i];
+          if (d2 < 0.0) {
+            const double step = -d1 / d2;
+            const double cap = 0.25 * L.zprev[i] + 0.75;
+            if (step < 100) {
+              z *= exp(step);
+              if (z < kZmin) z = kZmin;
+              if (z > cap) z = cap;
+            } else
+              z = cap;
+          }
+          if (z > kZmaxD) z = kZmaxD;
+          L.budget[i] -= 1;
+          if (fabs(z - L.zprev[i]) > L.zstep[i]) {
+            if (L.budget[i] < -20) { z = L.z0[i]; L.done[i] = 1; }
+          } else
+            L.done[i] = 1;
+          L.z[i] = z;
+        }
+        all = all && L.done[i];
+      }
+      L.iterations += 1;
+      L.all_done = all;
+    }
+    __syncthreads();
+    prelude();
+  }
+
+  // ---- results into pinned host memory, then the flag ----
+  if (tid < nb) { a.result_host->z[tid] = L.z[tid]; a.result_host->curvatOK[tid] = L.curvatOK[tid]; }
+  if (tid == 0) { a.result_host->iterations = L.iterations; a.result_host->xseq = L.xseq; a.result_host->peer_lost = L.peer_lost; }
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) *a.done_flag_host = a.seq;
+}
+
 int launch_newton_raphson(const NrArgs &a, int blocks, size_t staged_bytes, cudaStream_t s)
 {
-  if (blocks == 1 && staged_bytes) {               // one CTA, sum table in shared memory
+  if (blocks == 1 && staged_bytes) {               // one CTA, everything in shared memory
     static size_t configured[kMaxDevices];
-    const cudaError_t r = ensure_dynamic_smem(newton_raphson_kernel<true>, kNrStagedBytes, configured);
+    const cudaError_t r = ensure_dynamic_smem(newton_raphson_small_kernel, kNrStagedBytes, configured);
     if (r != cudaSuccess) return (int)r;
-    newton_raphson_kernel<true><<<1, kThreads, staged_bytes, s>>>(a);
+    newton_raphson_small_kernel<<<1, kThreads, staged_bytes, s>>>(a);
     return (int)cudaGetLastError();
   }
   if (blocks == 1) {                               // no grid barrier inside: an ordinary launch
-    newton_raphson_kernel<false><<<1, kThreads, 0, s>>>(a);
+    newton_raphson_kernel<<<1, kThreads, 0, s>>>(a);
     return (int)cudaGetLastError();
   }
   void *params[] = {(void *)&a};
-  return (int)cudaLaunchCooperativeKernel((const void *)newton_raphson_kernel<false>, dim3(blocks), dim3(kThreads), params, 0, s);
+  return (int)cudaLaunchCooperativeKernel((const void *)newton_raphson_kernel, dim3(blocks), dim3(kThreads), params, 0, s);
 }
 
 int newton_raphson_max_blocks(int device)
 {
   int per_sm = 0, sms = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, newton_raphson_kernel<false>, kThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, newton_raphson_kernel, kThreads, 0);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   return per_sm * sms;
 }

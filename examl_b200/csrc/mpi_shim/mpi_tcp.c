@@ -76,6 +76,8 @@ int MPI_Init(int *argc, char ***argv)
   static const char *const size_names[] = {"WORLD_SIZE", "PMI_SIZE", "OMPI_COMM_WORLD_SIZE", "SLURM_NTASKS", NULL};
   const char *addr = getenv("MASTER_ADDR"), *port_s = getenv("MASTER_PORT");
   int port = port_s ? atoi(port_s) : 29400, one = 1, i;
+  const char *tok_s = getenv("MPI_TCP_TOKEN");
+  const unsigned long long token = tok_s ? strtoull(tok_s, NULL, 16) : 0ULL;
   (void)argc; (void)argv;
   g_rank = env_int(rank_names, 0);
   g_size = env_int(size_names, 1);
@@ -89,7 +91,11 @@ int MPI_Init(int *argc, char ***argv)
     if (ls < 0) die("socket");
     setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
     memset(&sa, 0, sizeof sa);
-    sa.sin_family = AF_INET; sa.sin_addr.s_addr = htonl(INADDR_ANY); sa.sin_port = htons((unsigned short)port);
+    /* listen on MASTER_ADDR only (loopback for examl_b200/launch.py), not on every interface; MASTER_ADDR given as a
+       host name that is not a dotted quad: all interfaces as before.  MPI_TCP_TOKEN (set by the launcher) must be echoed
+       by every rank that connects. */
+    sa.sin_family = AF_INET; sa.sin_port = htons((unsigned short)port);
+    if (inet_pton(AF_INET, addr, &sa.sin_addr) != 1) sa.sin_addr.s_addr = htonl(INADDR_ANY);
     if (bind(ls, (struct sockaddr *)&sa, sizeof sa) < 0) die("bind");
     if (listen(ls, g_size) < 0) die("listen");
     for (i = 1; i < g_size; i++) {
@@ -97,6 +103,8 @@ int MPI_Init(int *argc, char ***argv)
       if (fd < 0) die("accept");
       setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
       recv_all(fd, &r, sizeof r);
+      { unsigned long long tok = 0; recv_all(fd, &tok, sizeof tok);
+        if (tok != token) { fprintf(stderr, "mpi_tcp: connection with a wrong token refused\n"); close(fd); i--; continue; } }
       if (r < 1 || r >= g_size || g_peer[r]) { fprintf(stderr, "mpi_tcp: bad rank %d announced\n", r); exit(70); }
       g_peer[r] = fd;
     }
@@ -120,6 +128,7 @@ int MPI_Init(int *argc, char ***argv)
     if (fd < 0) die("connect to rank 0");
     setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
     send_all(fd, &g_rank, sizeof g_rank);
+    send_all(fd, &token, sizeof token);
     g_peer[0] = fd;
   }
   return MPI_SUCCESS;
@@ -133,7 +142,14 @@ int MPI_Finalize(void)
   return MPI_SUCCESS;
 }
 
-int MPI_Abort(MPI_Comm comm, int errorcode) { (void)comm; exit(errorcode ? errorcode : 1); }
+/* Peers blocked in a collective notice the closed sockets (recv_all fails -> die) instead of waiting for ever. */
+int MPI_Abort(MPI_Comm comm, int errorcode)
+{
+  int i;
+  (void)comm;
+  for (i = 0; g_peer && i < g_size; i++) if (g_peer[i] > 0) shutdown(g_peer[i], SHUT_RDWR);
+  exit(errorcode > 0 && errorcode < 256 ? errorcode : 1);
+}
 int MPI_Comm_rank(MPI_Comm comm, int *rank) { (void)comm; *rank = g_rank; return MPI_SUCCESS; }
 int MPI_Comm_size(MPI_Comm comm, int *size) { (void)comm; *size = g_size; return MPI_SUCCESS; }
 

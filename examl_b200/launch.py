@@ -26,10 +26,12 @@ def free_port() -> int:
 
 def launch(np_: int, cmd, env=None, stdout=None, timeout=None) -> int:
     port = free_port()
+    token = "%016x" % int.from_bytes(os.urandom(8), "little")      # mpi_tcp.c: rank 0 only accepts ranks that echo it
     procs = []
     for r in range(np_):
         e = dict(os.environ if env is None else env)
-        e.update(RANK=str(r), WORLD_SIZE=str(np_), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        e.update(RANK=str(r), WORLD_SIZE=str(np_), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                 MPI_TCP_TOKEN=token)
         out = stdout if (stdout is not None and r == 0) else (subprocess.DEVNULL if stdout is not None else None)
         procs.append(subprocess.Popen(cmd, env=e, stdout=out, stderr=subprocess.STDOUT if out is not None else None))
     t0 = time.time()
