@@ -567,6 +567,17 @@ extern "C" int exb_commit(exb_engine *e)
       size_t tsz = c == CLS_AA ? (size_t)((e->tile_sites + aachunk - 1) / aachunk) * aachunk : (size_t)e->tile_sites;
       // tcgen05 path: one 32-site chunk per CTA unless told otherwise -- four co-resident CTAs per SM want many small tiles
       if (c == CLS_AA && e->aa_tc && !e->cat && !e->tile_sites_set) tsz = 32;
+      // AA GAMMA (one CTA per SM): ONE wave of equal tiles.  With fixed 288-site tiles C4 (200 k sites) is 695 tiles = 4.7
+      // waves on 148 SMs, i.e. 15 chunk-times where 14.1 would do; one tile per SM is 14 full chunks + 16 sites whose two
+      // warps sit on different schedulers (idle warps of a partial chunk skip the tensor work).  Not under -S, whose saving
+      // is per (node, tile) and wants small tiles.
+      if (c == CLS_AA && !e->aa_tc && !e->cat && !e->tile_sites_set && !e->sev) {
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+        const size_t per_sm = (p.width + (size_t)(sms > 0 ? sms : 148) - 1) / (size_t)(sms > 0 ? sms : 148);
+        const size_t want = (per_sm + 15) / 16 * 16;             // tip rows are staged with 16-byte granularity
+        tsz = std::max<size_t>(want, aachunk);
+      }
       // One big DNA partition on a few waves of CTAs (strong scaling: 125 k sites per GPU are 1.65 waves of 256-site
       // tiles): cut it into k full waves of equal tiles instead, so that the last wave is not a third empty.
       if (c == CLS_DNA && !e->cat && !e->tile_sites_set && e->P == 1) {

@@ -267,6 +267,7 @@ traverse_aa_kernel(const TraverseArgs a)
     }
     const size_t site0 = (size_t)tile.site0 + chunk0 + (CAT ? i0 : lsite[0]);   // CAT: slot c sits at site0 + 8c
     const size_t soff = site0 * XSPAN;
+    const bool warp_active = (unsigned)(CAT ? warp * 32 : warp * 8) < nchunk;      // any site of this chunk in my warp?
     double carry[4][3][2];                                // CLV of the entry just computed, C-fragment layout
     #pragma unroll
     for (int c = 0; c < 4; c++)
@@ -283,6 +284,31 @@ traverse_aa_kernel(const TraverseArgs a)
     for (int e = w0; e < w1; e++) {
       const SEntry en = ents[e - w0];
       if (en.flags & kFlagGapP) continue;       // -S: all sites of the tile are gaps below this node: nothing to compute or store
+      if (!warp_active) {
+        // a warp without sites in this (last, partial) chunk of a tile does no tensor work -- the chunk then costs what its
+        // busiest scheduler costs; its slot of a scoring entry still has to read zero
+        if (!CAT && (en.flags & kFlagScore) && lane == 0 && chunk0 == 0)
+          a.score_out[(size_t)en.poff * a.score_stride + (size_t)(a.sev_tile0 + (int)blockIdx.x) * (kAaThreads / 32) + warp] = make_double2(0.0, 0.0);
+        continue;
+      }
+      if (!CAT && e + 1 < w1) {
+        // the inner children of the NEXT entry that will be read from memory (neither tip nor carry) were written long ago
+        // and have mostly left L2 (one CLV of C4 is 128 MB): ask for this lane's lines now, one entry ahead
+        const SEntry nx = ents[e + 1 - w0];
+        if (!(nx.flags & kFlagGapP)) {
+          const char *base = reinterpret_cast<const char *>(a.clv + soff) + tq * 128;
+          if (nx.tipCase == 2 && !(nx.flags & (kFlagCarryA | kFlagGapA))) {
+            const char *p = base + nx.qoff * (long long)sizeof(double);
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+            if (tq == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + 512));
+          }
+          if (nx.tipCase != 0 && !(nx.flags & (kFlagCarryB | kFlagGapB))) {
+            const char *p = base + nx.roff * (long long)sizeof(double);
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+            if (tq == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + 512));
+          }
+        }
+      }
       const double *drow = drow0 + (size_t)e * dstride;
       const bool q_inner = en.tipCase == 2, r_inner = en.tipCase != 0;
       const int qsrc = !q_inner ? SRC_TIP : ((en.flags & kFlagCarryA) ? SRC_CARRY : SRC_LOAD);
