@@ -569,8 +569,9 @@ extern "C" int exb_commit(exb_engine *e)
       if (c == CLS_AA && e->aa_tc && !e->cat && !e->tile_sites_set) tsz = 32;
       // AA GAMMA (one CTA per SM): ONE wave of equal tiles.  With fixed 288-site tiles C4 (200 k sites) is 695 tiles = 4.7
       // waves on 148 SMs, i.e. 15 chunk-times where 14.1 would do; one tile per SM is 14 full chunks + 16 sites whose two
-      // warps sit on different schedulers (idle warps of a partial chunk skip the tensor work).  Not under -S, whose saving
-      // is per (node, tile) and wants small tiles.
+      // warps sit on different schedulers (idle warps of a partial chunk skip the tensor work).  Measured on C4, same box:
+      // 31.36 vs 31.85 ms (tools/r2_call14.sh; an L2 prefetch of the next entry's loaded children one entry ahead, tried in
+      // the same call, cost 0.3 ms and was dropped).  Not under -S, whose saving is per (node, tile) and wants small tiles.
       if (c == CLS_AA && !e->aa_tc && !e->cat && !e->tile_sites_set && !e->sev) {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);

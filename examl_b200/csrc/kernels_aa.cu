@@ -291,24 +291,6 @@ traverse_aa_kernel(const TraverseArgs a)
           a.score_out[(size_t)en.poff * a.score_stride + (size_t)(a.sev_tile0 + (int)blockIdx.x) * (kAaThreads / 32) + warp] = make_double2(0.0, 0.0);
         continue;
       }
-      if (!CAT && e + 1 < w1) {
-        // the inner children of the NEXT entry that will be read from memory (neither tip nor carry) were written long ago
-        // and have mostly left L2 (one CLV of C4 is 128 MB): ask for this lane's lines now, one entry ahead
-        const SEntry nx = ents[e + 1 - w0];
-        if (!(nx.flags & kFlagGapP)) {
-          const char *base = reinterpret_cast<const char *>(a.clv + soff) + tq * 128;
-          if (nx.tipCase == 2 && !(nx.flags & (kFlagCarryA | kFlagGapA))) {
-            const char *p = base + nx.qoff * (long long)sizeof(double);
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-            if (tq == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + 512));
-          }
-          if (nx.tipCase != 0 && !(nx.flags & (kFlagCarryB | kFlagGapB))) {
-            const char *p = base + nx.roff * (long long)sizeof(double);
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-            if (tq == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + 512));
-          }
-        }
-      }
       const double *drow = drow0 + (size_t)e * dstride;
       const bool q_inner = en.tipCase == 2, r_inner = en.tipCase != 0;
       const int qsrc = !q_inner ? SRC_TIP : ((en.flags & kFlagCarryA) ? SRC_CARRY : SRC_LOAD);

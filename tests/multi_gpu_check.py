@@ -37,6 +37,15 @@ def main():
     want = full.evaluateIterative(ti).copy()
     full.makenewzIterative(tree.partial_traversal(tree.start))
     want_d = full.execCore([np.log(0.7)])
+    # an insertion scan (exb_score_insertions) on the whole alignment: the table the sharded engines must reproduce
+    from examl_b200.spr import build_scan, remove_node, score_scan
+    from spr_util import prunable_nodes
+    scan_tree = random_case(40, [100003, 0, 5000], [4, 4, 20], seed=17)[0]       # a copy: pruning re-wires it
+    sp = prunable_nodes(scan_tree)[11]
+    sp1, sp2 = remove_node(scan_tree, sp, [a * b for a, b in zip(sp.next.z, sp.next.next.z)])
+    Likelihood(scan_tree, full, len(parts)).evaluateGeneric(scan_tree.start, True)
+    scan_ti, scan_cands = build_scan(scan_tree, sp, sp1, sp2, 1, 4)
+    want_scan = score_scan(full, scan_ti, len(scan_cands), full.max_entries())
     # the whole Newton-Raphson loop on one GPU (device kernel) and through the host loop
     inner = tree.start.back
     ti_nr = tree.partial_traversal(inner)          # built once: building it re-orients the tree's x flags
@@ -83,7 +92,13 @@ def main():
         except Exception:
             pass
 
-    ok = stable and nr_ok and bool(np.all(np.abs(got - want) <= 1e-11 * np.maximum(np.abs(want), 1.0)))
+    # the insertion scan across the ranks: per-candidate sums are all-reduced inside the call
+    eng.evaluateIterative(scan_tree.full_traversal())       # the pruned topology's CLVs on the sharded engine
+    got_scan = score_scan(eng, scan_ti, len(scan_cands), eng.max_entries())
+    scan_ok = len(scan_cands) > 3 and bool(np.all(np.abs(got_scan - want_scan) <= 1e-11 * np.maximum(np.abs(want_scan), 1.0)))
+    scan_ok = scan_ok and bool(np.array_equal(eng.evaluateIterative(ti), got))
+
+    ok = stable and nr_ok and scan_ok and bool(np.all(np.abs(got - want) <= 1e-11 * np.maximum(np.abs(want), 1.0)))
     ok = ok and abs(got_d[0][0] - want_d[0][0]) <= 1e-9 * max(1.0, abs(want_d[0][0]))
     ok = ok and abs(got_d[1][0] - want_d[1][0]) <= 1e-9 * max(1.0, abs(want_d[1][0]))
     # every rank holds bit-identical results (the all-reduce is part of the call)
@@ -96,7 +111,8 @@ def main():
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if int(flag.item()) else "FAIL", "allreduce", mode, "world", world, "lnL", got.tolist(), "want", want.tolist(),
               "d", [float(got_d[0][0]), float(got_d[1][0])], "want_d", [float(want_d[0][0]), float(want_d[1][0])],
-              "device NR z", float(got_z[0]), "iterations", got_it, "1-GPU", float(want_z[0]), want_it, "host loop", float(host_z[0]))
+              "device NR z", float(got_z[0]), "iterations", got_it, "1-GPU", float(want_z[0]), want_it, "host loop", float(host_z[0]),
+              "insertion scan", len(scan_cands), "candidates", "ok" if scan_ok else "MISMATCH")
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) else 1)
 

@@ -36,8 +36,16 @@ def _worker(rank, world, port, q):
     d1, d2 = eng.execCore([np.log(0.6)])
     d = torch.tensor([d1[0], d2[0]])
     dist.all_reduce(d)                       # makenewzGenericSpecial.c:1241-1248
+    # an insertion scan (exb_score_insertions): candidate-major per-partition sums, all-reduced like evaluate's output
+    from examl_b200.spr import build_scan, remove_node, score_scan
+    from spr_util import prunable_nodes
+    p = prunable_nodes(tree)[5]
+    p1, p2 = remove_node(tree, p, [a * b for a, b in zip(p.next.z, p.next.next.z)])
+    sti, cands = build_scan(tree, p, p1, p2, 1, 4)
+    scan = torch.tensor(score_scan(eng, sti, len(cands), 10_000))
+    dist.all_reduce(scan)
     if rank == 0:
-        q.put((lh.tolist(), d.tolist(), [p[2].shape[0] for p in shard]))
+        q.put((lh.tolist(), d.tolist(), [p[2].shape[0] for p in shard], scan.tolist()))
     dist.destroy_process_group()
 
 
@@ -50,9 +58,9 @@ def test_two_rank_sharding_matches_single_rank(oracle_factory):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    lh, d, widths0 = q.get(timeout=120)
+    lh, d, widths0, scan = q.get(timeout=600)
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=120)
         assert p.exitcode == 0
     assert widths0[1] == 1 or widths0[1] == 0           # the 1-site partition lives on exactly one rank
     tree, parts, models = random_case(12, [101, 1, 40], [4, 4, 20], seed=31)
@@ -62,3 +70,10 @@ def test_two_rank_sharding_matches_single_rank(oracle_factory):
     eng.makenewzIterative(tree.partial_traversal(tree.start))
     d1, d2 = eng.execCore([np.log(0.6)])
     np.testing.assert_allclose(d, [d1[0], d2[0]], rtol=1e-10)
+    from examl_b200.spr import build_scan, remove_node, score_scan
+    from spr_util import prunable_nodes
+    p = prunable_nodes(tree)[5]
+    p1, p2 = remove_node(tree, p, [a * b for a, b in zip(p.next.z, p.next.next.z)])
+    sti, cands = build_scan(tree, p, p1, p2, 1, 4)
+    np.testing.assert_allclose(scan, score_scan(eng, sti, len(cands), 10_000), rtol=1e-11)
+    assert len(cands) > 3
