@@ -37,21 +37,26 @@ def main():
     want = full.evaluateIterative(ti).copy()
     full.makenewzIterative(tree.partial_traversal(tree.start))
     want_d = full.execCore([np.log(0.7)])
-    # an insertion scan (exb_score_insertions) on the whole alignment: the table the sharded engines must reproduce
-    from examl_b200.spr import build_scan, remove_node, score_scan
-    from spr_util import prunable_nodes
-    scan_tree = random_case(40, [100003, 0, 5000], [4, 4, 20], seed=17)[0]       # a copy: pruning re-wires it
-    sp = prunable_nodes(scan_tree)[11]
-    sp1, sp2 = remove_node(scan_tree, sp, [a * b for a, b in zip(sp.next.z, sp.next.next.z)])
-    Likelihood(scan_tree, full, len(parts)).evaluateGeneric(scan_tree.start, True)
-    scan_ti, scan_cands = build_scan(scan_tree, sp, sp1, sp2, 1, 4)
-    want_scan = score_scan(full, scan_ti, len(scan_cands), full.max_entries())
     # the whole Newton-Raphson loop on one GPU (device kernel) and through the host loop
     inner = tree.start.back
     ti_nr = tree.partial_traversal(inner)          # built once: building it re-orients the tree's x flags
     z0 = list(inner.z)
     want_z, want_ok, want_it = full.makenewz(ti_nr, z0, 10)
     host_z = Likelihood(tree, full, len(parts)).makenewzGeneric(inner, inner.back, z0, 10)
+    # an insertion scan (exb_score_insertions) on the whole alignment: the table the sharded engines must reproduce
+    # (last on this engine: it recomputes CLVs for the pruned topology)
+    from examl_b200.spr import build_scan, remove_node, score_scan
+    from spr_util import prunable_nodes
+    scan_tree = random_case(40, [100003, 0, 5000], [4, 4, 20], seed=17)[0]       # a copy: pruning re-wires it
+    def holds_start(rec):                      # is tip 1 (the traversal root) inside the subtree behind rec?
+        if scan_tree.isTip(rec.number):
+            return rec.number == 1
+        return holds_start(rec.next.back) or holds_start(rec.next.next.back)
+    sp = [x for x in prunable_nodes(scan_tree) if not holds_start(x.back)][11]
+    sp1, sp2 = remove_node(scan_tree, sp, [a * b for a, b in zip(sp.next.z, sp.next.next.z)])
+    Likelihood(scan_tree, full, len(parts)).evaluateGeneric(scan_tree.start, True)
+    scan_ti, scan_cands = build_scan(scan_tree, sp, sp1, sp2, 1, 4)
+    want_scan = score_scan(full, scan_ti, len(scan_cands), full.max_entries())
     full.close()
 
     # sharded: rank r owns a contiguous slice of every partition (partition 1 is empty everywhere)

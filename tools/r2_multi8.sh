@@ -3,7 +3,7 @@
 # bench line at N=8 exactly as the driver launches it (C3 strong-scaled + secondary: C4 and the FULL C5, 10 000 partitions)
 mkdir -p gpurun_out
 timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py 2>&1 | grep MULTI_GPU_CHECK | cut -c1-400 | tee gpurun_out/multi8_check.txt
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 40 --warmup 3 2>gpurun_out/scale8.err | tail -1 > gpurun_out/scale8_p2p.json
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 20 --warmup 3 2>gpurun_out/scale8.err | tail -1 > gpurun_out/scale8_p2p.json
 tail -3 gpurun_out/scale8.err
 python - <<'PY'
 import json
