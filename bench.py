@@ -13,7 +13,8 @@ Workloads (BASELINE.json configs[2..4]):
   aa   C4  synthetic AA LG+GAMMA4, 200 k sites x 500 taxa, 1 partition (FP64 tensor-pipe kernel)
   c5   C5  10 k DNA partitions x 1 k sites, 354-taxon tree (the topology of testData/354.tree), per-partition
            GTR models; 1 250 whole partitions per GPU (= one GPU's share of C5; N = 8 is the full config)
-The default invocation prints ONE JSON line for `dna` and carries the other two in its "secondary" object.
+The default invocation prints ONE JSON line for `dna` and carries the other two in its "secondary" object (plus C4 in the
+tcgen05 mode and, on one GPU, `spr_scan`: the batched insertion scan of SURVEY 8 f-4 against the candidate-by-candidate path).
 
 A "step" is one evaluateGeneric(tr, tr->start, fullTraversal=TRUE): (taxa-2) newviews over all
 sites + evaluate + all-reduce (the reference's own timing loop).
@@ -567,6 +568,65 @@ def secondary_summary(r: dict) -> dict:
     return s
 
 
+def run_insertion_scan(local_rank: int) -> dict:
+    """SURVEY 8 f-4 at scale, single GPU: all lazy SPR insertions of a few pruned subtrees within a rearrangement radius,
+    scored (a) by ONE exb_score_insertions call per pruned subtree and (b) the reference's way, one newviewGeneric +
+    evaluateGeneric pair per candidate (testInsertBIG searchAlgo.c:682; tests/spr_util.reference_scan) through the same
+    engine -- so the two tables must agree to rounding (the pulley principle), and the first one against the oracle is
+    tests/test_gpu_parity.py::test_score_insertions_vs_oracle."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from examl_b200.capi import Engine
+    from examl_b200.likelihood import Likelihood
+    from examl_b200.phylo import hookup
+    from examl_b200.spr import build_scan, remove_node, score_scan
+    from spr_util import prunable_nodes, reference_scan
+    taxa, sites, radius, nprune = 200, 100_000, 5, 6
+    tree = Tree.random(taxa, seed=20260922)
+    rng = np.random.default_rng(11)
+    for a, _b in tree.branches():
+        a.z[:] = [float(rng.uniform(0.35, 0.97))]
+    tips = make_sites(tree, 0, sites, "dna")
+    eng = Engine(taxa, 1, 1, device=local_rank)
+    eng.set_partition(0, 4, np.ones(sites, dtype=np.int32), tips)
+    eng.commit()
+    eng.set_model(0, model_for("dna"))
+    eng.set_timing(False)
+    lk = Likelihood(tree, eng, 1)
+    lk.evaluateGeneric(tree.start, True)
+    nodes = prunable_nodes(tree)
+    tb = tr = worst = 0.0
+    ncand = 0
+    launches0 = eng.launch_count()
+    for pick in rng.choice(len(nodes), size=nprune, replace=False):
+        p = nodes[pick]
+        saved = (p.next.back, list(p.next.z), p.next.next.back, list(p.next.next.z))
+        p1, p2 = remove_node(tree, p, [a * b for a, b in zip(p.next.z, p.next.next.z)])
+        lk.newviewGeneric(p1); lk.newviewGeneric(p2)           # removeNodeBIG's makenewzGeneric leaves both looking at each other
+        ti, cands = build_scan(tree, p, p1, p2, 1, radius)
+        score_scan(eng, ti, len(cands), eng.max_entries())      # untimed: scratch CLVs are allocated on first use
+        t0 = time.perf_counter()
+        got = score_scan(eng, ti, len(cands), eng.max_entries())
+        tb += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        want = reference_scan(lk, p, p1, p2, 1, radius)
+        tr += time.perf_counter() - t0
+        ncand += len(cands)
+        for k, (_q, lh) in enumerate(want):
+            worst = max(worst, abs(got[k][0] - lh[0]) / abs(lh[0]))
+        hookup(p.next, saved[0], saved[1]); hookup(p.next.next, saved[2], saved[3])
+        lk.newviewGeneric(p)
+    out = {"metric": "lazy SPR insertions scored per second (exb_score_insertions, one call per pruned subtree)",
+           "value": ncand / tb, "unit": "insertions/s", "candidates": ncand, "pruned_subtrees": nprune,
+           "ms_batched": 1e3 * tb, "ms_candidate_by_candidate": 1e3 * tr, "speedup": tr / tb,
+           "parity": {"checked": "batched table vs newviewGeneric + evaluateGeneric per candidate on the same engine",
+                      "rel_err": float(worst)},
+           "gpu_launches": eng.launch_count() - launches0,
+           "config": {"workload": f"synthetic DNA GTR+GAMMA4, {sites} sites x {taxa} taxa, rearrangement radius {radius}",
+                      "reference_procedure": "testInsertBIG searchAlgo.c:682 (insertBIG non-thorough + newviewGeneric + evaluateGeneric)"}}
+    eng.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -646,6 +706,11 @@ def main():
                 if world > 1:
                     raise                                 # ... but ranks must not diverge
                 sec[key] = {"error": repr(ex)[:400]}
+        if world == 1:
+            try:                                          # the batched insertion scan against the per-candidate path
+                sec["spr_scan"] = run_insertion_scan(local_rank)
+            except Exception as ex:
+                sec["spr_scan"] = {"error": repr(ex)[:400]}
         if rank == 0:
             line["secondary"] = sec
     if rank == 0:
