@@ -25,6 +25,8 @@
  *     + MPI_Allreduce     (makenewzGenericSpecial.c:1241-1248)   (all-reduce inside, NCCL)
  *   topLevelMakenewz      (makenewzGenericSpecial.c:1133)      exb_makenewz (single rank: whole NR loop on the device)
  *   evaluatePartialGeneric (evaluatePartialGenericSpecial.c:259) exb_evaluate_partial (batched over sites and rates)
+ *   testInsertBIG, non-thorough (searchAlgo.c:682: insertBIG +    exb_score_insertions (all candidates of a pruned subtree
+ *     newviewGeneric + evaluateGeneric per candidate branch)        in one call; behind batchedInsertionScanBegin / End)
  *
  * The three public axml.h entry points (evaluateGeneric axml.h:1223, newviewGeneric :1232,
  * makenewzGeneric :1241) are exported by the companion translation unit

@@ -117,6 +117,27 @@ def test_batched_insertion_scan_behind_the_search(args, taxa):
             assert scans > 10 and calls == scans and served > scans and served <= scored and flushed == 0, m.group(0)
 
 
+def test_batched_insertion_scan_on_two_ranks():
+    """The scan's per-candidate sums are all-reduced inside exb_score_insertions (here: the oracle harness over mpi_tcp.c);
+    both ranks walk the same branches and must answer testInsertBIG identically -- the search ends where the reference's does."""
+    import re
+    with tempfile.TemporaryDirectory() as tmp:
+        binary, tree = small_dna_case(tmp, taxa=16, sites=500, seed=33)
+        args = ["-m", "GAMMA", "-f", "d"]
+        r0, best0, _ = run_mode(REFERENCE, binary, tree, tmp, "REF", args)
+        assert r0.returncode == 0
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+        env.update(ENV, EXAML_B200_SPR_STATS="1", PYTHONPATH=ROOT)
+        r = subprocess.run([sys.executable, "-m", "examl_b200.launch", "-np", "2", "--", hostcheck_build.EXE_SPR, "-s", binary, "-t", tree,
+                            "-n", "SPR2", "-w", tmp + "/"] + args,
+                           cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-3000:]
+        m = re.findall(r"Likelihood of best tree: (-?[0-9.]+)", r.stdout)
+        assert m and _rel(float(m[-1]), best0) < 1e-6, (m, best0)
+        st = re.search(r"batched insertion scoring: (\d+) scans, (\d+) engine calls, (\d+) candidates scored, (\d+) served", r.stdout)
+        assert st and int(st.group(1)) > 10 and int(st.group(4)) > int(st.group(1)), r.stdout[-800:]
+
+
 def test_restart_from_checkpoint():
     """-R: the search state comes back from ExaML_binaryCheckpoint (searchAlgo.c:1726); CLVs are not part of it, so the
     back-end must rebuild everything from the first full traversal after the restart."""
