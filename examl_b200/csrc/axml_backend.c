@@ -686,6 +686,7 @@ static void spr_walk(tree *tr, nodeptr q, int mintrav, int maxtrav, int depth, n
     if (g_spr.ncand == g_spr.ccap) {
       g_spr.ccap = 2 * g_spr.ccap + 64;
       g_spr.cand = (nodeptr *)realloc(g_spr.cand, (size_t)g_spr.ccap * sizeof(nodeptr));
+      if (!g_spr.cand) { fprintf(stderr, "out of memory\n"); MPI_Abort(MPI_COMM_WORLD, -1); exit(-1); }
     }
     spr_emit(tr, EXB_SCORE, g_spr.ncand, q->number, zz, uNumber, zz);
     g_spr.cand[g_spr.ncand++] = q;
@@ -725,14 +726,15 @@ void batchedInsertionScanBegin(tree *tr, nodeptr p, nodeptr p1, nodeptr p2, int 
   }
   if (g_spr.failed || g_spr.ncand == 0) return;
   g_spr.lnl = (double *)realloc(g_spr.lnl, (size_t)g_spr.ncand * P * sizeof(double));
+  if (!g_spr.lnl) { fprintf(stderr, "out of memory\n"); MPI_Abort(MPI_COMM_WORLD, -1); exit(-1); }
   for (m = 0; m < P; m++) g_mask[m] = tr->executeModel[m] ? 1 : 0;
   /* a descriptor holds exb_max_entries entries: cut the list anywhere (scratch CLVs persist), candidates renumbered per call */
   cap = exb_max_entries(g_engine) - 1;
   for (at = 1; at < g_spr.n; ) {
     const int n = (g_spr.n - at < cap) ? g_spr.n - at : cap;
     int first = -1, cnt = 0;
-    exb_entry e0 = g_spr.ent[at - 1];
-    double *q0 = (double *)malloc(2 * (size_t)nb * sizeof(double)), *r0 = q0 + nb;
+    const exb_entry e0 = g_spr.ent[at - 1];
+    double q0[NUM_BRANCHES], r0[NUM_BRANCHES];
     /* slot at-1 temporarily becomes entry 0 of this call */
     memcpy(q0, g_spr.qz + (size_t)(at - 1) * nb, (size_t)nb * sizeof(double));
     memcpy(r0, g_spr.rz + (size_t)(at - 1) * nb, (size_t)nb * sizeof(double));
@@ -746,7 +748,6 @@ void batchedInsertionScanBegin(tree *tr, nodeptr p, nodeptr p1, nodeptr p2, int 
     g_spr.ent[at - 1] = e0;
     memcpy(g_spr.qz + (size_t)(at - 1) * nb, q0, (size_t)nb * sizeof(double));
     memcpy(g_spr.rz + (size_t)(at - 1) * nb, r0, (size_t)nb * sizeof(double));
-    free(q0);
     if (m != EXB_OK) {
       static int told = 0;
       if (!told && processID == 0) printf("\nB200 back-end: batched insertion scoring not used (%s)\n", exb_last_error());

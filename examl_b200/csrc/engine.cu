@@ -142,11 +142,12 @@ score_reduce_kernel(const ScoreFinishArgs a)
 void launch_score_finish(const ScoreFinishArgs &a0, cudaStream_t s)
 {
   ScoreFinishArgs a = a0;
-  if (a.ncand <= 0) return;
   const size_t smem = (size_t)a.gs_stride * sizeof(unsigned int);
   const int blocks = a.nparts < 592 ? a.nparts : 592;
   a.gs_in_smem = smem <= 40 * 1024;               // else the scaler row is walked in place
-  score_chain_kernel<<<blocks, 32, a.gs_in_smem ? smem : 0, s>>>(a);
+  // (a piece of a scan that holds newview entries only still needs its scaler bookkeeping)
+  if (a.count > 1) score_chain_kernel<<<blocks, 32, a.gs_in_smem ? smem : 0, s>>>(a);
+  if (a.ncand <= 0) return;
   dim3 grid((unsigned)a.ncand, (unsigned)(a.nparts < 4096 ? a.nparts : 4096));
   score_reduce_kernel<<<grid, 128, 0, s>>>(a);
 }
