@@ -50,6 +50,13 @@ extern const unsigned int mask32[32];
 
 static exb_engine *g_engine = NULL;
 static int g_ranks = 1;
+/* Deferred newviewGeneric (below): node numbers whose CLV on the device is out of date.  A node on this list is treated
+   by the traversal builder exactly like a node that does not look the right way: it is recomputed, children first, by the
+   next call that needs it. */
+static unsigned char *g_stale = NULL;            /* [2 * mxtips] */
+static int g_defer_newviews = 0;                 /* set in backend_init (EXAML_B200_EAGER_NEWVIEWS=1 switches it off) */
+static int g_emit_marks_stale = 0;               /* computeTraversalInfo is building a list that will NOT be executed now */
+#define IS_STALE(rec) (g_stale && g_stale[(rec)->number])
 static exb_entry *g_entries = NULL;
 static double *g_qz = NULL, *g_rz = NULL;
 static unsigned char *g_mask = NULL;
@@ -106,7 +113,7 @@ static void backend_comm_init(void)
 }
 
 /* EXAML_B200_SPR_STATS=1: call statistics at exit */
-static long g_calls_eval_full = 0, g_calls_eval = 0, g_calls_newview = 0, g_calls_makenewz = 0, g_entries_total = 0;
+static long g_calls_eval_full = 0, g_calls_eval = 0, g_calls_newview = 0, g_calls_newview_deferred = 0, g_calls_makenewz = 0, g_entries_total = 0;
 static void spr_report(void);
 
 static void backend_init(tree *tr)
@@ -137,6 +144,8 @@ static void backend_init(tree *tr)
       backend_fail("exb_set_partition");
   }
   if (exb_commit(g_engine) != EXB_OK) backend_fail("exb_commit");
+  g_stale = (unsigned char *)calloc(2 * (size_t)tr->mxtips, 1);
+  g_defer_newviews = g_stale && !getenv("EXAML_B200_EAGER_NEWVIEWS");
   exb_set_timing(g_engine, 0);
   if (getenv("EXAML_B200_SPR_STATS")) atexit(spr_report);
   backend_comm_init();
@@ -281,6 +290,7 @@ static void emit_entry(traversalInfo *ti, int *counter, int tipCase, nodeptr p, 
     t->rz[b] = r->z[b];
   }
   *counter += 1;
+  if (g_stale) g_stale[p->number] = (unsigned char)g_emit_marks_stale;      /* about to be recomputed -- or deferred again */
 }
 
 /* Post-order list of the CLVs at and below p that have to be recomputed so that p's CLV looks away
@@ -304,15 +314,15 @@ void computeTraversalInfo(nodeptr p, traversalInfo *ti, int *counter, int maxTip
   }
   if (qTip || rTip) {
     nodeptr tip = qTip ? q : r, inner = qTip ? r : q;
-    if (!inner->x || !partialTraversal)
+    if (!inner->x || !partialTraversal || IS_STALE(inner))
       computeTraversalInfo(inner, ti, counter, maxTips, numBranches, partialTraversal);
     if (!p->x) getxnode(p);
     assert(p->x && inner->x);
     emit_entry(ti, counter, TIP_INNER, p, tip, inner, numBranches);
     return;
   }
-  if (!q->x || !partialTraversal) computeTraversalInfo(q, ti, counter, maxTips, numBranches, partialTraversal);
-  if (!r->x || !partialTraversal) computeTraversalInfo(r, ti, counter, maxTips, numBranches, partialTraversal);
+  if (!q->x || !partialTraversal || IS_STALE(q)) computeTraversalInfo(q, ti, counter, maxTips, numBranches, partialTraversal);
+  if (!r->x || !partialTraversal || IS_STALE(r)) computeTraversalInfo(r, ti, counter, maxTips, numBranches, partialTraversal);
   if (!p->x) getxnode(p);
   assert(p->x && q->x && r->x);
   emit_entry(ti, counter, INNER_INNER, p, q, r, numBranches);
@@ -402,8 +412,8 @@ void evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal)
     g_constants_stale = 1;
     computeTraversalInfo(q, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, FALSE);
   } else {
-    if (!p->x) computeTraversalInfo(p, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
-    if (!q->x) computeTraversalInfo(q, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
+    if (!p->x || IS_STALE(p)) computeTraversalInfo(p, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
+    if (!q->x || IS_STALE(q)) computeTraversalInfo(q, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
   }
   storeExecuteMaskInTraversalDescriptor(tr);
   tr->td[0].traversalHasChanged = TRUE;
@@ -424,6 +434,20 @@ void newviewGeneric(tree *tr, nodeptr p, boolean masked)
   if (!masked && scan_serve_newview(tr, p)) return;             /* the new node of a lazy insertion the scan has scored */
   scan_flush(tr);
 
+  /* Deferred: newviewGeneric leaves nothing behind that the host reads -- the CLVs are private to the replaced files
+      -- except the x flags.  So the flags are updated exactly as always (the same computeTraversalInfo walk),
+     but the listed nodes are only MARKED; whichever later call needs one of them finds it on its own walk (IS_STALE) and
+     recomputes it, children first, inside its own descriptor.  The thousands of one- and two-entry newview calls of a
+     smoothing pass thereby ride along with the makenewz / evaluate calls that follow them, and a CLV that is invalidated
+     again before anybody looked at it is never computed.  Masked calls (-M: only the unconverged partitions) stay eager. */
+  if (g_defer_newviews && !masked) {
+    g_emit_marks_stale = 1;
+    tr->td[0].count = 0;
+    computeTraversalInfo(p, tr->td[0].ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
+    g_emit_marks_stale = 0;
+    g_calls_newview_deferred++;
+    return;
+  }
   tr->td[0].count = 0;
   computeTraversalInfo(p, tr->td[0].ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
   tr->td[0].traversalHasChanged = TRUE;
@@ -547,8 +571,8 @@ void makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxiter, do
       assert(tr->executeModel[i]);
   }
   tr->td[0].count = 1;
-  if (!p->x) computeTraversalInfo(p, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
-  if (!q->x) computeTraversalInfo(q, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
+  if (!p->x || IS_STALE(p)) computeTraversalInfo(p, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
+  if (!q->x || IS_STALE(q)) computeTraversalInfo(q, ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
   g_calls_makenewz++;
   g_entries_total += tr->td[0].count - 1;
 
@@ -610,8 +634,9 @@ static long g_spr_scans = 0, g_spr_scored = 0, g_spr_served = 0, g_spr_flushed =
 static void spr_report(void)
 {
   if (processID == 0)
-    printf("B200 back-end, likelihood calls: %ld evaluateGeneric (full) + %ld (partial), %ld newviewGeneric, %ld makenewzGeneric; "
-           "%ld descriptor entries\n", g_calls_eval_full, g_calls_eval, g_calls_newview, g_calls_makenewz, g_entries_total);
+    printf("B200 back-end, likelihood calls: %ld evaluateGeneric (full) + %ld (partial), %ld newviewGeneric (+ %ld deferred), "
+           "%ld makenewzGeneric; %ld descriptor entries\n", g_calls_eval_full, g_calls_eval, g_calls_newview,
+           g_calls_newview_deferred, g_calls_makenewz, g_entries_total);
   if (processID == 0)
     printf("B200 back-end, batched insertion scoring: %ld scans, %ld engine calls, %ld candidates scored, %ld served from the table, "
            "%ld answered newviews computed after all\n", g_spr_scans, g_spr_calls, g_spr_scored, g_spr_served, g_spr_flushed);
@@ -649,7 +674,7 @@ static void spr_orient(tree *tr, nodeptr rec)
 {
   int cnt = 0, i, b;
   const int nb = tr->numBranches;
-  if (isTip(rec->number, tr->mxtips) || rec->x) return;
+  if (isTip(rec->number, tr->mxtips) || (rec->x && !IS_STALE(rec))) return;
   computeTraversalInfo(rec, tr->td[0].ti, &cnt, tr->mxtips, tr->numBranches, TRUE);   /* td[0] is free between calls */
   spr_reserve(tr, cnt);
   for (i = 0; i < cnt; i++) {
@@ -697,6 +722,17 @@ static void spr_walk(tree *tr, nodeptr q, int mintrav, int maxtrav, int depth, n
   }
 }
 
+/* The scan's list is not going to be executed (too deep, nothing to score, engine refused): the tree's own nodes it meant
+   to recompute have their x flags set by the walk already -- put them on the stale list so that the next call that needs
+   them recomputes them. */
+static void spr_abandon(tree *tr)
+{
+  int i;
+  for (i = 1; i < g_spr.n; i++)
+    if (!(g_spr.ent[i].tipCase & EXB_SCORE) && g_spr.ent[i].pNumber <= 2 * tr->mxtips - 2)
+      g_stale[g_spr.ent[i].pNumber] = 1;
+}
+
 void batchedInsertionScanBegin(tree *tr, nodeptr p, nodeptr p1, nodeptr p2, int mintrav, int maxtrav)
 {
   static int enabled = -1;
@@ -724,7 +760,7 @@ void batchedInsertionScanBegin(tree *tr, nodeptr p, nodeptr p1, nodeptr p2, int 
     spr_walk(tr, a->next->back, mintrav, maxtrav, 0, a, b->number);
     spr_walk(tr, a->next->next->back, mintrav, maxtrav, 0, a, b->number);
   }
-  if (g_spr.failed || g_spr.ncand == 0) return;
+  if (g_spr.failed || g_spr.ncand == 0) { spr_abandon(tr); return; }
   g_spr.lnl = (double *)realloc(g_spr.lnl, (size_t)g_spr.ncand * P * sizeof(double));
   if (!g_spr.lnl) { fprintf(stderr, "out of memory\n"); MPI_Abort(MPI_COMM_WORLD, -1); exit(-1); }
   for (m = 0; m < P; m++) g_mask[m] = tr->executeModel[m] ? 1 : 0;
@@ -752,6 +788,8 @@ void batchedInsertionScanBegin(tree *tr, nodeptr p, nodeptr p1, nodeptr p2, int 
       static int told = 0;
       if (!told && processID == 0) printf("\nB200 back-end: batched insertion scoring not used (%s)\n", exb_last_error());
       told = 1;
+      /* (entries of earlier pieces were executed; recomputing them once more is harmless) */
+      spr_abandon(tr);
       return;                                      /* candidates are scored one by one as before */
     }
     at += n;
