@@ -117,6 +117,28 @@ def test_batched_insertion_scan_behind_the_search(args, taxa):
             assert scans > 10 and calls == scans and served > scans and served <= scored and flushed == 0, m.group(0)
 
 
+def test_deferred_newviews_change_the_calls_not_the_results():
+    """newviewGeneric only marks its nodes; the next call that needs them recomputes them inside its own descriptor
+    (axml_backend.c).  Same search, same likelihood, no newview engine call left; EXAML_B200_EAGER_NEWVIEWS=1 is the
+    call-by-call behaviour."""
+    import re
+    with tempfile.TemporaryDirectory() as tmp:
+        binary, tree = small_dna_case(tmp, taxa=14, sites=300, seed=8)
+        out = {}
+        for tag, extra in (("EAGER", {"EXAML_B200_EAGER_NEWVIEWS": "1"}), ("LAZY", {})):
+            r, best, _ = run_mode(EXE, binary, tree, tmp, tag, ["-m", "GAMMA", "-f", "d"], env=dict(ENV, EXAML_B200_SPR_STATS="1", **extra))
+            assert r.returncode == 0, r.stdout[-1500:]
+            m = re.search(r"likelihood calls: (\d+) evaluateGeneric \(full\) \+ (\d+) \(partial\), (\d+) newviewGeneric \(\+ (\d+) deferred\), (\d+) makenewzGeneric; (\d+) descriptor entries", r.stdout)
+            assert m, r.stdout[-600:]
+            out[tag] = (best, [int(x) for x in m.groups()])
+        (b0, c0), (b1, c1) = out["EAGER"], out["LAZY"]
+        assert _rel(b1, b0) < 1e-9, (b0, b1)
+        assert c0[2] > 100 and c0[3] == 0                  # eager: every newviewGeneric is an engine call
+        assert c1[2] == 0 and c1[3] == c0[2]               # deferred: none is, the same calls were made by the host
+        assert c1[0] == c0[0] and c1[1] == c0[1] and c1[4] == c0[4]
+        assert c1[5] <= c0[5]                              # and no more node updates than before
+
+
 def test_batched_insertion_scan_on_two_ranks():
     """The scan's per-candidate sums are all-reduced inside exb_score_insertions (here: the oracle harness over mpi_tcp.c);
     both ranks walk the same branches and must answer testInsertBIG identically -- the search ends where the reference's does."""
