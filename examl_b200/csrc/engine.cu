@@ -1048,14 +1048,14 @@ static int run_traversal(exb_engine *e, const exb_entry *ti, int count, int firs
   FinishArgs f;
   memset(&f, 0, sizeof f);
   bool folded = false;
-  if (mode != MODE_SCORE) {
-  f.gs = e->gs; f.gs_stride = e->gs_stride; f.scale_inc = e->scale_inc;
-  f.entries = (const DevEntry *)(e->stage_use + e->o_entries);
-  f.count = count; f.first = first; f.mxtips = e->mxtips; f.nparts = e->P;
-  f.mask = e->stage_use + e->o_mask; f.part_has_sites = e->part_has_sites;
-  f.tile_out[0] = e->cls[0].tile_out; f.tile_out[1] = e->cls[1].tile_out;
-  f.part_tile_begin = e->part_tile_begin; f.part_tile_count = e->part_tile_count; f.part_cls = e->part_cls;
-  f.mode = mode; f.log_minlikelihood = log(kMinLikelihood); f.out = e->out_d;
+  if (mode != MODE_SCORE) {                        // (a scoring call ends in its own two kernels)
+    f.gs = e->gs; f.gs_stride = e->gs_stride; f.scale_inc = e->scale_inc;
+    f.entries = (const DevEntry *)(e->stage_use + e->o_entries);
+    f.count = count; f.first = first; f.mxtips = e->mxtips; f.nparts = e->P;
+    f.mask = e->stage_use + e->o_mask; f.part_has_sites = e->part_has_sites;
+    f.tile_out[0] = e->cls[0].tile_out; f.tile_out[1] = e->cls[1].tile_out;
+    f.part_tile_begin = e->part_tile_begin; f.part_tile_count = e->part_tile_count; f.part_cls = e->part_cls;
+    f.mode = mode; f.log_minlikelihood = log(kMinLikelihood); f.out = e->out_d;
     set_finish_outputs(e, f);
   }
   SmallCall sc;
