@@ -1411,6 +1411,11 @@ extern "C" int exb_can_score_insertions(exb_engine *e)
 {
   if (!e || !e->committed || e->cat || e->sev) return 0;
   if (e->aa_tc && !e->cls[CLS_AA].tiles_h.empty()) return 0;
+  // LG4M / LG4X partitions: the scoring tail has the per-category weights, but no parity test covers it yet -- refuse rather
+  // than answer unverified (the caller then scores candidate by candidate)
+  const ClassState &k = e->cls[CLS_AA];
+  for (int pc = 0; pc < k.nparts; pc++)
+    if (k.models_h[(size_t)pc * k.model_doubles + kAaLg4] != 0.0) return 0;
   return 1;
 }
 
@@ -1467,7 +1472,7 @@ extern "C" int exb_score_insertions(exb_engine *e, const exb_entry *ti, int coun
 {
   if (!e || !e->committed) return fail(EXB_ERR_STATE, "engine not committed");
   if (!exb_can_score_insertions(e))
-    return fail(EXB_ERR_STATE, "exb_score_insertions: not available under PSR, -S or the tf32x3 protein mode (score the candidates one by one)");
+    return fail(EXB_ERR_STATE, "exb_score_insertions: not available under PSR, -S, the tf32x3 protein mode or with LG4M / LG4X partitions (score the candidates one by one)");
   if (count < 1 || ncand < 0 || (ncand > 0 && !lnl)) return fail(EXB_ERR_ARG, "exb_score_insertions: bad arguments");
   int rc = run_traversal(e, ti, count, 1, qz, rz, executeModel, MODE_SCORE, ncand);
   if (rc) return rc;

@@ -220,8 +220,8 @@ int  exb_evaluate_partial(exb_engine *e, const exb_entry *entries, int count, co
  *                  pNumber of a scoring entry = index k of the candidate (0 <= k < ncand).
  * lnl[ncand * numPartitions] (candidate-major) is globally reduced like exb_evaluate's output; masked partitions
  * read 0.  Scratch CLVs and their scaler counts persist between calls, so a long scan may be cut into several calls
- * anywhere.  GAMMA, dense arena (not under EXB_CAT, -S or EXB_AA_TF32X3: EXB_ERR_STATE, the caller then scores the
- * candidates one by one as before). */
+ * anywhere.  GAMMA, dense arena (not under EXB_CAT, -S, EXB_AA_TF32X3 or with LG4M / LG4X partitions: EXB_ERR_STATE, the
+ * caller then scores the candidates one by one as before). */
 #define EXB_SCORE          4
 #define EXB_SCRATCH_NODES 64
 int  exb_score_insertions(exb_engine *e, const exb_entry *ti, int count, const double *qz, const double *rz,
