@@ -20,6 +20,10 @@
  *   EXAML_PROBE_NOTIPS=1        omit the alignment bytes / weights from <prefix>.first.json too
  *                               (the mkz / final dumps never carry them).
  *   EXAML_PROBE_EXIT_FIRST=1    exit(0) right after the first evaluateGeneric (and its dump).
+ *   EXAML_PROBE_TRACE=<file>    one line per evaluateGeneric call -- "E <p> <p->back> <fullTraversal> <tr->likelihood %.17g>" --
+ *                               up to EXAML_PROBE_TRACE_MAX lines (default 5000): the sequence of tree evaluations of a
+ *                               search, among them every lazy insertion testInsertBIG scores (searchAlgo.c:735).  Pins the
+ *                               batched insertion scan to the reference's own numbers (tests/golden/*.trace.gz).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -200,6 +204,18 @@ void __wrap_evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal)
   if (g_partial_n > 0 && !g_partial_dumped && prefix) dump_partial(tr);
   __real_evaluateGeneric(tr, p, fullTraversal);
   g_eval_calls++;
+  {
+    static FILE *trace = NULL;
+    static long left = -1;
+    const char *tf = getenv("EXAML_PROBE_TRACE");
+    if (tf && processID == 0 && left != 0) {
+      if (!trace) { trace = fopen(tf, "w"); left = getenv("EXAML_PROBE_TRACE_MAX") ? atol(getenv("EXAML_PROBE_TRACE_MAX")) : 5000; }
+      if (trace) {
+        fprintf(trace, "E %d %d %d %.17g\n", p->number, p->back->number, fullTraversal ? 1 : 0, tr->likelihood);
+        if (--left == 0) { fclose(trace); trace = NULL; } else fflush(trace);
+      }
+    }
+  }
   if (g_eval_calls == 1) {
     g_tr = tr;
     if (prefix) {

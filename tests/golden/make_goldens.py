@@ -12,6 +12,10 @@ alignments, and dumps, with %.17g:
   *.final  state at exit of `-f e` (optimised model + branch lengths) and its lnL
   *.partial (PSR) state during the first optimizeRateCategories and the first 160 evaluatePartialGeneric
            calls of every partition: (partition, site, rate, value)
+  dna49.search.trace.gz   the first 6000 evaluateGeneric calls of the default search (-f d) on testData/49, one line each:
+           "E <p> <p->back> <fullTraversal> <tr->likelihood>" -- 561 model-optimisation evaluations, then the lazy SPR
+           insertions testInsertBIG scores one by one (searchAlgo.c:735) and the evaluations in between.  The drop-in
+           must produce the same sequence, also when the insertions are answered from the batched scan's table.
 The parity tests replay those states through the oracle and the CUDA engine.
 
 Usage: python tests/golden/make_goldens.py            (about a minute)
@@ -67,10 +71,23 @@ def case(tag, alignment, tree_file, parser_args, examl_args, dumps=("first", "mk
         return out
 
 
+def search_trace(tag, alignment, tree_file, parser_args, lines=6000):
+    with tempfile.TemporaryDirectory() as tmp:
+        run([os.path.join(BIN, "parse-examl"), "-s", alignment, "-n", "aln"] + parser_args, tmp)
+        tf = os.path.join(tmp, "trace")
+        run([os.path.join(BIN, "examl-AVX"), "-s", "aln.binary", "-t", tree_file, "-m", "GAMMA", "-n", "T", "-w", tmp + "/", "-f", "d"],
+            tmp, {"EXAML_PROBE_TRACE": tf, "EXAML_PROBE_TRACE_MAX": str(lines)})
+        path = os.path.join(HERE, tag + ".search.trace.gz")
+        open(path, "wb").write(gzip.compress(open(tf, "rb").read(), 9, mtime=0))
+        print(f"  wrote {os.path.relpath(path, ROOT)} ({os.path.getsize(path)} bytes)")
+
+
 def main():
     if not os.path.exists(os.path.join(BIN, "examl-AVX")):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref", "-j8"])
     td = os.path.join(REF, "testData")
+    print("testData/49, default search: the sequence of evaluateGeneric results")
+    search_trace("dna49", f"{td}/49", f"{td}/49.tree", ["-m", "DNA"])
     with tempfile.TemporaryDirectory() as tmp:
         print("testData/49, DNA, unpartitioned, -f e")
         case("dna49", f"{td}/49", f"{td}/49.tree", ["-m", "DNA"], ["-f", "e"])

@@ -117,6 +117,42 @@ def test_batched_insertion_scan_behind_the_search(args, taxa):
             assert scans > 10 and calls == scans and served > scans and served <= scored and flushed == 0, m.group(0)
 
 
+@pytest.mark.parametrize("which", ["plain", "batched-scan"])
+def test_search_reproduces_the_references_evaluations(which):
+    """tests/golden/dna49.search.trace.gz holds what the REFERENCE's own binary saw in tr->likelihood after each of its
+    first 6000 evaluateGeneric calls of `-f d` on testData/49 -- model optimisation, then thousands of lazy SPR insertions
+    scored one by one by testInsertBIG (searchAlgo.c:682-735).  The drop-in's host logic must issue the same evaluations
+    in the same order and see the same numbers -- also when the insertions are answered from the table of the batched scan
+    (exb_score_insertions), which is thereby pinned to the reference's own values."""
+    import gzip
+    gold = [l.split() for l in gzip.open(os.path.join(ROOT, "tests", "golden", "dna49.search.trace.gz"), "rt")]
+    exe = EXE if which == "plain" else hostcheck_build.EXE_SPR
+    with tempfile.TemporaryDirectory() as tmp:
+        binary, tree, _ = write_inputs("dna49", tmp)
+        tf = os.path.join(tmp, "trace")
+        # the probe traces the first 6000 evaluations; the run is cut short afterwards (the whole search is covered elsewhere)
+        e = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+        e.update(ENV, EXAML_PROBE_TRACE=tf, EXAML_PROBE_TRACE_MAX=str(len(gold)), EXAML_B200_SPR_STATS="1")
+        p = subprocess.Popen([exe, "-s", binary, "-t", tree, "-m", "GAMMA", "-n", "TR", "-f", "d", "-w", tmp + "/"], cwd=tmp, env=e,
+                             stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
+        import time
+        t0 = time.time()
+        while p.poll() is None and time.time() - t0 < 900:
+            if os.path.exists(tf) and sum(1 for _ in open(tf)) >= len(gold):
+                p.terminate()
+                break
+            time.sleep(0.5)
+        p.wait(timeout=60)
+        got = [l.split() for l in open(tf)][:len(gold)]
+    assert len(got) == len(gold)
+    nins = 0
+    for i, (a, b) in enumerate(zip(gold, got)):
+        assert a[:4] == b[:4], (i, a, b)                                        # same branch, same kind of traversal
+        assert abs(float(a[4]) - float(b[4])) <= 1e-8 * abs(float(a[4])), (i, a, b)
+        nins += a[3] == "0"
+    assert nins > 5000          # of which this many are partial evaluations: the insertions and what happens between them
+
+
 def test_deferred_newviews_change_the_calls_not_the_results():
     """newviewGeneric only marks its nodes; the next call that needs them recomputes them inside its own descriptor
     (axml_backend.c).  Same search, same likelihood, no newview engine call left; EXAML_B200_EAGER_NEWVIEWS=1 is the
