@@ -24,11 +24,17 @@
  *                               up to EXAML_PROBE_TRACE_MAX lines (default 5000): the sequence of tree evaluations of a
  *                               search, among them every lazy insertion testInsertBIG scores (searchAlgo.c:735).  Pins the
  *                               batched insertion scan to the reference's own numbers (tests/golden/*.trace.gz).
+ *   EXAML_PROBE_TRACE_MKZ=1|2   (debugging aid) also one line per makenewzGeneric call -- "M <p> <q> <mask> <result...>" --;
+ *                               2: plus maxiter, the start values, partitionConverged and the derivatives of the branch's
+ *                               sum table at the start values as the binary's own execCore computes them.  (This is how the
+ *                               -M search on testData/49 was found to leave the reference's path at a branch whose fourth
+ *                               partition has derivatives of 1e-20: rounding noise, different in every implementation.)
  */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/time.h>
+#include <math.h>
 #include "axml.h"
 
 void __real_evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal);
@@ -48,6 +54,18 @@ static void dump_path(char *path, size_t n, const char *prefix, const char *kind
   else snprintf(path, n, "%s.r%d.%s.json", prefix, processID, kind);
 }
 static int g_eval_calls = 0, g_mkz_calls = 0;
+
+/* EXAML_PROBE_TRACE: one line per traced call, up to EXAML_PROBE_TRACE_MAX evaluateGeneric lines */
+static FILE *trace_file(int count_it)
+{
+  static FILE *trace = NULL;
+  static long left = -1;
+  const char *tf = getenv("EXAML_PROBE_TRACE");
+  if (!tf || processID != 0 || left == 0) return NULL;
+  if (!trace) { trace = fopen(tf, "w"); left = getenv("EXAML_PROBE_TRACE_MAX") ? atol(getenv("EXAML_PROBE_TRACE_MAX")) : 5000; }
+  if (trace && count_it && --left == 0) { FILE *f = trace; trace = NULL; return f; }    /* the caller writes the last line and closes */
+  return trace;
+}
 
 static double now_s(void)
 {
@@ -205,15 +223,10 @@ void __wrap_evaluateGeneric(tree *tr, nodeptr p, boolean fullTraversal)
   __real_evaluateGeneric(tr, p, fullTraversal);
   g_eval_calls++;
   {
-    static FILE *trace = NULL;
-    static long left = -1;
-    const char *tf = getenv("EXAML_PROBE_TRACE");
-    if (tf && processID == 0 && left != 0) {
-      if (!trace) { trace = fopen(tf, "w"); left = getenv("EXAML_PROBE_TRACE_MAX") ? atol(getenv("EXAML_PROBE_TRACE_MAX")) : 5000; }
-      if (trace) {
-        fprintf(trace, "E %d %d %d %.17g\n", p->number, p->back->number, fullTraversal ? 1 : 0, tr->likelihood);
-        if (--left == 0) { fclose(trace); trace = NULL; } else fflush(trace);
-      }
+    FILE *trace = trace_file(1);
+    if (trace) {
+      fprintf(trace, "E %d %d %d %.17g\n", p->number, p->back->number, fullTraversal ? 1 : 0, tr->likelihood);
+      fflush(trace);
     }
   }
   if (g_eval_calls == 1) {
@@ -253,6 +266,32 @@ void __wrap_makenewzGeneric(tree *tr, nodeptr p, nodeptr q, double *z0, int maxi
   for (b = 0; b < tr->numBranches; b++) z0copy[b] = z0[b];
   __real_makenewzGeneric(tr, p, q, z0, maxiter, result, mask);
   g_mkz_calls++;
+  if (getenv("EXAML_PROBE_TRACE_MKZ")) {           /* also the branch optimisations: "M <p> <q> <mask> <result...>" (debugging aid) */
+    FILE *trace = trace_file(0);
+    if (trace) {
+      fprintf(trace, "M %d %d %d", p->number, q->number, mask ? 1 : 0);
+      for (b = 0; b < tr->numBranches; b++) fprintf(trace, " %.17g", result[b]);
+      if (getenv("EXAML_PROBE_TRACE_MKZ")[0] == '2') {         /* ... and the inputs */
+        fprintf(trace, " | maxiter %d z0", maxiter);
+        for (b = 0; b < tr->numBranches; b++) fprintf(trace, " %.17g", z0copy[b]);
+        fprintf(trace, " conv");
+        for (b = 0; b < tr->numBranches; b++) fprintf(trace, " %d", tr->partitionConverged[b] ? 1 : 0);
+        {   /* derivatives of the branch's sum table at the start values, by the binary's own execCore */
+          volatile double d1[NUM_BRANCHES], d2[NUM_BRANCHES];
+          double lz[NUM_BRANCHES];
+          for (b = 0; b < tr->numBranches; b++) lz[b] = log(z0copy[b] < zmin ? zmin : z0copy[b]);
+          storeExecuteMaskInTraversalDescriptor(tr);
+          storeValuesInTraversalDescriptor(tr, lz);
+          execCore(tr, d1, d2);
+          fprintf(trace, " d1");
+          for (b = 0; b < tr->numBranches; b++) fprintf(trace, " %.12g", d1[b]);
+          fprintf(trace, " d2");
+          for (b = 0; b < tr->numBranches; b++) fprintf(trace, " %.12g", d2[b]);
+        }
+      }
+      fprintf(trace, "\n");
+    }
+  }
   if (g_mkz_calls == 1 && prefix) {
     char path[4096], extra[16384];
     int off = 0;
