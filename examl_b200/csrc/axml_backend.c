@@ -439,8 +439,10 @@ void newviewGeneric(tree *tr, nodeptr p, boolean masked)
      but the listed nodes are only MARKED; whichever later call needs one of them finds it on its own walk (IS_STALE) and
      recomputes it, children first, inside its own descriptor.  The thousands of one- and two-entry newview calls of a
      smoothing pass thereby ride along with the makenewz / evaluate calls that follow them, and a CLV that is invalidated
-     again before anybody looked at it is never computed.  Masked calls (-M: only the unconverged partitions) stay eager. */
-  if (g_defer_newviews && !masked) {
+     again before anybody looked at it is never computed.  Only with joint branch lengths: under -M the calls that would
+     later pick the marked nodes up run under partition masks (makenewzGeneric(..., mask = TRUE) in update(),
+     searchAlgo.c:150-157) and would recompute them for the unconverged partitions only, whereas this call is owed to all. */
+  if (g_defer_newviews && !masked && tr->numBranches == 1) {
     g_emit_marks_stale = 1;
     tr->td[0].count = 0;
     computeTraversalInfo(p, tr->td[0].ti, &tr->td[0].count, tr->mxtips, tr->numBranches, TRUE);
@@ -727,10 +729,26 @@ static void spr_walk(tree *tr, nodeptr q, int mintrav, int maxtrav, int depth, n
    them recomputes them. */
 static void spr_abandon(tree *tr)
 {
-  int i;
+  const int nb = tr->numBranches;
+  int i, n = 0, m;
+  if (nb == 1) {
+    for (i = 1; i < g_spr.n; i++)
+      if (!(g_spr.ent[i].tipCase & EXB_SCORE) && g_spr.ent[i].pNumber <= 2 * tr->mxtips - 2)
+        g_stale[g_spr.ent[i].pNumber] = 1;
+    return;
+  }
+  /* -M: later calls may run under partition masks, so nothing is left for them: the tree's own nodes of the list are
+     recomputed now, for all partitions (their entries are in execution order; they never read a scratch node) */
   for (i = 1; i < g_spr.n; i++)
-    if (!(g_spr.ent[i].tipCase & EXB_SCORE) && g_spr.ent[i].pNumber <= 2 * tr->mxtips - 2)
-      g_stale[g_spr.ent[i].pNumber] = 1;
+    if (!(g_spr.ent[i].tipCase & EXB_SCORE) && g_spr.ent[i].pNumber <= 2 * tr->mxtips - 2) {
+      g_spr.ent[n] = g_spr.ent[i];
+      memmove(g_spr.qz + (size_t)n * nb, g_spr.qz + (size_t)i * nb, (size_t)nb * sizeof(double));
+      memmove(g_spr.rz + (size_t)n * nb, g_spr.rz + (size_t)i * nb, (size_t)nb * sizeof(double));
+      n++;
+    }
+  for (m = 0; m < tr->NumberOfModels; m++) g_mask[m] = 1;
+  if (n > 0 && exb_newview(g_engine, g_spr.ent, n, g_spr.qz, g_spr.rz, g_mask) != EXB_OK) backend_fail("exb_newview");
+  g_spr.n = 0;
 }
 
 void batchedInsertionScanBegin(tree *tr, nodeptr p, nodeptr p1, nodeptr p2, int mintrav, int maxtrav)
